@@ -1,0 +1,169 @@
+/*
+ * qw_b200.h -- C ABI of the B200-native RK4 heatmap path.
+ *
+ * The reference (mgarbellini/Quantum-Walks-Time-Dependent-Hamiltonians) is plain Python
+ * with no FFI of its own; its boundary is a set of Python call signatures plus module
+ * globals.  This header is the C ABI placed directly beneath those
+ * signatures: plain pointers and sizes, no torch types.  Each entry point names the
+ * reference code it replaces (paths relative to the reference's Code/ directory).
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, <0 invalid argument (QW_E_*), >0 a cudaError_t.
+ *     qw_last_error() returns a human-readable message for the calling thread.
+ *   - "_dev" functions take DEVICE pointers, are stream-ordered (cudaStream_t passed as
+ *     void*; NULL = legacy default stream) and allocate nothing persistent, except the
+ *     large-N paths which take scratch from the stream-ordered pool (cudaMallocAsync).
+ *     Outputs are valid once the stream has been synchronised.
+ *   - "_host" functions take HOST pointers, do their own H2D/D2H copies on the given
+ *     device and return when the results are in the host buffers.
+ *   - the library keeps no global mutable state besides counters and is safe from one
+ *     host thread per GPU.
+ *   - complex128 arrays are interleaved (re, im) doubles, as numpy lays them out.
+ */
+#ifndef QW_B200_H
+#define QW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QW_ABI_VERSION 1
+
+/* topology -- QW_Search.py:70-81 (0 complete, 1 cycle); BCB.py:30-67 'complete'/'circular' */
+enum { QW_TOPO_COMPLETE = 0, QW_TOPO_CYCLE = 1 };
+
+/* schedule g_T(t/T) -- QW_Search.py:104-109 fixes 0..2; BCB.py:75-87 the rest;
+ * QW_SCHED_STATIC is the time-independent comparator H = L - gamma|w><w| (BCB.py:101-135) */
+enum {
+    QW_SCHED_CERF3 = 0, QW_SCHED_LIN = 1, QW_SCHED_SQRT = 2, QW_SCHED_CBRT = 3,
+    QW_SCHED_CERF5 = 4, QW_SCHED_CERF7 = 5, QW_SCHED_STATIC = 6
+};
+
+/* where gamma sits: H = (1-g) L - g*gamma |w><w|   (all reference code, BCB.py:93-97)
+ *               or  H = (1-g) gamma L - g |w><w|   (thesis Eq. 2.14 p.47) */
+enum { QW_GAMMA_ON_ORACLE = 0, QW_GAMMA_ON_LAPLACIAN = 1 };
+
+enum {
+    QW_E_NULL = -1,        /* required pointer is NULL */
+    QW_E_DIMENSION = -2,   /* n < 1, cycle graph with n < 3, target out of range */
+    QW_E_ENUM = -3,        /* unknown topology / schedule / gamma_on */
+    QW_E_STEPS = -4,       /* neither step_size > 0 nor n_steps >= 0 usable */
+    QW_E_SIZE = -5,        /* negative or inconsistent sizes */
+    QW_E_UNSUPPORTED = -6  /* configuration not supported by this build */
+};
+
+/* The module globals the reference reads at call time (BCB.py:20-24: dimension, topology,
+ * step_function) plus the fixed-step rule of QW_Search.py:149-164. */
+typedef struct qw_problem {
+    int64_t n;          /* 'dimension' */
+    int32_t topology;   /* QW_TOPO_* */
+    int32_t schedule;   /* QW_SCHED_* ('step_function') */
+    int32_t gamma_on;   /* QW_GAMMA_ON_* */
+    int32_t flags;      /* QW_FLAG_* */
+    int64_t target;     /* marked vertex; <0 = int((n-1)/2) as BCB.py:96-97 */
+    double  step_size;  /* >0: h = step_size, n = int(T/h) steps (QW_Search.py:153-154);
+                           else h = T/n_steps */
+    int64_t n_steps;    /* uniform step count when step_size <= 0 and no per-point array */
+} qw_problem;
+
+enum {
+    QW_FLAG_NONE = 0,
+    QW_FLAG_FORCE_GENERIC = 1,   /* use the global-memory kernel whatever n is (tests) */
+    QW_FLAG_FORCE_STREAM = 2,    /* use the tile-fused streaming kernel (cycle graph) */
+    QW_FLAG_EXACT_SUM = 4        /* complete graph: block-reduce sum(u) in every stage
+                                    instead of once per step (tests) */
+};
+
+/* ---- the hot path -------------------------------------------------------------------- */
+
+/* Batch of independent (T_q, gamma_q) points: replaces the body of the loops
+ * Schroedinger_Solver.py:438-441 / BCB.py:250-253, i.e. evaluate_probability (BCB.py:193-203)
+ * -> solve_schrodinger_equation (BCB.py:177-190) -> schrodinger_equation (BCB.py:163-174)
+ * -> generate_hamiltonian (BCB.py:28-99), with the fixed-step RK4 of QW_Search.py:149-164
+ * in place of solve_ivp.  Also the robustness / localization ensembles (Robustness.py).
+ *   T, gamma     [n_points] doubles
+ *   n_steps      [n_points] int64 or NULL (then prob->n_steps; ignored if step_size > 0)
+ *   order        [n_points] int64 or NULL: the q-th thread block handles point order[q]
+ *                (host-side longest-first ordering when work per point differs)
+ *   p, norm      [n_points] doubles: |psi_w|^2/||psi||^2 and ||psi||^2 (norm nullable)
+ *   psi          NULL or complex128[n_points][n]: psi(T), not renormalised
+ */
+int qw_rk4_batch_dev(const qw_problem *prob, const double *T, const double *gamma,
+                     const int64_t *n_steps, const int64_t *order, int64_t n_points,
+                     double *p, double *norm, void *psi, void *stream);
+
+/* Rows [beta_begin, beta_end) of the heatmap probability[beta][T]: replaces
+ * grid_probability_evaluation (Schroedinger_Solver.py:426-444) / grid_eval (BCB.py:239-259);
+ * one call = one Ray task of parallel_routine (BCB.py:279-281).
+ *   time_array [n_time], beta_array [n_beta] doubles
+ *   p, norm    [(beta_end-beta_begin)][n_time] row-major (norm nullable)
+ */
+int qw_rk4_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_time,
+                    const double *beta_array, int64_t n_beta, int64_t beta_begin,
+                    int64_t beta_end, double *p, double *norm, void *stream);
+
+/* Host-buffer forms of the two calls above (copies inside; device = CUDA ordinal). */
+int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gamma,
+                      const int64_t *n_steps, int64_t n_points, double *p, double *norm,
+                      void *psi, int device);
+int qw_rk4_grid_host(const qw_problem *prob, const double *time_array, int64_t n_time,
+                     const double *beta_array, int64_t n_beta, int64_t beta_begin,
+                     int64_t beta_end, double *p, double *norm, int device);
+
+/* One right-hand side dy = -i H(t) y: replaces schrodinger_equation(t, y, beta, T)
+ * (BCB.py:163-174) with the implicit operator; y, dy complex128[n] on the device. */
+int qw_rhs_dev(const qw_problem *prob, double t, double T, double gamma, const void *y,
+               void *dy, void *stream);
+
+/* ---- fused post-integration reductions ----------------------------------------------- */
+
+/* Ensemble statistics over p[n] (BASELINE config 4 / thesis section 2.3):
+ * out[0] = mean, out[1] = population std, out[2] = min, out[3] = max,
+ * out[4+k] = fraction with p >= thresholds[k]  (k < n_thresholds <= 8).
+ * out is a device buffer of 4 + n_thresholds doubles; deterministic summation order. */
+int qw_ensemble_stats_dev(const double *p, int64_t n, const double *thresholds,
+                          int32_t n_thresholds, double *out, void *stream);
+
+/* Robustness map of a heatmap probability[n_beta][n_time] (Robustness.py:25-31, unrounded):
+ * R[j][i] = ((p[j][i]-p[j+v][i]) + (p[j][i]-p[j-v][i]))/2 with python index wrap for
+ * j-v < 0 and NaN where j+v >= n_beta; plus, per time column, the first-maximum beta
+ * index (Robustness.py:41-45).  R is [n_beta][n_time] (nullable), argmax_beta [n_time]
+ * int64 (nullable). */
+int qw_heatmap_robustness_dev(const double *p, int64_t n_beta, int64_t n_time,
+                              int64_t variation, double *R, int64_t *argmax_beta,
+                              void *stream);
+
+/* ---- introspection ------------------------------------------------------------------- */
+
+typedef struct qw_plan {
+    int32_t path;            /* 0 resident-cycle, 1 resident-complete, 2 generic, 3 stream */
+    int32_t sites_per_thread;
+    int32_t threads_per_block;
+    int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */
+    int32_t regs_per_thread;
+    int32_t smem_bytes;
+    int32_t sm_count;
+    int32_t reserved;
+} qw_plan;
+
+/* Which kernel a problem would run on the current device. */
+int qw_plan_query(const qw_problem *prob, qw_plan *plan);
+
+/* Sustained DFMA throughput of the current device in TFLOP/s (FMA = 2 flops), measured
+ * with a dependent-free register-only kernel running for about `millis` ms: the FP64
+ * roofline denominator (MEASURED_PEAKS.json carries no FP64 figure). */
+int qw_fp64_peak_probe(double millis, double *tflops, void *stream);
+
+/* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
+int64_t qw_launch_count(void);
+
+const char *qw_last_error(void);
+int qw_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QW_B200_H */

@@ -1,0 +1,317 @@
+// C ABI of the library (include/qw_b200.h): validation, kernel selection, host-buffer
+// forms.  No torch types; the Python shim passes raw device pointers and a stream handle.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "qw_common.cuh"
+
+cudaError_t qw_launch_resident(QwParams prm, cudaStream_t st, qw_plan *plan);
+int qw_resident_sites_per_thread(int64_t n);
+cudaError_t qw_generic_geometry(const QwParams &prm, int *blocks, size_t *scratch_bytes,
+                                qw_plan *plan);
+cudaError_t qw_launch_generic(const QwParams &prm, int blocks, cudaStream_t st);
+bool qw_stream_supported(const QwParams &prm);
+cudaError_t qw_stream_plan(const QwParams &prm, qw_plan *plan);
+cudaError_t qw_launch_stream(const QwParams &prm, cudaStream_t st, int64_t *launches);
+cudaError_t qw_launch_rhs(int64_t n, int topology, int64_t w, double a, double d,
+                          const double2 *y, double2 *dy, cudaStream_t st);
+cudaError_t qw_launch_stats(const double *p, int64_t n, const double *thr, int nthr, double *out,
+                            cudaStream_t st);
+cudaError_t qw_launch_robustness(const double *p, int64_t nb, int64_t nt, int64_t v, double *R,
+                                 int64_t *arg, cudaStream_t st, int *launches);
+cudaError_t qw_run_fp64_probe(double millis, double *tflops, cudaStream_t st, int *launches);
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+int validate(const qw_problem *prob, QwParams *prm)
+{
+    if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
+    if (prob->topology != QW_TOPO_COMPLETE && prob->topology != QW_TOPO_CYCLE)
+        return fail(QW_E_ENUM, "undefined topology %d", prob->topology);
+    if (prob->schedule < QW_SCHED_CERF3 || prob->schedule > QW_SCHED_STATIC)
+        return fail(QW_E_ENUM, "step_function value not defined: %d", prob->schedule);
+    if (prob->gamma_on != QW_GAMMA_ON_ORACLE && prob->gamma_on != QW_GAMMA_ON_LAPLACIAN)
+        return fail(QW_E_ENUM, "undefined gamma_on %d", prob->gamma_on);
+    if (prob->n < 1) return fail(QW_E_DIMENSION, "dimension %lld < 1", (long long)prob->n);
+    if (prob->topology == QW_TOPO_CYCLE && prob->n < 3)
+        return fail(QW_E_DIMENSION, "cycle graph needs dimension >= 3, got %lld",
+                    (long long)prob->n);
+    int64_t w = prob->target < 0 ? (prob->n - 1) / 2 : prob->target;
+    if (w >= prob->n) return fail(QW_E_DIMENSION, "target %lld out of range", (long long)w);
+    if (!(prob->step_size > 0.0) && prob->n_steps < 0)
+        return fail(QW_E_STEPS, "need step_size > 0 or n_steps >= 0");
+    memset(prm, 0, sizeof(*prm));
+    prm->n = prob->n;
+    prm->topology = prob->topology;
+    prm->schedule = prob->schedule;
+    prm->gamma_on = prob->gamma_on;
+    prm->flags = prob->flags;
+    prm->target = w;
+    prm->step_size = prob->step_size > 0.0 ? prob->step_size : 0.0;
+    prm->n_steps_uniform = prob->n_steps;
+    return 0;
+}
+
+enum { PATH_RESIDENT = 0, PATH_GENERIC = 2, PATH_STREAM = 3 };
+
+int choose_path(const QwParams &prm)
+{
+    if (prm.flags & QW_FLAG_FORCE_GENERIC) return PATH_GENERIC;
+    if ((prm.flags & QW_FLAG_FORCE_STREAM) && qw_stream_supported(prm)) return PATH_STREAM;
+    if (qw_resident_sites_per_thread(prm.n) > 0) return PATH_RESIDENT;
+    if (qw_stream_supported(prm)) return PATH_STREAM;
+    return PATH_GENERIC;
+}
+
+int run(QwParams &prm, cudaStream_t st)
+{
+    if (prm.n_points == 0) return 0;
+    cudaError_t e;
+    switch (choose_path(prm)) {
+    case PATH_RESIDENT:
+        e = qw_launch_resident(prm, st, nullptr);
+        if (e != cudaSuccess) return cuda_fail(e, "resident kernel launch");
+        g_launches += 1;
+        return 0;
+    case PATH_STREAM: {
+        int64_t nl = 0;
+        e = qw_launch_stream(prm, st, &nl);
+        g_launches += nl;
+        if (e != cudaSuccess) return cuda_fail(e, "streaming kernel launch");
+        return 0;
+    }
+    default: {
+        int blocks = 0;
+        size_t bytes = 0;
+        e = qw_generic_geometry(prm, &blocks, &bytes, nullptr);
+        if (e != cudaSuccess) return cuda_fail(e, "generic kernel geometry");
+        void *scratch = nullptr;
+        e = cudaMallocAsync(&scratch, bytes, st);
+        if (e != cudaSuccess) return cuda_fail(e, "scratch allocation");
+        prm.scratch = (double2 *)scratch;
+        e = qw_launch_generic(prm, blocks, st);
+        g_launches += 1;
+        cudaError_t e2 = cudaFreeAsync(scratch, st);
+        if (e != cudaSuccess) return cuda_fail(e, "generic kernel launch");
+        if (e2 != cudaSuccess) return cuda_fail(e2, "scratch free");
+        return 0;
+    }
+    }
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int qw_rk4_batch_dev(const qw_problem *prob, const double *T, const double *gamma,
+                     const int64_t *n_steps, const int64_t *order, int64_t n_points,
+                     double *p, double *norm, void *psi, void *stream)
+{
+    QwParams prm;
+    int rc = validate(prob, &prm);
+    if (rc) return rc;
+    if (n_points < 0) return fail(QW_E_SIZE, "n_points < 0");
+    if (n_points > 0 && (!T || !gamma || !p)) return fail(QW_E_NULL, "T, gamma and p are required");
+    prm.T = T; prm.gamma = gamma; prm.n_steps = n_steps; prm.order = order;
+    prm.n_points = n_points;
+    prm.p = p; prm.norm = norm; prm.psi = (double2 *)psi;
+    return run(prm, (cudaStream_t)stream);
+}
+
+int qw_rk4_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_time,
+                    const double *beta_array, int64_t n_beta, int64_t beta_begin,
+                    int64_t beta_end, double *p, double *norm, void *stream)
+{
+    QwParams prm;
+    int rc = validate(prob, &prm);
+    if (rc) return rc;
+    if (n_time < 0 || n_beta < 0 || beta_begin < 0 || beta_end < beta_begin || beta_end > n_beta)
+        return fail(QW_E_SIZE, "bad grid extents");
+    prm.n_points = (beta_end - beta_begin) * n_time;
+    if (prm.n_points > 0 && (!time_array || !beta_array || !p))
+        return fail(QW_E_NULL, "time_array, beta_array and p are required");
+    prm.time_array = time_array; prm.beta_array = beta_array;
+    prm.n_time = n_time; prm.beta_begin = beta_begin;
+    prm.p = p; prm.norm = norm;
+    return run(prm, (cudaStream_t)stream);
+}
+
+int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gamma,
+                      const int64_t *n_steps, int64_t n_points, double *p, double *norm,
+                      void *psi, int device)
+{
+    if (n_points < 0) return fail(QW_E_SIZE, "n_points < 0");
+    if (n_points > 0 && (!T || !gamma || !p)) return fail(QW_E_NULL, "T, gamma and p are required");
+    if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t nb = (size_t)n_points * sizeof(double);
+    DevBuf dT, dG, dS, dP, dN, dPsi;
+    if ((e = dT.alloc(nb)) || (e = dG.alloc(nb)) || (e = dP.alloc(nb)) || (e = dN.alloc(nb)))
+        return cuda_fail(e, "cudaMalloc");
+    if (n_steps && (e = dS.alloc((size_t)n_points * sizeof(int64_t)))) return cuda_fail(e, "cudaMalloc");
+    const size_t psib = psi ? (size_t)n_points * (size_t)prob->n * sizeof(double2) : 0;
+    if (psi && (e = dPsi.alloc(psib))) return cuda_fail(e, "cudaMalloc");
+    cudaStream_t st = nullptr;
+    if ((e = cudaMemcpyAsync(dT.p, T, nb, cudaMemcpyHostToDevice, st)) ||
+        (e = cudaMemcpyAsync(dG.p, gamma, nb, cudaMemcpyHostToDevice, st)))
+        return cuda_fail(e, "H2D copy");
+    if (n_steps && (e = cudaMemcpyAsync(dS.p, n_steps, (size_t)n_points * sizeof(int64_t),
+                                        cudaMemcpyHostToDevice, st)))
+        return cuda_fail(e, "H2D copy");
+    int rc = qw_rk4_batch_dev(prob, (double *)dT.p, (double *)dG.p, (int64_t *)dS.p, nullptr,
+                              n_points, (double *)dP.p, (double *)dN.p, dPsi.p, st);
+    if (rc) return rc;
+    if ((e = cudaMemcpyAsync(p, dP.p, nb, cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H copy");
+    if (norm && (e = cudaMemcpyAsync(norm, dN.p, nb, cudaMemcpyDeviceToHost, st)))
+        return cuda_fail(e, "D2H copy");
+    if (psi && (e = cudaMemcpyAsync(psi, dPsi.p, psib, cudaMemcpyDeviceToHost, st)))
+        return cuda_fail(e, "D2H copy");
+    if ((e = cudaStreamSynchronize(st))) return cuda_fail(e, "kernel execution");
+    return 0;
+}
+
+int qw_rk4_grid_host(const qw_problem *prob, const double *time_array, int64_t n_time,
+                     const double *beta_array, int64_t n_beta, int64_t beta_begin,
+                     int64_t beta_end, double *p, double *norm, int device)
+{
+    if (n_time < 0 || n_beta < 0 || beta_begin < 0 || beta_end < beta_begin || beta_end > n_beta)
+        return fail(QW_E_SIZE, "bad grid extents");
+    if (!time_array || !beta_array || !p) return fail(QW_E_NULL, "time_array, beta_array and p are required");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t np = (size_t)(beta_end - beta_begin) * (size_t)n_time * sizeof(double);
+    DevBuf dT, dB, dP, dN;
+    if ((e = dT.alloc((size_t)n_time * 8)) || (e = dB.alloc((size_t)n_beta * 8)) ||
+        (e = dP.alloc(np)) || (e = dN.alloc(np)))
+        return cuda_fail(e, "cudaMalloc");
+    cudaStream_t st = nullptr;
+    if ((e = cudaMemcpyAsync(dT.p, time_array, (size_t)n_time * 8, cudaMemcpyHostToDevice, st)) ||
+        (e = cudaMemcpyAsync(dB.p, beta_array, (size_t)n_beta * 8, cudaMemcpyHostToDevice, st)))
+        return cuda_fail(e, "H2D copy");
+    int rc = qw_rk4_grid_dev(prob, (double *)dT.p, n_time, (double *)dB.p, n_beta, beta_begin,
+                             beta_end, (double *)dP.p, (double *)dN.p, st);
+    if (rc) return rc;
+    if ((e = cudaMemcpyAsync(p, dP.p, np, cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H copy");
+    if (norm && (e = cudaMemcpyAsync(norm, dN.p, np, cudaMemcpyDeviceToHost, st)))
+        return cuda_fail(e, "D2H copy");
+    if ((e = cudaStreamSynchronize(st))) return cuda_fail(e, "kernel execution");
+    return 0;
+}
+
+int qw_rhs_dev(const qw_problem *prob, double t, double T, double gamma, const void *y, void *dy,
+               void *stream)
+{
+    QwParams prm;
+    qw_problem tmp;
+    if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
+    tmp = *prob;
+    if (!(tmp.step_size > 0.0) && tmp.n_steps < 0) tmp.n_steps = 0;   // irrelevant here
+    int rc = validate(&tmp, &prm);
+    if (rc) return rc;
+    if (!y || !dy) return fail(QW_E_NULL, "y and dy are required");
+    // BCB.py:72-73: time == 0 or T == 0 -> H = L; every schedule has g(0) = 0 anyway
+    double2 ad;
+    if ((t == 0.0 || T == 0.0) && prm.schedule != QW_SCHED_STATIC)
+        ad = make_double2(prm.gamma_on == QW_GAMMA_ON_ORACLE ? 1.0 : gamma, 0.0);
+    else
+        ad = qw_operator_scalars(t / T, gamma, prm.schedule, prm.gamma_on);
+    const double a = ad.x, d = ad.y;
+    cudaError_t e = qw_launch_rhs(prm.n, prm.topology, prm.target, a, d, (const double2 *)y,
+                                  (double2 *)dy, (cudaStream_t)stream);
+    g_launches += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "rhs kernel launch");
+    return 0;
+}
+
+int qw_ensemble_stats_dev(const double *p, int64_t n, const double *thresholds,
+                          int32_t n_thresholds, double *out, void *stream)
+{
+    if (!p || !out) return fail(QW_E_NULL, "p and out are required");
+    if (n < 1 || n_thresholds < 0 || n_thresholds > 8) return fail(QW_E_SIZE, "bad sizes");
+    if (n_thresholds > 0 && !thresholds) return fail(QW_E_NULL, "thresholds is NULL");
+    cudaError_t e = qw_launch_stats(p, n, thresholds, n_thresholds, out, (cudaStream_t)stream);
+    g_launches += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "stats kernel launch");
+    return 0;
+}
+
+int qw_heatmap_robustness_dev(const double *p, int64_t n_beta, int64_t n_time, int64_t variation,
+                              double *R, int64_t *argmax_beta, void *stream)
+{
+    if (!p) return fail(QW_E_NULL, "p is required");
+    if (n_beta < 1 || n_time < 1 || variation < 0 || variation > n_beta)
+        return fail(QW_E_SIZE, "bad sizes");
+    int nl = 0;
+    cudaError_t e = qw_launch_robustness(p, n_beta, n_time, variation, R, argmax_beta,
+                                         (cudaStream_t)stream, &nl);
+    g_launches += nl;
+    if (e != cudaSuccess) return cuda_fail(e, "robustness kernel launch");
+    return 0;
+}
+
+int qw_plan_query(const qw_problem *prob, qw_plan *plan)
+{
+    QwParams prm;
+    int rc = validate(prob, &prm);
+    if (rc) return rc;
+    if (!plan) return fail(QW_E_NULL, "plan is NULL");
+    memset(plan, 0, sizeof(*plan));
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "device query");
+    prm.n_points = 1 << 20;
+    switch (choose_path(prm)) {
+    case PATH_RESIDENT: e = qw_launch_resident(prm, nullptr, plan); break;
+    case PATH_STREAM: e = qw_stream_plan(prm, plan); break;
+    default: {
+        int blocks; size_t bytes;
+        e = qw_generic_geometry(prm, &blocks, &bytes, plan);
+    }
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "plan query");
+    return 0;
+}
+
+int qw_fp64_peak_probe(double millis, double *tflops, void *stream)
+{
+    if (!tflops) return fail(QW_E_NULL, "tflops is NULL");
+    int nl = 0;
+    cudaError_t e = qw_run_fp64_probe(millis, tflops, (cudaStream_t)stream, &nl);
+    g_launches += nl;
+    if (e != cudaSuccess) return cuda_fail(e, "fp64 probe");
+    return 0;
+}
+
+int64_t qw_launch_count(void) { return g_launches.load(); }
+const char *qw_last_error(void) { return g_err; }
+int qw_version(void) { return QW_ABI_VERSION; }
+
+}  // extern "C"

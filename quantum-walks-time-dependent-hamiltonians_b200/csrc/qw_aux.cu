@@ -1,0 +1,215 @@
+// Small kernels around the integrator: a single right-hand side, the fused post-integration
+// reductions (ensemble statistics, robustness map, first-maximum search) and the FP64
+// throughput probe that provides the roofline denominator.
+#include "qw_common.cuh"
+
+namespace {
+
+// dy = -i (a L + d |w><w|) y  -- schrodinger_equation(t, y, beta, T), BCB.py:163-174.
+// Complete graph: the sum is a first pass by the same single block.
+__global__ void __launch_bounds__(1024) rhs_kernel(int64_t n, int topology, int64_t w, double a,
+                                                   double d, const double2 *__restrict__ y,
+                                                   double2 *__restrict__ dy)
+{
+    __shared__ double red[64];
+    double2 sum = make_double2(0.0, 0.0);
+    if (topology == QW_TOPO_COMPLETE) {
+        double sr = 0.0, si = 0.0;
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) { sr += y[j].x; si += y[j].y; }
+        sum = qw_block_sum2(sr, si, red);
+    }
+    const double nd = (double)n;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const double2 c = y[j];
+        double vr, vi;
+        if (topology == QW_TOPO_CYCLE) {
+            const double2 l = y[j == 0 ? n - 1 : j - 1];
+            const double2 r = y[j == n - 1 ? 0 : j + 1];
+            vr = a * fma(2.0, c.x, -(l.x + r.x));
+            vi = a * fma(2.0, c.y, -(l.y + r.y));
+        } else {
+            vr = a * fma(nd, c.x, -sum.x);
+            vi = a * fma(nd, c.y, -sum.y);
+        }
+        if (j == w) { vr = fma(d, c.x, vr); vi = fma(d, c.y, vi); }
+        dy[j] = make_double2(vi, -vr);
+    }
+}
+
+// Deterministic single-block statistics of p[n]: mean, population std (two-pass), min,
+// max, fraction >= threshold_k.
+__global__ void __launch_bounds__(1024) stats_kernel(const double *__restrict__ p, int64_t n,
+                                                     const double *__restrict__ thr, int nthr,
+                                                     double *__restrict__ out)
+{
+    __shared__ double red[64];
+    double s = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const double v = p[j];
+        s += v; mn = fmin(mn, v); mx = fmax(mx, v);
+    }
+    const double mean = qw_block_sum2(s, 0.0, red).x / (double)n;
+    double q = 0.0;
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+        const double dlt = p[j] - mean;
+        q = fma(dlt, dlt, q);
+    }
+    const double var = qw_block_sum2(q, 0.0, red).x / (double)n;
+    // min / max through the sum tree of their negated-exponent trick is not exact; use shuffles
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ double smn[32], smx[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { smn[warp] = mn; smx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < nw; ++i) { mn = fmin(mn, smn[i]); mx = fmax(mx, smx[i]); }
+        out[0] = mean; out[1] = sqrt(var); out[2] = mn; out[3] = mx;
+    }
+    for (int k = 0; k < nthr; ++k) {
+        const double th = thr[k];
+        double c = 0.0;
+        for (int64_t j = threadIdx.x; j < n; j += blockDim.x) c += (p[j] >= th) ? 1.0 : 0.0;
+        const double tot = qw_block_sum2(c, 0.0, red).x;
+        if (threadIdx.x == 0) out[4 + k] = tot / (double)n;
+    }
+}
+
+// R[j][i] of Robustness.py:25-31 (python negative-index wrap kept, out-of-range -> NaN)
+__global__ void robustness_kernel(const double *__restrict__ p, int64_t nb, int64_t nt,
+                                  int64_t v, double *__restrict__ R)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nb * nt) return;
+    const int64_t j = idx / nt, i = idx - j * nt;
+    int64_t jm = j - v, jp = j + v;
+    if (jm < 0) jm += nb;                       // numpy negative index
+    if (jp < 0) jp += nb;
+    double r = NAN;
+    if (jp < nb && jm >= 0 && jm < nb) {
+        const double p0 = p[idx];
+        r = ((p0 - p[jp * nt + i]) + (p0 - p[jm * nt + i])) / 2.0;
+    }
+    R[idx] = r;
+}
+
+// first-maximum beta index per time column: strict '>' scan from j = 0 against 0
+// (Robustness.py:41-45); -1 when no entry is > 0.
+__global__ void argmax_beta_kernel(const double *__restrict__ p, int64_t nb, int64_t nt,
+                                   int64_t *__restrict__ arg)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    double best = 0.0;
+    int64_t bj = -1;
+    for (int64_t j = 0; j < nb; ++j) {
+        const double v = p[j * nt + i];
+        if (v > best) { best = v; bj = j; }
+    }
+    arg[i] = bj;
+}
+
+// Register-only DFMA stream: 16 independent chains per thread, no memory traffic.
+constexpr int PROBE_CHAINS = 16;
+constexpr int PROBE_INNER = 64;
+__global__ void __launch_bounds__(256, 2) fp64_probe_kernel(int iters, double seed, double *sink)
+{
+    double acc[PROBE_CHAINS];
+#pragma unroll
+    for (int c = 0; c < PROBE_CHAINS; ++c) acc[c] = seed + c + threadIdx.x;
+    const double m = 1.0 + 1e-9 * seed, b = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < PROBE_INNER; ++k)
+#pragma unroll
+            for (int c = 0; c < PROBE_CHAINS; ++c) acc[c] = fma(acc[c], m, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < PROBE_CHAINS; ++c) s += acc[c];
+    if (s == 123.456) sink[0] = s;      // never true; keeps the chains alive
+}
+
+}  // namespace
+
+cudaError_t qw_launch_rhs(int64_t n, int topology, int64_t w, double a, double d,
+                          const double2 *y, double2 *dy, cudaStream_t st)
+{
+    int threads = n < 1024 ? (int)((n + 31) / 32 * 32) : 1024;
+    rhs_kernel<<<1, threads, 0, st>>>(n, topology, w, a, d, y, dy);
+    return cudaGetLastError();
+}
+
+cudaError_t qw_launch_stats(const double *p, int64_t n, const double *thr, int nthr, double *out,
+                            cudaStream_t st)
+{
+    stats_kernel<<<1, 1024, 0, st>>>(p, n, thr, nthr, out);
+    return cudaGetLastError();
+}
+
+cudaError_t qw_launch_robustness(const double *p, int64_t nb, int64_t nt, int64_t v, double *R,
+                                 int64_t *arg, cudaStream_t st, int *launches)
+{
+    *launches = 0;
+    if (R) {
+        const int64_t tot = nb * nt;
+        robustness_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(p, nb, nt, v, R);
+        ++*launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (arg) {
+        argmax_beta_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(p, nb, nt, arg);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+// Runs the probe for roughly `millis` ms and returns sustained TFLOP/s (FMA = 2 flops).
+cudaError_t qw_run_fp64_probe(double millis, double *tflops, cudaStream_t st, int *launches)
+{
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    double *sink = nullptr;
+    e = cudaMalloc(&sink, sizeof(double));
+    if (e != cudaSuccess) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int blocks = sms * 2 * 4, threads = 256;
+    auto run = [&](int iters, float *ms) -> cudaError_t {
+        cudaEventRecord(e0, st);
+        fp64_probe_kernel<<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+        ++*launches;
+        cudaEventRecord(e1, st);
+        cudaError_t err = cudaEventSynchronize(e1);
+        if (err != cudaSuccess) return err;
+        return cudaEventElapsedTime(ms, e0, e1);
+    };
+    float ms = 0.f;
+    int iters = 64;
+    e = run(iters, &ms);                                  // warm-up + calibration
+    if (e == cudaSuccess) e = run(iters, &ms);
+    if (e == cudaSuccess) {
+        double want = millis > 1.0 ? millis : 1.0;
+        double scale = want / (ms > 1e-3 ? ms : 1e-3);
+        long long it2 = (long long)(iters * scale);
+        if (it2 < 16) it2 = 16;
+        if (it2 > (1 << 24)) it2 = 1 << 24;
+        iters = (int)it2;
+        e = run(iters, &ms);
+    }
+    if (e == cudaSuccess) {
+        const double fmas = (double)blocks * threads * (double)iters * PROBE_INNER * PROBE_CHAINS;
+        *tflops = 2.0 * fmas / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return e;
+}

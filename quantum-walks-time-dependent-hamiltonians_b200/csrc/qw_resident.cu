@@ -1,0 +1,351 @@
+// Register-resident fixed-step RK4 for one (T, gamma) point per thread block (sm_100a).
+//
+// Replaces solve_schrodinger_equation + evaluate_probability (BCB.py:177-203) with the
+// fixed-step rule of QW_Search.py:149-164.  psi, the current stage input and the RK4
+// accumulator live in registers for the whole integration: each thread owns R consecutive
+// sites of the ring (cycle graph) or of the vertex list (complete graph).  The graph is
+// relabelled so that the marked vertex is site 0 of thread 0 (both graphs are vertex
+// transitive and the initial state is uniform), which makes the oracle term a single
+// predicated update with static register indices.
+//
+// Cycle graph: the only data that crosses threads per stage is one complex value on each
+//   side of a thread's segment; it goes through a double-buffered shared-memory mailbox,
+//   one __syncthreads() per stage.
+// Complete graph: (L x)_j = N x_j - sum(x).  sum(x) of the step's first stage is a block
+//   reduction; for the later stages it follows exactly from column sums of L being zero:
+//   sum(y + c k) = sum(y) - i c d x_w, so thread 0 publishes it one stage ahead.
+//
+// FP64 work per site-update: 22 DFMA + 8 DADD (cycle), the algorithmic 52 flops of
+// SURVEY.md section 8d.
+#include "qw_common.cuh"
+
+namespace {
+
+template <int R>
+struct State {
+    double yr[R], yi[R];   // psi_n
+    double ur[R], ui[R];   // stage input
+    double ar[R], ai[R];   // RK4 accumulator
+};
+
+// One RK4 stage on a thread's R sites.  lap(x) is supplied by the caller through the
+// neighbour values (cycle) or the global sum (complete):
+//   v      = lap(x)                                   (unscaled Laplacian)
+//   k      = -i v  ->  k.re = v.im, k.im = -v.re
+//   STAGE 0: x = y;  u = y + A k;  acc = y + B k
+//   STAGE 1,2: x = u;  u = y + A k;  acc += B k
+//   STAGE 3: x = u;  y = acc + B k
+// `own`: this thread holds the marked vertex in slot 0; D = (DA, DB) weights of d(t).
+template <int R, int STAGE, bool CYCLE>
+__device__ __forceinline__ void rk_stage(State<R> &s, const double A, const double B,
+                                         const double2 hl, const double2 hr,
+                                         const double2 sum, const double nd,
+                                         const bool own, const double2 D)
+{
+    double pr = hl.x, pi = hl.y;
+    const double x0r = (STAGE == 0) ? s.yr[0] : s.ur[0];
+    const double x0i = (STAGE == 0) ? s.yi[0] : s.ui[0];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double cr = (STAGE == 0) ? s.yr[r] : s.ur[r];
+        const double ci = (STAGE == 0) ? s.yi[r] : s.ui[r];
+        double vr, vi;
+        if (CYCLE) {
+            const double nr = (r + 1 < R) ? ((STAGE == 0) ? s.yr[r + 1] : s.ur[r + 1]) : hr.x;
+            const double ni = (r + 1 < R) ? ((STAGE == 0) ? s.yi[r + 1] : s.ui[r + 1]) : hr.y;
+            vr = fma(2.0, cr, -(pr + nr));
+            vi = fma(2.0, ci, -(pi + ni));
+            pr = cr;
+            pi = ci;
+        } else {
+            vr = fma(nd, cr, -sum.x);
+            vi = fma(nd, ci, -sum.y);
+        }
+        if (STAGE == 0) {
+            s.ar[r] = fma(B, vi, s.yr[r]);
+            s.ai[r] = fma(-B, vr, s.yi[r]);
+        } else if (STAGE < 3) {
+            s.ar[r] = fma(B, vi, s.ar[r]);
+            s.ai[r] = fma(-B, vr, s.ai[r]);
+        }
+        if (STAGE < 3) {
+            s.ur[r] = fma(A, vi, s.yr[r]);
+            s.ui[r] = fma(-A, vr, s.yi[r]);
+        } else {
+            s.yr[r] = fma(B, vi, s.ar[r]);
+            s.yi[r] = fma(-B, vr, s.ai[r]);
+        }
+    }
+    if (own) {   // oracle term d(t) x_w on the marked vertex
+        if (STAGE < 3) {
+            s.ur[0] = fma(D.x, x0i, s.ur[0]);
+            s.ui[0] = fma(-D.x, x0r, s.ui[0]);
+            s.ar[0] = fma(D.y, x0i, s.ar[0]);
+            s.ai[0] = fma(-D.y, x0r, s.ai[0]);
+        } else {
+            s.yr[0] = fma(D.y, x0i, s.yr[0]);
+            s.yi[0] = fma(-D.y, x0r, s.yi[0]);
+        }
+    }
+}
+
+struct Tables {
+    double2 ab[4 * QW_CHUNK];
+    double2 d[4 * QW_CHUNK];
+    double2 ad[3 * QW_CHUNK];
+    double red[2 * 2 * 32];      // double-buffered warp partials
+    double2 bcast[2];            // complete graph: sum(x) of the coming stage
+};
+
+// all-threads block sum of a complex value; one barrier; buf alternates between calls
+__device__ __forceinline__ double2 block_sum_all(double2 v, double *red, int buf)
+{
+    v.x = qw_warp_sum(v.x);
+    v.y = qw_warp_sum(v.y);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    double *slot = red + buf * 64;
+    if (lane == 0) { slot[2 * warp] = v.x; slot[2 * warp + 1] = v.y; }
+    __syncthreads();
+    double2 w = make_double2(0.0, 0.0);
+    if (lane < nwarps) w = make_double2(slot[2 * lane], slot[2 * lane + 1]);
+    w.x = qw_warp_sum(w.x);
+    w.y = qw_warp_sum(w.y);
+    return w;
+}
+
+template <int R>
+__device__ __forceinline__ void epilogue(const State<R> &s, const QwParams &prm,
+                                         const QwPoint &pt, double *red, const int t)
+{
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    double pw = (t == 0) ? fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]) : 0.0;
+    __syncthreads();
+    double2 tot = block_sum_all(make_double2(nrm, pw), red, 0);
+    if (t == 0) {
+        prm.p[pt.q] = tot.y / tot.x;
+        if (prm.norm) prm.norm[pt.q] = tot.x;
+    }
+    if (prm.psi && t < prm.nact) {      // undo the relabelling: logical l -> (l + w) mod n
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t j = (int64_t)t * R + r + prm.target;
+            if (j >= prm.n) j -= prm.n;
+            out[j] = make_double2(s.yr[r], s.yi[r]);
+        }
+    }
+}
+
+template <int R, int MAXNT, int MINB>
+__global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_resident(const QwParams prm)
+{
+    extern __shared__ double2 mbox[];         // [2][2][blockDim.x]: parity, first/last
+    __shared__ Tables tb;
+    const int t = threadIdx.x, nt = blockDim.x, nact = prm.nact;
+    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const bool active = t < nact;
+    const bool own = (t == 0);
+    // ring neighbours among the active threads; idle threads talk to themselves (zeros)
+    const int tl = active ? (t == 0 ? nact - 1 : t - 1) : t;
+    const int tr = active ? (t == nact - 1 ? 0 : t + 1) : t;
+
+    State<R> s;
+    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+    }
+    int par = 0;
+    double2 *first = mbox, *last = mbox + 2 * nt;      // [parity][thread]
+    first[t] = make_double2(s.yr[0], s.yi[0]);
+    last[t] = make_double2(s.yr[R - 1], s.yi[R - 1]);
+
+    const double2 zero2 = make_double2(0.0, 0.0);
+    for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
+        qw_fill_table(tb.ab, tb.d, tb.ad, pt, n0, prm.schedule, prm.gamma_on);
+        const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+#define QW_CYCLE_STAGE(K)                                                               \
+            {                                                                           \
+                __syncthreads();                                                        \
+                const double2 hl = last[par * nt + tl];                                 \
+                const double2 hr = first[par * nt + tr];                                \
+                const double2 ab = tb.ab[4 * sidx + K];                                 \
+                const double2 dd = own ? tb.d[4 * sidx + K] : zero2;                    \
+                rk_stage<R, K, true>(s, ab.x, ab.y, hl, hr, zero2, 0.0, own, dd);       \
+                par ^= 1;                                                               \
+                if (K < 3) {                                                            \
+                    first[par * nt + t] = make_double2(s.ur[0], s.ui[0]);               \
+                    last[par * nt + t] = make_double2(s.ur[R - 1], s.ui[R - 1]);        \
+                } else {                                                                \
+                    first[par * nt + t] = make_double2(s.yr[0], s.yi[0]);               \
+                    last[par * nt + t] = make_double2(s.yr[R - 1], s.yi[R - 1]);        \
+                }                                                                       \
+            }
+            QW_CYCLE_STAGE(0)
+            QW_CYCLE_STAGE(1)
+            QW_CYCLE_STAGE(2)
+            QW_CYCLE_STAGE(3)
+#undef QW_CYCLE_STAGE
+        }
+    }
+    epilogue<R>(s, prm, pt, tb.red, t);
+}
+
+template <int R>
+__device__ __forceinline__ double2 local_sum_y(const State<R> &s)
+{
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { a += s.yr[r]; b += s.yi[r]; }
+    return make_double2(a, b);
+}
+
+template <int R>
+__device__ __forceinline__ double2 local_sum_u(const State<R> &s)
+{
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { a += s.ur[r]; b += s.ui[r]; }
+    return make_double2(a, b);
+}
+
+template <int R, int MAXNT, int MINB, bool EXACT>
+__global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_resident(const QwParams prm)
+{
+    __shared__ Tables tb;
+    const int t = threadIdx.x, nact = prm.nact;
+    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const bool active = t < nact;
+    const bool own = (t == 0);
+    const double nd = active ? (double)prm.n : 0.0;   // idle threads stay at zero
+
+    State<R> s;
+    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+    }
+    int rbuf = 0;
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 sy = block_sum_all(local_sum_y<R>(s), tb.red, rbuf);   // sum(y), every thread
+    rbuf ^= 1;
+
+    for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
+        qw_fill_table(tb.ab, tb.d, tb.ad, pt, n0, prm.schedule, prm.gamma_on);
+        const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+#define QW_COMPLETE_STAGE(K)                                                            \
+            {                                                                           \
+                double2 sx;                                                             \
+                if (K == 0) sx = sy;                                                    \
+                else if (EXACT) { sx = block_sum_all(local_sum_u<R>(s), tb.red, rbuf); rbuf ^= 1; } \
+                else { __syncthreads(); sx = tb.bcast[K & 1]; }                         \
+                if (!active) sx = zero2;                                                \
+                const double2 ab = tb.ab[4 * sidx + K];                                 \
+                const double2 dd = own ? tb.d[4 * sidx + K] : zero2;                    \
+                if (!EXACT && own && K < 3) {                                           \
+                    /* sum of the next stage input: sum(y) - i (c d) x_w */             \
+                    const double xr = (K == 0) ? s.yr[0] : s.ur[0];                     \
+                    const double xi = (K == 0) ? s.yi[0] : s.ui[0];                     \
+                    tb.bcast[(K + 1) & 1] = make_double2(fma(dd.x, xi, sy.x),           \
+                                                         fma(-dd.x, xr, sy.y));         \
+                }                                                                       \
+                rk_stage<R, K, false>(s, ab.x, ab.y, zero2, zero2, sx, nd, own, dd);    \
+            }
+            QW_COMPLETE_STAGE(0)
+            QW_COMPLETE_STAGE(1)
+            QW_COMPLETE_STAGE(2)
+            QW_COMPLETE_STAGE(3)
+#undef QW_COMPLETE_STAGE
+            sy = block_sum_all(local_sum_y<R>(s), tb.red, rbuf);
+            rbuf ^= 1;
+        }
+    }
+    epilogue<R>(s, prm, pt, tb.red, t);
+}
+
+template <typename K>
+cudaError_t launch(K kernel, const QwParams &prm, int threads, size_t smem, cudaStream_t st,
+                   qw_plan *plan)
+{
+    if (plan) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem);
+        if (e != cudaSuccess) return e;
+        plan->threads_per_block = threads;
+        plan->blocks_per_sm = nb;
+        plan->regs_per_thread = fa.numRegs;
+        plan->smem_bytes = (int)(fa.sharedSizeBytes + smem);
+        return cudaSuccess;
+    }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kernel<<<(unsigned)prm.n_points, threads, smem, st>>>(prm);
+    return cudaGetLastError();
+}
+
+template <int R>
+cudaError_t dispatch_threads(const QwParams &prm, int threads, cudaStream_t st, qw_plan *plan)
+{
+    const bool cyc = prm.topology == QW_TOPO_CYCLE;
+    const bool exact = (prm.flags & QW_FLAG_EXACT_SUM) != 0;
+    const size_t smem = cyc ? (size_t)threads * 4 * sizeof(double2) : 0;
+#define QW_LAUNCH(MAXNT, MINB)                                                             \
+    return cyc ? launch(rk4_cycle_resident<R, MAXNT, MINB>, prm, threads, smem, st, plan)  \
+               : (exact ? launch(rk4_complete_resident<R, MAXNT, MINB, true>, prm, threads, \
+                                 smem, st, plan)                                           \
+                        : launch(rk4_complete_resident<R, MAXNT, MINB, false>, prm,        \
+                                 threads, smem, st, plan));
+    if (threads <= 128) { QW_LAUNCH(128, 4) }
+    if (threads <= 256) { QW_LAUNCH(256, 2) }
+    if (threads <= 512) { QW_LAUNCH(512, 1) }
+    if constexpr (R <= 2) { QW_LAUNCH(1024, 1) }      // 64-register cap: R <= 2 only
+    return cudaErrorInvalidConfiguration;
+#undef QW_LAUNCH
+}
+
+}  // namespace
+
+// Sites per thread for the resident path, or 0 when n does not fit it.  R*threads == n
+// exactly; the largest R that still fills a warp wins (more sites per thread = fewer
+// cross-thread exchanges per FP64 instruction).  Register budget: R = 8 and 4 need up to
+// 128 registers, so at most 512 threads; R <= 2 fits the 64-register cap of 1024 threads.
+int qw_resident_sites_per_thread(int64_t n)
+{
+    if (n < 32) return n >= 1 ? 1 : 0;
+    const int cand[4] = {8, 4, 2, 1};
+    for (int i = 0; i < 4; ++i) {
+        const int R = cand[i];
+        if (n % R == 0 && n / R >= 32 && n / R <= (R >= 4 ? 512 : 1024)) return R;
+    }
+    return 0;
+}
+
+cudaError_t qw_launch_resident(QwParams prm, cudaStream_t st, qw_plan *plan)
+{
+    const int R = qw_resident_sites_per_thread(prm.n);
+    prm.nact = (int)(prm.n / R);
+    const int threads = ((prm.nact + 31) / 32) * 32;
+    if (plan) {
+        plan->path = prm.topology == QW_TOPO_CYCLE ? 0 : 1;
+        plan->sites_per_thread = R;
+    }
+    switch (R) {
+    case 8: return dispatch_threads<8>(prm, threads, st, plan);
+    case 4: return dispatch_threads<4>(prm, threads, st, plan);
+    case 2: return dispatch_threads<2>(prm, threads, st, plan);
+    default: return dispatch_threads<1>(prm, threads, st, plan);
+    }
+}

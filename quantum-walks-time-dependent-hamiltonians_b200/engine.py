@@ -1,0 +1,323 @@
+"""Host side of the B200 RK4 heatmap path: buffers, streams and sharding around the C ABI.
+
+PyTorch is used for device memory, streams and ``torch.distributed`` only; all arithmetic
+happens in the kernels of ``libqw_b200.so``.  Host arrays (numpy / CPU tensors) in -> numpy
+out, with the H2D / D2H copies done here; CUDA tensors in -> CUDA tensors out, stream
+ordered and without synchronisation.
+
+Reference call sites this replaces: the double loop of ``grid_probability_evaluation``
+(Schroedinger_Solver.py:438-441) / ``grid_eval`` (BCB.py:250-253) and the Ray fan-out of
+``parallel_routine`` (BCB.py:279-292).
+"""
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _schedule_id(s):
+    """The reference's three schedule encodings (SS ints 1/2/3 are handled by the SS
+    shim; here: BCB strings, QW_Search ints)."""
+    if isinstance(s, str):
+        if s == "independent":
+            s = "static"
+        if s not in _lib.SCHEDULES:
+            raise ValueError("step_function value not defined: %r" % (s,))
+        return _lib.SCHEDULES[s]
+    return int(s)
+
+
+def _topology_id(t):
+    if isinstance(t, str):
+        try:
+            return {"complete": _lib.TOPO_COMPLETE, "circular": _lib.TOPO_CYCLE,
+                    "cycle": _lib.TOPO_CYCLE}[t]
+        except KeyError:
+            raise ValueError("undefined topology: %r" % (t,))
+    return int(t)
+
+
+def _gamma_on_id(g):
+    if isinstance(g, str):
+        try:
+            return {"oracle": _lib.GAMMA_ON_ORACLE, "laplacian": _lib.GAMMA_ON_LAPLACIAN}[g]
+        except KeyError:
+            raise ValueError("undefined gamma_on: %r" % (g,))
+    return int(g)
+
+
+@dataclass
+class Problem:
+    """What the reference keeps in module globals (BCB.py:20-24) plus the step rule."""
+    n: int
+    topology: object = "circular"
+    schedule: object = "lin"
+    gamma_on: object = "oracle"
+    target: Optional[int] = None
+    n_steps: Optional[int] = None        # h = T / n_steps
+    step_size: Optional[float] = None    # h fixed, n = int(T/h)   (QW_Search.py:153-154)
+    flags: int = 0
+
+    def c_struct(self, per_point_steps=False):
+        """``per_point_steps``: the call carries its own n_steps array (or needs none)."""
+        if self.n_steps is not None and self.step_size is not None:
+            raise ValueError("give exactly one of n_steps / step_size")
+        if self.n_steps is None and self.step_size is None and not per_point_steps:
+            raise ValueError("give exactly one of n_steps / step_size")
+        return _lib.QwProblem(
+            n=int(self.n), topology=_topology_id(self.topology),
+            schedule=_schedule_id(self.schedule), gamma_on=_gamma_on_id(self.gamma_on),
+            flags=int(self.flags), target=-1 if self.target is None else int(self.target),
+            step_size=float(self.step_size) if self.step_size is not None else 0.0,
+            n_steps=int(self.n_steps) if self.n_steps is not None else 0)
+
+
+def _device(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("qw_b200 needs a CUDA device (there is no CPU fallback)")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _as_dev(x, dev, dtype=torch.float64):
+    """-> (contiguous CUDA tensor, was_on_host)."""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            return x.to(dtype).contiguous(), False
+        return x.to(dtype).contiguous().to(dev, non_blocking=True), True
+    arr = np.ascontiguousarray(np.atleast_1d(np.asarray(x)),
+                               dtype=np.float64 if dtype == torch.float64 else np.int64)
+    return torch.from_numpy(arr).to(dev, non_blocking=True), True
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def longest_first_order(n_steps):
+    """Launch order for unequal work per point (step_size rule: work ~ T)."""
+    n_steps = np.asarray(n_steps)
+    return np.argsort(-n_steps, kind="stable").astype(np.int64)
+
+
+def rk4_batch(problem, T, gamma, n_steps=None, order=None, return_psi=False, device=None):
+    """Integrate independent (T_q, gamma_q) points.  Returns (p, norm[, psi])."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        dT, host = _as_dev(T, dev)
+        dG, _ = _as_dev(gamma, dev)
+        if dG.numel() == 1 and dT.numel() > 1:
+            dG = dG.expand(dT.numel()).contiguous()
+        if dT.numel() != dG.numel():
+            raise ValueError("T and gamma must have the same length")
+        P = dT.numel()
+        dS = _as_dev(n_steps, dev, torch.int64)[0] if n_steps is not None else None
+        if dS is not None and dS.numel() != P:
+            raise ValueError("n_steps must have one entry per point")
+        dO = _as_dev(order, dev, torch.int64)[0] if order is not None else None
+        prob = problem.c_struct(per_point_steps=n_steps is not None)
+        p = torch.empty(P, dtype=torch.float64, device=dev)
+        norm = torch.empty(P, dtype=torch.float64, device=dev)
+        psi = (torch.empty((P, int(problem.n)), dtype=torch.complex128, device=dev)
+               if return_psi else None)
+        _lib.check(lib.qw_rk4_batch_dev(ctypes.byref(prob), _ptr(dT), _ptr(dG), _ptr(dS),
+                                        _ptr(dO), P, _ptr(p), _ptr(norm), _ptr(psi),
+                                        _stream()))
+        out = (p, norm) + ((psi,) if return_psi else ())
+        if host:
+            out = tuple(t.cpu().numpy() for t in out)
+        return out
+
+
+def rk4_heatmap(problem, time_array, beta_array, rows=None, device=None):
+    """probability[beta][T] (and ||psi||^2) for rows [rows[0], rows[1]) of the beta axis,
+    in the reference's layout (BCB.py:247, SS:436)."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        dT, host = _as_dev(time_array, dev)
+        dB, _ = _as_dev(beta_array, dev)
+        nT, nB = dT.numel(), dB.numel()
+        b0, b1 = (0, nB) if rows is None else (int(rows[0]), int(rows[1]))
+        p = torch.empty((b1 - b0, nT), dtype=torch.float64, device=dev)
+        norm = torch.empty((b1 - b0, nT), dtype=torch.float64, device=dev)
+        prob = problem.c_struct()
+        _lib.check(lib.qw_rk4_grid_dev(ctypes.byref(prob), _ptr(dT), nT, _ptr(dB), nB, b0, b1,
+                                       _ptr(p), _ptr(norm), _stream()))
+        if host:
+            return p.cpu().numpy(), norm.cpu().numpy()
+        return p, norm
+
+
+def rk4_heatmap_host(problem, time_array, beta_array, rows=None, device=0):
+    """Same through the host-pointer C entry point (copies inside the library)."""
+    lib = _lib.load()
+    t = np.ascontiguousarray(time_array, dtype=np.float64)
+    b = np.ascontiguousarray(beta_array, dtype=np.float64)
+    b0, b1 = (0, b.size) if rows is None else (int(rows[0]), int(rows[1]))
+    p = np.empty((b1 - b0, t.size))
+    norm = np.empty((b1 - b0, t.size))
+    prob = problem.c_struct()
+    _lib.check(lib.qw_rk4_grid_host(ctypes.byref(prob), t.ctypes.data, t.size, b.ctypes.data,
+                                    b.size, b0, b1, p.ctypes.data, norm.ctypes.data,
+                                    int(device)))
+    return p, norm
+
+
+def rk4_batch_host(problem, T, gamma, n_steps=None, return_psi=False, device=0):
+    lib = _lib.load()
+    T = np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
+    g = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(gamma), T.shape), dtype=np.float64)
+    S = None if n_steps is None else np.ascontiguousarray(
+        np.broadcast_to(np.asarray(n_steps), T.shape), dtype=np.int64)
+    p, norm = np.empty(T.size), np.empty(T.size)
+    psi = np.empty((T.size, int(problem.n)), dtype=np.complex128) if return_psi else None
+    prob = problem.c_struct(per_point_steps=n_steps is not None)
+    _lib.check(lib.qw_rk4_batch_host(
+        ctypes.byref(prob), T.ctypes.data, g.ctypes.data, None if S is None else S.ctypes.data,
+        T.size, p.ctypes.data, norm.ctypes.data, None if psi is None else psi.ctypes.data,
+        int(device)))
+    return (p, norm, psi) if return_psi else (p, norm)
+
+
+def rhs(problem, t, T, gamma, y, device=None):
+    """-i H(t) y for one state: schrodinger_equation(t, y, beta, T) (BCB.py:163-174)."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        host = not (isinstance(y, torch.Tensor) and y.is_cuda)
+        dy_in = (y if not host else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(y), dtype=np.complex128)).to(dev))
+        dy_in = dy_in.to(torch.complex128).contiguous()
+        if dy_in.numel() != int(problem.n):
+            raise ValueError("state has %d entries, dimension is %d" % (dy_in.numel(), problem.n))
+        out = torch.empty_like(dy_in)
+        prob = problem.c_struct(per_point_steps=True)
+        _lib.check(lib.qw_rhs_dev(ctypes.byref(prob), float(t), float(T), float(gamma),
+                                  _ptr(dy_in), _ptr(out), _stream()))
+        return out.cpu().numpy() if host else out
+
+
+def ensemble_stats(p, thresholds=(0.8, 0.9, 0.95, 0.99), device=None):
+    """mean / std / min / max / fraction >= threshold over an ensemble of probabilities
+    (contour levels of SS:415; thesis section 2.3)."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        dp, _ = _as_dev(np.asarray(p).ravel() if not isinstance(p, torch.Tensor)
+                        else p.reshape(-1), dev)
+        thr, _ = _as_dev(np.asarray(thresholds, dtype=np.float64), dev)
+        out = torch.empty(4 + thr.numel(), dtype=torch.float64, device=dev)
+        _lib.check(lib.qw_ensemble_stats_dev(_ptr(dp), dp.numel(), _ptr(thr), thr.numel(),
+                                             _ptr(out), _stream()))
+        o = out.cpu().numpy()
+    return {"mean": float(o[0]), "std": float(o[1]), "min": float(o[2]), "max": float(o[3]),
+            "fraction_ge": {float(t): float(f) for t, f in zip(thresholds, o[4:])}}
+
+
+def robustness_map(probability, variation, device=None):
+    """R[beta][T] of Robustness.py:25-31 (unrounded) and the per-column first-max beta index
+    (Robustness.py:41-45)."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        host = not (isinstance(probability, torch.Tensor) and probability.is_cuda)
+        dp = (probability if not host else torch.from_numpy(
+            np.ascontiguousarray(probability, dtype=np.float64)).to(dev)).contiguous()
+        nb, nt = dp.shape
+        R = torch.empty_like(dp)
+        arg = torch.empty(nt, dtype=torch.int64, device=dev)
+        _lib.check(lib.qw_heatmap_robustness_dev(_ptr(dp), nb, nt, int(variation), _ptr(R),
+                                                 _ptr(arg), _stream()))
+        if host:
+            return R.cpu().numpy(), arg.cpu().numpy()
+        return R, arg
+
+
+def plan(problem, device=None):
+    dev = _device(device)
+    lib = _lib.load()
+    pl = _lib.QwPlan()
+    with torch.cuda.device(dev):
+        _lib.check(lib.qw_plan_query(ctypes.byref(problem.c_struct()), ctypes.byref(pl)))
+    d = {k: getattr(pl, k) for k, _ in _lib.QwPlan._fields_ if k != "reserved"}
+    d["path"] = _lib.PATH_NAMES.get(pl.path, str(pl.path))
+    return d
+
+
+def fp64_peak_tflops(millis=200.0, device=None):
+    dev = _device(device)
+    lib = _lib.load()
+    out = ctypes.c_double(0.0)
+    with torch.cuda.device(dev):
+        _lib.check(lib.qw_fp64_peak_probe(float(millis), ctypes.byref(out), _stream()))
+    return out.value
+
+
+def launch_count():
+    return int(_lib.load().qw_launch_count())
+
+
+# ---- sharding over GPUs: one process per GPU, rows of the beta axis ------------------------
+
+def shard_rows(n_rows, world_size, rank):
+    """Contiguous beta-row blocks, like the Ray tasks of BCB.py:279-281; uneven row counts
+    are spread over the first ranks."""
+    base, extra = divmod(int(n_rows), int(world_size))
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def heatmap_sharded(problem, time_array, beta_array, group=None, compute=None,
+                    gather=True):
+    """Every rank integrates its block of beta rows; one all_gather assembles
+    probability[beta][T] on all ranks (``np.concatenate`` of BCB.py:288-292).
+
+    ``compute(problem, time_array, beta_array, rows) -> (p, norm)`` defaults to the CUDA
+    path; CPU tests of the sharding logic inject their own.  Returns numpy arrays
+    (p, norm) of the full heatmap, or this rank's block when ``gather`` is False.
+    """
+    import torch.distributed as dist
+    time_array = np.asarray(time_array, dtype=np.float64)
+    beta_array = np.asarray(beta_array, dtype=np.float64)
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    b0, b1 = shard_rows(beta_array.size, world, rank)
+    on_gpu = compute is None
+    if on_gpu:
+        dev = _device()
+        p, norm = rk4_heatmap(problem, torch.from_numpy(time_array).to(dev),
+                              torch.from_numpy(beta_array).to(dev), rows=(b0, b1))
+    else:
+        p, norm = compute(problem, time_array, beta_array, (b0, b1))
+        p, norm = torch.from_numpy(np.ascontiguousarray(p)), torch.from_numpy(
+            np.ascontiguousarray(norm))
+    if world == 1 or not gather:
+        return p.cpu().numpy(), norm.cpu().numpy()
+    # pad to the largest block so a single all_gather_into_tensor-style call suffices
+    nT = time_array.size
+    rows_max = -(-beta_array.size // world)
+    send = torch.zeros((2, rows_max, nT), dtype=torch.float64, device=p.device)
+    send[0, :b1 - b0] = p
+    send[1, :b1 - b0] = norm
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    ps, ns = [], []
+    for r in range(world):
+        r0, r1 = shard_rows(beta_array.size, world, r)
+        ps.append(recv[r][0, :r1 - r0])
+        ns.append(recv[r][1, :r1 - r0])
+    return torch.cat(ps).cpu().numpy(), torch.cat(ns).cpu().numpy()

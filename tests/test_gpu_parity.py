@@ -1,0 +1,261 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the golden
+fixtures produced by the reference's own code.
+
+Tolerances (BASELINE.json north_star): |dp| <= 1e-10 absolute per success probability,
+argmax (T, gamma) indices identical.  psi is compared at 1e-11.
+"""
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, rk4_numpy as rk
+from oracle.defs import default_target
+
+pytestmark = pytest.mark.gpu
+
+P_TOL = 1e-10
+PSI_TOL = 1e-11
+
+
+def _problem(qw, n, topo, sched, rule, **kw):
+    return qw.Problem(n=n, topology=topo, schedule=sched, **rule, **kw)
+
+
+def test_golden_rk4_over_reference_rhs(qw, golden):
+    """Every RK4 trajectory driven by the reference's own schrodinger_equation."""
+    meta, arr = golden
+    for c in meta["rk4_L0"]:
+        prob = _problem(qw, c["n"], c["topology"], c["schedule"], c["rule"])
+        p, norm, psi = qw.rk4_batch(prob, [c["T"]], [c["beta"]], return_psi=True)
+        assert abs(p[0] - c["p"]) <= P_TOL, c
+        assert abs(norm[0] - c["norm"]) <= P_TOL, c
+        assert np.abs(psi[0] - arr["L0_psi_%d" % c["key"]]).max() <= PSI_TOL, c
+
+
+def test_golden_rhs(qw, golden):
+    meta, arr = golden
+    for c in meta["rhs"]:
+        prob = qw.Problem(n=c["n"], topology=c["topology"], schedule=c["schedule"], n_steps=1)
+        dy = qw.rhs(prob, c["t"], c["T"], c["beta"], arr["rhs_y_%d" % c["key"]])
+        ref = arr["rhs_dy_%d" % c["key"]]
+        assert np.abs(dy - ref).max() <= 1e-12 * np.abs(ref).max(), c
+
+
+def test_golden_static_and_rk45_are_close(qw, golden):
+    meta, _ = golden
+    for c in meta["static"]:
+        prob = qw.Problem(n=c["n"], topology="circular", schedule="static",
+                          n_steps=c["n_steps"])
+        p, _ = qw.rk4_batch(prob, [c["time"]], [c["gamma"]])
+        assert abs(p[0] - c["p_rk4"]) <= P_TOL
+        assert abs(p[0] - c["p_expm"]) <= 1e-8           # RK4 truncation vs exact expm
+    for c in meta["rk45"]:
+        prob = qw.Problem(n=c["n"], topology=c["topology"], schedule=c["schedule"],
+                          n_steps=8192)
+        p, _ = qw.rk4_batch(prob, [c["T"]], [c["beta"]])
+        tol = 2e-4 if c["schedule"] in ("sqrt", "cbrt") else 3e-5
+        assert abs(p[0] - c["p"]) <= tol                  # the reference as shipped (RK45)
+
+
+@pytest.mark.parametrize("topo", ["circular", "complete"])
+@pytest.mark.parametrize("n", [3, 5, 16, 17, 31, 32, 33, 51, 64, 71, 100, 255, 256, 1000, 1024])
+def test_random_batches_vs_oracle(qw, topo, n):
+    rng = np.random.default_rng(1000 * n + (topo == "complete"))
+    scheds = ["lin", "sqrt", "cbrt", "cerf_3", "cerf_5", "cerf_7", "static"]
+    for sched in scheds:
+        P = 5
+        if topo == "circular":
+            T = rng.uniform(0.0, 12.0, P)
+            g = rng.uniform(0.0, 2.5, P)
+            S = 96
+        else:                         # spectral radius ~ N: keep h * N small
+            T = rng.uniform(0.0, 40.0 / n, P)
+            g = rng.uniform(0.0, 2.0 * n, P)
+            S = 160
+        T[0] = 0.0                    # T == 0 guard
+        prob = qw.Problem(n=n, topology=topo, schedule=sched, n_steps=S)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, topo, sched, T, g, n_steps=S, return_psi=True)
+        assert np.abs(p - po).max() <= P_TOL, (n, topo, sched)
+        assert np.abs(norm - no).max() <= P_TOL, (n, topo, sched)
+        assert np.abs(psi - psio).max() <= PSI_TOL, (n, topo, sched)
+        assert p[0] == pytest.approx(1.0 / n, abs=1e-15)
+
+
+@pytest.mark.parametrize("n,flags", [(48, 1), (1024, 1), (2050, 0), (1031, 0), (96, 4), (4096, 4)])
+def test_generic_and_exact_sum_paths(qw, n, flags):
+    """flags: 1 = force the global-memory kernel, 4 = block-reduce sum(u) in every stage;
+    n = 2050 / 1031 do not fit the resident kernels at all."""
+    rng = np.random.default_rng(n)
+    for topo in ("circular", "complete"):
+        if flags == 4 and topo == "circular":
+            continue
+        T = rng.uniform(1.0, 6.0, 3) / (1.0 if topo == "circular" else n / 8.0)
+        g = rng.uniform(0.1, 2.0, 3) * (1.0 if topo == "circular" else n / 2.0)
+        prob = qw.Problem(n=n, topology=topo, schedule="cerf_3", n_steps=64, flags=flags)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, topo, "cerf_3", T, g, n_steps=64,
+                                             return_psi=True)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+        assert np.abs(psi - psio).max() <= PSI_TOL
+
+
+def test_gamma_on_laplacian_and_custom_target(qw):
+    n = 64
+    T, g = np.array([20.0, 35.0]), np.array([1.1 / n, 0.9 / n])
+    prob = qw.Problem(n=n, topology="complete", schedule="cerf_3", gamma_on="laplacian",
+                      n_steps=400)
+    p, norm = qw.rk4_batch(prob, T, g)
+    po, no, _ = c_oracle.rk4_batch(n, "complete", "cerf_3", T, g, n_steps=400,
+                                   gamma_on="laplacian")
+    assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+    prob = qw.Problem(n=40, topology="circular", schedule="lin", target=3, n_steps=200)
+    p, norm, psi = qw.rk4_batch(prob, [9.0], [1.3], return_psi=True)
+    po, no, psio, _ = c_oracle.rk4_batch(40, "circular", "lin", [9.0], [1.3], n_steps=200,
+                                         target=3, return_psi=True)
+    assert abs(p[0] - po[0]) <= P_TOL and np.abs(psi - psio).max() <= PSI_TOL
+
+
+def test_heatmap_layout_argmax_and_row_shards(qw):
+    """config 2 shape scaled down: cycle N=64, [beta][T] layout, identical argmax."""
+    n, S = 64, 256
+    t, b = np.linspace(0.1, 64, 20), np.linspace(0, 2.5, 16)
+    for sched in ("lin", "cerf_3", "static"):
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S)
+        p, norm = qw.rk4_heatmap(prob, t, b)
+        po, no = c_oracle.heatmap(n, "circular", sched, t, b, n_steps=S)
+        assert p.shape == (16, 20)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+        assert np.argmax(p) == np.argmax(po)                       # bit-exact indices
+        assert (np.argmax(p, axis=0) == np.argmax(po, axis=0)).all()
+        top2 = np.sort(po.ravel())[-2:]
+        assert top2[1] - top2[0] > 100 * P_TOL                     # margin makes it meaningful
+        lo, _ = qw.rk4_heatmap(prob, t, b, rows=(3, 9))
+        assert np.array_equal(lo, p[3:9])                          # shards are bitwise equal
+        ph, nh = qw.rk4_heatmap_host(prob, t, b, rows=(3, 9))
+        assert np.array_equal(ph, p[3:9]) and np.array_equal(nh, norm[3:9])
+
+
+def test_step_size_rule_ragged(qw):
+    T = np.array([0.0, 0.004, 1.0, 2.5001, 7.0, 0.3])
+    g = np.array([1.0, 0.5, 2.0, 0.1, 1.5, 0.7])
+    for n, topo in ((9, "circular"), (128, "circular"), (24, "complete")):
+        gg = g if topo == "circular" else g * 5
+        prob = qw.Problem(n=n, topology=topo, schedule="sqrt", step_size=1e-2)
+        p, norm = qw.rk4_batch(prob, T, gg)
+        po, no, _ = c_oracle.rk4_batch(n, topo, "sqrt", T, gg, step_size=1e-2)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+        S = np.array([int(x / 1e-2) for x in T])
+        order = qw.longest_first_order(S)
+        p2, _ = qw.rk4_batch(prob, T, gg, order=order)
+        assert np.array_equal(p, p2)
+        ph, nh = qw.rk4_batch_host(prob, T, gg)
+        assert np.array_equal(p, ph) and np.array_equal(norm, nh)
+    prob = qw.Problem(n=16, topology="circular", schedule="lin")
+    S = np.array([10, 0, 33, 64, 7, 128])
+    p, norm = qw.rk4_batch(prob, T, g, n_steps=S)
+    po, no, _ = c_oracle.rk4_batch(16, "circular", "lin", T, g, n_steps=S)
+    assert np.abs(p - po).max() <= P_TOL
+
+
+def test_full_size_configs_on_a_sample(qw):
+    """BASELINE sizes, a few points each, against the C oracle."""
+    # config 5: cycle N=1024, S=4096 (points taken from the 1024x1024 grid)
+    t, b = np.linspace(0.1, 1024, 1024), np.linspace(0, 2.5, 1024)
+    T, g = t[[5, 300, 1023]], b[[700, 410, 9]]
+    prob = qw.Problem(n=1024, topology="circular", schedule="lin", n_steps=4096)
+    p, norm = qw.rk4_batch(prob, T, g)
+    po, no, _ = c_oracle.rk4_batch(1024, "circular", "lin", T, g, n_steps=4096)
+    assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+    # config 3: complete N=4096, gamma on the Laplacian, S=2048
+    n = 4096
+    T, g = np.array([0.1, 200.0, 512.0]), np.array([0.5, 1.0, 2.5]) / n
+    prob = qw.Problem(n=n, topology="complete", schedule="cerf_3", gamma_on="laplacian",
+                      n_steps=2048)
+    p, norm = qw.rk4_batch(prob, T, g)
+    po, no, _ = c_oracle.rk4_batch(n, "complete", "cerf_3", T, g, n_steps=2048,
+                                   gamma_on="laplacian")
+    assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+    # config 4: cycle N=256, S=512, noisy (T, gamma) ensemble
+    rng = np.random.default_rng(20200912)
+    T0, g0 = (np.pi / 2) * 16.0, 1.0
+    T = np.clip(T0 * (1 + 0.05 * rng.standard_normal(64)), 0, None)
+    g = np.clip(g0 * (1 + 0.05 * rng.standard_normal(64)), 0, None)
+    prob = qw.Problem(n=256, topology="circular", schedule="lin", n_steps=512)
+    p, norm = qw.rk4_batch(prob, T, g)
+    po, no, _ = c_oracle.rk4_batch(256, "circular", "lin", T, g, n_steps=512)
+    assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+
+
+def test_size_independent_properties_at_full_size(qw):
+    """Properties that need no oracle: complete graph == 2-variable ODE, mirror symmetry
+    of the ring about the marked vertex, norm defect of RK4, p(T=0) = 1/N."""
+    n, S = 4096, 2048
+    for go, T, g in (("laplacian", 300.0, 1.0 / n), ("oracle", 0.3, 0.8 * n)):
+        prob = qw.Problem(n=n, topology="complete", schedule="cerf_3", gamma_on=go, n_steps=S)
+        p, norm, psi = qw.rk4_batch(prob, [T], [g], return_psi=True)
+        p2, n2 = rk.complete_two_variable(n, "cerf_3", T, g, S, gamma_on=go)
+        assert abs(p[0] - p2) <= P_TOL and abs(norm[0] - n2) <= P_TOL
+        others = np.delete(psi[0], default_target(n))
+        assert np.abs(others - others[0]).max() <= 1e-14
+    n = 1024
+    prob = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=4096)
+    p, norm, psi = qw.rk4_batch(prob, [700.0, 0.0], [1.2, 1.2], return_psi=True)
+    w, k = default_target(n), np.arange(1, n // 2)
+    assert np.abs(psi[0][(w + k) % n] - psi[0][(w - k) % n]).max() <= 1e-13
+    assert abs(norm[0] - 1.0) < 1e-6 and 0.0 <= p[0] <= 1.0
+    assert p[1] == pytest.approx(1.0 / n, abs=1e-15)
+
+
+def test_rhs_is_linear(qw):
+    rng = np.random.default_rng(7)
+    n = 300
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    y = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    for topo in ("circular", "complete"):
+        prob = qw.Problem(n=n, topology=topo, schedule="cerf_5", n_steps=1)
+        f = lambda v: qw.rhs(prob, 1.3, 4.0, 0.9, v)
+        lhs = f(2.5 * x - 1.5j * y)
+        assert np.abs(lhs - (2.5 * f(x) - 1.5j * f(y))).max() <= 1e-11 * np.abs(lhs).max()
+
+
+def test_ensemble_stats_and_robustness(qw, golden):
+    meta, arr = golden
+    rng = np.random.default_rng(3)
+    p = rng.random(100001)
+    st = qw.ensemble_stats(p, thresholds=(0.8, 0.9, 0.95, 0.99))
+    assert st["mean"] == pytest.approx(p.mean(), abs=1e-13)
+    assert st["std"] == pytest.approx(p.std(), abs=1e-13)
+    assert st["min"] == p.min() and st["max"] == p.max()
+    for th, f in st["fraction_ge"].items():
+        assert f == pytest.approx((p >= th).mean(), abs=1e-15)
+    prob = arr["rob_prob"]
+    for c in meta["robustness"]:
+        R, arg = qw.robustness_map(prob, c["variation"])
+        assert round(float(R[c["beta_index"], c["time_index"]]), 4) == c["R"]
+        for i in range(prob.shape[1]):
+            assert arg[i] == rk.first_argmax(prob[:, i])
+
+
+def test_error_behaviour(qw):
+    with pytest.raises(ValueError):
+        qw.rk4_batch(qw.Problem(n=2, topology="circular", n_steps=4), [1.0], [1.0])
+    with pytest.raises(ValueError):
+        qw.rk4_batch(qw.Problem(n=8, topology="star", n_steps=4), [1.0], [1.0])
+    with pytest.raises(ValueError):
+        qw.rk4_batch(qw.Problem(n=8, schedule="quartic", n_steps=4), [1.0], [1.0])
+    with pytest.raises(ValueError):
+        qw.rk4_batch(qw.Problem(n=8), [1.0], [1.0])
+    p, norm = qw.rk4_batch(qw.Problem(n=8, n_steps=4), np.zeros(0), np.zeros(0))
+    assert p.shape == (0,)
+
+
+def test_plan_reports_native_kernels(qw):
+    pl = qw.plan(qw.Problem(n=1024, topology="circular", n_steps=1))
+    assert pl["path"] == "resident-cycle" and pl["sites_per_thread"] == 8
+    assert pl["threads_per_block"] == 128 and pl["sm_count"] >= 100
+    pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1))
+    assert pl["path"] == "resident-complete" and pl["threads_per_block"] == 512
+    before = qw.launch_count()
+    qw.rk4_batch(qw.Problem(n=16, n_steps=4), [1.0], [1.0])
+    assert qw.launch_count() == before + 1
