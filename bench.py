@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- RK4 site-updates/s and heatmap grid-points/s of the B200 path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c5|c2|c3|c4] [--rows-per-gpu R]
+
+One "step" is one pass of the hot path over the workload's (T, gamma) points.  The default
+workload is BASELINE config 5: cycle graph N=1024, n_steps=4096, schedule lin,
+T = linspace(0.1, 1024, 1024); every GPU integrates a block of 128 gamma rows of
+gamma = linspace(0, 2.5, 128*N_gpus), so that 8 GPUs compute exactly the named
+1024 x 1024 heatmap (weak scaling, no data-path collective; the e2e leg adds the final
+all_gather that replaces ray.get + np.concatenate of BCB.py:284-292).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in HBM,
+CUDA events, max over ranks); `e2e` goes through the public Python API with pinned host
+inputs, H2D/D2H (and the gather) inside the timed region; `roofline` is the FP64-pipe
+roofline of the resident kernel against a DFMA peak measured in this same process;
+`cpu_baseline` is the C/OpenMP port of the oracle on this host's cores (bounded sample).
+`--impl reference` times that CPU port alone (the reference itself is Python + SciPy RK45
+and cannot run these sizes: BASELINE.md section 2).
+"""
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_SITE_UPDATE = 52          # SURVEY.md section 8d (22 DFMA + 8 DADD)
+METRIC = "rk4_site_updates_per_sec"
+
+WORKLOADS = {
+    # name: n, topology, schedule, gamma_on, n_steps, n_time, T range, gamma range, rows/GPU
+    "c5": dict(n=1024, topology="circular", schedule="lin", gamma_on="oracle", n_steps=4096,
+               n_time=1024, t=(0.1, 1024.0), g=(0.0, 2.5), rows=128,
+               label="C5 cycle N=1024 n_steps=4096 lin, 1024 T x 128 gamma rows per GPU "
+                     "(the full 1024x1024 heatmap at 8 GPUs)"),
+    "c2": dict(n=64, topology="circular", schedule="lin", gamma_on="oracle", n_steps=1024,
+               n_time=100, t=(0.1, 64.0), g=(0.0, 2.5), rows=100,
+               label="C2 cycle N=64 n_steps=1024 lin, 100x100 heatmap per GPU"),
+    "c3": dict(n=4096, topology="complete", schedule="cerf_3", gamma_on="laplacian",
+               n_steps=2048, n_time=256, t=(0.1, 512.0), g=(0.5 / 4096, 2.5 / 4096), rows=32,
+               label="C3 complete N=4096 n_steps=2048 cerf_3 gamma-on-Laplacian, "
+                     "256 T x 32 gamma rows per GPU (256x256 at 8 GPUs)"),
+    "c4": dict(n=256, topology="circular", schedule="lin", gamma_on="oracle", n_steps=512,
+               n_time=1000, t=(20.0, 30.0), g=(0.8, 1.2), rows=100,
+               label="C4-shaped cycle N=256 n_steps=512 lin, 1e5 points per GPU"),
+}
+
+
+def _workload(name, n_gpus, rows_per_gpu=None):
+    w = dict(WORKLOADS[name])
+    if rows_per_gpu:
+        w["rows"] = int(rows_per_gpu)
+    w["time_array"] = np.linspace(w["t"][0], w["t"][1], w["n_time"])
+    w["beta_array"] = np.linspace(w["g"][0], w["g"][1], w["rows"] * n_gpus)
+    w["site_updates_per_point"] = w["n"] * w["n_steps"]
+    return w
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons while the timed region runs (nvidia-smi semantics)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.reasons, self.sm_max, self.power = [], set(), None, []
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self.stop_flag.is_set():
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception:
+                    pass
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.1)
+        except Exception as exc:                      # NVML missing: report it, do not die
+            self.reasons.add("nvml_unavailable:%s" % type(exc).__name__)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=2.0)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "power_w_max": max(self.power) if self.power else None,
+                "samples": len(self.sm)}
+
+
+def cpu_port_rate(w, seconds, threads=0):
+    """C/OpenMP oracle port on a bounded sample of the workload's own points."""
+    from oracle import c_oracle
+    nthr = c_oracle.max_threads() if threads <= 0 else threads
+    t_arr, b_arr = w["time_array"], w["beta_array"]
+    rng = np.random.default_rng(5)
+
+    def sample(k):
+        return t_arr[rng.integers(0, t_arr.size, k)], b_arr[rng.integers(0, b_arr.size, k)]
+
+    def run(k):
+        T, g = sample(k)
+        t0 = time.perf_counter()
+        c_oracle.rk4_batch(w["n"], w["topology"], w["schedule"], T, g, n_steps=w["n_steps"],
+                           gamma_on=w["gamma_on"], n_threads=nthr)
+        return time.perf_counter() - t0
+
+    run(nthr)                                         # warm the thread pool / caches
+    t1 = run(nthr)
+    k = int(nthr * max(1, min(256, round(seconds / max(t1, 1e-3)))))
+    dt = run(k)
+    return {"value": k * w["site_updates_per_point"] / dt, "unit": "site-updates/s",
+            "cores": nthr, "kind": "port", "grid_points_per_sec": k / dt,
+            "sample": "%d random points of the workload grid, oracle/rk4_oracle.c with "
+                      "OpenMP over points, %.1f s" % (k, dt)}, k, dt
+
+
+def run_reference(args):
+    """CPU arm: rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    w = _workload(args.workload, args.gpus, args.rows_per_gpu)
+    per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_port_rate(w, per_step * 0.25)
+    tot_pts, tot_t, info = 0, 0.0, None
+    for _ in range(args.steps):
+        info, k, dt = cpu_port_rate(w, per_step)
+        tot_pts += k
+        tot_t += dt
+    value = tot_pts * w["site_updates_per_point"] / tot_t
+    info["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "site-updates/s",
+            "grid_points_per_sec": tot_pts / tot_t, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": w["label"],
+                                            "note": "bounded sample per step on host cores"},
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": "site-updates/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import qwtdh_b200 as qw
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)"
+                         % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = _workload(args.workload, world, args.rows_per_gpu)
+    prob = qw.Problem(n=w["n"], topology=w["topology"], schedule=w["schedule"],
+                      gamma_on=w["gamma_on"], n_steps=w["n_steps"])
+    rows = qw.shard_rows(w["beta_array"].size, world, rank)
+    pts_local = (rows[1] - rows[0]) * w["n_time"]
+    pts_total = w["beta_array"].size * w["n_time"]
+    d_time = torch.from_numpy(w["time_array"]).to(dev)
+    d_beta = torch.from_numpy(w["beta_array"]).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # FP64 roofline denominator, measured here (MEASURED_PEAKS.json has no FP64 entry)
+    fp64_peak = qw.fp64_peak_tflops(300.0)
+    plan = qw.plan(prob)
+
+    # ---- device-resident: K steps, CUDA events per step on the launching stream ---------
+    for _ in range(args.warmup):
+        flush.zero_()
+        qw.rk4_heatmap(prob, d_time, d_beta, rows=rows)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = qw.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    for a, b in ev:
+        flush.zero_()                                 # L2 flush between timed iterations
+        a.record()
+        p_dev, n_dev = qw.rk4_heatmap(prob, d_time, d_beta, rows=rows)
+        b.record()
+    barrier()
+    launches = qw.launch_count() - launches0
+    clocks = sampler.summary()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    dev_ms = max_over_ranks(dev_ms)
+    ms_per_step = dev_ms / args.steps
+    value = pts_total * w["site_updates_per_point"] / (ms_per_step * 1e-3)
+
+    # ---- end to end: pinned host inputs -> public API -> host heatmap --------------------
+    h_time = torch.from_numpy(w["time_array"]).pin_memory()
+    h_beta = torch.from_numpy(w["beta_array"]).pin_memory()
+
+    def e2e_step():
+        if world == 1:
+            p, nrm = qw.rk4_heatmap(prob, h_time, h_beta, rows=rows)
+        else:
+            p, nrm = qw.heatmap_sharded(prob, h_time.numpy(), h_beta.numpy())
+        return p, nrm
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        p_host, n_host = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    e2e_value = pts_total * w["site_updates_per_point"] / (e2e_ms * 1e-3)
+    h2d = (h_time.numel() + h_beta.numel()) * 8
+    d2h = 2 * pts_local * 8
+
+    ok = bool(np.isfinite(p_host).all() and (p_host >= 0).all() and (p_host <= 1 + 1e-9).all()
+              and np.array_equal(p_host[rows[0] if world > 1 else 0:][:rows[1] - rows[0]],
+                                 p_dev.cpu().numpy()))
+
+    if rank == 0:
+        kernel_s = ms_per_step * 1e-3                 # one launch per step and per GPU
+        achieved = FLOPS_PER_SITE_UPDATE * pts_local * w["site_updates_per_point"] / kernel_s / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "site-updates/s",
+            "grid_points_per_sec": pts_total / (ms_per_step * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["label"], "points_per_gpu": pts_local,
+                       "points_total": pts_total, "site_updates_per_point":
+                       w["site_updates_per_point"], "l2": "flushed (256 MiB write) between "
+                       "timed iterations; state is register-resident",
+                       "kernel": plan, "results_sane_and_e2e_equals_device": ok},
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                         "peak_source": "qw_fp64_peak_probe: dependent-free DFMA stream "
+                                        "measured in this process (MEASURED_PEAKS.json has "
+                                        "no FP64 entry; nominal 148 SM x 64 DFMA/clk x 2 x "
+                                        "1.965 GHz = 37.2)",
+                         "algorithmic_flops_per_site_update": FLOPS_PER_SITE_UPDATE,
+                         "max_frac_of_fma_peak": 52.0 / 60.0},
+            "e2e": {"value": e2e_value, "unit": "site-updates/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "grid_points_per_sec": pts_total / (e2e_ms * 1e-3)},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_port_rate(w, args.cpu_seconds)[0]
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows-per-gpu", type=int, default=None)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("note: warmup < 3 does not meet the timing rules", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -203,7 +203,7 @@ def test_size_independent_properties_at_full_size(qw):
     p, norm, psi = qw.rk4_batch(prob, [700.0, 0.0], [1.2, 1.2], return_psi=True)
     w, k = default_target(n), np.arange(1, n // 2)
     assert np.abs(psi[0][(w + k) % n] - psi[0][(w - k) % n]).max() <= 1e-13
-    assert abs(norm[0] - 1.0) < 1e-6 and 0.0 <= p[0] <= 1.0
+    assert abs(norm[0] - 1.0) < 1e-4 and 0.0 <= p[0] <= 1.0      # RK4 norm defect at h = 0.17
     assert p[1] == pytest.approx(1.0 / n, abs=1e-15)
 
 
