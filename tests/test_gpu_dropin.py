@@ -1,0 +1,178 @@
+"""GPU: the drop-in modules, called the way the reference's scripts call their own
+functions (module globals, [beta, T] arguments, negative probabilities, file names)."""
+
+import importlib
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+PKG = "quantum-walks-time-dependent-hamiltonians_b200"
+
+
+def _mod(name):
+    return importlib.import_module(PKG + "." + name)
+
+
+def _site(n):
+    w = np.zeros((n, 1))
+    w[int((n - 1) / 2)][0] = 1
+    return w
+
+
+def test_bcb_evaluate_probability_against_golden(golden):
+    meta, arr = golden
+    bcb = _mod("BCB")
+    for c in meta["rk4_L0"]:
+        bcb.dimension, bcb.topology, bcb.step_function = c["n"], c["topology"], c["schedule"]
+        bcb.n_steps, bcb.step_size = c["rule"].get("n_steps"), c["rule"].get("step_size", 1e-3)
+        val = bcb.evaluate_probability([c["beta"], c["T"]], _site(c["n"]))
+        assert val.shape == (1,) and val[0] <= 0
+        assert abs(-val[0] - c["p"]) <= 1e-10, c
+        psi = bcb.solve_schrodinger_equation(c["T"], c["beta"])
+        ref = arr["L0_psi_%d" % c["key"]]
+        assert np.abs(psi - ref / np.sqrt(c["norm"])).max() <= 1e-11      # BCB normalises
+        assert np.vdot(psi, psi).real == pytest.approx(1.0, abs=1e-13)
+    bcb.n_steps, bcb.step_size = None, 1e-3
+
+
+def test_default_step_rule_tracks_the_shipped_rk45(golden):
+    """With the stub's default step_size = 1e-3 the drop-in reproduces what the reference
+    prints today (RK45, tol 1e-6) to the accuracy of RK45 itself."""
+    meta, _ = golden
+    bcb = _mod("BCB")
+    bcb.n_steps, bcb.step_size = None, 1e-3
+    for c in meta["rk45"]:
+        bcb.dimension, bcb.topology, bcb.step_function = c["n"], c["topology"], c["schedule"]
+        val = bcb.evaluate_probability([c["beta"], c["T"]], _site(c["n"]))
+        tol = 2e-4 if c["schedule"] in ("sqrt", "cbrt") else 3e-5
+        assert abs(-val[0] - c["p"]) <= tol, c
+
+
+def test_schroedinger_solver_module(golden):
+    meta, arr = golden
+    ss, rke = _mod("Schroedinger_Solver"), _mod("Runge_Kutta_Error")
+    hm = [c for c in meta["heatmaps"] if c["kind"] == "RK45"][0]
+    ss.dimension, ss.step_function, ss.n_steps, ss.step_size = 5, 1, None, 1e-3
+    p = ss.grid_probability_evaluation(5, 1, 20, 4, 0.1, 5, 3, 0.92, 7)
+    assert p.shape == (3, 4) and np.abs(p - arr[hm["key"]]).max() <= 3e-5
+    ss.dimension, ss.step_function, ss.n_steps = 17, 3, 1024           # 3 = cbrt (SS:59)
+    psi = ss.solve_schrodinger_equation(12.0, 2.0)
+    c = [c for c in meta["rk4_L0"] if c["n"] == 17][0]
+    assert np.abs(psi - arr["L0_psi_%d" % c["key"]]).max() <= 1e-11       # SS returns raw psi
+    val = ss.evaluate_probability([2.0, 12.0], _site(17))
+    assert abs(-val[0] - c["p"]) <= 1e-10
+    other = np.zeros((17, 1))
+    other[3][0] = 1                                                     # another projector
+    val = ss.evaluate_probability([2.0, 12.0], other)
+    assert val.shape == (1,)
+    assert abs(-val[0] - abs(psi[3]) ** 2 / c["norm"]) <= 1e-12
+    rke.dimension, rke.step_function, rke.n_steps = 17, 3, 1024
+    assert abs(rke.solve_schrodinger_equation(12.0, 2.0) - c["norm"]) <= 1e-10
+    assert abs(rke.norm_defect(12.0, 2.0) - (1 - c["norm"])) <= 1e-10
+    assert ss.single_evaluation_benchmark([2.0, 12.0]) == 1
+    ss.n_steps = rke.n_steps = None
+
+
+def test_rhs_and_time_independent_comparator(golden):
+    meta, arr = golden
+    bcb = _mod("BCB")
+    for c in meta["rhs"]:
+        bcb.dimension, bcb.topology, bcb.step_function = c["n"], c["topology"], c["schedule"]
+        dy = bcb.schrodinger_equation(c["t"], arr["rhs_y_%d" % c["key"]], c["beta"], c["T"])
+        ref = arr["rhs_dy_%d" % c["key"]]
+        assert isinstance(dy, list) and len(dy) == c["n"]
+        assert np.abs(np.array(dy) - ref).max() <= 1e-12 * np.abs(ref).max()
+    bcb.topology = "circular"
+    for c in meta["static"]:
+        bcb.dimension, bcb.n_steps = c["n"], c["n_steps"]
+        val = bcb.evaluate_time_independent_probability(c["time"], c["gamma"], _site(c["n"]))
+        assert val.shape == (1, 1)
+        assert abs(-val[0, 0] - c["p_expm"]) <= 1e-8
+        assert abs(-val[0, 0] - c["p_rk4"] * c["norm_rk4"]) <= 1e-10
+    bcb.n_steps = None
+
+
+def test_grid_eval_and_type_of_qw():
+    bcb = _mod("BCB")
+    bcb.dimension, bcb.topology, bcb.step_function, bcb.n_steps = 21, "circular", "cerf_3", 128
+    t, b = np.linspace(0.1, 21, 6), np.linspace(0, 2.5, 4)
+    bcb.type_of_qw = "dependent"
+    p = bcb.grid_eval(t, b)
+    po, _ = c_oracle.heatmap(21, "circular", "cerf_3", t, b, n_steps=128)
+    assert p.shape == (4, 6) and np.abs(p - po).max() <= 1e-10
+    bcb.type_of_qw = "independent"
+    p = bcb.grid_eval(t, b)
+    po, _ = c_oracle.heatmap(21, "circular", "static", t, b, n_steps=128)
+    assert np.abs(p - po).max() <= 1e-10
+    bcb.type_of_qw = "dependent"
+    bcb.n_steps = None
+
+
+def test_parallel_routine_file_contract_and_robustness(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    bcb, bl, rob = _mod("BCB"), _mod("BCB_latest"), _mod("Robustness")
+    bcb.dimension, bcb.topology, bcb.step_function, bcb.type_of_qw = 9, "circular", "lin", "dependent"
+    bcb.n_steps = 64
+    assert bcb.parallel_routine(0.1, 9, 0, 2) == 0
+    p = np.load("9_circular_probability_lin.npy")
+    t, b = np.load("9_circ_time.npy"), np.load("9_circ_beta.npy")
+    assert p.shape == (24, 24) and t.shape == (24,) and b.shape == (24,)
+    po, _ = c_oracle.heatmap(9, "circular", "lin", t, b, n_steps=64)
+    assert np.abs(p - po).max() <= 1e-10
+    bcb.n_steps = None
+
+    bl.dimension, bl.step_function, bl.type_of_qw, bl.n_steps = 11, "sqrt", "dependent", 64
+    assert bl.parallel_routine() == 0
+    p = np.load("11_probability_sqrt.npy")
+    assert p.shape == (75, 4)
+    t, b = np.load("11_circ_time.npy"), np.load("11_circ_beta.npy")
+    assert t[2] == (np.pi / 2) * np.sqrt(11) and b.tolist() == bl.PRODUCTION_BETA
+    po, _ = c_oracle.heatmap(11, "circular", "sqrt", t, b, n_steps=64)
+    assert np.abs(p - po).max() <= 1e-10
+    dim, r2, r4 = rob.routine(11, 2)                       # flag 2 = sqrt (Robustness.py:13)
+    j = int(np.argmax(po[:, 2]))
+    assert r2 == round(float(((po[j, 2] - po[j + 2, 2]) + (po[j, 2] - po[j - 2, 2])) / 2), 4)
+    bl.n_steps = None
+
+
+def test_qw_search_state_evolve():
+    qws = _mod("QW_Search")
+    qws.n_steps, qws.step_size = 256, None
+    HC = qws.Hamiltonian(16, 1, 1, 7, 1, 1.0)              # time-dependent, cycle, lin
+    HC.build_laplacian()
+    HC.build_hamiltonian()
+    psi = qws.State(16)
+    psi.set_initial(0)
+    psi.set_hamiltonian(HC)
+    psi.evolve(16.0)
+    po, no, psio, _ = c_oracle.rk4_batch(16, "circular", "lin", [16.0], [1.0], n_steps=256,
+                                         return_psi=True)
+    assert np.abs(psi.ket - psio[0]).max() <= 1e-11
+    assert abs(psi.success_probability() - po[0]) <= 1e-10
+    HI = qws.Hamiltonian(5, 0, 0, 1, 0, 5.0)               # time-independent, complete
+    HI.build_laplacian()
+    HI.build_hamiltonian()
+    st = qws.State(5)
+    st.set_initial(0)
+    st.set_hamiltonian(HI)
+    st.evolve(np.pi / (2 * np.sqrt(5)))
+    assert abs(st.success_probability() - 1.0) <= 1e-9     # thesis Eq. 1.28
+    qws.n_steps, qws.step_size = None, 1e-3
+
+
+def test_robustness_ensemble_stats():
+    rob = _mod("Robustness")
+    qw = importlib.import_module(PKG)
+    rng = np.random.default_rng(20200912)
+    T0, g0 = (np.pi / 2) * 16.0, 1.0
+    T = np.clip(T0 * (1 + 0.05 * rng.standard_normal(512)), 0, None)
+    g = np.clip(g0 * (1 + 0.05 * rng.standard_normal(512)), 0, None)
+    prob = qw.Problem(n=256, topology="circular", schedule="lin", n_steps=128)
+    st = rob.ensemble(prob, T, g, p_reference=0.5)
+    po, _, _ = c_oracle.rk4_batch(256, "circular", "lin", T, g, n_steps=128)
+    assert st["mean"] == pytest.approx(po.mean(), abs=1e-11)
+    assert st["std"] == pytest.approx(po.std(), abs=1e-11)
+    assert st["R_sampled"] == pytest.approx(0.5 - po.mean(), abs=1e-11)
