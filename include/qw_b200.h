@@ -73,8 +73,11 @@ enum {
     QW_FLAG_NONE = 0,
     QW_FLAG_FORCE_GENERIC = 1,   /* use the global-memory kernel whatever n is (tests) */
     QW_FLAG_FORCE_STREAM = 2,    /* use the tile-fused streaming kernel (cycle graph) */
-    QW_FLAG_EXACT_SUM = 4        /* complete graph: block-reduce sum(u) in every stage
+    QW_FLAG_EXACT_SUM = 4,       /* complete graph: block-reduce sum(u) in every stage
                                     instead of once per step (tests) */
+    QW_FLAG_STREAM_KB1 = 8,      /* streaming kernel: 1 RK4 step per pass over HBM (the plain
+                                    32 B/site-update roofline) instead of the default 4 */
+    QW_FLAG_STREAM_KB2 = 16      /* streaming kernel: 2 steps per pass */
 };
 
 /* ---- the hot path -------------------------------------------------------------------- */
@@ -146,7 +149,7 @@ typedef struct qw_plan {
     int32_t regs_per_thread;
     int32_t smem_bytes;
     int32_t sm_count;
-    int32_t reserved;
+    int32_t steps_per_pass;  /* streaming path: RK4 steps fused per pass over HBM, else 0 */
 } qw_plan;
 
 /* Which kernel a problem would run on the current device. */

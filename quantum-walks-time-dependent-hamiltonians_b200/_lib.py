@@ -13,6 +13,7 @@ SCHEDULES = {"cerf_3": 0, "lin": 1, "sqrt": 2, "cbrt": 3, "cerf_5": 4, "cerf_7":
              "static": 6}
 GAMMA_ON_ORACLE, GAMMA_ON_LAPLACIAN = 0, 1
 FLAG_FORCE_GENERIC, FLAG_FORCE_STREAM, FLAG_EXACT_SUM = 1, 2, 4
+FLAG_STREAM_KB1, FLAG_STREAM_KB2 = 8, 16
 PATH_NAMES = {0: "resident-cycle", 1: "resident-complete", 2: "generic", 3: "stream"}
 
 
@@ -27,7 +28,7 @@ class QwPlan(ctypes.Structure):
     _fields_ = [("path", ctypes.c_int32), ("sites_per_thread", ctypes.c_int32),
                 ("threads_per_block", ctypes.c_int32), ("blocks_per_sm", ctypes.c_int32),
                 ("regs_per_thread", ctypes.c_int32), ("smem_bytes", ctypes.c_int32),
-                ("sm_count", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("sm_count", ctypes.c_int32), ("steps_per_pass", ctypes.c_int32)]
 
 
 _vp, _i64, _i32, _dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double

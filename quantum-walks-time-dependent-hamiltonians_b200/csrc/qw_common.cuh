@@ -37,8 +37,10 @@ struct QwParams {
     double2 *psi;
     // geometry of the resident kernels
     int32_t nact;                 // active threads per point (n / sites_per_thread)
-    // scratch of the global-memory kernels: 3 complex vectors per concurrently running block
+    // scratch of the global-memory kernels (generic: 5 complex vectors per running block;
+    // streaming: two psi buffers per point of the chunk in flight)
     double2 *scratch;
+    int64_t point_offset;         // streaming: first point of the chunk in flight
 };
 
 struct QwPoint {
@@ -112,9 +114,9 @@ __device__ __forceinline__ QwPoint qw_point(const QwParams &prm, int64_t b)
 // operator evaluations.  Ends with a __syncthreads().
 __device__ __forceinline__ void qw_fill_table(double2 *tabAB, double2 *tabD, double2 *ad,
                                               const QwPoint &pt, int64_t n0, int schedule,
-                                              int gamma_on)
+                                              int gamma_on, int count = QW_CHUNK)
 {
-    for (int i = threadIdx.x; i < 3 * QW_CHUNK; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 3 * count; i += blockDim.x) {
         int s = i / 3, k = i - 3 * s;
         double t = (double)(n0 + s) * pt.h;
         if (k == 1) t += 0.5 * pt.h;
@@ -123,7 +125,7 @@ __device__ __forceinline__ void qw_fill_table(double2 *tabAB, double2 *tabD, dou
     }
     __syncthreads();
     const double h = pt.h;
-    for (int i = threadIdx.x; i < 4 * QW_CHUNK; i += blockDim.x) {
+    for (int i = threadIdx.x; i < 4 * count; i += blockDim.x) {
         int s = i >> 2, k = i & 3;
         double2 c = ad[3 * s + (k == 0 ? 0 : (k == 3 ? 2 : 1))];
         double wa = (k < 2) ? 0.5 * h : (k == 2 ? h : 0.0);

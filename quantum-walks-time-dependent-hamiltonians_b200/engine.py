@@ -251,7 +251,7 @@ def plan(problem, device=None):
     pl = _lib.QwPlan()
     with torch.cuda.device(dev):
         _lib.check(lib.qw_plan_query(ctypes.byref(problem.c_struct()), ctypes.byref(pl)))
-    d = {k: getattr(pl, k) for k, _ in _lib.QwPlan._fields_ if k != "reserved"}
+    d = {k: getattr(pl, k) for k, _ in _lib.QwPlan._fields_}
     d["path"] = _lib.PATH_NAMES.get(pl.path, str(pl.path))
     return d
 
