@@ -259,3 +259,48 @@ def test_plan_reports_native_kernels(qw):
     before = qw.launch_count()
     qw.rk4_batch(qw.Problem(n=16, n_steps=4), [1.0], [1.0])
     assert qw.launch_count() == before + 1
+
+
+@pytest.mark.parametrize("n", [8, 64, 1000, 1016, 1024, 2050, 4100, 9001])
+@pytest.mark.parametrize("kb_flag", [8, 16, 0])
+def test_streaming_kernel_vs_oracle(qw, n, kb_flag):
+    """Tile-fused HBM-streaming kernel (flags: 2 = force it, 8 / 16 = 1 / 2 steps per pass,
+    default 4), windows that wrap, ragged last tiles, marked vertex in a halo copy."""
+    rng = np.random.default_rng(n + kb_flag)
+    T = np.concatenate([[0.0], rng.uniform(1.0, 9.0, 3)])
+    g = rng.uniform(0.1, 2.4, 4)
+    for sched, S in (("lin", 37), ("cbrt", 24)):
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S,
+                          flags=2 | kb_flag)
+        assert qw.plan(prob)["path"] == "stream"
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, n_steps=S,
+                                             return_psi=True)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+        assert np.abs(psi - psio).max() <= PSI_TOL
+
+
+def test_streaming_kernel_step_size_rule_and_targets(qw):
+    T = np.array([0.0, 0.31, 0.117, 0.25])
+    g = np.array([1.0, 0.5, 2.0, 0.1])
+    for target in (None, 0, 1015, 1016, 2999):
+        prob = qw.Problem(n=3000, topology="circular", schedule="sqrt", step_size=1e-2,
+                          target=target, flags=2)
+        p, norm = qw.rk4_batch(prob, T, g)
+        po, no, _ = c_oracle.rk4_batch(3000, "circular", "sqrt", T, g, step_size=1e-2,
+                                       target=target)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+
+
+def test_config5_streaming_variant_on_a_sample(qw):
+    """cycle N=65536, n_steps=256 (BASELINE config 5, streaming variant): two grid points
+    against the C oracle, plus mirror symmetry about the marked vertex."""
+    n, S = 65536, 256
+    T, g = np.array([0.1, 64.0]), np.array([0.6, 2.1])
+    prob = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=S)
+    assert qw.plan(prob)["path"] == "stream"
+    p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+    po, no, _ = c_oracle.rk4_batch(n, "circular", "lin", T, g, n_steps=S)
+    assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+    w, k = default_target(n), np.arange(1, 4000)
+    assert np.abs(psi[1][(w + k) % n] - psi[1][(w - k) % n]).max() <= 1e-13
