@@ -107,6 +107,51 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.sm)}
 
 
+def hbm_peak_gbs():
+    """Measured copy bandwidth of this pool's B200s (driver-written), else the fallback of
+    /opt/skills/guides/B200_PROFILING.md."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6.65 TB/s of B200_PROFILING.md (of fallback)"
+
+
+def stream_measure(qw, torch, dev, reps=3):
+    """HBM-streaming variant of config 5: cycle N=65536, n_steps=256, 32x32 (T, gamma) grid
+    = 1024 points in flight (2 GiB of psi ping-pong buffers, far above the 126 MB L2).
+    KB = RK4 steps fused per pass over HBM: KB=1 is the plain 32 B/site-update stream."""
+    n, S, nT, nB = 65536, 256, 32, 32
+    t = torch.linspace(0.1, 64.0, nT, dtype=torch.float64, device=dev)
+    b = torch.linspace(0.0, 2.5, nB, dtype=torch.float64, device=dev)
+    peak, src = hbm_peak_gbs()
+    out = {"workload": "cycle N=65536 n_steps=256 lin, 32x32 heatmap (1024 points, 2 GiB "
+                       "working set > L2)", "peak_gbs": peak, "peak_source": src, "variants": []}
+    for kb, flag in ((1, 8), (2, 16), (4, 0)):
+        prob = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=S, flags=flag)
+        qw.rk4_heatmap(prob, t, b)
+        best = 1e30
+        l0 = qw.launch_count()
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            qw.rk4_heatmap(prob, t, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        launches = (qw.launch_count() - l0) // reps
+        rate = nT * nB * n * S / (best * 1e-3)
+        halo = 1024.0 / (1024.0 - 8.0 * kb)
+        out["variants"].append({
+            "steps_per_pass": kb, "ms": best, "site_updates_per_sec": rate,
+            "launches_per_heatmap": launches,
+            "algorithmic_gbs_at_32B_per_site_update": 32.0 * rate / 1e9,
+            "frac_of_hbm_peak_algorithmic": 32.0 * rate / 1e9 / peak,
+            "actual_gbs_incl_halo_rereads": 32.0 / kb * halo * rate / 1e9,
+            "frac_of_hbm_peak_actual": 32.0 / kb * halo * rate / 1e9 / peak})
+    return out
+
+
 def cpu_port_rate(w, seconds, threads=0):
     """C/OpenMP oracle port on a bounded sample of the workload's own points."""
     from oracle import c_oracle
@@ -202,7 +247,10 @@ def run_b200(args):
         return float(t.item())
 
     # FP64 roofline denominator, measured here (MEASURED_PEAKS.json has no FP64 entry)
-    fp64_peak = qw.fp64_peak_tflops(300.0)
+    probe_clock = ClockSampler(local)
+    probe_clock.start()
+    fp64_peak = qw.fp64_peak_tflops(600.0)
+    probe_clock = probe_clock.summary()
     plan = qw.plan(prob)
 
     # ---- device-resident: K steps, CUDA events per step on the launching stream ---------
@@ -269,11 +317,17 @@ def run_b200(args):
                        "timed iterations; state is register-resident",
                        "kernel": plan, "results_sane_and_e2e_equals_device": ok},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         "traffic": 80128,
+                         "traffic_note": "dram__bytes_read+write of an 8192-point launch "
+                                         "(ncu --set full, profiles/): the kernel is "
+                                         "register-resident, DRAM sees only T, gamma, p, norm",
                          "peak_source": "qw_fp64_peak_probe: dependent-free DFMA stream "
-                                        "measured in this process (MEASURED_PEAKS.json has "
-                                        "no FP64 entry; nominal 148 SM x 64 DFMA/clk x 2 x "
-                                        "1.965 GHz = 37.2)",
+                                        "measured in this process, best of 8/16/24 warps per "
+                                        "SM (MEASURED_PEAKS.json has no FP64 entry)",
+                         "peak_nominal": 148 * 64 * 2 * 1.965e-3,
+                         "frac_of_nominal": achieved / (148 * 64 * 2 * 1.965e-3),
+                         "probe_clocks": probe_clock,
                          "algorithmic_flops_per_site_update": FLOPS_PER_SITE_UPDATE,
                          "max_frac_of_fma_peak": 52.0 / 60.0},
             "e2e": {"value": e2e_value, "unit": "site-updates/s", "ms_per_step": e2e_ms,
@@ -281,6 +335,8 @@ def run_b200(args):
                     "grid_points_per_sec": pts_total / (e2e_ms * 1e-3)},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if world == 1 and not args.no_stream:
+            line["streaming"] = stream_measure(qw, torch, dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_port_rate(w, args.cpu_seconds)[0]
         print(json.dumps(line))
@@ -298,6 +354,8 @@ def main():
     ap.add_argument("--rows-per-gpu", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream", action="store_true",
+                    help="skip the N=65536 HBM-streaming side measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         print("note: warmup < 3 does not meet the timing rules", file=sys.stderr)

@@ -19,6 +19,7 @@
 // SURVEY.md section 8d.
 #include "qw_common.cuh"
 #include "qw_stage.cuh"
+#include "qw_cycle_v2.cuh"
 
 namespace {
 
@@ -129,6 +130,53 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_resident(const QwParams
     epilogue<R>(s, prm, pt, tb.red, t);
 }
 
+// Second-generation cycle kernel (qw_cycle_v2.cuh): edge sites first, early publication,
+// mbarrier arrive / wait instead of a block barrier per stage, oracle term in warp 0 only.
+template <int R, int MAXNT, int MINB, bool SPLIT>
+__global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_resident_v2(const QwParams prm)
+{
+    extern __shared__ double2 mbox[];         // [2][2][blockDim.x]: parity, first/last
+    __shared__ CycleShared sh;
+    const int t = threadIdx.x, nt = blockDim.x, nact = prm.nact;
+    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const bool active = t < nact;
+    const int tl = active ? (t == 0 ? nact - 1 : t - 1) : t;
+    const int tr = active ? (t == nact - 1 ? 0 : t + 1) : t;
+
+    State<R> s;
+    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+    }
+    if (SPLIT) {
+        if (t == 0) qw_mbar_init(&sh.mbar, nt >> 5);
+        __syncthreads();
+    }
+    int par = 0;
+    uint32_t phase = 0;
+    double2 *first = mbox, *last = mbox + 2 * nt;
+    first[t] = make_double2(s.yr[0], s.yi[0]);
+    last[t] = make_double2(s.yr[R - 1], s.yi[R - 1]);
+    if (SPLIT) {
+        __syncwarp();
+        if ((t & 31) == 0) qw_mbar_arrive(&sh.mbar);
+    }
+
+    for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
+        qw_fill_table(sh.ab, sh.d, sh.ad, pt, n0, prm.schedule, prm.gamma_on);
+        const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
+        if (SPLIT) {
+            if (t < 32) qw_cycle_steps<R, true, SPLIT>(s, sh, first, last, nt, t, tl, tr, cnt, par, phase);
+            else qw_cycle_steps<R, false, SPLIT>(s, sh, first, last, nt, t, tl, tr, cnt, par, phase);
+        } else {
+            qw_cycle_steps<R, true, SPLIT>(s, sh, first, last, nt, t, tl, tr, cnt, par, phase);
+        }
+    }
+    epilogue<R>(s, prm, pt, sh.red, t);
+}
+
 template <int R>
 __device__ __forceinline__ double2 local_sum_y(const State<R> &s)
 {
@@ -235,13 +283,22 @@ cudaError_t dispatch_threads(const QwParams &prm, int threads, cudaStream_t st, 
     const bool cyc = prm.topology == QW_TOPO_CYCLE;
     const bool exact = (prm.flags & QW_FLAG_EXACT_SUM) != 0;
     const size_t smem = cyc ? (size_t)threads * 4 * sizeof(double2) : 0;
+    const bool legacy = (prm.flags & QW_FLAG_CYCLE_LEGACY) != 0;
+    const bool split = (prm.flags & QW_FLAG_CYCLE_SPLIT) != 0;
 #define QW_LAUNCH(MAXNT, MINB)                                                             \
-    return cyc ? launch(rk4_cycle_resident<R, MAXNT, MINB>, prm, threads, smem, st, plan)  \
-               : (exact ? launch(rk4_complete_resident<R, MAXNT, MINB, true>, prm, threads, \
-                                 smem, st, plan)                                           \
-                        : launch(rk4_complete_resident<R, MAXNT, MINB, false>, prm,        \
-                                 threads, smem, st, plan));
-    if (threads <= 128) { QW_LAUNCH(128, 4) }
+    if (cyc && legacy)                                                                     \
+        return launch(rk4_cycle_resident<R, MAXNT, MINB>, prm, threads, smem, st, plan);   \
+    if (cyc && split)                                                                      \
+        return launch(rk4_cycle_resident_v2<R, MAXNT, MINB, true>, prm, threads, smem, st, plan); \
+    if (cyc)                                                                               \
+        return launch(rk4_cycle_resident_v2<R, MAXNT, MINB, false>, prm, threads, smem, st, plan); \
+    return exact ? launch(rk4_complete_resident<R, MAXNT, MINB, true>, prm, threads, smem, \
+                          st, plan)                                                        \
+                 : launch(rk4_complete_resident<R, MAXNT, MINB, false>, prm, threads, smem, \
+                          st, plan);
+    // <= 128 threads: 3 blocks/SM (168 registers, no spills) measured faster than 4 (128)
+    if (threads <= 128 && (prm.flags & QW_FLAG_OCC4)) { QW_LAUNCH(128, 4) }
+    if (threads <= 128) { QW_LAUNCH(128, 3) }
     if (threads <= 256) { QW_LAUNCH(256, 2) }
     if (threads <= 512) { QW_LAUNCH(512, 1) }
     if constexpr (R <= 2) { QW_LAUNCH(1024, 1) }      // 64-register cap: R <= 2 only

@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""A/B timing of kernel variants selected by qw_problem.flags (development tool).
+
+    python tools/ab_kernels.py [--rows 16] [--reps 3] [--workload c5|c3|c4]
+
+Prints site-updates/s per variant (CUDA events, best of reps) and checks that all variants
+agree with the first to 1e-12.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qwtdh_b200 as qw  # noqa: E402
+
+VARIANTS = {
+    "c5": [("v2 occ3 (default)", 0), ("v2 occ4", 128), ("v2 mbarrier occ3", 64),
+           ("v2 mbarrier occ4", 64 | 128), ("v1 legacy occ3", 32), ("v1 legacy occ4", 32 | 128)],
+    "c4": [("v2 occ3 (default)", 0), ("v2 occ4", 128), ("v1 legacy occ3", 32),
+           ("v1 legacy occ4", 32 | 128)],
+    "c3": [("complete default", 0), ("complete exact-sum", 4)],
+}
+SHAPES = {
+    "c5": dict(n=1024, topology="circular", schedule="lin", n_steps=4096, nT=1024, t=(0.1, 1024), g=(0, 2.5)),
+    "c4": dict(n=256, topology="circular", schedule="lin", n_steps=512, nT=1000, t=(20, 30), g=(0.8, 1.2)),
+    "c3": dict(n=4096, topology="complete", schedule="cerf_3", n_steps=2048, nT=256, t=(0.1, 512),
+               g=(0.5 / 4096, 2.5 / 4096), gamma_on="laplacian"),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=16)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--workload", default="c5")
+    a = ap.parse_args()
+    sh = SHAPES[a.workload]
+    dev = torch.device("cuda")
+    t = torch.linspace(sh["t"][0], sh["t"][1], sh["nT"], dtype=torch.float64, device=dev)
+    b = torch.linspace(sh["g"][0], sh["g"][1], a.rows, dtype=torch.float64, device=dev)
+    ref = None
+    for name, flags in VARIANTS[a.workload]:
+        prob = qw.Problem(n=sh["n"], topology=sh["topology"], schedule=sh["schedule"],
+                          n_steps=sh["n_steps"], gamma_on=sh.get("gamma_on", "oracle"),
+                          flags=flags)
+        pl = qw.plan(prob)
+        best = 1e30
+        for _ in range(a.reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            p, nrm = qw.rk4_heatmap(prob, t, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        if ref is None:
+            ref = p.clone()
+        err = float((p - ref).abs().max())
+        rate = a.rows * sh["nT"] * sh["n"] * sh["n_steps"] / (best * 1e-3)
+        print("%-22s %8.2f ms  %.4e site-updates/s  regs=%d blocks/SM=%d  |dp|max vs first=%.1e"
+              % (name, best, rate, pl["regs_per_thread"], pl["blocks_per_sm"], err))
+
+
+if __name__ == "__main__":
+    main()
