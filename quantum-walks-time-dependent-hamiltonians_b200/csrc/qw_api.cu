@@ -83,11 +83,30 @@ int choose_path(const QwParams &prm)
     return PATH_GENERIC;
 }
 
+// The large-N paths take their scratch from the device's stream-ordered pool.  Keep freed
+// scratch cached in the pool (default: released to the OS at the next synchronisation, which
+// costs milliseconds per GiB on every call).
+void keep_pool_cached()
+{
+    static std::atomic<uint32_t> done_mask{0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
+    if (done_mask.load() & (1u << dev)) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_mask.fetch_or(1u << dev);
+}
+
 int run(QwParams &prm, cudaStream_t st)
 {
     if (prm.n_points == 0) return 0;
     cudaError_t e;
-    switch (choose_path(prm)) {
+    const int path = choose_path(prm);
+    if (path != PATH_RESIDENT) keep_pool_cached();
+    switch (path) {
     case PATH_RESIDENT:
         e = qw_launch_resident(prm, st, nullptr);
         if (e != cudaSuccess) return cuda_fail(e, "resident kernel launch");

@@ -1,15 +1,20 @@
 // Tile-fused HBM-streaming RK4 for rings too large for one SM's registers (cycle graph,
 // N = 65 536 in BASELINE config 5), sm_100a.
 //
-// psi of every point in flight lives in HBM (two buffers, ping-pong).  One launch advances
-// every point by KB RK4 steps: a thread block loads a window of W = 128 threads x 8 sites
-// (coalesced, transposed through padded shared memory), runs the same register-resident
-// stage code as qw_resident.cu on it with open ends, and writes back the W - 2*HALO
-// central sites (HALO = 4*KB: every stage invalidates one more site at each open end, so
-// all four stages of KB steps are fused per tile).  Algorithmic traffic: one read and one
-// write of psi per pass = 32 B per site per pass, i.e. 32/KB bytes per site-update; KB = 1
-// is the plain "read psi_n, write psi_n+1" streaming roofline of SURVEY.md section 8d,
-// KB = 4 (default) is temporal blocking that turns the path FP64-bound again.
+// psi of every point in flight lives in HBM (two buffers, ping-pong).  One launch ("pass")
+// advances every point by KB RK4 steps.  Work unit = one window of W = 128 threads x 8
+// sites of one point: load it (cp.async, coalesced 16 B per lane, into a padded shared
+// buffer), run the register-resident stage code of qw_resident.cu on it with open ends,
+// write back the W - 2*HALO central sites (HALO = 4*KB: every stage invalidates one more
+// site at each open end, so all four stages of KB steps are fused per window).  Thread
+// blocks are persistent and software-pipelined: while a block computes window i its
+// cp.async loads for window i + gridDim.x are already in flight into the other shared
+// buffer, so HBM latency is not exposed once per window.
+//
+// Algorithmic traffic: one read and one write of psi per pass = 32 B per site per pass,
+// i.e. 32/KB bytes per site-update.  KB = 1 is the plain "read psi_n, write psi_n+1"
+// streaming roofline of SURVEY.md section 8d; KB = 4 (default) is temporal blocking, which
+// makes the path FP64-bound again.
 //
 // Replaces the same reference path as the resident kernels (BCB.py:163-203 with the step
 // rule of QW_Search.py:149-164); vertices keep their physical labels, so the marked vertex
@@ -22,15 +27,68 @@ constexpr int SR = 8;                  // sites per thread
 constexpr int SNT = 128;               // threads per block
 constexpr int SW = SR * SNT;           // window
 constexpr int SPAD = SW + SW / SR;     // one pad element per thread segment: no bank conflicts
+constexpr int SBLOCKS_PER_SM = 3;
 
 __device__ __forceinline__ int pad_index(int e) { return e + e / SR; }
 
-struct StreamTables {
-    double2 ab[4 * 4];
-    double2 d[4 * 4];
-    double2 ad[3 * 4];
-    double red[128];
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait_pending()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
+
+
+// Per point and per pass, computed once by stream_pass_tables instead of once per window:
+// the step plan of the point and the stage-weighted operator scalars of the KB steps.
+struct PassEntry {
+    double2 ab[4 * 4];                 // (A, B) per stage
+    double2 d[4 * 4];                  // (DA, DB) per stage
+    int32_t kb;                        // steps this point still takes in this pass
+    int32_t pad[3];
 };
+
+constexpr int SDEPTH = 3;              // ring of shared window buffers (prefetch depth 2)
+
+struct StreamShared {
+    double2 xbuf[SDEPTH][SPAD];        // window ring (load target, then store staging)
+    PassEntry tab[SDEPTH];             // the point's pass entry travels with its window
+    double2 mbox[4 * SNT];             // [parity][first/last][thread]
+};
+
+__global__ void stream_pass_tables(const QwParams prm, int64_t count, int64_t step0, int kbmax,
+                                   PassEntry *__restrict__ tab)
+{
+    const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= count) return;
+    const QwPoint pt = qw_point(prm, prm.point_offset + local);
+    const int64_t todo = pt.steps - step0;
+    const int kb = todo < 0 ? 0 : (todo > kbmax ? kbmax : (int)todo);
+    PassEntry &e = tab[local];
+    e.kb = kb;
+    const double h = pt.h;
+    for (int s = 0; s < kb; ++s) {
+        const double t0 = (double)(step0 + s) * h;
+        const double2 c0 = qw_operator_scalars(t0 / pt.T, pt.gamma, prm.schedule, prm.gamma_on);
+        const double2 c1 = qw_operator_scalars((t0 + 0.5 * h) / pt.T, pt.gamma, prm.schedule,
+                                               prm.gamma_on);
+        const double2 c2 = qw_operator_scalars((t0 + h) / pt.T, pt.gamma, prm.schedule,
+                                               prm.gamma_on);
+        e.ab[4 * s + 0] = make_double2(0.5 * h * c0.x, h / 6.0 * c0.x);
+        e.d[4 * s + 0] = make_double2(0.5 * h * c0.y, h / 6.0 * c0.y);
+        e.ab[4 * s + 1] = make_double2(0.5 * h * c1.x, h / 3.0 * c1.x);
+        e.d[4 * s + 1] = make_double2(0.5 * h * c1.y, h / 3.0 * c1.y);
+        e.ab[4 * s + 2] = make_double2(h * c1.x, h / 3.0 * c1.x);
+        e.d[4 * s + 2] = make_double2(h * c1.y, h / 3.0 * c1.y);
+        e.ab[4 * s + 3] = make_double2(0.0 * c2.x, h / 6.0 * c2.x);
+        e.d[4 * s + 3] = make_double2(0.0 * c2.y, h / 6.0 * c2.y);
+    }
+}
 
 template <int STAGE>
 __device__ __forceinline__ void read_slot(const State<SR> &s, int slot, double &xr, double &xi)
@@ -62,99 +120,139 @@ __device__ __forceinline__ void fix_slot(State<SR> &s, int slot, double2 D, doub
         }
 }
 
+// issue the loads of window `idx` (point idx / tiles, tile idx % tiles) and of its point's
+// pass entry into ring slot `slot`; one cp.async group
 template <int KB>
-__global__ void __launch_bounds__(SNT, 4)
-rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__restrict__ out,
-                 int64_t step0, int tiles)
+__device__ __forceinline__ void prefetch_window(StreamShared &sh, int slot, const double2 *in,
+                                                const PassEntry *tab, int64_t n, uint32_t idx,
+                                                uint32_t tiles, int t)
 {
-    constexpr int HALO = 4 * KB;
-    constexpr int TILE = SW - 2 * HALO;
-    __shared__ double2 xbuf[SPAD];                 // transpose buffer
-    __shared__ double2 mbox[4 * SNT];              // [parity][first/last][thread]
-    __shared__ StreamTables tb;
-
-    const int t = threadIdx.x;
-    const int64_t local = blockIdx.x / tiles;      // point within the chunk in flight
-    const int tile = blockIdx.x - (int)(local * tiles);
-    const QwPoint pt = qw_point(prm, prm.point_offset + local);
-    const int64_t n = prm.n;
-    const double2 *src = in + local * n;
-    double2 *dst = out + local * n;
-    const int64_t first = (int64_t)tile * TILE - HALO;         // window start (may be < 0)
-    int64_t base = first % n;
+    constexpr int HALO = 4 * KB, TILE = SW - 2 * HALO;
+    const uint32_t local = idx / tiles, tile = idx - local * tiles;
+    const double2 *src = in + (int64_t)local * n;
+    double2 *xb = sh.xbuf[slot];
+    int64_t base = ((int64_t)tile * TILE - HALO) % n;
     if (base < 0) base += n;
-
-    int64_t todo = pt.steps - step0;
-    const int kb = todo < 0 ? 0 : (todo > KB ? KB : (int)todo);
-
-    // coalesced load -> padded shared memory -> 8 consecutive sites per thread
 #pragma unroll
     for (int i = 0; i < SR; ++i) {
         const int e = i * SNT + t;
         int64_t j = base + e;
         if (j >= n) { j -= n; if (j >= n) j %= n; }
-        xbuf[pad_index(e)] = src[j];
+        cp_async16(&xb[pad_index(e)], &src[j]);
     }
-    __syncthreads();
-    State<SR> s;
+    if (t < (int)(sizeof(PassEntry) / 16))
+        cp_async16(reinterpret_cast<char *>(&sh.tab[slot]) + 16 * t,
+                   reinterpret_cast<const char *>(tab + local) + 16 * t);
+    cp_async_commit();
+}
+
+template <int KB>
+__global__ void __launch_bounds__(SNT, SBLOCKS_PER_SM)
+rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__restrict__ out,
+                 const PassEntry *__restrict__ tab, uint32_t tiles, uint32_t total)
+{
+    constexpr int HALO = 4 * KB;
+    constexpr int TILE = SW - 2 * HALO;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StreamShared &sh = *reinterpret_cast<StreamShared *>(smem_raw);
+
+    const int t = threadIdx.x;
+    const int64_t n = prm.n;
+    const int tl = t == 0 ? 0 : t - 1, tr = t == SNT - 1 ? SNT - 1 : t + 1;   // open ends
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 *fst = sh.mbox, *lst = sh.mbox + 2 * SNT;
+    const uint32_t stride = gridDim.x;
+
+    // ring of SDEPTH shared buffers: windows i+1 .. i+SDEPTH-1 are in flight while window i
+    // is being integrated.  One cp.async group per ring slot (empty past the end) keeps
+    // wait_group's count uniform.
+    uint32_t idx = blockIdx.x;
 #pragma unroll
-    for (int r = 0; r < SR; ++r) {
-        const double2 v = xbuf[pad_index(t * SR + r)];
-        s.yr[r] = v.x; s.yi[r] = v.y;
-        s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+    for (int k = 0; k < SDEPTH - 1; ++k) {
+        const uint64_t w = (uint64_t)idx + (uint64_t)k * stride;
+        if (w < total) prefetch_window<KB>(sh, k, in, tab, n, (uint32_t)w, tiles, t);
+        else cp_async_commit();
     }
 
-    if (kb > 0) {
-        // slot of the marked vertex in this thread's segment, or -1 (windows repeat mod n)
-        int64_t wrel = (prm.target - first - (int64_t)t * SR) % n;
-        if (wrel < 0) wrel += n;
-        const int own_slot = wrel < SR ? (int)wrel : -1;
-        const int tl = t == 0 ? 0 : t - 1, tr = t == SNT - 1 ? SNT - 1 : t + 1;   // open ends
-        const double2 zero2 = make_double2(0.0, 0.0);
-        double2 *fst = mbox, *lst = mbox + 2 * SNT;
-        int par = 0;
-        fst[t] = make_double2(s.yr[0], s.yi[0]);
-        lst[t] = make_double2(s.yr[SR - 1], s.yi[SR - 1]);
-        qw_fill_table(tb.ab, tb.d, tb.ad, pt, step0, prm.schedule, prm.gamma_on, kb);
-        for (int sidx = 0; sidx < kb; ++sidx) {
+    int slot = 0;
+    for (; idx < total; idx += stride, slot = (slot + 1 == SDEPTH) ? 0 : slot + 1) {
+        const uint32_t local = idx / tiles, tile = idx - local * tiles;
+        const int64_t first = (int64_t)tile * TILE - HALO;     // window start (may be < 0)
+
+        cp_async_wait_pending<SDEPTH - 2>();
+        __syncthreads();               // window idx has landed; the slot freed last round is free
+        const PassEntry &pe = sh.tab[slot];
+        const int kb = pe.kb;
+        State<SR> s;
+#pragma unroll
+        for (int r = 0; r < SR; ++r) {
+            const double2 v = sh.xbuf[slot][pad_index(t * SR + r)];
+            s.yr[r] = v.x; s.yi[r] = v.y;
+            s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+        }
+        {
+            const uint64_t w = (uint64_t)idx + (uint64_t)(SDEPTH - 1) * stride;
+            const int ps = (slot + SDEPTH - 1) % SDEPTH;
+            if (w < total) prefetch_window<KB>(sh, ps, in, tab, n, (uint32_t)w, tiles, t);
+            else cp_async_commit();
+        }
+
+        if (kb > 0) {
+            // slot of the marked vertex in this thread's segment, or -1 (windows repeat mod n)
+            int64_t wrel = prm.target - first - (int64_t)t * SR;     // in (-W, n + HALO]
+            if (wrel < 0) { wrel += n; if (wrel < 0) wrel = wrel % n + n; }
+            if (wrel >= n) wrel -= n;
+            const int own_slot = wrel < SR ? (int)wrel : -1;
+            const bool warp_owns = __ballot_sync(0xffffffffu, own_slot >= 0) != 0u;
+            int par = 0;
+            fst[t] = make_double2(s.yr[0], s.yi[0]);
+            lst[t] = make_double2(s.yr[SR - 1], s.yi[SR - 1]);
+            __syncthreads();                   // edge values published
+            for (int sidx = 0; sidx < kb; ++sidx) {
 #define QW_STREAM_STAGE(K)                                                              \
-            {                                                                           \
-                __syncthreads();                                                        \
-                const double2 hl = lst[par * SNT + tl];                                 \
-                const double2 hr = fst[par * SNT + tr];                                 \
-                const double2 ab = tb.ab[4 * sidx + K];                                 \
-                double xr = 0.0, xi = 0.0;                                              \
-                if (own_slot >= 0) read_slot<K>(s, own_slot, xr, xi);                   \
-                rk_stage<SR, K, true>(s, ab.x, ab.y, hl, hr, zero2, 0.0, false, zero2); \
-                if (own_slot >= 0) fix_slot<K>(s, own_slot, tb.d[4 * sidx + K], xr, xi); \
-                par ^= 1;                                                               \
-                if (K < 3) {                                                            \
-                    fst[par * SNT + t] = make_double2(s.ur[0], s.ui[0]);                \
-                    lst[par * SNT + t] = make_double2(s.ur[SR - 1], s.ui[SR - 1]);      \
-                } else {                                                                \
-                    fst[par * SNT + t] = make_double2(s.yr[0], s.yi[0]);                \
-                    lst[par * SNT + t] = make_double2(s.yr[SR - 1], s.yi[SR - 1]);      \
-                }                                                                       \
-            }
-            QW_STREAM_STAGE(0)
-            QW_STREAM_STAGE(1)
-            QW_STREAM_STAGE(2)
-            QW_STREAM_STAGE(3)
+                {                                                                       \
+                    if (K > 0 || sidx > 0) __syncthreads();                             \
+                    const double2 hl = lst[par * SNT + tl];                             \
+                    const double2 hr = fst[par * SNT + tr];                             \
+                    const double2 ab = pe.ab[4 * sidx + K];                             \
+                    double xr = 0.0, xi = 0.0;                                          \
+                    if (warp_owns) read_slot<K>(s, own_slot, xr, xi);                   \
+                    rk_stage<SR, K, true>(s, ab.x, ab.y, hl, hr, zero2, 0.0, false, zero2); \
+                    if (warp_owns) fix_slot<K>(s, own_slot, pe.d[4 * sidx + K], xr, xi);  \
+                    par ^= 1;                                                           \
+                    if (K < 3) {                                                        \
+                        fst[par * SNT + t] = make_double2(s.ur[0], s.ui[0]);            \
+                        lst[par * SNT + t] = make_double2(s.ur[SR - 1], s.ui[SR - 1]);  \
+                    } else {                                                            \
+                        fst[par * SNT + t] = make_double2(s.yr[0], s.yi[0]);            \
+                        lst[par * SNT + t] = make_double2(s.yr[SR - 1], s.yi[SR - 1]);  \
+                    }                                                                   \
+                }
+                QW_STREAM_STAGE(0)
+                QW_STREAM_STAGE(1)
+                QW_STREAM_STAGE(2)
+                QW_STREAM_STAGE(3)
 #undef QW_STREAM_STAGE
+            }
+        }
+
+        // registers -> padded shared memory -> coalesced store of the central TILE sites
+        // (xbuf[slot] was consumed into registers by every thread before the barriers above,
+        // or, for kb == 0, is only rewritten with the values just read from it)
+        if (kb == 0) __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SR; ++r)
+            sh.xbuf[slot][pad_index(t * SR + r)] = make_double2(s.yr[r], s.yi[r]);
+        __syncthreads();
+        double2 *dst = out + (int64_t)local * n;
+#pragma unroll
+        for (int i = 0; i < SR; ++i) {
+            const int e = i * SNT + t;
+            const int64_t j = first + e;
+            if (e >= HALO && e < HALO + TILE && j < n) dst[j] = sh.xbuf[slot][pad_index(e)];
         }
     }
-
-    // registers -> padded shared memory -> coalesced store of the central TILE sites
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < SR; ++r) xbuf[pad_index(t * SR + r)] = make_double2(s.yr[r], s.yi[r]);
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < SR; ++i) {
-        const int e = i * SNT + t;
-        const int64_t j = first + e;
-        if (e >= HALO && e < HALO + TILE && j < n) dst[j] = xbuf[pad_index(e)];
-    }
+    cp_async_wait_pending<0>();
 }
 
 __global__ void stream_init(double2 *buf, int64_t total, double amp)
@@ -201,14 +299,61 @@ int stream_kb(const QwParams &prm)
     return 4;
 }
 
+int g_sm_count = 0;
+
+int sm_count()
+{
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
 template <int KB>
-cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, int64_t step0,
-                        int64_t points, cudaStream_t st)
+cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, PassEntry *tab,
+                        int64_t step0, int64_t points, cudaStream_t st)
 {
     constexpr int TILE = SW - 8 * KB;
-    const int tiles = (int)((prm.n + TILE - 1) / TILE);
-    rk4_cycle_stream<KB><<<(unsigned)(points * tiles), SNT, 0, st>>>(prm, in, out, step0, tiles);
+    stream_pass_tables<<<(unsigned)((points + 127) / 128), 128, 0, st>>>(prm, points, step0, KB,
+                                                                         tab);
+    const uint32_t tiles = (uint32_t)((prm.n + TILE - 1) / TILE);
+    const uint64_t total = (uint64_t)points * tiles;
+    uint32_t grid = (uint32_t)(sm_count() * SBLOCKS_PER_SM);       // persistent blocks
+    if (total < grid) grid = (uint32_t)total;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(rk4_cycle_stream<KB>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(StreamShared));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    rk4_cycle_stream<KB><<<grid, SNT, sizeof(StreamShared), st>>>(prm, in, out, tab, tiles,
+                                                                  (uint32_t)total);
     return cudaGetLastError();
+}
+
+template <int KB>
+cudaError_t plan_of(qw_plan *plan)
+{
+    cudaFuncAttributes fa;
+    int occ = 0;
+    cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB>);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(rk4_cycle_stream<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(StreamShared));
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<KB>, SNT,
+                                                          sizeof(StreamShared));
+    if (e != cudaSuccess) return e;
+    plan->blocks_per_sm = occ;
+    plan->regs_per_thread = fa.numRegs;
+    plan->smem_bytes = (int)(fa.sharedSizeBytes + sizeof(StreamShared));
+    plan->steps_per_pass = KB;
+    return cudaSuccess;
 }
 
 }  // namespace
@@ -220,29 +365,11 @@ bool qw_stream_supported(const QwParams &prm)
 
 cudaError_t qw_stream_plan(const QwParams &prm, qw_plan *plan)
 {
-    cudaFuncAttributes fa;
-    int occ = 0;
-    cudaError_t e;
-    const int kb = stream_kb(prm);
-    if (kb == 1) {
-        e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<1>);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<1>, SNT, 0);
-    } else if (kb == 2) {
-        e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<2>);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<2>, SNT, 0);
-    } else {
-        e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<4>);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<4>, SNT, 0);
-    }
-    if (e != cudaSuccess) return e;
     plan->path = 3;
     plan->sites_per_thread = SR;
     plan->threads_per_block = SNT;
-    plan->blocks_per_sm = occ;
-    plan->regs_per_thread = fa.numRegs;
-    plan->smem_bytes = (int)fa.sharedSizeBytes;
-    plan->steps_per_pass = kb;
-    return cudaSuccess;
+    const int kb = stream_kb(prm);
+    return kb == 1 ? plan_of<1>(plan) : (kb == 2 ? plan_of<2>(plan) : plan_of<4>(plan));
 }
 
 cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *launches)
@@ -250,8 +377,10 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     QwParams prm = prm_in;
     const int kb = stream_kb(prm);
     const int64_t n = prm.n;
-    // points in flight: bounded by ~8 GiB of ping-pong scratch
+    // points in flight: bounded by ~8 GiB of ping-pong scratch and by 32-bit window indices
     int64_t chunk = (int64_t)(8ull << 30) / (2 * n * (int64_t)sizeof(double2));
+    const int64_t tiles_min = (n + (SW - 8) - 1) / (SW - 32) + 1;
+    if (chunk > (int64_t)0x7fffffff / tiles_min) chunk = (int64_t)0x7fffffff / tiles_min;
     if (chunk < 1) chunk = 1;
     if (chunk > prm.n_points) chunk = prm.n_points;
     double2 *bufA = nullptr;
@@ -259,10 +388,13 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     cudaError_t e = cudaMallocAsync((void **)&bufA, (size_t)chunk * 2 * n * sizeof(double2), st);
     if (e != cudaSuccess) return e;
     double2 *bufB = bufA + chunk * n;
+    PassEntry *tab = nullptr;
+    e = cudaMallocAsync((void **)&tab, (size_t)chunk * sizeof(PassEntry), st);
+    if (e != cudaSuccess) { cudaFreeAsync(bufA, st); return e; }
     const bool varying = prm.step_size > 0.0 || prm.n_steps != nullptr;
     if (varying) {
         e = cudaMallocAsync((void **)&dmax, sizeof(unsigned long long), st);
-        if (e != cudaSuccess) { cudaFreeAsync(bufA, st); return e; }
+        if (e != cudaSuccess) { cudaFreeAsync(bufA, st); cudaFreeAsync(tab, st); return e; }
     }
     const double amp = 1.0 / sqrt((double)n);
 
@@ -280,14 +412,14 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
             if (e != cudaSuccess) break;
             max_steps = (int64_t)h;
         }
-        stream_init<<<1184, 256, 0, st>>>(bufA, cnt * n, amp);
+        stream_init<<<sm_count() * 8, 256, 0, st>>>(bufA, cnt * n, amp);
         ++*launches;
         double2 *cur = bufA, *nxt = bufB;
         for (int64_t s0 = 0; s0 < max_steps && e == cudaSuccess; s0 += kb) {
-            if (kb == 1) e = launch_pass<1>(prm, cur, nxt, s0, cnt, st);
-            else if (kb == 2) e = launch_pass<2>(prm, cur, nxt, s0, cnt, st);
-            else e = launch_pass<4>(prm, cur, nxt, s0, cnt, st);
-            ++*launches;
+            if (kb == 1) e = launch_pass<1>(prm, cur, nxt, tab, s0, cnt, st);
+            else if (kb == 2) e = launch_pass<2>(prm, cur, nxt, tab, s0, cnt, st);
+            else e = launch_pass<4>(prm, cur, nxt, tab, s0, cnt, st);
+            *launches += 2;
             double2 *tmp = cur; cur = nxt; nxt = tmp;
         }
         if (e != cudaSuccess) break;
@@ -296,6 +428,7 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
         e = cudaGetLastError();
     }
     cudaFreeAsync(bufA, st);
+    cudaFreeAsync(tab, st);
     if (dmax) cudaFreeAsync(dmax, st);
     return e;
 }
