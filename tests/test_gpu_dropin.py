@@ -176,3 +176,22 @@ def test_robustness_ensemble_stats():
     assert st["mean"] == pytest.approx(po.mean(), abs=1e-11)
     assert st["std"] == pytest.approx(po.std(), abs=1e-11)
     assert st["R_sampled"] == pytest.approx(0.5 - po.mean(), abs=1e-11)
+
+
+def test_integration_md_stub_runs():
+    """The ctypes stub printed in INTEGRATION.md, executed verbatim against the built .so."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S)
+             if "qw_b200_stub" in b][0]
+    so = os.path.join(root, PKG, "libqw_b200.so")
+    ns = {}
+    exec(block.replace('"libqw_b200.so"', repr(so)), ns)
+    t, b = np.linspace(0.1, 16, 5), np.linspace(0, 2.5, 4)
+    p = ns["grid_eval"](16, "circular", "cerf_3", t, b, step_size=1e-2)
+    po, _ = c_oracle.heatmap(16, "circular", "cerf_3", t, b, step_size=1e-2)
+    assert p.shape == (4, 5) and np.abs(p - po).max() <= 1e-10
+    with pytest.raises(ValueError):
+        ns["grid_eval"](2, "circular", "lin", t, b)
