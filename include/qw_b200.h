@@ -78,8 +78,9 @@ enum {
     QW_FLAG_STREAM_KB1 = 8,      /* streaming kernel: 1 RK4 step per pass over HBM (the plain
                                     32 B/site-update roofline) instead of the default 4 */
     QW_FLAG_STREAM_KB2 = 16,     /* streaming kernel: 2 steps per pass */
-    QW_FLAG_CYCLE_LEGACY = 32,   /* resident cycle kernel, first generation (one block barrier
-                                    per stage); kept for A/B measurements */
+    QW_FLAG_CYCLE_LEGACY = 32,   /* first-generation resident kernels (cycle: stage code without
+                                    edge-first ordering; complete: blocking reduction per
+                                    step); kept for A/B measurements */
     QW_FLAG_CYCLE_SPLIT = 64,    /* second generation with mbarrier arrive/wait instead of one
                                     __syncthreads per stage (measured slower; A/B only) */
     QW_FLAG_OCC4 = 128           /* resident kernels, <= 128 threads: 4 blocks/SM at 128

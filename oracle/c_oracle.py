@@ -39,7 +39,12 @@ def lib():
 
 
 def max_threads():
-    return int(lib().qwo_max_threads())
+    """Host threads this process may use.  Not omp_get_max_threads(): torchrun exports
+    OMP_NUM_THREADS=1, which would silently make the host baseline single-threaded."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def rk4_batch(n, topology, schedule, T, gamma, n_steps=None, step_size=None,
@@ -66,7 +71,8 @@ def rk4_batch(n, topology, schedule, T, gamma, n_steps=None, step_size=None,
         T.ctypes.data_as(dp), gamma.ctypes.data_as(dp),
         S.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), h, P,
         p.ctypes.data_as(dp), norm.ctypes.data_as(dp),
-        psi.ctypes.data_as(dp) if return_psi else None, int(n_threads))
+        psi.ctypes.data_as(dp) if return_psi else None,
+        int(n_threads) if n_threads > 0 else max_threads())
     if rc < 0:
         raise ValueError("qwo_rk4_batch failed with %d" % rc)
     if return_psi:

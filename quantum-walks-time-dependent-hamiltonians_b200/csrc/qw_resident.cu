@@ -251,6 +251,112 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_resident(const QwPar
     epilogue<R>(s, prm, pt, tb.red, t);
 }
 
+// Second-generation complete-graph kernel.  No block reduction sits on the critical path:
+//   * thread 0 carries an estimate S of sum(y) and advances it with the exact identity
+//     sum(y + c k) = sum(y) - i c d x_w (column sums of L vanish); it publishes the sum every
+//     stage needs one stage ahead (16 B broadcast, one __syncthreads per stage);
+//   * at the end of each step every warp leaves the direct sum of its part of y_{n+1} in
+//     shared memory (local adds + one warp butterfly, nobody waits for it); during step n+1
+//     warp 0 adds the partials and thread 0 folds the difference to its estimate into the
+//     sum of step n+2.  The estimate is therefore re-anchored to a direct summation every
+//     step with a lag of one step: rounding cannot accumulate, and the reduction latency is
+//     hidden.
+//   * the oracle term is a separate instantiation of the stage code run by warp 0 only.
+template <int R, int MAXNT, int MINB>
+__global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_resident_v2(const QwParams prm)
+{
+    __shared__ Tables tb;
+    const int t = threadIdx.x, nact = prm.nact;
+    const int warp = t >> 5, lane = t & 31, nwarps = (blockDim.x + 31) >> 5;
+    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const bool active = t < nact;
+    const double nd = active ? (double)prm.n : 0.0;   // idle threads stay at zero
+    const double2 zero2 = make_double2(0.0, 0.0);
+
+    State<R> s;
+    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+    }
+    // warp partials of sum(y): tb.red[parity][2*warp .. 2*warp+1]
+    int spar = 0;
+    {
+        double2 loc = local_sum_y<R>(s);
+        loc.x = qw_warp_sum(loc.x);
+        loc.y = qw_warp_sum(loc.y);
+        if (lane == 0) { tb.red[2 * warp] = loc.x; tb.red[2 * warp + 1] = loc.y; }
+    }
+    __syncthreads();
+    double2 shat = zero2, delta = zero2, sinc = zero2;      // meaningful in thread 0 only
+    if (t == 0) {
+        for (int w = 0; w < nwarps; ++w) { shat.x += tb.red[2 * w]; shat.y += tb.red[2 * w + 1]; }
+        tb.bcast[0] = shat;
+    }
+
+    for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
+        qw_fill_table(tb.ab, tb.d, tb.ad, pt, n0, prm.schedule, prm.gamma_on);
+        const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+#define QW_COMPLETE2_STAGE(K)                                                           \
+            {                                                                           \
+                __syncthreads();                                                        \
+                double2 sx = tb.bcast[K & 1];                                           \
+                if (!active) sx = zero2;                                                \
+                const double2 ab = tb.ab[4 * sidx + K];                                 \
+                if (warp == 0) {                                                        \
+                    const double2 dd = (t == 0) ? tb.d[4 * sidx + K] : zero2;           \
+                    if (K == 0) {                                                       \
+                        /* direct sum of this step's y from the warp partials */        \
+                        double2 dsum = zero2;                                           \
+                        if (lane < nwarps)                                              \
+                            dsum = make_double2(tb.red[spar * 64 + 2 * lane],           \
+                                                tb.red[spar * 64 + 2 * lane + 1]);      \
+                        dsum.x = qw_warp_sum(dsum.x);                                   \
+                        dsum.y = qw_warp_sum(dsum.y);                                   \
+                        delta = make_double2(dsum.x - shat.x, dsum.y - shat.y);         \
+                        sinc = zero2;                                                   \
+                    }                                                                   \
+                    if (t == 0) {                                                       \
+                        const double xr = (K == 0) ? s.yr[0] : s.ur[0];                 \
+                        const double xi = (K == 0) ? s.yi[0] : s.ui[0];                 \
+                        sinc.x = fma(dd.y, xi, sinc.x);                                 \
+                        sinc.y = fma(-dd.y, xr, sinc.y);                                \
+                        if (K < 3) {                                                    \
+                            tb.bcast[(K + 1) & 1] = make_double2(fma(dd.x, xi, shat.x), \
+                                                                 fma(-dd.x, xr, shat.y)); \
+                        } else {                                                        \
+                            shat.x += sinc.x + delta.x;                                 \
+                            shat.y += sinc.y + delta.y;                                 \
+                            tb.bcast[0] = shat;                                         \
+                        }                                                               \
+                    }                                                                   \
+                    rk_stage<R, K, false>(s, ab.x, ab.y, zero2, zero2, sx, nd, t == 0, dd); \
+                } else {                                                                \
+                    rk_stage<R, K, false>(s, ab.x, ab.y, zero2, zero2, sx, nd, false, zero2); \
+                }                                                                       \
+            }
+            QW_COMPLETE2_STAGE(0)
+            QW_COMPLETE2_STAGE(1)
+            QW_COMPLETE2_STAGE(2)
+            QW_COMPLETE2_STAGE(3)
+#undef QW_COMPLETE2_STAGE
+            // leave this warp's part of sum(y_{n+1}) for warp 0 to pick up next step
+            spar ^= 1;
+            double2 loc = local_sum_y<R>(s);
+            loc.x = qw_warp_sum(loc.x);
+            loc.y = qw_warp_sum(loc.y);
+            if (lane == 0) {
+                tb.red[spar * 64 + 2 * warp] = loc.x;
+                tb.red[spar * 64 + 2 * warp + 1] = loc.y;
+            }
+        }
+    }
+    __syncthreads();
+    epilogue<R>(s, prm, pt, tb.red, t);
+}
+
 template <typename K>
 cudaError_t launch(K kernel, const QwParams &prm, int threads, size_t smem, cudaStream_t st,
                    qw_plan *plan)
@@ -292,10 +398,11 @@ cudaError_t dispatch_threads(const QwParams &prm, int threads, cudaStream_t st, 
         return launch(rk4_cycle_resident_v2<R, MAXNT, MINB, true>, prm, threads, smem, st, plan); \
     if (cyc)                                                                               \
         return launch(rk4_cycle_resident_v2<R, MAXNT, MINB, false>, prm, threads, smem, st, plan); \
-    return exact ? launch(rk4_complete_resident<R, MAXNT, MINB, true>, prm, threads, smem, \
-                          st, plan)                                                        \
-                 : launch(rk4_complete_resident<R, MAXNT, MINB, false>, prm, threads, smem, \
-                          st, plan);
+    if (exact)                                                                             \
+        return launch(rk4_complete_resident<R, MAXNT, MINB, true>, prm, threads, smem, st, plan); \
+    if (legacy)                                                                            \
+        return launch(rk4_complete_resident<R, MAXNT, MINB, false>, prm, threads, smem, st, plan); \
+    return launch(rk4_complete_resident_v2<R, MAXNT, MINB>, prm, threads, smem, st, plan);
     // <= 128 threads: 3 blocks/SM (168 registers, no spills) measured faster than 4 (128)
     if (threads <= 128 && (prm.flags & QW_FLAG_OCC4)) { QW_LAUNCH(128, 4) }
     if (threads <= 128) { QW_LAUNCH(128, 3) }

@@ -21,7 +21,7 @@ VARIANTS = {
            ("v2 mbarrier occ4", 64 | 128), ("v1 legacy occ3", 32), ("v1 legacy occ4", 32 | 128)],
     "c4": [("v2 occ3 (default)", 0), ("v2 occ4", 128), ("v1 legacy occ3", 32),
            ("v1 legacy occ4", 32 | 128)],
-    "c3": [("complete default", 0), ("complete exact-sum", 4)],
+    "c3": [("complete v2 (default)", 0), ("complete v1 legacy", 32), ("complete exact-sum", 4)],
 }
 SHAPES = {
     "c5": dict(n=1024, topology="circular", schedule="lin", n_steps=4096, nT=1024, t=(0.1, 1024), g=(0, 2.5)),
