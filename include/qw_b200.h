@@ -146,6 +146,14 @@ int qw_heatmap_robustness_dev(const double *p, int64_t n_beta, int64_t n_time,
                               int64_t variation, double *R, int64_t *argmax_beta,
                               void *stream);
 
+/* Heatmap summary (thesis Eq. 2.10-2.11, the numbers the thesis tabulates per N):
+ * out[0] = max p, out[1], out[2] = its beta / time index (first maximum in numpy's flattened
+ * [beta][T] order); out[3] = min of tau = T/p over cells with T >= t_min (T_min = (pi/2)
+ * sqrt(N), thesis p.41), out[4], out[5] = its indices; I = 1/p follows from out[0].
+ * out: 6 doubles on the device. */
+int qw_heatmap_summary_dev(const double *p, const double *time_array, int64_t n_beta,
+                           int64_t n_time, double t_min, double *out, void *stream);
+
 /* ---- introspection ------------------------------------------------------------------- */
 
 typedef struct qw_plan {

@@ -22,6 +22,8 @@ cudaError_t qw_launch_stats(const double *p, int64_t n, const double *thr, int n
 cudaError_t qw_launch_robustness(const double *p, int64_t nb, int64_t nt, int64_t v, double *R,
                                  int64_t *arg, cudaStream_t st, int *launches);
 cudaError_t qw_run_fp64_probe(double millis, double *tflops, cudaStream_t st, int *launches);
+cudaError_t qw_launch_summary(const double *p, const double *tarr, int64_t nb, int64_t nt,
+                              double t_min, double *out, cudaStream_t st);
 
 namespace {
 
@@ -292,6 +294,18 @@ int qw_heatmap_robustness_dev(const double *p, int64_t n_beta, int64_t n_time, i
                                          (cudaStream_t)stream, &nl);
     g_launches += nl;
     if (e != cudaSuccess) return cuda_fail(e, "robustness kernel launch");
+    return 0;
+}
+
+int qw_heatmap_summary_dev(const double *p, const double *time_array, int64_t n_beta,
+                           int64_t n_time, double t_min, double *out, void *stream)
+{
+    if (!p || !time_array || !out) return fail(QW_E_NULL, "p, time_array and out are required");
+    if (n_beta < 1 || n_time < 1) return fail(QW_E_SIZE, "bad sizes");
+    cudaError_t e = qw_launch_summary(p, time_array, n_beta, n_time, t_min, out,
+                                      (cudaStream_t)stream);
+    g_launches += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "summary kernel launch");
     return 0;
 }
 

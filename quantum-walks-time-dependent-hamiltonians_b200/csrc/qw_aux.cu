@@ -111,6 +111,57 @@ __global__ void argmax_beta_kernel(const double *__restrict__ p, int64_t nb, int
     arg[i] = bj;
 }
 
+// Heatmap summary (thesis Eq. 2.10-2.11): the first maximum of p over the flattened
+// [beta][T] grid (numpy argmax order) and the minimum of tau = T/p over T >= t_min
+// (first minimum in the same order).  out = {p_max, beta_idx, time_idx, tau_min, beta_idx,
+// time_idx}; indices are -1 when nothing qualifies.  Single block, deterministic.
+__global__ void __launch_bounds__(1024) summary_kernel(const double *__restrict__ p,
+                                                       const double *__restrict__ tarr,
+                                                       int64_t nb, int64_t nt, double t_min,
+                                                       double *__restrict__ out)
+{
+    __shared__ double sv[2][1024];
+    __shared__ long long si[2][1024];
+    const int64_t tot = nb * nt;
+    double bp = -INFINITY, bt = INFINITY;
+    long long ip = -1, it = -1;
+    for (int64_t q = threadIdx.x; q < tot; q += blockDim.x) {       // ascending q per thread
+        const double v = p[q];
+        if (v > bp) { bp = v; ip = q; }
+        const double T = tarr[q % nt];
+        if (T >= t_min && v > 0.0) {
+            const double tau = T / v;
+            if (tau < bt) { bt = tau; it = q; }
+        }
+    }
+    sv[0][threadIdx.x] = bp; si[0][threadIdx.x] = ip;
+    sv[1][threadIdx.x] = bt; si[1][threadIdx.x] = it;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const int a = threadIdx.x, b = threadIdx.x + o;
+            // maximum, ties -> smaller flat index
+            if (si[0][b] >= 0 && (si[0][a] < 0 || sv[0][b] > sv[0][a] ||
+                                  (sv[0][b] == sv[0][a] && si[0][b] < si[0][a]))) {
+                sv[0][a] = sv[0][b]; si[0][a] = si[0][b];
+            }
+            if (si[1][b] >= 0 && (si[1][a] < 0 || sv[1][b] < sv[1][a] ||
+                                  (sv[1][b] == sv[1][a] && si[1][b] < si[1][a]))) {
+                sv[1][a] = sv[1][b]; si[1][a] = si[1][b];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[0] = sv[0][0];
+        out[1] = si[0][0] >= 0 ? (double)(si[0][0] / nt) : -1.0;
+        out[2] = si[0][0] >= 0 ? (double)(si[0][0] % nt) : -1.0;
+        out[3] = sv[1][0];
+        out[4] = si[1][0] >= 0 ? (double)(si[1][0] / nt) : -1.0;
+        out[5] = si[1][0] >= 0 ? (double)(si[1][0] % nt) : -1.0;
+    }
+}
+
 // Register-only DFMA stream: 16 independent chains per thread, no memory traffic.
 constexpr int PROBE_CHAINS = 16;
 constexpr int PROBE_INNER = 64;
@@ -164,6 +215,13 @@ cudaError_t qw_launch_robustness(const double *p, int64_t nb, int64_t nt, int64_
         argmax_beta_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(p, nb, nt, arg);
         ++*launches;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t qw_launch_summary(const double *p, const double *tarr, int64_t nb, int64_t nt,
+                              double t_min, double *out, cudaStream_t st)
+{
+    summary_kernel<<<1, 1024, 0, st>>>(p, tarr, nb, nt, t_min, out);
     return cudaGetLastError();
 }
 

@@ -245,6 +245,25 @@ def robustness_map(probability, variation, device=None):
         return R, arg
 
 
+def heatmap_summary(probability, time_array, t_min=0.0, device=None):
+    """Best cell of a heatmap and the thesis' figures of merit (Eq. 2.10-2.11): first-maximum
+    (beta, T) indices of p, I = 1/p_max, and tau = min T/p over T >= t_min."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        dp, _ = _as_dev(probability if isinstance(probability, torch.Tensor)
+                        else np.ascontiguousarray(probability, dtype=np.float64).ravel(), dev)
+        nb, nt = probability.shape
+        dt, _ = _as_dev(time_array, dev)
+        out = torch.empty(6, dtype=torch.float64, device=dev)
+        _lib.check(lib.qw_heatmap_summary_dev(_ptr(dp), _ptr(dt), nb, nt, float(t_min),
+                                              _ptr(out), _stream()))
+        o = out.cpu().numpy()
+    return {"p_max": float(o[0]), "argmax": (int(o[1]), int(o[2])),
+            "iterations": float(1.0 / o[0]) if o[0] > 0 else float("inf"),
+            "tau_min": float(o[3]), "tau_argmin": (int(o[4]), int(o[5]))}
+
+
 def plan(problem, device=None):
     dev = _device(device)
     lib = _lib.load()

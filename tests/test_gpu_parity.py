@@ -304,3 +304,17 @@ def test_config5_streaming_variant_on_a_sample(qw):
     assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
     w, k = default_target(n), np.arange(1, 4000)
     assert np.abs(psi[1][(w + k) % n] - psi[1][(w - k) % n]).max() <= 1e-13
+
+
+def test_heatmap_summary(qw):
+    rng = np.random.default_rng(11)
+    p = rng.random((37, 53))
+    p[5, 7] = p[20, 3] = 2.0                      # tie: the first in flattened order wins
+    t = np.linspace(0.1, 30, 53)
+    s = qw.heatmap_summary(p, t, t_min=12.0)
+    assert s["p_max"] == 2.0 and s["argmax"] == (5, 7) and s["iterations"] == 0.5
+    tau = np.where(t[None, :] >= 12.0, t[None, :] / p, np.inf)
+    j, i = np.unravel_index(np.argmin(tau), tau.shape)
+    assert s["tau_argmin"] == (j, i) and s["tau_min"] == tau[j, i]
+    s = qw.heatmap_summary(p, t, t_min=1e9)
+    assert s["tau_argmin"] == (-1, -1)

@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Run every BASELINE.json config at full size on one GPU and print a markdown table
+(SURVEY.md section 8d): wall time (CUDA events), site-updates/s, grid-points/s, the physics
+read-outs (best cell, tau, I, robustness) and a parity spot-check against the C oracle.
+
+    python tools/run_configs.py [--skip-long] > profiles/rNN_configs.md
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qwtdh_b200 as qw  # noqa: E402
+from oracle import c_oracle  # noqa: E402  (checker only)
+
+DEV = torch.device("cuda")
+
+
+def timed(fn, reps=1):
+    fn()                                           # warm-up (module load, pool)
+    best, out = 1e30, None
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best, out
+
+
+def spot_check(prob_kw, t, b, p, k=6, seed=1):
+    rng = np.random.default_rng(seed)
+    jj, ii = rng.integers(0, len(b), k), rng.integers(0, len(t), k)
+    po, _, _ = c_oracle.rk4_batch(prob_kw["n"], prob_kw["topology"], prob_kw["schedule"],
+                                  t[ii], b[jj], n_steps=prob_kw["n_steps"],
+                                  gamma_on=prob_kw.get("gamma_on", "oracle"))
+    return float(np.abs(p[jj, ii] - po).max())
+
+
+def heatmap_row(name, kw, t, b, reps=1, check=True):
+    prob = qw.Problem(**kw)
+    dt, db = torch.from_numpy(t).to(DEV), torch.from_numpy(b).to(DEV)
+    ms, (p, nrm) = timed(lambda: qw.rk4_heatmap(prob, dt, db), reps)
+    pts = len(t) * len(b)
+    su = pts * kw["n"] * kw["n_steps"]
+    summ = qw.heatmap_summary(p, dt, t_min=(np.pi / 2) * np.sqrt(kw["n"]))
+    ph = p.cpu().numpy()
+    err = spot_check(kw, t, b, ph) if check else float("nan")
+    pl = qw.plan(prob)
+    j, i = summ["argmax"]
+    tj, ti = summ["tau_argmin"]
+    print("| %s | %s R=%d x %d thr | %d | %.1f | %.3e | %.3e | p_max=%.6f at (gamma=%.4g, T=%.4g), "
+          "I=%.2f, tau_min=%.4g at (gamma=%.4g, T=%.4g), norm defect max %.1e | %.1e |"
+          % (name, pl["path"], pl["sites_per_thread"], pl["threads_per_block"], pts, ms,
+             su / (ms * 1e-3), pts / (ms * 1e-3), summ["p_max"], b[j], t[i], summ["iterations"],
+             summ["tau_min"], b[tj] if tj >= 0 else float("nan"),
+             t[ti] if ti >= 0 else float("nan"),
+             float((nrm - 1).abs().max()), err), flush=True)
+    return ph
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--skip-long", action="store_true")
+    a = ap.parse_args()
+    print("# BASELINE configs at full size, one B200 (%s)" % torch.cuda.get_device_name(0))
+    print()
+    print("Device-resident inputs, CUDA events, one warm-up run; parity = max |dp| against the C "
+          "oracle on 6 random cells of the same grid. FP64 peak measured: %.2f TFLOP/s."
+          % qw.fp64_peak_tflops(300.0))
+    print()
+    print("| config | kernel | points | ms | site-updates/s | grid-points/s | read-out | parity |")
+    print("|---|---|---|---|---|---|---|---|")
+
+    # C1: cycle N=16, single point, n_steps 1024
+    prob = qw.Problem(n=16, topology="circular", schedule="lin", n_steps=1024)
+    T1, g1 = torch.tensor([16.0], dtype=torch.float64, device=DEV), torch.tensor(
+        [1.0], dtype=torch.float64, device=DEV)
+    ms, (p, nrm) = timed(lambda: qw.rk4_batch(prob, T1, g1), reps=5)
+    t0 = time.perf_counter()
+    ph, _ = qw.rk4_batch(prob, [16.0], [1.0])
+    host_us = (time.perf_counter() - t0) * 1e6
+    print("| C1 cycle N=16 (T,gamma)=(16,1) lin S=1024 | resident-cycle R=1 x 32 thr | 1 | %.3f | "
+          "%.3e | %.3e | p=%.14f (reference RK4 n=1024: 0.42038739054526); %.0f us per point "
+          "device, %.0f us through the host API | %.1e |"
+          % (ms, 16 * 1024 / (ms * 1e-3), 1 / (ms * 1e-3), ph[0], ms * 1e3, host_us,
+             abs(ph[0] - 0.4203873905452587)), flush=True)
+
+    # C2: cycle N=64, 100x100, lin / cerf_3 / static
+    t, b = np.linspace(0.1, 64, 100), np.linspace(0, 2.5, 100)
+    for sched in ("lin", "cerf_3", "static"):
+        heatmap_row("C2 cycle N=64 100x100 %s S=1024" % sched,
+                    dict(n=64, topology="circular", schedule=sched, n_steps=1024), t, b, reps=3)
+
+    # C3: complete N=4096, 256x256, gamma on the Laplacian
+    n = 4096
+    t, b = np.linspace(0.1, 512, 256), np.linspace(0.5 / n, 2.5 / n, 256)
+    for sched in ("cerf_3", "lin"):
+        heatmap_row("C3 complete N=4096 256x256 %s S=2048 gamma-on-L" % sched,
+                    dict(n=n, topology="complete", schedule=sched, gamma_on="laplacian",
+                         n_steps=2048), t, b)
+
+    # C4: robustness ensemble, cycle N=256, 1e5 noisy realisations
+    n = 256
+    T0 = (np.pi / 2) * np.sqrt(n)
+    gam = np.linspace(0, 2.5, 101)
+    prob = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=512)
+    pc, _ = qw.rk4_batch(prob, np.full(101, T0), gam)
+    g0, p0 = gam[int(np.argmax(pc))], float(pc.max())
+    rng = np.random.default_rng(20200912)
+    g = np.clip(g0 * (1 + 0.05 * rng.standard_normal(100000)), 0, None)
+    T = np.clip(T0 * (1 + 0.05 * rng.standard_normal(100000)), 0, None)
+    dT, dg = torch.from_numpy(T).to(DEV), torch.from_numpy(g).to(DEV)
+    ms, (p, nrm) = timed(lambda: qw.rk4_batch(prob, dT, dg), reps=3)
+    st = qw.ensemble_stats(p)
+    po, _, _ = c_oracle.rk4_batch(n, "circular", "lin", T[:8], g[:8], n_steps=512)
+    print("| C4 cycle N=256 1e5 noisy (T,gamma), sigma=5%%, S=512 | resident-cycle R=8 x 32 thr | "
+          "100000 | %.1f | %.3e | %.3e | centre (T0=%.4f, gamma0=%.3f, p0=%.6f); mean %.6f std "
+          "%.6f, R=p0-mean=%.6f, frac>=0.8/0.9/0.95/0.99 = %s | %.1e |"
+          % (ms, 1e5 * n * 512 / (ms * 1e-3), 1e5 / (ms * 1e-3), T0, g0, p0, st["mean"], st["std"],
+             p0 - st["mean"], "/".join("%.4f" % v for v in st["fraction_ge"].values()),
+             float(np.abs(p[:8].cpu().numpy() - po).max())), flush=True)
+    if not a.skip_long:
+        # localization ensemble: T0 = N^2/2, S = 131072
+        T0l = n * n / 2.0
+        Tl = np.clip(T0l * (1 + 0.05 * rng.standard_normal(20000)), 0, None)
+        gl = np.clip(g0 * (1 + 0.05 * rng.standard_normal(20000)), 0, None)
+        probl = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=131072)
+        dT, dg = torch.from_numpy(Tl).to(DEV), torch.from_numpy(gl).to(DEV)
+        ms, (p, nrm) = timed(lambda: qw.rk4_batch(probl, dT, dg))
+        st = qw.ensemble_stats(p)
+        print("| C4 localization: cycle N=256, T0=N^2/2=32768, S=131072, 2e4 realisations | "
+              "resident-cycle R=8 x 32 thr | 20000 | %.1f | %.3e | %.3e | mean %.6f std %.6f, "
+              "frac>=0.8/0.9/0.95/0.99 = %s | n/a |"
+              % (ms, 2e4 * n * 131072 / (ms * 1e-3), 2e4 / (ms * 1e-3), st["mean"], st["std"],
+                 "/".join("%.4f" % v for v in st["fraction_ge"].values())), flush=True)
+
+    # C5: cycle N=1024, 1024x1024 (full on one GPU unless --skip-long: 128 rows)
+    rows = 128 if a.skip_long else 1024
+    t, b = np.linspace(0.1, 1024, 1024), np.linspace(0, 2.5, rows)
+    heatmap_row("C5 cycle N=1024 %dx1024 lin S=4096" % rows,
+                dict(n=1024, topology="circular", schedule="lin", n_steps=4096), t, b)
+    # C5 streaming variant
+    t, b = np.linspace(0.1, 64, 32), np.linspace(0, 2.5, 32)
+    for flag, kb in ((8, 1), (0, 4)):
+        heatmap_row("C5-stream cycle N=65536 32x32 lin S=256, %d step(s)/pass" % kb,
+                    dict(n=65536, topology="circular", schedule="lin", n_steps=256, flags=flag),
+                    t, b, reps=2, check=(kb == 4))
+
+
+if __name__ == "__main__":
+    main()
