@@ -82,13 +82,17 @@ def test_random_batches_vs_oracle(qw, topo, n):
         assert p[0] == pytest.approx(1.0 / n, abs=1e-15)
 
 
-@pytest.mark.parametrize("n,flags", [(48, 1), (1024, 1), (2050, 0), (1031, 0), (96, 4), (4096, 4)])
+@pytest.mark.parametrize("n,flags", [(48, 1), (1024, 1), (2050, 0), (1031, 0), (96, 4), (4096, 4),
+                                     (1024, 256), (512, 256), (4096, 256), (1024, 256 | 32),
+                                     (1024, 256 | 64), (1024, 256 | 128), (2048, 0), (3072, 0),
+                                     (4096, 256 | 32), (512, 0), (528, 0)])
 def test_generic_and_exact_sum_paths(qw, n, flags):
-    """flags: 1 = force the global-memory kernel, 4 = block-reduce sum(u) in every stage;
-    n = 2050 / 1031 do not fit the resident kernels at all."""
+    """flags: 1 = force the global-memory kernel, 4 = block-reduce sum(u) in every stage,
+    256 = at most 8 sites per thread, 32 / 64 / 128 = first-generation / mbarrier / 4-blocks
+    variants of the resident kernels; n = 2050 / 1031 do not fit the resident kernels."""
     rng = np.random.default_rng(n)
     for topo in ("circular", "complete"):
-        if flags == 4 and topo == "circular":
+        if (flags & 4) and topo == "circular":
             continue
         T = rng.uniform(1.0, 6.0, 3) / (1.0 if topo == "circular" else n / 8.0)
         g = rng.uniform(0.1, 2.0, 3) * (1.0 if topo == "circular" else n / 2.0)
@@ -252,10 +256,12 @@ def test_error_behaviour(qw):
 
 def test_plan_reports_native_kernels(qw):
     pl = qw.plan(qw.Problem(n=1024, topology="circular", n_steps=1))
-    assert pl["path"] == "resident-cycle" and pl["sites_per_thread"] == 8
-    assert pl["threads_per_block"] == 128 and pl["sm_count"] >= 100
+    assert pl["path"] == "resident-cycle" and pl["sites_per_thread"] == 16
+    assert pl["threads_per_block"] == 64 and pl["sm_count"] >= 100
+    pl = qw.plan(qw.Problem(n=1024, topology="circular", n_steps=1, flags=256))
+    assert pl["sites_per_thread"] == 8 and pl["threads_per_block"] == 128
     pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1))
-    assert pl["path"] == "resident-complete" and pl["threads_per_block"] == 512
+    assert pl["path"] == "resident-complete" and pl["threads_per_block"] == 256
     before = qw.launch_count()
     qw.rk4_batch(qw.Problem(n=16, n_steps=4), [1.0], [1.0])
     assert qw.launch_count() == before + 1

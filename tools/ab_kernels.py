@@ -17,11 +17,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import qwtdh_b200 as qw  # noqa: E402
 
 VARIANTS = {
-    "c5": [("v2 occ3 (default)", 0), ("v2 occ4", 128), ("v2 mbarrier occ3", 64),
-           ("v2 mbarrier occ4", 64 | 128), ("v1 legacy occ3", 32), ("v1 legacy occ4", 32 | 128)],
+    "c5": [("v2 R=16 (default)", 0), ("v2 R=8 occ3", 256), ("v2 R=8 occ4", 256 | 128),
+           ("v2 R=8 mbarrier occ3", 256 | 64), ("v1 R=8 legacy occ3", 256 | 32),
+           ("v1 R=8 legacy occ4", 256 | 32 | 128)],
     "c4": [("v2 occ3 (default)", 0), ("v2 occ4", 128), ("v1 legacy occ3", 32),
            ("v1 legacy occ4", 32 | 128)],
-    "c3": [("complete v2 (default)", 0), ("complete v1 legacy", 32), ("complete exact-sum", 4)],
+    "c3": [("complete v2 R=16 (default)", 0), ("complete v2 R=8", 256), ("complete v1 R=8 legacy", 256 | 32),
+           ("complete R=8 exact-sum", 256 | 4)],
 }
 SHAPES = {
     "c5": dict(n=1024, topology="circular", schedule="lin", n_steps=4096, nT=1024, t=(0.1, 1024), g=(0, 2.5)),
