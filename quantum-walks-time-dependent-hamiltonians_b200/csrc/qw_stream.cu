@@ -2,14 +2,14 @@
 // N = 65 536 in BASELINE config 5), sm_100a.
 //
 // psi of every point in flight lives in HBM (two buffers, ping-pong).  One launch ("pass")
-// advances every point by KB RK4 steps.  Work unit = one window of W = 128 threads x 8
+// advances every point by KB RK4 steps.  Work unit = one window of W = 128 threads x SR
 // sites of one point: load it (cp.async, coalesced 16 B per lane, into a padded shared
 // buffer), run the register-resident stage code of qw_resident.cu on it with open ends,
 // write back the W - 2*HALO central sites (HALO = 4*KB: every stage invalidates one more
 // site at each open end, so all four stages of KB steps are fused per window).  Thread
-// blocks are persistent and software-pipelined: while a block computes window i its
-// cp.async loads for window i + gridDim.x are already in flight into the other shared
-// buffer, so HBM latency is not exposed once per window.
+// blocks are persistent and software-pipelined: while a block integrates window i its
+// cp.async loads for the next windows are already in flight into the other slots of a
+// shared-memory ring, so HBM latency is not exposed once per window.
 //
 // Algorithmic traffic: one read and one write of psi per pass = 32 B per site per pass,
 // i.e. 32/KB bytes per site-update.  KB = 1 is the plain "read psi_n, write psi_n+1"
@@ -23,13 +23,18 @@
 
 namespace {
 
-constexpr int SR = 8;                  // sites per thread
 constexpr int SNT = 128;               // threads per block
-constexpr int SW = SR * SNT;           // window
-constexpr int SPAD = SW + SW / SR;     // one pad element per thread segment: no bank conflicts
-constexpr int SBLOCKS_PER_SM = 3;
+constexpr int SDEPTH = 3;              // ring of shared window buffers (prefetch depth 2)
 
-__device__ __forceinline__ int pad_index(int e) { return e + e / SR; }
+// Geometry for SR sites per thread: SR = 8 -> 1024-site windows, 3 blocks/SM;
+// SR = 16 -> 2048-site windows, 2 blocks/SM (half the halo and per-window overhead).
+template <int SR>
+struct Geo {
+    static constexpr int W = SR * SNT;                 // window
+    static constexpr int PAD = W + W / SR;             // one pad element per thread segment
+    static constexpr int BLOCKS_PER_SM = SR == 8 ? 3 : 2;
+    static __device__ __forceinline__ int pad(int e) { return e + e / SR; }
+};
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -43,7 +48,6 @@ __device__ __forceinline__ void cp_async_wait_pending()
     asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
 }
 
-
 // Per point and per pass, computed once by stream_pass_tables instead of once per window:
 // the step plan of the point and the stage-weighted operator scalars of the KB steps.
 struct PassEntry {
@@ -53,12 +57,11 @@ struct PassEntry {
     int32_t pad[3];
 };
 
-constexpr int SDEPTH = 3;              // ring of shared window buffers (prefetch depth 2)
-
+template <int SR>
 struct StreamShared {
-    double2 xbuf[SDEPTH][SPAD];        // window ring (load target, then store staging)
-    PassEntry tab[SDEPTH];             // the point's pass entry travels with its window
-    double2 mbox[4 * SNT];             // [parity][first/last][thread]
+    double2 xbuf[SDEPTH][Geo<SR>::PAD];   // window ring (load target, then store staging)
+    PassEntry tab[SDEPTH];                // the point's pass entry travels with its window
+    double2 mbox[4 * SNT];                // [parity][first/last][thread]
 };
 
 __global__ void stream_pass_tables(const QwParams prm, int64_t count, int64_t step0, int kbmax,
@@ -90,7 +93,7 @@ __global__ void stream_pass_tables(const QwParams prm, int64_t count, int64_t st
     }
 }
 
-template <int STAGE>
+template <int SR, int STAGE>
 __device__ __forceinline__ void read_slot(const State<SR> &s, int slot, double &xr, double &xi)
 {
 #pragma unroll
@@ -102,7 +105,7 @@ __device__ __forceinline__ void read_slot(const State<SR> &s, int slot, double &
 }
 
 // oracle term d(t) x_w applied to whichever slot holds the marked vertex
-template <int STAGE>
+template <int SR, int STAGE>
 __device__ __forceinline__ void fix_slot(State<SR> &s, int slot, double2 D, double xr, double xi)
 {
 #pragma unroll
@@ -122,12 +125,12 @@ __device__ __forceinline__ void fix_slot(State<SR> &s, int slot, double2 D, doub
 
 // issue the loads of window `idx` (point idx / tiles, tile idx % tiles) and of its point's
 // pass entry into ring slot `slot`; one cp.async group
-template <int KB>
-__device__ __forceinline__ void prefetch_window(StreamShared &sh, int slot, const double2 *in,
+template <int KB, int SR>
+__device__ __forceinline__ void prefetch_window(StreamShared<SR> &sh, int slot, const double2 *in,
                                                 const PassEntry *tab, int64_t n, uint32_t idx,
                                                 uint32_t tiles, int t)
 {
-    constexpr int HALO = 4 * KB, TILE = SW - 2 * HALO;
+    constexpr int HALO = 4 * KB, TILE = Geo<SR>::W - 2 * HALO;
     const uint32_t local = idx / tiles, tile = idx - local * tiles;
     const double2 *src = in + (int64_t)local * n;
     double2 *xb = sh.xbuf[slot];
@@ -138,7 +141,7 @@ __device__ __forceinline__ void prefetch_window(StreamShared &sh, int slot, cons
         const int e = i * SNT + t;
         int64_t j = base + e;
         if (j >= n) { j -= n; if (j >= n) j %= n; }
-        cp_async16(&xb[pad_index(e)], &src[j]);
+        cp_async16(&xb[Geo<SR>::pad(e)], &src[j]);
     }
     if (t < (int)(sizeof(PassEntry) / 16))
         cp_async16(reinterpret_cast<char *>(&sh.tab[slot]) + 16 * t,
@@ -146,15 +149,15 @@ __device__ __forceinline__ void prefetch_window(StreamShared &sh, int slot, cons
     cp_async_commit();
 }
 
-template <int KB>
-__global__ void __launch_bounds__(SNT, SBLOCKS_PER_SM)
+template <int KB, int SR>
+__global__ void __launch_bounds__(SNT, Geo<SR>::BLOCKS_PER_SM)
 rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__restrict__ out,
                  const PassEntry *__restrict__ tab, uint32_t tiles, uint32_t total)
 {
     constexpr int HALO = 4 * KB;
-    constexpr int TILE = SW - 2 * HALO;
+    constexpr int TILE = Geo<SR>::W - 2 * HALO;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    StreamShared &sh = *reinterpret_cast<StreamShared *>(smem_raw);
+    StreamShared<SR> &sh = *reinterpret_cast<StreamShared<SR> *>(smem_raw);
 
     const int t = threadIdx.x;
     const int64_t n = prm.n;
@@ -170,7 +173,7 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
 #pragma unroll
     for (int k = 0; k < SDEPTH - 1; ++k) {
         const uint64_t w = (uint64_t)idx + (uint64_t)k * stride;
-        if (w < total) prefetch_window<KB>(sh, k, in, tab, n, (uint32_t)w, tiles, t);
+        if (w < total) prefetch_window<KB, SR>(sh, k, in, tab, n, (uint32_t)w, tiles, t);
         else cp_async_commit();
     }
 
@@ -186,14 +189,14 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
         State<SR> s;
 #pragma unroll
         for (int r = 0; r < SR; ++r) {
-            const double2 v = sh.xbuf[slot][pad_index(t * SR + r)];
+            const double2 v = sh.xbuf[slot][Geo<SR>::pad(t * SR + r)];
             s.yr[r] = v.x; s.yi[r] = v.y;
             s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
         }
         {
             const uint64_t w = (uint64_t)idx + (uint64_t)(SDEPTH - 1) * stride;
             const int ps = (slot + SDEPTH - 1) % SDEPTH;
-            if (w < total) prefetch_window<KB>(sh, ps, in, tab, n, (uint32_t)w, tiles, t);
+            if (w < total) prefetch_window<KB, SR>(sh, ps, in, tab, n, (uint32_t)w, tiles, t);
             else cp_async_commit();
         }
 
@@ -216,9 +219,9 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
                     const double2 hr = fst[par * SNT + tr];                             \
                     const double2 ab = pe.ab[4 * sidx + K];                             \
                     double xr = 0.0, xi = 0.0;                                          \
-                    if (warp_owns) read_slot<K>(s, own_slot, xr, xi);                   \
+                    if (warp_owns) read_slot<SR, K>(s, own_slot, xr, xi);               \
                     rk_stage<SR, K, true>(s, ab.x, ab.y, hl, hr, zero2, 0.0, false, zero2); \
-                    if (warp_owns) fix_slot<K>(s, own_slot, pe.d[4 * sidx + K], xr, xi);  \
+                    if (warp_owns) fix_slot<SR, K>(s, own_slot, pe.d[4 * sidx + K], xr, xi); \
                     par ^= 1;                                                           \
                     if (K < 3) {                                                        \
                         fst[par * SNT + t] = make_double2(s.ur[0], s.ui[0]);            \
@@ -242,14 +245,14 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
         if (kb == 0) __syncthreads();
 #pragma unroll
         for (int r = 0; r < SR; ++r)
-            sh.xbuf[slot][pad_index(t * SR + r)] = make_double2(s.yr[r], s.yi[r]);
+            sh.xbuf[slot][Geo<SR>::pad(t * SR + r)] = make_double2(s.yr[r], s.yi[r]);
         __syncthreads();
         double2 *dst = out + (int64_t)local * n;
 #pragma unroll
         for (int i = 0; i < SR; ++i) {
             const int e = i * SNT + t;
             const int64_t j = first + e;
-            if (e >= HALO && e < HALO + TILE && j < n) dst[j] = sh.xbuf[slot][pad_index(e)];
+            if (e >= HALO && e < HALO + TILE && j < n) dst[j] = sh.xbuf[slot][Geo<SR>::pad(e)];
         }
     }
     cp_async_wait_pending<0>();
@@ -299,6 +302,12 @@ int stream_kb(const QwParams &prm)
     return 4;
 }
 
+// 16 sites per thread (2048-site windows) unless the ring is short or QW_FLAG_R8 is set
+int stream_sr(const QwParams &prm)
+{
+    return ((prm.flags & QW_FLAG_R8) || prm.n < 4096) ? 8 : 16;
+}
+
 int g_sm_count = 0;
 
 int sm_count()
@@ -312,49 +321,60 @@ int sm_count()
     return g_sm_count;
 }
 
-template <int KB>
+template <int KB, int SR>
+cudaError_t configure()
+{
+    static bool configured = false;
+    if (configured) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(rk4_cycle_stream<KB, SR>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(StreamShared<SR>));
+    if (e == cudaSuccess) configured = true;
+    return e;
+}
+
+template <int KB, int SR>
 cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, PassEntry *tab,
                         int64_t step0, int64_t points, cudaStream_t st)
 {
-    constexpr int TILE = SW - 8 * KB;
+    constexpr int TILE = Geo<SR>::W - 8 * KB;
     stream_pass_tables<<<(unsigned)((points + 127) / 128), 128, 0, st>>>(prm, points, step0, KB,
                                                                          tab);
     const uint32_t tiles = (uint32_t)((prm.n + TILE - 1) / TILE);
     const uint64_t total = (uint64_t)points * tiles;
-    uint32_t grid = (uint32_t)(sm_count() * SBLOCKS_PER_SM);       // persistent blocks
+    uint32_t grid = (uint32_t)(sm_count() * Geo<SR>::BLOCKS_PER_SM);       // persistent blocks
     if (total < grid) grid = (uint32_t)total;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rk4_cycle_stream<KB>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(StreamShared));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    rk4_cycle_stream<KB><<<grid, SNT, sizeof(StreamShared), st>>>(prm, in, out, tab, tiles,
-                                                                  (uint32_t)total);
+    cudaError_t e = configure<KB, SR>();
+    if (e != cudaSuccess) return e;
+    rk4_cycle_stream<KB, SR><<<grid, SNT, sizeof(StreamShared<SR>), st>>>(prm, in, out, tab, tiles,
+                                                                          (uint32_t)total);
     return cudaGetLastError();
 }
 
-template <int KB>
+template <int KB, int SR>
 cudaError_t plan_of(qw_plan *plan)
 {
     cudaFuncAttributes fa;
     int occ = 0;
-    cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB>);
+    cudaError_t e = configure<KB, SR>();
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB, SR>);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(rk4_cycle_stream<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(StreamShared));
-    if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<KB>, SNT,
-                                                          sizeof(StreamShared));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<KB, SR>, SNT,
+                                                          sizeof(StreamShared<SR>));
     if (e != cudaSuccess) return e;
+    plan->sites_per_thread = SR;
     plan->blocks_per_sm = occ;
     plan->regs_per_thread = fa.numRegs;
-    plan->smem_bytes = (int)(fa.sharedSizeBytes + sizeof(StreamShared));
+    plan->smem_bytes = (int)(fa.sharedSizeBytes + sizeof(StreamShared<SR>));
     plan->steps_per_pass = KB;
     return cudaSuccess;
 }
+
+#define QW_STREAM_DISPATCH(FN, ...)                                                     \
+    (sr == 16 ? (kb == 1 ? FN<1, 16>(__VA_ARGS__) : kb == 2 ? FN<2, 16>(__VA_ARGS__)    \
+                                                            : FN<4, 16>(__VA_ARGS__))   \
+              : (kb == 1 ? FN<1, 8>(__VA_ARGS__) : kb == 2 ? FN<2, 8>(__VA_ARGS__)      \
+                                                           : FN<4, 8>(__VA_ARGS__)))
 
 }  // namespace
 
@@ -366,21 +386,20 @@ bool qw_stream_supported(const QwParams &prm)
 cudaError_t qw_stream_plan(const QwParams &prm, qw_plan *plan)
 {
     plan->path = 3;
-    plan->sites_per_thread = SR;
     plan->threads_per_block = SNT;
-    const int kb = stream_kb(prm);
-    return kb == 1 ? plan_of<1>(plan) : (kb == 2 ? plan_of<2>(plan) : plan_of<4>(plan));
+    const int kb = stream_kb(prm), sr = stream_sr(prm);
+    return QW_STREAM_DISPATCH(plan_of, plan);
 }
 
 cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *launches)
 {
     QwParams prm = prm_in;
-    const int kb = stream_kb(prm);
+    const int kb = stream_kb(prm), sr = stream_sr(prm);
     const int64_t n = prm.n;
     // points in flight: bounded by ~8 GiB of ping-pong scratch and by 32-bit window indices
     int64_t chunk = (int64_t)(8ull << 30) / (2 * n * (int64_t)sizeof(double2));
-    const int64_t tiles_min = (n + (SW - 8) - 1) / (SW - 32) + 1;
-    if (chunk > (int64_t)0x7fffffff / tiles_min) chunk = (int64_t)0x7fffffff / tiles_min;
+    const int64_t tiles_max = n / (8 * SNT - 32) + 2;
+    if (chunk > (int64_t)0x7fffffff / tiles_max) chunk = (int64_t)0x7fffffff / tiles_max;
     if (chunk < 1) chunk = 1;
     if (chunk > prm.n_points) chunk = prm.n_points;
     double2 *bufA = nullptr;
@@ -416,9 +435,7 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
         ++*launches;
         double2 *cur = bufA, *nxt = bufB;
         for (int64_t s0 = 0; s0 < max_steps && e == cudaSuccess; s0 += kb) {
-            if (kb == 1) e = launch_pass<1>(prm, cur, nxt, tab, s0, cnt, st);
-            else if (kb == 2) e = launch_pass<2>(prm, cur, nxt, tab, s0, cnt, st);
-            else e = launch_pass<4>(prm, cur, nxt, tab, s0, cnt, st);
+            e = QW_STREAM_DISPATCH(launch_pass, prm, cur, nxt, tab, s0, cnt, st);
             *launches += 2;
             double2 *tmp = cur; cur = nxt; nxt = tmp;
         }

@@ -268,10 +268,11 @@ def test_plan_reports_native_kernels(qw):
 
 
 @pytest.mark.parametrize("n", [8, 64, 1000, 1016, 1024, 2050, 4100, 9001])
-@pytest.mark.parametrize("kb_flag", [8, 16, 0])
+@pytest.mark.parametrize("kb_flag", [8, 16, 0, 256, 256 | 8])
 def test_streaming_kernel_vs_oracle(qw, n, kb_flag):
     """Tile-fused HBM-streaming kernel (flags: 2 = force it, 8 / 16 = 1 / 2 steps per pass,
-    default 4), windows that wrap, ragged last tiles, marked vertex in a halo copy."""
+    default 4; 256 = 8 instead of 16 sites per thread for n >= 4096), windows that wrap,
+    ragged last tiles, marked vertex in a halo copy."""
     rng = np.random.default_rng(n + kb_flag)
     T = np.concatenate([[0.0], rng.uniform(1.0, 9.0, 3)])
     g = rng.uniform(0.1, 2.4, 4)
