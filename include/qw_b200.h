@@ -125,6 +125,21 @@ int qw_rk4_grid_host(const qw_problem *prob, const double *time_array, int64_t n
                      const double *beta_array, int64_t n_beta, int64_t beta_begin,
                      int64_t beta_end, double *p, double *norm, int device);
 
+/* Exact time-independent evolution psi(t) = exp(-i H t) psi0 with H = L - gamma|w><w| (or
+ * gamma L - |w><w| under QW_GAMMA_ON_LAPLACIAN): replaces evaluate_time_independent_probability
+ * (BCB.py:137-159), whose dense scipy.linalg.expm becomes a Chebyshev expansion over the
+ * implicit stencil, accurate to ~1e-14.  Cycle graph with a register-resident dimension only
+ * (QW_E_UNSUPPORTED otherwise; schedule 'static' through qw_rk4_* covers the rest).
+ * p = |psi_w|^2 (not renormalised, as in the reference), norm = ||psi||^2 (nullable), psi
+ * nullable complex128[n_points][n].  Points whose a*|t| exceeds the Bessel table (~3800,
+ * a = half the spectral width) come back as NaN.  prob->schedule / step rule are ignored. */
+int qw_ti_exact_batch_dev(const qw_problem *prob, const double *time, const double *gamma,
+                          const int64_t *order, int64_t n_points, double *p, double *norm,
+                          void *psi, void *stream);
+int qw_ti_exact_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_time,
+                         const double *beta_array, int64_t n_beta, int64_t beta_begin,
+                         int64_t beta_end, double *p, double *norm, void *stream);
+
 /* One right-hand side dy = -i H(t) y: replaces schrodinger_equation(t, y, beta, T)
  * (BCB.py:163-174) with the implicit operator; y, dy complex128[n] on the device. */
 int qw_rhs_dev(const qw_problem *prob, double t, double T, double gamma, const void *y,

@@ -271,3 +271,21 @@ def first_argmax(values):
         if v > best:
             best, idx = v, j
     return idx
+
+
+def ti_exact(n, time, gamma, gamma_on=GAMMA_ON_ORACLE, target=None, topology="circular"):
+    """exp(-i H t)|s> by dense diagonalisation: the reference's time-independent comparator
+    (BCB.py:137-159 uses scipy.linalg.expm on the same H = L - gamma|w><w|).
+    Returns (|psi_w|^2, ||psi||^2, psi)."""
+    w = default_target(n) if target is None else int(target)
+    lap = laplacian_dense(n, topology)
+    if gamma_on_id(gamma_on) == GAMMA_ON_ORACLE:
+        H = lap.copy()
+        H[w, w] += -gamma
+    else:
+        H = gamma * lap
+        H[w, w] += -1.0
+    lam, V = np.linalg.eigh(H)
+    psi0 = np.full(n, 1 / np.sqrt(n))
+    psi = V @ (np.exp(-1j * lam * time) * (V.T @ psi0))
+    return float(abs(psi[w]) ** 2), float(np.vdot(psi, psi).real), psi

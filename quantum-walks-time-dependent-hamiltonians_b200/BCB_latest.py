@@ -15,6 +15,7 @@ atolerance = 1e-6
 n_steps = None
 step_size = 1e-3
 gamma_on = "oracle"
+ti_method = "exact"         # time-independent comparator: 'exact' (Chebyshev) or 'rk4'
 device = None
 
 # 0.1 ... 3.95 in steps of 0.05 without 1.05, 2.05, 3.05 (BCB_latest.py:242-245)

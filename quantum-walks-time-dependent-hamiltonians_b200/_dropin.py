@@ -152,7 +152,15 @@ def install(g, flavor):
 
     def evaluate_time_independent_probability(time, gamma, oracle_site_state):
         """-|<w|exp(-iHt)|s>|^2, shape (1, 1) (BCB.py:137-159).  Argument order is
-        (time, gamma).  Integrated with the same RK4 kernel under schedule 'static'."""
+        (time, gamma); always the cycle graph, as in the reference.  ``ti_method='exact'``
+        (default) evaluates the propagator by a Chebyshev expansion on the device, matching
+        the reference's scipy expm; ``'rk4'`` integrates schedule 'static' with the fixed-step
+        kernel instead."""
+        if g.get("ti_method", "exact") == "exact":
+            prob = _problem(g, flavor, schedule="static", topology="circular")
+            p, norm = engine.ti_exact_batch(prob, [float(time)], [float(gamma)],
+                                            device=g.get("device"))
+            return -np.array([[p[0]]])
         p, norm = _integrate(time, gamma, False, schedule="static", topology="circular")
         return -np.array([[p[0] * norm[0]]])          # the reference does not renormalise
 
@@ -180,6 +188,12 @@ def install(g, flavor):
         if kind == "dependent":
             return _heatmap(time_array, beta_array)
         if kind == "independent":
+            if g.get("ti_method", "exact") == "exact":
+                p, _ = engine.ti_exact_heatmap(
+                    _problem(g, flavor, schedule="static", topology="circular"),
+                    np.asarray(time_array, dtype=np.float64),
+                    np.asarray(beta_array, dtype=np.float64), device=g.get("device"))
+                return p
             return _heatmap(time_array, beta_array, schedule="static", topology="circular")
         raise ValueError("undefined type_of_qw: %r" % (kind,))
 

@@ -24,6 +24,8 @@ cudaError_t qw_launch_robustness(const double *p, int64_t nb, int64_t nt, int64_
 cudaError_t qw_run_fp64_probe(double millis, double *tflops, cudaStream_t st, int *launches);
 cudaError_t qw_launch_summary(const double *p, const double *tarr, int64_t nb, int64_t nt,
                               double t_min, double *out, cudaStream_t st);
+bool qw_cheb_supported(const QwParams &prm);
+cudaError_t qw_launch_cheb(QwParams prm, cudaStream_t st);
 
 namespace {
 
@@ -181,6 +183,59 @@ int qw_rk4_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_
     prm.n_time = n_time; prm.beta_begin = beta_begin;
     prm.p = p; prm.norm = norm;
     return run(prm, (cudaStream_t)stream);
+}
+
+static int run_ti_exact(QwParams &prm, cudaStream_t st)
+{
+    if (!qw_cheb_supported(prm))
+        return fail(QW_E_UNSUPPORTED, "exact propagator: cycle graph with a register-resident "
+                                      "dimension only (use schedule 'static' with RK4 otherwise)");
+    if (prm.n_points == 0) return 0;
+    cudaError_t e = qw_launch_cheb(prm, st);
+    g_launches += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "Chebyshev kernel launch");
+    return 0;
+}
+
+int qw_ti_exact_batch_dev(const qw_problem *prob, const double *time, const double *gamma,
+                          const int64_t *order, int64_t n_points, double *p, double *norm,
+                          void *psi, void *stream)
+{
+    QwParams prm;
+    qw_problem tmp;
+    if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
+    tmp = *prob;
+    if (!(tmp.step_size > 0.0) && tmp.n_steps < 0) tmp.n_steps = 0;   // no step rule needed
+    int rc = validate(&tmp, &prm);
+    if (rc) return rc;
+    if (n_points < 0) return fail(QW_E_SIZE, "n_points < 0");
+    if (n_points > 0 && (!time || !gamma || !p))
+        return fail(QW_E_NULL, "time, gamma and p are required");
+    prm.T = time; prm.gamma = gamma; prm.order = order; prm.n_points = n_points;
+    prm.p = p; prm.norm = norm; prm.psi = (double2 *)psi;
+    return run_ti_exact(prm, (cudaStream_t)stream);
+}
+
+int qw_ti_exact_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_time,
+                         const double *beta_array, int64_t n_beta, int64_t beta_begin,
+                         int64_t beta_end, double *p, double *norm, void *stream)
+{
+    QwParams prm;
+    qw_problem tmp;
+    if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
+    tmp = *prob;
+    if (!(tmp.step_size > 0.0) && tmp.n_steps < 0) tmp.n_steps = 0;
+    int rc = validate(&tmp, &prm);
+    if (rc) return rc;
+    if (n_time < 0 || n_beta < 0 || beta_begin < 0 || beta_end < beta_begin || beta_end > n_beta)
+        return fail(QW_E_SIZE, "bad grid extents");
+    prm.n_points = (beta_end - beta_begin) * n_time;
+    if (prm.n_points > 0 && (!time_array || !beta_array || !p))
+        return fail(QW_E_NULL, "time_array, beta_array and p are required");
+    prm.time_array = time_array; prm.beta_array = beta_array;
+    prm.n_time = n_time; prm.beta_begin = beta_begin;
+    prm.p = p; prm.norm = norm;
+    return run_ti_exact(prm, (cudaStream_t)stream);
 }
 
 int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gamma,

@@ -86,6 +86,15 @@ __device__ __forceinline__ QwPoint qw_point(const QwParams &prm, int64_t b)
 {
     QwPoint pt;
     int64_t q = prm.order ? prm.order[b] : b;
+    if (prm.time_array && prm.step_size > 0.0 && !prm.order) {
+        // fixed step size: work per point ~ T.  Walk the grid column by column from the
+        // longest T to the shortest so that the last blocks to start are the cheapest
+        // (longest-processing-time-first; blocks are dispatched in blockIdx order).
+        const int64_t rows = prm.n_points / prm.n_time;
+        const int64_t col = b / rows, row = b - col * rows;
+        const bool ascending = prm.time_array[0] <= prm.time_array[prm.n_time - 1];
+        q = row * prm.n_time + (ascending ? prm.n_time - 1 - col : col);
+    }
     pt.q = q;
     if (prm.time_array) {
         pt.T = prm.time_array[q % prm.n_time];

@@ -88,11 +88,15 @@ def test_rhs_and_time_independent_comparator(golden):
     bcb.topology = "circular"
     for c in meta["static"]:
         bcb.dimension, bcb.n_steps = c["n"], c["n_steps"]
+        bcb.ti_method = "exact"                      # Chebyshev propagator vs the reference expm
         val = bcb.evaluate_time_independent_probability(c["time"], c["gamma"], _site(c["n"]))
         assert val.shape == (1, 1)
+        assert abs(-val[0, 0] - c["p_expm"]) <= 1e-12
+        bcb.ti_method = "rk4"                        # fixed-step RK4 on the static Hamiltonian
+        val = bcb.evaluate_time_independent_probability(c["time"], c["gamma"], _site(c["n"]))
         assert abs(-val[0, 0] - c["p_expm"]) <= 1e-8
         assert abs(-val[0, 0] - c["p_rk4"] * c["norm_rk4"]) <= 1e-10
-    bcb.n_steps = None
+    bcb.n_steps, bcb.ti_method = None, "exact"
 
 
 def test_grid_eval_and_type_of_qw():
@@ -103,10 +107,15 @@ def test_grid_eval_and_type_of_qw():
     p = bcb.grid_eval(t, b)
     po, _ = c_oracle.heatmap(21, "circular", "cerf_3", t, b, n_steps=128)
     assert p.shape == (4, 6) and np.abs(p - po).max() <= 1e-10
-    bcb.type_of_qw = "independent"
+    bcb.type_of_qw, bcb.ti_method = "independent", "rk4"
     p = bcb.grid_eval(t, b)
-    po, _ = c_oracle.heatmap(21, "circular", "static", t, b, n_steps=128)
+    po, no = c_oracle.heatmap(21, "circular", "static", t, b, n_steps=128)
     assert np.abs(p - po).max() <= 1e-10
+    bcb.ti_method = "exact"
+    p = bcb.grid_eval(t, b)
+    from oracle import rk4_numpy as rk
+    pe = np.array([[rk.ti_exact(21, tt, bb)[0] for tt in t] for bb in b])
+    assert p.shape == (4, 6) and np.abs(p - pe).max() <= 1e-12
     bcb.type_of_qw = "dependent"
     bcb.n_steps = None
 

@@ -325,3 +325,45 @@ def test_heatmap_summary(qw):
     assert s["tau_argmin"] == (j, i) and s["tau_min"] == tau[j, i]
     s = qw.heatmap_summary(p, t, t_min=1e9)
     assert s["tau_argmin"] == (-1, -1)
+
+
+def test_ti_exact_golden_expm(qw, golden):
+    """Chebyshev propagator against the reference's own scipy expm values."""
+    meta, _ = golden
+    for c in meta["static"]:
+        prob = qw.Problem(n=c["n"], topology="circular", schedule="static")
+        p, nrm = qw.ti_exact_batch(prob, [c["time"]], [c["gamma"]])
+        assert abs(p[0] - c["p_expm"]) <= 1e-12 and abs(nrm[0] - 1) <= 1e-12, c
+
+
+@pytest.mark.parametrize("n", [3, 5, 17, 32, 51, 64, 100, 256, 512, 1000, 1024, 2048])
+def test_ti_exact_vs_dense_diagonalisation(qw, n):
+    rng = np.random.default_rng(n)
+    T = np.concatenate([[0.0, 1e-3], rng.uniform(0.5, 90.0, 4), [-7.5]])
+    g = np.concatenate([[1.0, 0.3], rng.uniform(0.0, 2.5, 3), [-0.8, 1.7]])
+    for go, tgt in (("oracle", None), ("laplacian", None), ("oracle", 1)):
+        if tgt is not None and n < 3:
+            continue
+        prob = qw.Problem(n=n, topology="circular", schedule="static", gamma_on=go, target=tgt)
+        p, nrm, psi = qw.ti_exact_batch(prob, T, g, return_psi=True)
+        for k in range(len(T)):
+            pe, ne, psie = rk.ti_exact(n, T[k], g[k], gamma_on=go, target=tgt)
+            assert abs(p[k] - pe) <= 2e-12 and abs(nrm[k] - 1.0) <= 2e-12, (n, go, k)
+            assert np.abs(psi[k] - psie).max() <= 2e-12, (n, go, k)
+    t, b = np.linspace(0.1, 40, 7), np.linspace(0, 2.5, 5)
+    prob = qw.Problem(n=n, topology="circular", schedule="static")
+    hp, hn = qw.ti_exact_heatmap(prob, t, b)
+    lo, _ = qw.ti_exact_heatmap(prob, t, b, rows=(1, 4))
+    assert hp.shape == (5, 7) and np.array_equal(lo, hp[1:4])
+    assert abs(hp[3, 2] - rk.ti_exact(n, t[2], b[3])[0]) <= 2e-12
+
+
+def test_ti_exact_limits(qw):
+    prob = qw.Problem(n=64, topology="circular", schedule="static")
+    p, nrm = qw.ti_exact_batch(prob, [1200.0, 5000.0], [1.0, 1.0])
+    pe, _, _ = rk.ti_exact(64, 1200.0, 1.0)
+    assert abs(p[0] - pe) <= 1e-11 and np.isnan(p[1])         # a|t| beyond the Bessel table
+    with pytest.raises(ValueError):
+        qw.ti_exact_batch(qw.Problem(n=64, topology="complete", schedule="static"), [1.0], [1.0])
+    with pytest.raises(ValueError):
+        qw.ti_exact_batch(qw.Problem(n=1031, topology="circular", schedule="static"), [1.0], [1.0])

@@ -155,3 +155,10 @@ def test_live_reference_rhs_and_L0():
     p2, n2, psi2 = rk.rk4_L2(12, "circular", "cerf_3", [6.0], [1.7], n_steps=200,
                              return_psi=True)
     assert abs(p0 - p2[0]) <= P_TOL and np.abs(psi0 - psi2[0]).max() <= PSI_TOL
+
+
+def test_ti_exact_oracle_matches_reference_expm(golden):
+    meta, _ = golden
+    for c in meta["static"]:
+        p, nrm, _ = rk.ti_exact(c["n"], c["time"], c["gamma"])
+        assert abs(p - c["p_expm"]) <= 1e-13 and abs(nrm - 1) <= 1e-13, c
