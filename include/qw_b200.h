@@ -85,8 +85,9 @@ enum {
                                     __syncthreads per stage (measured slower; A/B only) */
     QW_FLAG_OCC4 = 128,          /* resident kernels, <= 128 threads: 4 blocks/SM at 128
                                     registers instead of the default 3 at 168 (A/B only) */
-    QW_FLAG_R8 = 256             /* resident kernels: at most 8 sites per thread (default: 16
+    QW_FLAG_R8 = 256,            /* resident kernels: at most 8 sites per thread (default: 16
                                     where n % 16 == 0 and n/16 >= 32; A/B only) */
+    QW_FLAG_NO_PACK = 512        /* do not use the warp-packed kernel for small rings (A/B) */
 };
 
 /* ---- the hot path -------------------------------------------------------------------- */
@@ -174,14 +175,16 @@ int qw_heatmap_summary_dev(const double *p, const double *time_array, int64_t n_
 /* ---- introspection ------------------------------------------------------------------- */
 
 typedef struct qw_plan {
-    int32_t path;            /* 0 resident-cycle, 1 resident-complete, 2 generic, 3 stream */
+    int32_t path;            /* 0 resident-cycle, 1 resident-complete, 2 generic, 3 stream,
+                                4 warp-packed cycle */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */
     int32_t regs_per_thread;
     int32_t smem_bytes;
     int32_t sm_count;
-    int32_t steps_per_pass;  /* streaming path: RK4 steps fused per pass over HBM, else 0 */
+    int32_t steps_per_pass;  /* streaming path: RK4 steps fused per pass over HBM; packed
+                                path: points per warp; else 0 */
 } qw_plan;
 
 /* Which kernel a problem would run on the current device. */

@@ -6,7 +6,7 @@ import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["qw_api.cu", "qw_resident.cu", "qw_generic.cu", "qw_stream.cu", "qw_cheb.cu",
+SOURCES = ["qw_api.cu", "qw_resident.cu", "qw_generic.cu", "qw_stream.cu", "qw_packed.cu", "qw_cheb.cu",
            "qw_aux.cu"]
 OUT = os.path.join(_HERE, "libqw_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

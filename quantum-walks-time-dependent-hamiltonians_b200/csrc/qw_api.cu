@@ -24,6 +24,8 @@ cudaError_t qw_launch_robustness(const double *p, int64_t nb, int64_t nt, int64_
 cudaError_t qw_run_fp64_probe(double millis, double *tflops, cudaStream_t st, int *launches);
 cudaError_t qw_launch_summary(const double *p, const double *tarr, int64_t nb, int64_t nt,
                               double t_min, double *out, cudaStream_t st);
+bool qw_packed_supported(const QwParams &prm);
+cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan);
 bool qw_cheb_supported(const QwParams &prm);
 cudaError_t qw_launch_cheb(QwParams prm, cudaStream_t st);
 
@@ -76,12 +78,14 @@ int validate(const qw_problem *prob, QwParams *prm)
     return 0;
 }
 
-enum { PATH_RESIDENT = 0, PATH_GENERIC = 2, PATH_STREAM = 3 };
+enum { PATH_RESIDENT = 0, PATH_GENERIC = 2, PATH_STREAM = 3, PATH_PACKED = 4 };
 
 int choose_path(const QwParams &prm)
 {
     if (prm.flags & QW_FLAG_FORCE_GENERIC) return PATH_GENERIC;
     if ((prm.flags & QW_FLAG_FORCE_STREAM) && qw_stream_supported(prm)) return PATH_STREAM;
+    if (!(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_NO_PACK)) && qw_packed_supported(prm))
+        return PATH_PACKED;
     if (qw_resident_sites_per_thread(prm.n) > 0) return PATH_RESIDENT;
     if (qw_stream_supported(prm)) return PATH_STREAM;
     return PATH_GENERIC;
@@ -114,6 +118,11 @@ int run(QwParams &prm, cudaStream_t st)
     case PATH_RESIDENT:
         e = qw_launch_resident(prm, st, nullptr);
         if (e != cudaSuccess) return cuda_fail(e, "resident kernel launch");
+        g_launches += 1;
+        return 0;
+    case PATH_PACKED:
+        e = qw_launch_packed(prm, st, nullptr);
+        if (e != cudaSuccess) return cuda_fail(e, "packed kernel launch");
         g_launches += 1;
         return 0;
     case PATH_STREAM: {
@@ -378,6 +387,7 @@ int qw_plan_query(const qw_problem *prob, qw_plan *plan)
     prm.n_points = 1 << 20;
     switch (choose_path(prm)) {
     case PATH_RESIDENT: e = qw_launch_resident(prm, nullptr, plan); break;
+    case PATH_PACKED: e = qw_launch_packed(prm, nullptr, plan); break;
     case PATH_STREAM: e = qw_stream_plan(prm, plan); break;
     default: {
         int blocks; size_t bytes;

@@ -20,14 +20,16 @@ VARIANTS = {
     "c5": [("v2 R=16 (default)", 0), ("v2 R=8 occ3", 256), ("v2 R=8 occ4", 256 | 128),
            ("v2 R=8 mbarrier occ3", 256 | 64), ("v1 R=8 legacy occ3", 256 | 32),
            ("v1 R=8 legacy occ4", 256 | 32 | 128)],
-    "c4": [("v2 occ3 (default)", 0), ("v2 occ4", 128), ("v1 legacy occ3", 32),
+    "c4": [("packed (default)", 0), ("v2 occ3", 512), ("v2 occ4", 128), ("v1 legacy occ3", 32),
            ("v1 legacy occ4", 32 | 128)],
+    "c2": [("packed (default)", 0), ("packed R<=8", 256), ("v2 R=2 CTA-per-point", 512)],
     "c3": [("complete v2 R=16 (default)", 0), ("complete v2 R=8", 256), ("complete v1 R=8 legacy", 256 | 32),
            ("complete R=8 exact-sum", 256 | 4)],
 }
 SHAPES = {
     "c5": dict(n=1024, topology="circular", schedule="lin", n_steps=4096, nT=1024, t=(0.1, 1024), g=(0, 2.5)),
     "c4": dict(n=256, topology="circular", schedule="lin", n_steps=512, nT=1000, t=(20, 30), g=(0.8, 1.2)),
+    "c2": dict(n=64, topology="circular", schedule="lin", n_steps=1024, nT=100, t=(0.1, 64), g=(0, 2.5)),
     "c3": dict(n=4096, topology="complete", schedule="cerf_3", n_steps=2048, nT=256, t=(0.1, 512),
                g=(0.5 / 4096, 2.5 / 4096), gamma_on="laplacian"),
 }

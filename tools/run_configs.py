@@ -85,7 +85,8 @@ def main():
     t0 = time.perf_counter()
     ph, _ = qw.rk4_batch(prob, [16.0], [1.0])
     host_us = (time.perf_counter() - t0) * 1e6
-    print("| C1 cycle N=16 (T,gamma)=(16,1) lin S=1024 | resident-cycle R=1 x 32 thr | 1 | %.3f | "
+    print("| C1 cycle N=16 (T,gamma)=(16,1) lin S=1024 | packed-cycle, small batch: R=1 x 16 "
+          "lanes | 1 | %.3f | "
           "%.3e | %.3e | p=%.14f (reference RK4 n=1024: 0.42038739054526); %.0f us per point "
           "device, %.0f us through the host API | %.1e |"
           % (ms, 16 * 1024 / (ms * 1e-3), 1 / (ms * 1e-3), ph[0], ms * 1e3, host_us,
