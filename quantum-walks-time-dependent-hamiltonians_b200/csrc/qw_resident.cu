@@ -391,17 +391,22 @@ cudaError_t dispatch_threads(const QwParams &prm, int threads, cudaStream_t st, 
     const size_t smem = cyc ? (size_t)threads * 4 * sizeof(double2) : 0;
     const bool legacy = (prm.flags & QW_FLAG_CYCLE_LEGACY) != 0;
     const bool split = (prm.flags & QW_FLAG_CYCLE_SPLIT) != 0;
+    // The first-generation and mbarrier variants exist for the A/B record only (R = 8).
 #define QW_LAUNCH(MAXNT, MINB)                                                             \
-    if (cyc && legacy)                                                                     \
-        return launch(rk4_cycle_resident<R, MAXNT, MINB>, prm, threads, smem, st, plan);   \
-    if (cyc && split)                                                                      \
-        return launch(rk4_cycle_resident_v2<R, MAXNT, MINB, true>, prm, threads, smem, st, plan); \
+    if constexpr (R == 8) {                                                                \
+        if (cyc && legacy)                                                                 \
+            return launch(rk4_cycle_resident<R, MAXNT, MINB>, prm, threads, smem, st, plan); \
+        if (cyc && split)                                                                  \
+            return launch(rk4_cycle_resident_v2<R, MAXNT, MINB, true>, prm, threads, smem, st, \
+                          plan);                                                           \
+        if (!cyc && !exact && legacy)                                                      \
+            return launch(rk4_complete_resident<R, MAXNT, MINB, false>, prm, threads, smem, st, \
+                          plan);                                                           \
+    }                                                                                      \
     if (cyc)                                                                               \
         return launch(rk4_cycle_resident_v2<R, MAXNT, MINB, false>, prm, threads, smem, st, plan); \
     if (exact)                                                                             \
         return launch(rk4_complete_resident<R, MAXNT, MINB, true>, prm, threads, smem, st, plan); \
-    if (legacy)                                                                            \
-        return launch(rk4_complete_resident<R, MAXNT, MINB, false>, prm, threads, smem, st, plan); \
     return launch(rk4_complete_resident_v2<R, MAXNT, MINB>, prm, threads, smem, st, plan);
     // <= 128 threads: 3 blocks/SM (168 registers, no spills) measured faster than 4 (128)
     if (threads <= 128 && (prm.flags & QW_FLAG_OCC4)) { QW_LAUNCH(128, 4) }
