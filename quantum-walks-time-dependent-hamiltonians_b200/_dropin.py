@@ -220,6 +220,53 @@ def install(g, flavor):
         print()
         return 1
 
+    def optimization_precision(x, probability, context):
+        """Callback of SS:125-130: stop once p >= 0.99."""
+        return bool(probability <= -0.99)
+
+    def arrange_local_maxima(results):
+        """SS:133-143."""
+        local_maxima = np.empty([len(results.funl), 3])
+        for i in range(len(results.funl)):
+            local_maxima[i][0] = -results.funl[i]
+            local_maxima[i][1] = results.xl[i][0]
+            local_maxima[i][2] = results.xl[i][1]
+        return local_maxima
+
+    def optimization(par_bnds, optimization_method, its):
+        """Maximise p over (beta, T) in ``par_bnds`` (SS:283-361).  'SHGO', 'BH' and 'DUAL'
+        drive the same SciPy optimisers as the reference with the GPU objective (one point
+        per call); 'GPU' evaluates whole candidate sets per launch
+        (``engine.maximize_probability``).  Return values as in the reference."""
+        n = int(g["dimension"])
+        osite = np.zeros((n, 1))
+        osite[_marked_vertex(n)][0] = 1
+        tic = _time.perf_counter()
+        if optimization_method == 'GPU':
+            p, beta, T, loc = engine.maximize_probability(
+                _problem(g, flavor), par_bnds[0], par_bnds[1], device=g.get("device"))
+            comp_time = int(_time.perf_counter() - tic) / 60
+            return [n, p, beta, T, comp_time], loc, [0, 0, 0, 0, 0]
+        from scipy.optimize import basinhopping, dual_annealing, shgo
+        objective = g["evaluate_probability"]
+        if optimization_method == 'SHGO':
+            res = shgo(objective, par_bnds, n=40, iters=1, args=(osite,),
+                       sampling_method='sobol')
+            comp_time = int(_time.perf_counter() - tic) / 60
+            return ([n, float(-res.fun), res.x[0], res.x[1], comp_time],
+                    arrange_local_maxima(res), [0, 0, 0, 0, 0])
+        if optimization_method == 'BH':
+            kwargs = dict(method="L-BFGS-B", bounds=par_bnds, args=osite)
+            res = basinhopping(objective, np.array([1., 10]), minimizer_kwargs=kwargs,
+                               niter=its)
+            comp_time = int(_time.perf_counter() - tic) / 60
+            return [n, float(-res.fun), res.x[0], res.x[1], comp_time]
+        if optimization_method == 'DUAL':
+            res = dual_annealing(objective, par_bnds, args=(osite,), maxiter=its)
+            comp_time = int(_time.perf_counter() - tic) / 60
+            return [n, float(-res.fun), res.x[0], res.x[1], comp_time]
+        raise ValueError('invalid optimization method: %r' % (optimization_method,))
+
     def _save_and_report(prob, time_array, beta, file_probability, tic):
         import torch.distributed as dist
         n = g["dimension"]
@@ -277,7 +324,9 @@ def install(g, flavor):
              evaluate_probability=evaluate_probability, heatmap2d=heatmap2d)
     if flavor in ("SS", "RKE"):
         g.update(grid_probability_evaluation=grid_probability_evaluation,
-                 single_evaluation_benchmark=single_evaluation_benchmark)
+                 single_evaluation_benchmark=single_evaluation_benchmark,
+                 optimization=optimization, optimization_precision=optimization_precision,
+                 arrange_local_maxima=arrange_local_maxima)
     else:
         g.update(generate_time_independent_hamiltonian=generate_time_independent_hamiltonian,
                  evaluate_time_independent_probability=evaluate_time_independent_probability,

@@ -311,6 +311,61 @@ def heatmap_summary(probability, time_array, t_min=0.0, device=None):
             "tau_min": float(o[3]), "tau_argmin": (int(o[4]), int(o[5]))}
 
 
+def _halton(n, base):
+    out = np.zeros(n)
+    for i in range(n):
+        f, k, x = 1.0, i + 1, 0.0
+        while k > 0:
+            f /= base
+            x += f * (k % base)
+            k //= base
+        out[i] = x
+    return out
+
+
+def maximize_probability(problem, beta_bounds, time_bounds, n_samples=4096, keep=16, rounds=14,
+                         stencil=5, device=None):
+    """Batched maximisation of p(beta, T) -- the job of the reference's SciPy optimisers
+    (Schroedinger_Solver.py:283-361: shgo / basinhopping / dual_annealing, one point per
+    objective call) done with whole candidate sets per kernel launch.
+
+    One launch scans a low-discrepancy (Halton) sample of the box; the ``keep`` best cells
+    are then refined together by a shrinking ``stencil`` x ``stencil`` pattern search, one
+    launch per round.  Returns (p_max, beta, T, local_maxima[keep, 3]) with rows
+    (p, beta, T) sorted by p, like ``arrange_local_maxima`` (SS:134-144)."""
+    dev = _device(device)
+    b0, b1 = float(beta_bounds[0]), float(beta_bounds[1])
+    t0, t1 = float(time_bounds[0]), float(time_bounds[1])
+    with torch.cuda.device(dev):
+        beta = torch.from_numpy(b0 + (b1 - b0) * _halton(n_samples, 2)).to(dev)
+        time = torch.from_numpy(t0 + (t1 - t0) * _halton(n_samples, 3)).to(dev)
+        p, _ = rk4_batch(problem, time, beta, device=dev)
+        top = torch.topk(p, min(keep, n_samples))
+        cb, ct, cp = beta[top.indices].clone(), time[top.indices].clone(), top.values.clone()
+        k = cb.numel()
+        rb = torch.full((k,), (b1 - b0) / np.sqrt(n_samples), dtype=torch.float64, device=dev)
+        rt = torch.full((k,), (t1 - t0) / np.sqrt(n_samples), dtype=torch.float64, device=dev)
+        off = torch.linspace(-1.0, 1.0, stencil, dtype=torch.float64, device=dev)
+        ob, ot = torch.meshgrid(off, off, indexing="ij")
+        ob, ot = ob.reshape(1, -1), ot.reshape(1, -1)
+        for _ in range(rounds):
+            gb = (cb[:, None] + rb[:, None] * ob).clamp(b0, b1)
+            gt = (ct[:, None] + rt[:, None] * ot).clamp(t0, t1)
+            gp, _ = rk4_batch(problem, gt.reshape(-1), gb.reshape(-1), device=dev)
+            gp = gp.reshape(k, -1)
+            best = gp.argmax(dim=1)
+            bp = gp.gather(1, best[:, None])[:, 0]
+            improved = bp > cp
+            cb = torch.where(improved, gb.gather(1, best[:, None])[:, 0], cb)
+            ct = torch.where(improved, gt.gather(1, best[:, None])[:, 0], ct)
+            cp = torch.where(improved, bp, cp)
+            shrink = torch.where(improved, 1.0, 0.5)
+            rb, rt = rb * shrink, rt * shrink
+        order = torch.argsort(cp, descending=True)
+        loc = torch.stack([cp[order], cb[order], ct[order]], dim=1).cpu().numpy()
+    return float(loc[0, 0]), float(loc[0, 1]), float(loc[0, 2]), loc
+
+
 def plan(problem, device=None):
     dev = _device(device)
     lib = _lib.load()

@@ -204,3 +204,27 @@ def test_integration_md_stub_runs():
     assert p.shape == (4, 5) and np.abs(p - po).max() <= 1e-10
     with pytest.raises(ValueError):
         ns["grid_eval"](2, "circular", "lin", t, b)
+
+
+def test_batched_optimisation_and_scipy_drop_in():
+    """Row f3: the optimisers of Schroedinger_Solver.py:283-361.  The batched search must
+    find at least the best cell of a dense oracle scan; the SciPy-driven drop-in (same
+    calls as the reference, GPU objective) must agree with it."""
+    ss = _mod("Schroedinger_Solver")
+    ss.dimension, ss.step_function, ss.n_steps, ss.step_size = 5, 1, 200, None
+    bnds = ([0.1, 5.0], [1.0, 20.0])
+    res, loc, adi = ss.optimization(bnds, 'GPU', 0)
+    t, b = np.linspace(1, 20, 60), np.linspace(0.1, 5, 60)
+    po, _ = c_oracle.heatmap(5, "circular", "lin", t, b, n_steps=200)
+    assert res[0] == 5 and res[1] >= po.max() - 1e-9 and res[1] <= 1.0
+    assert 0.1 <= res[2] <= 5.0 and 1.0 <= res[3] <= 20.0
+    pchk, _, _ = c_oracle.rk4_batch(5, "circular", "lin", [res[3]], [res[2]], n_steps=200)
+    assert abs(pchk[0] - res[1]) <= 1e-10                       # the reported optimum is real
+    assert loc.shape[1] == 3 and (np.diff(loc[:, 0]) <= 0).all()
+    res2, loc2, _ = ss.optimization(bnds, 'SHGO', 0)
+    assert res2[1] <= res[1] + 1e-6 and res2[1] > 0.9           # shgo finds a good local maximum
+    res3 = ss.optimization(bnds, 'DUAL', 30)
+    assert abs(res3[1] - res[1]) < 5e-3
+    assert ss.optimization_precision(None, -0.995, None) and not ss.optimization_precision(
+        None, -0.5, None)
+    ss.n_steps, ss.step_size = None, 1e-3
