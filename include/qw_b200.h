@@ -141,6 +141,21 @@ int qw_ti_exact_grid_dev(const qw_problem *prob, const double *time_array, int64
                          const double *beta_array, int64_t n_beta, int64_t beta_begin,
                          int64_t beta_end, double *p, double *norm, void *stream);
 
+/* Adaptive Dormand-Prince RK45 with SciPy's step-size controller: the integrator the reference
+ * ships, solve_ivp(schrodinger_equation, [0, T], y0, method='RK45', atol, rtol)
+ * (BCB.py:177-190, Schroedinger_Solver.py:88-103), on the implicit operator.  Reproduces the
+ * reference's printed probabilities to ~1e-10.  rtol / atol = the module globals
+ * rtolerance / atolerance (BCB.py:339-340).  Dimension up to 1024 (2048 if even).
+ * nfev: optional int64[n_points], right-hand-side evaluations (solve_ivp's sol.nfev).
+ * prob->schedule applies; the step rule is ignored.  p is renormalised as in qw_rk4_*. */
+int qw_rk45_batch_dev(const qw_problem *prob, const double *T, const double *gamma,
+                      const int64_t *order, int64_t n_points, double rtol, double atol,
+                      double *p, double *norm, void *psi, int64_t *nfev, void *stream);
+int qw_rk45_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_time,
+                     const double *beta_array, int64_t n_beta, int64_t beta_begin,
+                     int64_t beta_end, double rtol, double atol, double *p, double *norm,
+                     void *stream);
+
 /* One right-hand side dy = -i H(t) y: replaces schrodinger_equation(t, y, beta, T)
  * (BCB.py:163-174) with the implicit operator; y, dy complex128[n] on the device. */
 int qw_rhs_dev(const qw_problem *prob, double t, double T, double gamma, const void *y,

@@ -289,3 +289,28 @@ def ti_exact(n, time, gamma, gamma_on=GAMMA_ON_ORACLE, target=None, topology="ci
     psi0 = np.full(n, 1 / np.sqrt(n))
     psi = V @ (np.exp(-1j * lam * time) * (V.T @ psi0))
     return float(abs(psi[w]) ** 2), float(np.vdot(psi, psi).real), psi
+
+
+def rk45_scipy(n, topology, schedule, T, gamma, rtol=1e-6, atol=1e-6, gamma_on=GAMMA_ON_ORACLE,
+               target=None):
+    """The reference's shipped integrator restated: scipy solve_ivp RK45 (BCB.py:177-190) over
+    the implicit right-hand side.  Returns (p, norm, psi, nfev)."""
+    from scipy.integrate import solve_ivp
+    w = default_target(n) if target is None else int(target)
+    topo = topology_id(topology)
+    y0 = np.full(n, 1 / np.sqrt(n), dtype=complex)
+    if T == 0:
+        p, norm = _finish(y0, w)
+        return p, norm, y0, 0
+
+    def fun(t, y):
+        if t == 0 and schedule_id(schedule) != _STATIC:          # BCB.py:72-73
+            a, d = (1.0 if gamma_on_id(gamma_on) == GAMMA_ON_ORACLE else gamma), 0.0
+        else:
+            a, d = operator_scalars(t / T, gamma, schedule, gamma_on)
+        return apply_rhs(y[None, :], float(a), float(d), topo, w)[0]
+
+    sol = solve_ivp(fun, [0.0, T], y0, method="RK45", atol=atol, rtol=rtol)
+    psi = sol.y[:, -1]
+    p, norm = _finish(psi, w)
+    return p, norm, psi, sol.nfev

@@ -19,6 +19,7 @@ atolerance = 1e-6
 n_steps = None
 step_size = 1e-3
 gamma_on = "oracle"
+integrator = "rk4"           # 'rk45': SciPy's adaptive RK45 as the reference ships it
 ti_method = "exact"         # time-independent comparator: 'exact' (Chebyshev) or 'rk4'
 device = None
 

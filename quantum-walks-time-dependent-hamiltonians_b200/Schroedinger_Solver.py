@@ -11,11 +11,12 @@ from . import _dropin
 
 dimension = None
 step_function = 1
-rtolerance = 1e-6          # accepted for compatibility; the integrator is fixed-step RK4
+rtolerance = 1e-6          # used by integrator = 'rk45' only
 atolerance = 1e-6
 n_steps = None             # h = T / n_steps when set
 step_size = 1e-3           # else n = int(T / step_size) steps (QW_Search.py:153-154)
 gamma_on = "oracle"
+integrator = "rk4"           # 'rk45': SciPy's adaptive RK45 as the reference ships it
 device = None
 
 _dropin.install(globals(), "SS")

@@ -7,8 +7,9 @@ each drop-in module calls ``install(globals(), flavor)`` and gets functions with
 reference's names and argument meaning that read *that module's* globals on every call.
 New knobs live beside the old ones: ``n_steps`` / ``step_size`` (fixed-step rule,
 QW_Search.py:149-164; default step_size = 1e-3 as in the stub), ``gamma_on``, ``device``.
-``rtolerance`` / ``atolerance`` are accepted and ignored (the integrator is fixed-step RK4,
-not SciPy's RK45 -- BASELINE.md section 1).
+``integrator`` selects the fixed-step RK4 of the north star ('rk4', default; ``rtolerance`` /
+``atolerance`` unused) or SciPy's adaptive RK45 as the reference ships it ('rk45', tolerances
+honoured -- BASELINE.md section 1).
 
 Everything that integrates goes to the CUDA kernels through ``engine``; nothing here
 falls back to the CPU.
@@ -111,10 +112,19 @@ def install(g, flavor):
                         device=g.get("device"))
         return list(dy)
 
+    def _rk45():
+        """integrator = 'rk45': the reference's shipped SciPy RK45 (rtolerance / atolerance
+        honoured) instead of the fixed-step RK4 of the north star."""
+        return g.get("integrator", "rk4") == "rk45"
+
     def _integrate(T, beta, want_psi, schedule=None, topology=None):
-        out = engine.rk4_batch(_problem(g, flavor, schedule, topology), [float(T)],
-                               [float(beta)], return_psi=want_psi, device=g.get("device"))
-        return out
+        prob = _problem(g, flavor, schedule, topology)
+        if _rk45():
+            return engine.rk45_batch(prob, [float(T)], [float(beta)],
+                                     rtol=g.get("rtolerance", 1e-6), atol=g.get("atolerance", 1e-6),
+                                     return_psi=want_psi, device=g.get("device"))
+        return engine.rk4_batch(prob, [float(T)], [float(beta)], return_psi=want_psi,
+                                device=g.get("device"))
 
     def solve_schrodinger_equation(time, beta):
         """psi(T): SS returns it raw (SS:102), BCB normalised (BCB:189-190),
@@ -174,11 +184,15 @@ def install(g, flavor):
         from . import heatmap_generator
         return heatmap_generator.render(*args, dimension=g.get("dimension"), **kwargs)
 
-    def _heatmap(time_array, beta_array, schedule=None, topology=None):
-        p, _ = engine.rk4_heatmap(_problem(g, flavor, schedule, topology),
-                                  np.asarray(time_array, dtype=np.float64),
-                                  np.asarray(beta_array, dtype=np.float64),
-                                  device=g.get("device"))
+    def _heatmap(time_array, beta_array, schedule=None, topology=None, dimension=None):
+        prob = _problem(g, flavor, schedule, topology, dimension)
+        t = np.asarray(time_array, dtype=np.float64)
+        b = np.asarray(beta_array, dtype=np.float64)
+        if _rk45():
+            p, _ = engine.rk45_heatmap(prob, t, b, rtol=g.get("rtolerance", 1e-6),
+                                       atol=g.get("atolerance", 1e-6), device=g.get("device"))
+        else:
+            p, _ = engine.rk4_heatmap(prob, t, b, device=g.get("device"))
         return p
 
     def grid_eval(time_array, beta_array):
@@ -203,8 +217,7 @@ def install(g, flavor):
         """SS:426-444 -- one kernel launch instead of the double loop."""
         time_array = np.linspace(time_lb, time_up, time_sampling_points)
         beta_array = np.linspace(beta_lb, beta_up, beta_sampling_points)
-        p, _ = engine.rk4_heatmap(_problem(g, flavor, dimension=dimension), time_array,
-                                  beta_array, device=g.get("device"))
+        p = _heatmap(time_array, beta_array, dimension=dimension)
         g["heatmap2d"](p, time_array, beta_array, non_time, non_prob)
         return p
 
@@ -286,7 +299,13 @@ def install(g, flavor):
             prob = _problem(g, flavor, schedule="static", topology="circular")
         else:
             raise ValueError("undefined type_of_qw: %r" % (kind,))
-        p, _ = engine.heatmap_sharded(prob, time_array, beta)
+        compute = None
+        if _rk45() and kind == "dependent":
+            def compute(problem, t, b, rows):
+                return engine.rk45_heatmap(problem, t, b, rtol=g.get("rtolerance", 1e-6),
+                                           atol=g.get("atolerance", 1e-6), rows=rows,
+                                           device=g.get("device"))
+        p, _ = engine.heatmap_sharded(prob, time_array, beta, compute=compute)
         return p
 
     def parallel_routine_bcb(lb_time, ub_time, lb_beta, ub_beta):

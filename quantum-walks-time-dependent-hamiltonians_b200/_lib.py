@@ -44,6 +44,10 @@ SIGNATURES = {
                                         ctypes.c_int]),
     "qw_ti_exact_batch_dev": (ctypes.c_int, [_pp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "qw_ti_exact_grid_dev": (ctypes.c_int, [_pp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "qw_rk45_batch_dev": (ctypes.c_int, [_pp, _vp, _vp, _vp, _i64, _dbl, _dbl, _vp, _vp, _vp, _vp,
+                                         _vp]),
+    "qw_rk45_grid_dev": (ctypes.c_int, [_pp, _vp, _i64, _vp, _i64, _i64, _i64, _dbl, _dbl, _vp,
+                                        _vp, _vp]),
     "qw_rhs_dev": (ctypes.c_int, [_pp, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "qw_ensemble_stats_dev": (ctypes.c_int, [_vp, _i64, _vp, _i32, _vp, _vp]),
     "qw_heatmap_robustness_dev": (ctypes.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),

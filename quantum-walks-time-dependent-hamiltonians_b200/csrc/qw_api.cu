@@ -26,6 +26,8 @@ cudaError_t qw_launch_summary(const double *p, const double *tarr, int64_t nb, i
                               double t_min, double *out, cudaStream_t st);
 bool qw_packed_supported(const QwParams &prm);
 cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan);
+bool qw_rk45_supported(const QwParams &prm);
+cudaError_t qw_launch_rk45(QwParams prm, double rtol, double atol, int64_t *nfev, cudaStream_t st);
 bool qw_cheb_supported(const QwParams &prm);
 cudaError_t qw_launch_cheb(QwParams prm, cudaStream_t st);
 
@@ -245,6 +247,61 @@ int qw_ti_exact_grid_dev(const qw_problem *prob, const double *time_array, int64
     prm.n_time = n_time; prm.beta_begin = beta_begin;
     prm.p = p; prm.norm = norm;
     return run_ti_exact(prm, (cudaStream_t)stream);
+}
+
+static int run_rk45(QwParams &prm, double rtol, double atol, int64_t *nfev, cudaStream_t st)
+{
+    if (!qw_rk45_supported(prm))
+        return fail(QW_E_UNSUPPORTED, "RK45: dimension up to 1024 (or even, up to 2048)");
+    if (!(rtol > 0.0) || !(atol > 0.0)) return fail(QW_E_STEPS, "rtol and atol must be > 0");
+    if (prm.n_points == 0) return 0;
+    // solve_ivp raises rtol to 100 eps when it is smaller (scipy/integrate/_ivp/common.py)
+    if (rtol < 100.0 * 2.220446049250313e-16) rtol = 100.0 * 2.220446049250313e-16;
+    cudaError_t e = qw_launch_rk45(prm, rtol, atol, nfev, st);
+    g_launches += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "RK45 kernel launch");
+    return 0;
+}
+
+int qw_rk45_batch_dev(const qw_problem *prob, const double *T, const double *gamma,
+                      const int64_t *order, int64_t n_points, double rtol, double atol,
+                      double *p, double *norm, void *psi, int64_t *nfev, void *stream)
+{
+    QwParams prm;
+    qw_problem tmp;
+    if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
+    tmp = *prob;
+    if (!(tmp.step_size > 0.0) && tmp.n_steps < 0) tmp.n_steps = 0;   // no step rule needed
+    int rc = validate(&tmp, &prm);
+    if (rc) return rc;
+    if (n_points < 0) return fail(QW_E_SIZE, "n_points < 0");
+    if (n_points > 0 && (!T || !gamma || !p)) return fail(QW_E_NULL, "T, gamma and p are required");
+    prm.T = T; prm.gamma = gamma; prm.order = order; prm.n_points = n_points;
+    prm.p = p; prm.norm = norm; prm.psi = (double2 *)psi;
+    return run_rk45(prm, rtol, atol, nfev, (cudaStream_t)stream);
+}
+
+int qw_rk45_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_time,
+                     const double *beta_array, int64_t n_beta, int64_t beta_begin,
+                     int64_t beta_end, double rtol, double atol, double *p, double *norm,
+                     void *stream)
+{
+    QwParams prm;
+    qw_problem tmp;
+    if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
+    tmp = *prob;
+    if (!(tmp.step_size > 0.0) && tmp.n_steps < 0) tmp.n_steps = 0;
+    int rc = validate(&tmp, &prm);
+    if (rc) return rc;
+    if (n_time < 0 || n_beta < 0 || beta_begin < 0 || beta_end < beta_begin || beta_end > n_beta)
+        return fail(QW_E_SIZE, "bad grid extents");
+    prm.n_points = (beta_end - beta_begin) * n_time;
+    if (prm.n_points > 0 && (!time_array || !beta_array || !p))
+        return fail(QW_E_NULL, "time_array, beta_array and p are required");
+    prm.time_array = time_array; prm.beta_array = beta_array;
+    prm.n_time = n_time; prm.beta_begin = beta_begin;
+    prm.p = p; prm.norm = norm;
+    return run_rk45(prm, rtol, atol, nullptr, (cudaStream_t)stream);
 }
 
 int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gamma,

@@ -191,6 +191,56 @@ def rk4_batch_host(problem, T, gamma, n_steps=None, return_psi=False, device=0):
     return (p, norm, psi) if return_psi else (p, norm)
 
 
+def rk45_batch(problem, T, gamma, rtol=1e-6, atol=1e-6, order=None, return_psi=False,
+               return_nfev=False, device=None):
+    """The reference's shipped integrator -- SciPy RK45 with its step-size controller
+    (BCB.py:177-190) -- on the device.  Returns (p, norm[, psi][, nfev])."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        dT, host = _as_dev(T, dev)
+        dG, _ = _as_dev(gamma, dev)
+        if dG.numel() == 1 and dT.numel() > 1:
+            dG = dG.expand(dT.numel()).contiguous()
+        if dT.numel() != dG.numel():
+            raise ValueError("T and gamma must have the same length")
+        P = dT.numel()
+        dO = _as_dev(order, dev, torch.int64)[0] if order is not None else None
+        p = torch.empty(P, dtype=torch.float64, device=dev)
+        norm = torch.empty(P, dtype=torch.float64, device=dev)
+        psi = (torch.empty((P, int(problem.n)), dtype=torch.complex128, device=dev)
+               if return_psi else None)
+        nfev = torch.zeros(P, dtype=torch.int64, device=dev) if return_nfev else None
+        prob = problem.c_struct(per_point_steps=True)
+        _lib.check(lib.qw_rk45_batch_dev(ctypes.byref(prob), _ptr(dT), _ptr(dG), _ptr(dO), P,
+                                         float(rtol), float(atol), _ptr(p), _ptr(norm),
+                                         _ptr(psi), _ptr(nfev), _stream()))
+        out = (p, norm) + ((psi,) if return_psi else ()) + ((nfev,) if return_nfev else ())
+        if host:
+            out = tuple(t.cpu().numpy() for t in out)
+        return out
+
+
+def rk45_heatmap(problem, time_array, beta_array, rtol=1e-6, atol=1e-6, rows=None, device=None):
+    """probability[beta][T] with the adaptive RK45 integrator of the reference."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        dT, host = _as_dev(time_array, dev)
+        dB, _ = _as_dev(beta_array, dev)
+        nT, nB = dT.numel(), dB.numel()
+        b0, b1 = (0, nB) if rows is None else (int(rows[0]), int(rows[1]))
+        p = torch.empty((b1 - b0, nT), dtype=torch.float64, device=dev)
+        norm = torch.empty((b1 - b0, nT), dtype=torch.float64, device=dev)
+        prob = problem.c_struct(per_point_steps=True)
+        _lib.check(lib.qw_rk45_grid_dev(ctypes.byref(prob), _ptr(dT), nT, _ptr(dB), nB, b0, b1,
+                                        float(rtol), float(atol), _ptr(p), _ptr(norm),
+                                        _stream()))
+        if host:
+            return p.cpu().numpy(), norm.cpu().numpy()
+        return p, norm
+
+
 def ti_exact_batch(problem, time, gamma, order=None, return_psi=False, device=None):
     """|<w|exp(-iHt)|s>|^2 (not renormalised) and ||psi||^2 [, psi] for independent (t, gamma)
     points: the Chebyshev propagator behind evaluate_time_independent_probability

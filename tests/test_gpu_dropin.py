@@ -228,3 +228,20 @@ def test_batched_optimisation_and_scipy_drop_in():
     assert ss.optimization_precision(None, -0.995, None) and not ss.optimization_precision(
         None, -0.5, None)
     ss.n_steps, ss.step_size = None, 1e-3
+
+
+def test_integrator_rk45_reproduces_reference_printouts(golden):
+    """With ``integrator = 'rk45'`` the drop-in prints what the reference prints today."""
+    meta, arr = golden
+    bcb, ss = _mod("BCB"), _mod("Schroedinger_Solver")
+    bcb.integrator, bcb.rtolerance, bcb.atolerance = "rk45", 1e-6, 1e-6
+    for c in meta["rk45"]:
+        bcb.dimension, bcb.topology, bcb.step_function = c["n"], c["topology"], c["schedule"]
+        val = bcb.evaluate_probability([c["beta"], c["T"]], _site(c["n"]))
+        assert val.shape == (1,) and abs(-val[0] - c["p"]) <= 1e-9, c
+    bcb.integrator, bcb.topology = "rk4", "circular"
+    hm = [c for c in meta["heatmaps"] if c["kind"] == "RK45"][0]
+    ss.dimension, ss.step_function, ss.integrator = 5, 1, "rk45"
+    p = ss.grid_probability_evaluation(5, 1, 20, 4, 0.1, 5, 3, 0.92, 7)
+    assert np.abs(p - arr[hm["key"]]).max() <= 1e-9
+    ss.integrator = "rk4"

@@ -370,3 +370,40 @@ def test_ti_exact_limits(qw):
         qw.ti_exact_batch(qw.Problem(n=64, topology="complete", schedule="static"), [1.0], [1.0])
     with pytest.raises(ValueError):
         qw.ti_exact_batch(qw.Problem(n=1031, topology="circular", schedule="static"), [1.0], [1.0])
+
+
+def test_rk45_reproduces_the_reference_as_shipped(qw, golden):
+    """Adaptive RK45 with SciPy's controller on the device vs the numbers the reference's own
+    evaluate_probability / grid_probability_evaluation printed (tests/golden), and vs SciPy
+    over the stencil RHS (same accepted-step sequence: identical nfev)."""
+    meta, arr = golden
+    for c in meta["rk45"]:
+        prob = qw.Problem(n=c["n"], topology=c["topology"], schedule=c["schedule"])
+        p, nrm, nfev = qw.rk45_batch(prob, [c["T"]], [c["beta"]], rtol=1e-6, atol=1e-6,
+                                     return_nfev=True)
+        assert abs(p[0] - c["p"]) <= 1e-9, (c, p[0])
+        po, no, _, nf = rk.rk45_scipy(c["n"], c["topology"], c["schedule"], c["T"], c["beta"])
+        assert abs(p[0] - po) <= 1e-9 and abs(nrm[0] - no) <= 1e-9 and nfev[0] == nf, c
+    hm = [c for c in meta["heatmaps"] if c["kind"] == "RK45"][0]
+    t = np.linspace(*hm["time"][:2], int(hm["time"][2]))
+    b = np.linspace(*hm["beta"][:2], int(hm["beta"][2]))
+    prob = qw.Problem(n=hm["n"], topology="circular", schedule="lin")
+    hp, _ = qw.rk45_heatmap(prob, t, b)
+    assert np.abs(hp - arr[hm["key"]]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("n,topo", [(3, "circular"), (16, "circular"), (51, "circular"),
+                                    (71, "circular"), (256, "circular"), (1024, "circular"),
+                                    (1500, "circular"), (15, "complete"), (64, "complete")])
+def test_rk45_vs_scipy_on_the_stencil(qw, n, topo):
+    rng = np.random.default_rng(n)
+    for sched, tol in (("lin", 1e-6), ("cerf_3", 1e-8), ("sqrt", 1e-6), ("static", 1e-7)):
+        T = float(rng.uniform(2.0, 12.0)) / (1.0 if topo == "circular" else n / 4.0)
+        g = float(rng.uniform(0.2, 2.4)) * (1.0 if topo == "circular" else n / 3.0)
+        prob = qw.Problem(n=n, topology=topo, schedule=sched)
+        p, nrm, psi, nfev = qw.rk45_batch(prob, [T, 0.0], [g, g], rtol=tol, atol=tol,
+                                          return_psi=True, return_nfev=True)
+        po, no, psio, nf = rk.rk45_scipy(n, topo, sched, T, g, rtol=tol, atol=tol)
+        assert abs(p[0] - po) <= 1e-9 and np.abs(psi[0] - psio).max() <= 1e-9, (n, topo, sched)
+        assert abs(int(nfev[0]) - nf) <= 6, (n, topo, sched, nfev[0], nf)
+        assert p[1] == pytest.approx(1.0 / n, abs=1e-15) and nfev[1] == 0

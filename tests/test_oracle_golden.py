@@ -162,3 +162,11 @@ def test_ti_exact_oracle_matches_reference_expm(golden):
     for c in meta["static"]:
         p, nrm, _ = rk.ti_exact(c["n"], c["time"], c["gamma"])
         assert abs(p - c["p_expm"]) <= 1e-13 and abs(nrm - 1) <= 1e-13, c
+
+
+def test_rk45_restatement_matches_the_shipped_reference(golden):
+    """SciPy RK45 over the stencil RHS vs the reference's own evaluate_probability output."""
+    meta, arr = golden
+    for c in meta["rk45"]:
+        p, _, _, _ = rk.rk45_scipy(c["n"], c["topology"], c["schedule"], c["T"], c["beta"])
+        assert abs(p - c["p"]) <= 1e-10, (c, p)
