@@ -2,8 +2,8 @@
 // N = 65 536 in BASELINE config 5), sm_100a.
 //
 // psi of every point in flight lives in HBM (two buffers, ping-pong).  One launch ("pass")
-// advances every point by KB RK4 steps.  Work unit = one window of W = 128 threads x SR
-// sites of one point: load it (cp.async, coalesced 16 B per lane, into a padded shared
+// advances every point by KB RK4 steps.  Work unit = one window of W = 1024 consecutive
+// sites of one point (64 threads x 16 sites, or 128 x 8): load it (cp.async, coalesced 16 B per lane, into a padded shared
 // buffer), run the register-resident stage code of qw_resident.cu on it with open ends,
 // write back the W - 2*HALO central sites (HALO = 4*KB: every stage invalidates one more
 // site at each open end, so all four stages of KB steps are fused per window).  Thread
@@ -23,16 +23,19 @@
 
 namespace {
 
-constexpr int SNT = 128;               // threads per block
-constexpr int SDEPTH = 3;              // ring of shared window buffers (prefetch depth 2)
-
-// Geometry for SR sites per thread: SR = 8 -> 1024-site windows, 3 blocks/SM;
-// SR = 16 -> 2048-site windows, 2 blocks/SM (half the halo and per-window overhead).
+// Geometry for SR sites per thread; windows are 1024 sites either way.
+//   SR = 16: 64 threads (2 warps) per block, 4 blocks/SM -- the geometry of the fastest
+//            resident kernel: a stage barrier involves two warps only;
+//   SR = 8:  128 threads, 3 blocks/SM.
 template <int SR>
 struct Geo {
-    static constexpr int W = SR * SNT;                 // window
+    static constexpr int NT = SR == 16 ? 64 : 128;     // threads per block
+    static constexpr int W = SR * NT;                  // window
     static constexpr int PAD = W + W / SR;             // one pad element per thread segment
-    static constexpr int BLOCKS_PER_SM = SR == 8 ? 3 : 2;
+    static constexpr int BLOCKS_PER_SM = SR == 16 ? 4 : 3;
+    // ring of shared window buffers: SR = 8 keeps two windows in flight behind the one being
+    // integrated (HBM-bound KB = 1 passes); SR = 16 one (4 blocks/SM must fit 228 KB)
+    static constexpr int DEPTH = SR == 16 ? 2 : 3;
     static __device__ __forceinline__ int pad(int e) { return e + e / SR; }
 };
 
@@ -59,9 +62,9 @@ struct PassEntry {
 
 template <int SR>
 struct StreamShared {
-    double2 xbuf[SDEPTH][Geo<SR>::PAD];   // window ring (load target, then store staging)
-    PassEntry tab[SDEPTH];                // the point's pass entry travels with its window
-    double2 mbox[4 * SNT];                // [parity][first/last][thread]
+    double2 xbuf[Geo<SR>::DEPTH][Geo<SR>::PAD];   // window ring (load target, store staging)
+    PassEntry tab[Geo<SR>::DEPTH];        // the point's pass entry travels with its window
+    double2 mbox[4 * Geo<SR>::NT];        // [parity][first/last][thread]
 };
 
 __global__ void stream_pass_tables(const QwParams prm, int64_t count, int64_t step0, int kbmax,
@@ -130,7 +133,7 @@ __device__ __forceinline__ void prefetch_window(StreamShared<SR> &sh, int slot, 
                                                 const PassEntry *tab, int64_t n, uint32_t idx,
                                                 uint32_t tiles, int t)
 {
-    constexpr int HALO = 4 * KB, TILE = Geo<SR>::W - 2 * HALO;
+    constexpr int HALO = 4 * KB, TILE = Geo<SR>::W - 2 * HALO, SNT = Geo<SR>::NT;
     const uint32_t local = idx / tiles, tile = idx - local * tiles;
     const double2 *src = in + (int64_t)local * n;
     double2 *xb = sh.xbuf[slot];
@@ -150,12 +153,14 @@ __device__ __forceinline__ void prefetch_window(StreamShared<SR> &sh, int slot, 
 }
 
 template <int KB, int SR>
-__global__ void __launch_bounds__(SNT, Geo<SR>::BLOCKS_PER_SM)
+__global__ void __launch_bounds__(Geo<SR>::NT, Geo<SR>::BLOCKS_PER_SM)
 rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__restrict__ out,
                  const PassEntry *__restrict__ tab, uint32_t tiles, uint32_t total)
 {
     constexpr int HALO = 4 * KB;
     constexpr int TILE = Geo<SR>::W - 2 * HALO;
+    constexpr int SNT = Geo<SR>::NT;
+    constexpr int SDEPTH = Geo<SR>::DEPTH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StreamShared<SR> &sh = *reinterpret_cast<StreamShared<SR> *>(smem_raw);
 
@@ -302,10 +307,11 @@ int stream_kb(const QwParams &prm)
     return 4;
 }
 
-// 16 sites per thread (2048-site windows) unless the ring is short or QW_FLAG_R8 is set
+// Temporal blocking (KB >= 2) is FP64-bound: 64 x 16 blocks.  KB = 1 is HBM-bound and wants
+// the deeper prefetch ring of the 128 x 8 geometry; so do QW_FLAG_R8 and short rings.
 int stream_sr(const QwParams &prm)
 {
-    return ((prm.flags & QW_FLAG_R8) || prm.n < 4096) ? 8 : 16;
+    return ((prm.flags & (QW_FLAG_R8 | QW_FLAG_STREAM_KB1)) || prm.n < 4096) ? 8 : 16;
 }
 
 int g_sm_count = 0;
@@ -346,7 +352,7 @@ cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, Pa
     if (total < grid) grid = (uint32_t)total;
     cudaError_t e = configure<KB, SR>();
     if (e != cudaSuccess) return e;
-    rk4_cycle_stream<KB, SR><<<grid, SNT, sizeof(StreamShared<SR>), st>>>(prm, in, out, tab, tiles,
+    rk4_cycle_stream<KB, SR><<<grid, Geo<SR>::NT, sizeof(StreamShared<SR>), st>>>(prm, in, out, tab, tiles,
                                                                           (uint32_t)total);
     return cudaGetLastError();
 }
@@ -359,10 +365,11 @@ cudaError_t plan_of(qw_plan *plan)
     cudaError_t e = configure<KB, SR>();
     if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB, SR>);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<KB, SR>, SNT,
-                                                          sizeof(StreamShared<SR>));
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<KB, SR>,
+                                                          Geo<SR>::NT, sizeof(StreamShared<SR>));
     if (e != cudaSuccess) return e;
     plan->sites_per_thread = SR;
+    plan->threads_per_block = Geo<SR>::NT;
     plan->blocks_per_sm = occ;
     plan->regs_per_thread = fa.numRegs;
     plan->smem_bytes = (int)(fa.sharedSizeBytes + sizeof(StreamShared<SR>));
@@ -386,7 +393,6 @@ bool qw_stream_supported(const QwParams &prm)
 cudaError_t qw_stream_plan(const QwParams &prm, qw_plan *plan)
 {
     plan->path = 3;
-    plan->threads_per_block = SNT;
     const int kb = stream_kb(prm), sr = stream_sr(prm);
     return QW_STREAM_DISPATCH(plan_of, plan);
 }
@@ -398,7 +404,7 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     const int64_t n = prm.n;
     // points in flight: bounded by ~8 GiB of ping-pong scratch and by 32-bit window indices
     int64_t chunk = (int64_t)(8ull << 30) / (2 * n * (int64_t)sizeof(double2));
-    const int64_t tiles_max = n / (8 * SNT - 32) + 2;
+    const int64_t tiles_max = n / (1024 - 32) + 2;
     if (chunk > (int64_t)0x7fffffff / tiles_max) chunk = (int64_t)0x7fffffff / tiles_max;
     if (chunk < 1) chunk = 1;
     if (chunk > prm.n_points) chunk = prm.n_points;
