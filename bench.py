@@ -141,7 +141,8 @@ def stream_measure(qw, torch, dev, reps=3):
             best = min(best, e0.elapsed_time(e1))
         launches = (qw.launch_count() - l0) // reps
         rate = nT * nB * n * S / (best * 1e-3)
-        halo = 1024.0 / (1024.0 - 8.0 * kb)
+        sr = 8 if kb == 1 else 16                   # sites per thread of the variant
+        halo = 1024.0 / (1024.0 - 2.0 * (-(-4 * kb // sr) * sr))   # window / written sites
         out["variants"].append({
             "steps_per_pass": kb, "ms": best, "site_updates_per_sec": rate,
             "launches_per_heatmap": launches,

@@ -41,6 +41,7 @@ struct QwParams {
     // streaming: two psi buffers per point of the chunk in flight)
     double2 *scratch;
     int64_t point_offset;         // streaming: first point of the chunk in flight
+    int64_t stream_rot;           // streaming: psi is stored rotated, logical l = (j - rot) mod n
 };
 
 struct QwPoint {

@@ -126,14 +126,39 @@ __device__ __forceinline__ void fix_slot(State<SR> &s, int slot, double2 D, doub
         }
 }
 
+template <int SR, int STAGE>
+__device__ __forceinline__ void fix_slot0(State<SR> &s, double2 D, double xr, double xi)
+{
+    if (STAGE < 3) {
+        s.ur[0] = fma(D.x, xi, s.ur[0]);
+        s.ui[0] = fma(-D.x, xr, s.ui[0]);
+        s.ar[0] = fma(D.y, xi, s.ar[0]);
+        s.ai[0] = fma(-D.y, xr, s.ai[0]);
+    } else {
+        s.yr[0] = fma(D.y, xi, s.yr[0]);
+        s.yi[0] = fma(-D.y, xr, s.yi[0]);
+    }
+}
+
 // issue the loads of window `idx` (point idx / tiles, tile idx % tiles) and of its point's
 // pass entry into ring slot `slot`; one cp.async group
-template <int KB, int SR>
+// HALO: sites invalidated at each open end by KB steps (4 per step).  In the ALIGNED variant
+// it is rounded up to a multiple of SR so that every window starts on a thread-segment
+// boundary of the (rotated) ring: the marked vertex, stored at logical site 0, is then always
+// slot 0 of some thread and the oracle term needs no slot search.
+template <int KB, int SR, bool ALIGNED>
+struct Win {
+    static constexpr int HALO = ALIGNED ? ((4 * KB + SR - 1) / SR) * SR : 4 * KB;
+    static constexpr int TILE = Geo<SR>::W - 2 * HALO;
+};
+
+template <int KB, int SR, bool ALIGNED>
 __device__ __forceinline__ void prefetch_window(StreamShared<SR> &sh, int slot, const double2 *in,
                                                 const PassEntry *tab, int64_t n, uint32_t idx,
                                                 uint32_t tiles, int t)
 {
-    constexpr int HALO = 4 * KB, TILE = Geo<SR>::W - 2 * HALO, SNT = Geo<SR>::NT;
+    constexpr int HALO = Win<KB, SR, ALIGNED>::HALO, TILE = Win<KB, SR, ALIGNED>::TILE,
+                  SNT = Geo<SR>::NT;
     const uint32_t local = idx / tiles, tile = idx - local * tiles;
     const double2 *src = in + (int64_t)local * n;
     double2 *xb = sh.xbuf[slot];
@@ -152,13 +177,13 @@ __device__ __forceinline__ void prefetch_window(StreamShared<SR> &sh, int slot, 
     cp_async_commit();
 }
 
-template <int KB, int SR>
+template <int KB, int SR, bool ALIGNED>
 __global__ void __launch_bounds__(Geo<SR>::NT, Geo<SR>::BLOCKS_PER_SM)
 rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__restrict__ out,
                  const PassEntry *__restrict__ tab, uint32_t tiles, uint32_t total)
 {
-    constexpr int HALO = 4 * KB;
-    constexpr int TILE = Geo<SR>::W - 2 * HALO;
+    constexpr int HALO = Win<KB, SR, ALIGNED>::HALO;
+    constexpr int TILE = Win<KB, SR, ALIGNED>::TILE;
     constexpr int SNT = Geo<SR>::NT;
     constexpr int SDEPTH = Geo<SR>::DEPTH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -178,7 +203,7 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
 #pragma unroll
     for (int k = 0; k < SDEPTH - 1; ++k) {
         const uint64_t w = (uint64_t)idx + (uint64_t)k * stride;
-        if (w < total) prefetch_window<KB, SR>(sh, k, in, tab, n, (uint32_t)w, tiles, t);
+        if (w < total) prefetch_window<KB, SR, ALIGNED>(sh, k, in, tab, n, (uint32_t)w, tiles, t);
         else cp_async_commit();
     }
 
@@ -201,16 +226,17 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
         {
             const uint64_t w = (uint64_t)idx + (uint64_t)(SDEPTH - 1) * stride;
             const int ps = (slot + SDEPTH - 1) % SDEPTH;
-            if (w < total) prefetch_window<KB, SR>(sh, ps, in, tab, n, (uint32_t)w, tiles, t);
+            if (w < total) prefetch_window<KB, SR, ALIGNED>(sh, ps, in, tab, n, (uint32_t)w, tiles, t);
             else cp_async_commit();
         }
 
         if (kb > 0) {
             // slot of the marked vertex in this thread's segment, or -1 (windows repeat mod n)
-            int64_t wrel = prm.target - first - (int64_t)t * SR;     // in (-W, n + HALO]
+            // (the marked vertex is logical site target - rot: 0 in the ALIGNED layout)
+            int64_t wrel = (prm.target - prm.stream_rot) - first - (int64_t)t * SR;
             if (wrel < 0) { wrel += n; if (wrel < 0) wrel = wrel % n + n; }
             if (wrel >= n) wrel -= n;
-            const int own_slot = wrel < SR ? (int)wrel : -1;
+            const int own_slot = wrel < SR ? (int)wrel : -1;     // ALIGNED: 0 or -1
             const bool warp_owns = __ballot_sync(0xffffffffu, own_slot >= 0) != 0u;
             int par = 0;
             fst[t] = make_double2(s.yr[0], s.yi[0]);
@@ -224,9 +250,16 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
                     const double2 hr = fst[par * SNT + tr];                             \
                     const double2 ab = pe.ab[4 * sidx + K];                             \
                     double xr = 0.0, xi = 0.0;                                          \
-                    if (warp_owns) read_slot<SR, K>(s, own_slot, xr, xi);               \
+                    if (ALIGNED) {                                                      \
+                        xr = (K == 0) ? s.yr[0] : s.ur[0];                              \
+                        xi = (K == 0) ? s.yi[0] : s.ui[0];                              \
+                    } else if (warp_owns) read_slot<SR, K>(s, own_slot, xr, xi);        \
                     rk_stage<SR, K, true>(s, ab.x, ab.y, hl, hr, zero2, 0.0, false, zero2); \
-                    if (warp_owns) fix_slot<SR, K>(s, own_slot, pe.d[4 * sidx + K], xr, xi); \
+                    if (warp_owns) {                                                    \
+                        if (ALIGNED) {                                                  \
+                            if (own_slot == 0) fix_slot0<SR, K>(s, pe.d[4 * sidx + K], xr, xi); \
+                        } else fix_slot<SR, K>(s, own_slot, pe.d[4 * sidx + K], xr, xi); \
+                    }                                                                   \
                     par ^= 1;                                                           \
                     if (K < 3) {                                                        \
                         fst[par * SNT + t] = make_double2(s.ur[0], s.ui[0]);            \
@@ -290,11 +323,15 @@ __global__ void __launch_bounds__(512) stream_finish(const QwParams prm, const d
     for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
         const double2 v = src[j];
         nrm = fma(v.x, v.x, fma(v.y, v.y, nrm));
-        if (prm.psi) prm.psi[(size_t)pt.q * (size_t)n + j] = v;
+        if (prm.psi) {                          // undo the rotation: physical (l + rot) mod n
+            int64_t jp = j + prm.stream_rot;
+            if (jp >= n) jp -= n;
+            prm.psi[(size_t)pt.q * (size_t)n + jp] = v;
+        }
     }
     const double2 tot = qw_block_sum2(nrm, 0.0, red);
     if (threadIdx.x == 0) {
-        const double2 v = src[prm.target];
+        const double2 v = src[prm.target - prm.stream_rot];
         prm.p[pt.q] = fma(v.x, v.x, v.y * v.y) / tot.x;
         if (prm.norm) prm.norm[pt.q] = tot.x;
     }
@@ -327,34 +364,42 @@ int sm_count()
     return g_sm_count;
 }
 
-template <int KB, int SR>
+template <int KB, int SR, bool ALIGNED>
 cudaError_t configure()
 {
     static bool configured = false;
     if (configured) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(rk4_cycle_stream<KB, SR>,
+    cudaError_t e = cudaFuncSetAttribute(rk4_cycle_stream<KB, SR, ALIGNED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(StreamShared<SR>));
     if (e == cudaSuccess) configured = true;
     return e;
 }
 
-template <int KB, int SR>
-cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, PassEntry *tab,
-                        int64_t step0, int64_t points, cudaStream_t st)
+template <int KB, int SR, bool ALIGNED>
+cudaError_t launch_pass_a(const QwParams &prm, const double2 *in, double2 *out, PassEntry *tab,
+                          int64_t step0, int64_t points, cudaStream_t st)
 {
-    constexpr int TILE = Geo<SR>::W - 8 * KB;
+    constexpr int TILE = Win<KB, SR, ALIGNED>::TILE;
     stream_pass_tables<<<(unsigned)((points + 127) / 128), 128, 0, st>>>(prm, points, step0, KB,
                                                                          tab);
     const uint32_t tiles = (uint32_t)((prm.n + TILE - 1) / TILE);
     const uint64_t total = (uint64_t)points * tiles;
     uint32_t grid = (uint32_t)(sm_count() * Geo<SR>::BLOCKS_PER_SM);       // persistent blocks
     if (total < grid) grid = (uint32_t)total;
-    cudaError_t e = configure<KB, SR>();
+    cudaError_t e = configure<KB, SR, ALIGNED>();
     if (e != cudaSuccess) return e;
-    rk4_cycle_stream<KB, SR><<<grid, Geo<SR>::NT, sizeof(StreamShared<SR>), st>>>(prm, in, out, tab, tiles,
-                                                                          (uint32_t)total);
+    rk4_cycle_stream<KB, SR, ALIGNED><<<grid, Geo<SR>::NT, sizeof(StreamShared<SR>), st>>>(
+        prm, in, out, tab, tiles, (uint32_t)total);
     return cudaGetLastError();
+}
+
+template <int KB, int SR>
+cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, PassEntry *tab,
+                        int64_t step0, int64_t points, cudaStream_t st)
+{
+    return prm.n % SR == 0 ? launch_pass_a<KB, SR, true>(prm, in, out, tab, step0, points, st)
+                           : launch_pass_a<KB, SR, false>(prm, in, out, tab, step0, points, st);
 }
 
 template <int KB, int SR>
@@ -362,10 +407,10 @@ cudaError_t plan_of(qw_plan *plan)
 {
     cudaFuncAttributes fa;
     int occ = 0;
-    cudaError_t e = configure<KB, SR>();
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB, SR>);
+    cudaError_t e = configure<KB, SR, true>();
+    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB, SR, true>);
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<KB, SR>,
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<KB, SR, true>,
                                                           Geo<SR>::NT, sizeof(StreamShared<SR>));
     if (e != cudaSuccess) return e;
     plan->sites_per_thread = SR;
@@ -402,6 +447,7 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     QwParams prm = prm_in;
     const int kb = stream_kb(prm), sr = stream_sr(prm);
     const int64_t n = prm.n;
+    prm.stream_rot = (n % sr == 0) ? prm.target : 0;     // aligned layout: marked vertex first
     // points in flight: bounded by ~8 GiB of ping-pong scratch and by 32-bit window indices
     int64_t chunk = (int64_t)(8ull << 30) / (2 * n * (int64_t)sizeof(double2));
     const int64_t tiles_max = n / (1024 - 32) + 2;
