@@ -3,7 +3,9 @@
 (SURVEY.md section 8d): wall time (CUDA events), site-updates/s, grid-points/s, the physics
 read-outs (best cell, tau, I, robustness) and a parity spot-check against the C oracle.
 
-    python tools/run_configs.py [--skip-long] > profiles/rNN_configs.md
+    python tests/run_configs.py [--skip-long] > profiles/rNN_configs.md
+
+Lives under tests/ because it uses the oracle as the checker.
 """
 import argparse
 import os
