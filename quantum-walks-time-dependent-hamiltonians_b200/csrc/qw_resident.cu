@@ -357,6 +357,155 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_resident_v2(const Qw
     epilogue<R>(s, prm, pt, tb.red, t);
 }
 
+// Barrier-free variant of the complete-graph kernel (QW_FLAG_COMPLETE_FREE; A/B record): no
+// block barrier inside a 32-step chunk.  Measured on C3 (N = 4096): 4.22e11 site-updates/s
+// at R = 16, the same as the one-barrier-per-stage kernel above (4.23e11), so that one stays
+// the default -- with 8 warps per SM the limit is FP64 dependency latency, not the barrier.
+//
+// The only value a stage needs from outside its thread is sum(x) of the stage input, and
+// that follows exactly from the marked vertex alone (column sums of L vanish):
+//     sum(y + c k) = sum(y) - i c d x_w,     sum(y_{n+1}) = sum(y_n) - i sum_m b_m d_m x_{m,w}.
+// Thread 0 owns the marked vertex, so warp 0 is the producer of all 128 stage sums of a chunk
+// and writes each into its own slot of a shared table one stage before it is needed, followed
+// by a release of the `published` counter; the other warps acquire the counter (a bounded
+// spin on shared memory that is almost always satisfied at the first read) instead of meeting
+// at a __syncthreads().  Warps of a block are thereby decoupled: nobody waits for the slowest
+// warp four times per step, only for warp 0 if it falls behind.
+// sum(y) is carried in double-double by thread 0 (no rounding drift from the running
+// accumulation) and re-anchored to a direct block reduction of the state at every chunk
+// start, where the coefficient-table refill synchronises the block anyway.
+struct FreeShared {
+    double2 sums[4 * QW_CHUNK + 1];     // sums[g]: sum of the input of stage g of the chunk
+    double2 hi, lo, inc;                // thread 0: double-double sum(y), per-step increment
+    int published;                      // sums[0 .. published-1] are valid
+    int failed;
+};
+
+__device__ __forceinline__ int ld_acquire_shared(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_shared(int *p, int v)
+{
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// blocking: spin (bounded) until sums[g] has been published
+__device__ __forceinline__ double2 acquire_sum(FreeShared &fs, int g)
+{
+    int spins = 0;
+    while (ld_acquire_shared(&fs.published) <= g) {           // bounded: safety net only
+        if (*((volatile int *)&fs.failed)) break;
+        if (++spins > (1 << 22)) { fs.failed = 1; break; }
+    }
+    return fs.sums[g];
+}
+
+// non-blocking: sums[g] if it is already there (ok = true); issued one stage ahead so that
+// the shared-memory latency hides behind the current stage's arithmetic
+__device__ __forceinline__ double2 try_sum(FreeShared &fs, int g, bool &ok)
+{
+    ok = ld_acquire_shared(&fs.published) > g;
+    return fs.sums[g];
+}
+
+template <int R, int MAXNT, int MINB>
+__global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_resident_v3(const QwParams prm)
+{
+    __shared__ Tables tb;
+    __shared__ FreeShared fs;
+    const int t = threadIdx.x, nact = prm.nact;
+    const int warp = t >> 5;
+    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const bool active = t < nact;
+    const double nd = active ? (double)prm.n : 0.0;   // idle threads stay at zero
+    const double2 zero2 = make_double2(0.0, 0.0);
+
+    State<R> s;
+    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+    }
+    if (t == 0) fs.failed = 0;
+    int rbuf = 0;
+
+    for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
+        __syncthreads();                               // every warp has left the last chunk
+        const double2 sy = block_sum_all(local_sum_y<R>(s), tb.red, rbuf);    // re-anchor
+        rbuf ^= 1;
+        if (t == 0) {
+            fs.hi = sy; fs.lo = zero2;
+            fs.sums[0] = sy;
+            fs.published = 1;
+        }
+        qw_fill_table(tb.ab, tb.d, tb.ad, pt, n0, prm.schedule, prm.gamma_on);
+        const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
+        bool pf_ok = false;                            // prefetched sum of the coming stage
+        double2 pf = zero2;
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+#define QW_COMPLETE3_STAGE(K)                                                           \
+            {                                                                           \
+                const int g = 4 * sidx + K;                                             \
+                double2 sx = pf_ok ? pf : acquire_sum(fs, g);                           \
+                if (!active) sx = zero2;                                                \
+                const double2 ab = tb.ab[g];                                            \
+                if (warp == 0) {                                                        \
+                    const double2 dd = (t == 0) ? tb.d[g] : zero2;                      \
+                    if (t == 0) {                                                       \
+                        const double xr = (K == 0) ? s.yr[0] : s.ur[0];                 \
+                        const double xi = (K == 0) ? s.yi[0] : s.ui[0];                 \
+                        double2 inc = (K == 0) ? zero2 : fs.inc;                        \
+                        inc.x = fma(dd.y, xi, inc.x);                                   \
+                        inc.y = fma(-dd.y, xr, inc.y);                                  \
+                        double2 hi = fs.hi;                                             \
+                        double2 nxt;                                                    \
+                        if (K < 3) {                                                    \
+                            fs.inc = inc;                                               \
+                            nxt = make_double2(fma(dd.x, xi, hi.x), fma(-dd.x, xr, hi.y)); \
+                        } else {          /* sum(y_{n+1}) = (hi + lo) + inc, TwoSum */   \
+                            double2 lo = fs.lo;                                         \
+                            const double sxr = hi.x + inc.x, bxr = sxr - hi.x;          \
+                            lo.x += (hi.x - (sxr - bxr)) + (inc.x - bxr);               \
+                            const double sxi = hi.y + inc.y, bxi = sxi - hi.y;          \
+                            lo.y += (hi.y - (sxi - bxi)) + (inc.y - bxi);               \
+                            hi = make_double2(sxr + lo.x, sxi + lo.y);                  \
+                            lo = make_double2(lo.x - (hi.x - sxr), lo.y - (hi.y - sxi)); \
+                            fs.hi = hi; fs.lo = lo;                                     \
+                            nxt = hi;                                                   \
+                        }                                                               \
+                        fs.sums[g + 1] = nxt;                                           \
+                        st_release_shared(&fs.published, g + 2);                        \
+                    }                                                                   \
+                    __syncwarp();                                                       \
+                    pf = try_sum(fs, g + 1, pf_ok);                                     \
+                    rk_stage<R, K, false>(s, ab.x, ab.y, zero2, zero2, sx, nd, t == 0, dd); \
+                } else {                                                                \
+                    pf = try_sum(fs, g + 1, pf_ok);                                     \
+                    rk_stage<R, K, false>(s, ab.x, ab.y, zero2, zero2, sx, nd, false, zero2); \
+                }                                                                       \
+            }
+            QW_COMPLETE3_STAGE(0)
+            QW_COMPLETE3_STAGE(1)
+            QW_COMPLETE3_STAGE(2)
+            QW_COMPLETE3_STAGE(3)
+#undef QW_COMPLETE3_STAGE
+        }
+    }
+    __syncthreads();
+    if (fs.failed) {                                    // spin limit hit: poison the result
+#pragma unroll
+        for (int r = 0; r < R; ++r) s.yr[r] = NAN;
+    }
+    epilogue<R>(s, prm, pt, tb.red, t);
+}
+
 template <typename K>
 cudaError_t launch(K kernel, const QwParams &prm, int threads, size_t smem, cudaStream_t st,
                    qw_plan *plan)
@@ -407,6 +556,11 @@ cudaError_t dispatch_threads(const QwParams &prm, int threads, cudaStream_t st, 
         return launch(rk4_cycle_resident_v2<R, MAXNT, MINB, false>, prm, threads, smem, st, plan); \
     if (exact)                                                                             \
         return launch(rk4_complete_resident<R, MAXNT, MINB, true>, prm, threads, smem, st, plan); \
+    if constexpr (R == 8) {                                                                \
+        if (prm.flags & QW_FLAG_COMPLETE_FREE)                                             \
+            return launch(rk4_complete_resident_v3<R, MAXNT, MINB>, prm, threads, smem, st, \
+                          plan);                                                           \
+    }                                                                                      \
     return launch(rk4_complete_resident_v2<R, MAXNT, MINB>, prm, threads, smem, st, plan);
     // <= 128 threads: 3 blocks/SM (168 registers, no spills) measured faster than 4 (128)
     if (threads <= 128 && (prm.flags & QW_FLAG_OCC4)) { QW_LAUNCH(128, 4) }
@@ -435,6 +589,8 @@ cudaError_t dispatch_r16(const QwParams &prm, int threads, cudaStream_t st, qw_p
         if (threads <= 256)
             return launch(rk4_cycle_resident_v2<16, 256, 1, false>, prm, threads, smem, st, plan);
     } else if (threads <= 256) {
+        if (prm.flags & QW_FLAG_COMPLETE_FREE)
+            return launch(rk4_complete_resident_v3<16, 256, 1>, prm, threads, smem, st, plan);
         return launch(rk4_complete_resident_v2<16, 256, 1>, prm, threads, smem, st, plan);
     }
     return cudaErrorInvalidConfiguration;

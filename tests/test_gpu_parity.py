@@ -87,12 +87,14 @@ def test_random_batches_vs_oracle(qw, topo, n):
                                      (1024, 256 | 64), (1024, 256 | 128), (2048, 0), (3072, 0),
                                      (4096, 256 | 32), (512, 0), (528, 0), (16, 512), (64, 512),
                                      (256, 512), (96, 512), (8, 0), (24, 0), (40, 0), (56, 0),
-                                     (112, 0), (192, 0), (224, 0)])
+                                     (112, 0), (192, 0), (224, 0), (4096, 1024), (4096, 256 | 1024),
+                                     (96, 1024), (2048, 1024)])
 def test_generic_and_exact_sum_paths(qw, n, flags):
     """flags: 1 = force the global-memory kernel, 4 = block-reduce sum(u) in every stage,
     256 = at most 8 sites per thread, 32 / 64 / 128 = first-generation / mbarrier / 4-blocks
     variants of the resident kernels, 512 = no warp packing for small rings; n = 2050 / 1031
-    do not fit the resident kernels; 8 ... 224 exercise every R of the packed kernel."""
+    do not fit the resident kernels; 8 ... 224 exercise every R of the packed kernel; 1024 =
+    barrier-free variant of the complete-graph kernel."""
     rng = np.random.default_rng(n)
     for topo in ("circular", "complete"):
         if (flags & 4) and topo == "circular":
