@@ -150,6 +150,14 @@ def stream_measure(qw, torch, dev, reps=3):
             "frac_of_hbm_peak_algorithmic": 32.0 * rate / 1e9 / peak,
             "actual_gbs_incl_halo_rereads": 32.0 / kb * halo * rate / 1e9,
             "frac_of_hbm_peak_actual": 32.0 / kb * halo * rate / 1e9 / peak})
+    kb1 = out["variants"][0]
+    out["roofline"] = {            # the plain read-psi_n / write-psi_n+1 stream (KB = 1)
+        "bound": "hbm", "achieved": kb1["algorithmic_gbs_at_32B_per_site_update"],
+        "peak": peak, "unit": "GB/s", "frac": kb1["frac_of_hbm_peak_algorithmic"],
+        "traffic": 2103516000,
+        "traffic_note": "dram__bytes_read+write of one pass over 1024 points (ncu --set full, "
+                        "profiles/r1_stream_kb1_ncu_full.md); algorithmic bytes per pass = "
+                        "1024 x 65536 x 32 = 2147483648"}
     return out
 
 
@@ -319,10 +327,11 @@ def run_b200(args):
                        "kernel": plan, "results_sane_and_e2e_equals_device": ok},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": 80128,
-                         "traffic_note": "dram__bytes_read+write of an 8192-point launch "
-                                         "(ncu --set full, profiles/): the kernel is "
-                                         "register-resident, DRAM sees only T, gamma, p, norm",
+                         "traffic": 46080,
+                         "traffic_note": "dram__bytes_read+write of an 8192-point launch (ncu "
+                                         "--set full, profiles/r1_cycle_resident_r16_ncu_full"
+                                         ".md): the kernel is register-resident, DRAM sees "
+                                         "only T, gamma, p, norm",
                          "peak_source": "qw_fp64_peak_probe: dependent-free DFMA stream "
                                         "measured in this process, best of 8/16/24 warps per "
                                         "SM (MEASURED_PEAKS.json has no FP64 entry)",
