@@ -245,3 +245,18 @@ def test_integrator_rk45_reproduces_reference_printouts(golden):
     p = ss.grid_probability_evaluation(5, 1, 20, 4, 0.1, 5, 3, 0.92, 7)
     assert np.abs(p - arr[hm["key"]]).max() <= 1e-9
     ss.integrator = "rk4"
+
+
+def test_runge_kutta_error_main_block():
+    """The __main__ of Runge_Kutta_Error.py (RKE:463-532): norm defect 1 - <psi|psi> of RK45
+    at N = 51, beta = 0.5, T = 300, for atol in {1e-6, 1e-7, 1e-8} (rtol = 1e-6)."""
+    from oracle import rk4_numpy as rk
+    rke = _mod("Runge_Kutta_Error")
+    rke.dimension, rke.step_function, rke.integrator = 51, 1, "rk45"
+    for atol in (1e-6, 1e-7, 1e-8):
+        rke.rtolerance, rke.atolerance = 1e-6, atol
+        defect = rke.norm_defect(300.0, 0.5)
+        _, norm, _, _ = rk.rk45_scipy(51, "circular", "lin", 300.0, 0.5, rtol=1e-6, atol=atol)
+        assert abs(defect - (1 - norm)) <= 1e-9, (atol, defect, 1 - norm)
+        assert abs(defect) < 1e-3                    # "error in the order of <10^-4" (SS:112)
+    rke.integrator, rke.rtolerance, rke.atolerance = "rk4", 1e-6, 1e-6
