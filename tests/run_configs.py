@@ -100,6 +100,52 @@ def main():
         heatmap_row("C2 cycle N=64 100x100 %s S=1024" % sched,
                     dict(n=64, topology="circular", schedule=sched, n_steps=1024), t, b, reps=3)
 
+    # C2, time-independent side with the exact propagator (the reference's expm comparator)
+    prob = qw.Problem(n=64, topology="circular", schedule="static")
+    dt, db = torch.from_numpy(t).to(DEV), torch.from_numpy(b).to(DEV)
+    ms, (p, nrm) = timed(lambda: qw.ti_exact_heatmap(prob, dt, db), 3)
+    summ = qw.heatmap_summary(p, dt, t_min=(np.pi / 2) * 8.0)
+    from oracle import rk4_numpy as rk
+    jj, ii = [5, 50, 99], [7, 60, 99]
+    err = max(abs(float(p[j, i]) - rk.ti_exact(64, t[i], b[j])[0]) for j, i in zip(jj, ii))
+    print("| C2 cycle N=64 100x100 time-independent, exact Chebyshev propagator | cheb_cycle R=8 x "
+          "32 thr | 10000 | %.2f | n/a | %.3e | p_max=%.6f at (gamma=%.4g, T=%.4g), I=%.2f, "
+          "tau_min=%.4g, norm defect max %.1e | %.1e (vs dense diagonalisation) |"
+          % (ms, 1e4 / (ms * 1e-3), summ["p_max"], b[summ["argmax"][0]], t[summ["argmax"][1]],
+             summ["iterations"], summ["tau_min"], float((nrm - 1).abs().max()), err), flush=True)
+
+    # the thesis' production sweep, BCB_latest.py:309-320: 4 schedules x odd N in [3, 71] x
+    # (75 beta x 4 T), then Robustness.py over the files it wrote
+    import importlib
+    import tempfile
+    bl = importlib.import_module(qw.__name__ + ".BCB_latest")
+    rob = importlib.import_module(qw.__name__ + ".Robustness")
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            for label, kw in (("RK4 step_size=1e-3 (QW_Search.py:153)", dict(integrator="rk4")),
+                              ("RK45 rtol=atol=1e-6 (as shipped)", dict(integrator="rk45"))):
+                bl.integrator, bl.n_steps, bl.step_size = kw["integrator"], None, 1e-3
+                bl.type_of_qw = "dependent"
+                import contextlib
+                import io
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    bl.production_sweep()
+                    torch.cuda.synchronize()
+                    for dim in range(7, 72, 2):
+                        rob.routine(dim, 1)
+                wall = time.perf_counter() - t0
+                nfiles = len([f for f in os.listdir(tmp) if f.endswith(".npy")])
+                print("| thesis production sweep (BCB_latest.py:309-320 + Robustness.py:56-66), %s | "
+                      "drop-in modules, 140 heatmaps of 75x4 | 42000 | %.0f | n/a | %.3e | %d .npy "
+                      "files written and read back by Robustness.routine | see tests |"
+                      % (label, wall * 1e3, 42000 / wall, nfiles), flush=True)
+        finally:
+            os.chdir(cwd)
+            bl.integrator, bl.step_size = "rk4", 1e-3
+
     # C3: complete N=4096, 256x256, gamma on the Laplacian
     n = 4096
     t, b = np.linspace(0.1, 512, 256), np.linspace(0.5 / n, 2.5 / n, 256)
