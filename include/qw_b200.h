@@ -88,9 +88,16 @@ enum {
     QW_FLAG_R8 = 256,            /* resident kernels: at most 8 sites per thread (default: 16
                                     where n % 16 == 0 and n/16 >= 32; A/B only) */
     QW_FLAG_NO_PACK = 512,       /* do not use the warp-packed kernel for small rings (A/B) */
-    QW_FLAG_COMPLETE_FREE = 1024 /* complete graph: barrier-free variant (stage sums through an
+    QW_FLAG_COMPLETE_FREE = 1024,/* complete graph: barrier-free variant (stage sums through an
                                     acquire/release table) instead of one barrier per stage;
                                     measured equal, A/B only */
+    QW_FLAG_NO_HORNER = 2048,    /* resident kernels: classic stage form (stage input +
+                                    accumulator, 30 FP64 instructions per site-update) instead
+                                    of the nested form with tabulated oracle corrections (24);
+                                    A/B and cross-checks */
+    QW_FLAG_NO_ROTATE = 4096     /* nested-form kernels: keep the marked vertex in warp 0 of
+                                    every block instead of alternating the owner warp with the
+                                    physical warp slot (A/B) */
 };
 
 /* ---- the hot path -------------------------------------------------------------------- */
@@ -194,7 +201,7 @@ int qw_heatmap_summary_dev(const double *p, const double *time_array, int64_t n_
 
 typedef struct qw_plan {
     int32_t path;            /* 0 resident-cycle, 1 resident-complete, 2 generic, 3 stream,
-                                4 warp-packed cycle */
+                                4 warp-packed cycle, 5 resident-cycle in nested form */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */

@@ -28,6 +28,8 @@ bool qw_packed_supported(const QwParams &prm);
 cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan);
 bool qw_rk45_supported(const QwParams &prm);
 cudaError_t qw_launch_rk45(QwParams prm, double rtol, double atol, int64_t *nfev, cudaStream_t st);
+int qw_horner_sites_per_thread(const QwParams &prm);
+cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan);
 bool qw_cheb_supported(const QwParams &prm);
 cudaError_t qw_launch_cheb(QwParams prm, cudaStream_t st);
 
@@ -80,7 +82,7 @@ int validate(const qw_problem *prob, QwParams *prm)
     return 0;
 }
 
-enum { PATH_RESIDENT = 0, PATH_GENERIC = 2, PATH_STREAM = 3, PATH_PACKED = 4 };
+enum { PATH_RESIDENT = 0, PATH_GENERIC = 2, PATH_STREAM = 3, PATH_PACKED = 4, PATH_HORNER = 5 };
 
 int choose_path(const QwParams &prm)
 {
@@ -88,6 +90,9 @@ int choose_path(const QwParams &prm)
     if ((prm.flags & QW_FLAG_FORCE_STREAM) && qw_stream_supported(prm)) return PATH_STREAM;
     if (!(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_NO_PACK)) && qw_packed_supported(prm))
         return PATH_PACKED;
+    if (!(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_CYCLE_SPLIT | QW_FLAG_NO_HORNER)) &&
+        qw_horner_sites_per_thread(prm) > 0)
+        return PATH_HORNER;
     if (qw_resident_sites_per_thread(prm.n) > 0) return PATH_RESIDENT;
     if (qw_stream_supported(prm)) return PATH_STREAM;
     return PATH_GENERIC;
@@ -120,6 +125,11 @@ int run(QwParams &prm, cudaStream_t st)
     case PATH_RESIDENT:
         e = qw_launch_resident(prm, st, nullptr);
         if (e != cudaSuccess) return cuda_fail(e, "resident kernel launch");
+        g_launches += 1;
+        return 0;
+    case PATH_HORNER:
+        e = qw_launch_horner(prm, st, nullptr);
+        if (e != cudaSuccess) return cuda_fail(e, "nested-form kernel launch");
         g_launches += 1;
         return 0;
     case PATH_PACKED:
@@ -445,6 +455,7 @@ int qw_plan_query(const qw_problem *prob, qw_plan *plan)
     switch (choose_path(prm)) {
     case PATH_RESIDENT: e = qw_launch_resident(prm, nullptr, plan); break;
     case PATH_PACKED: e = qw_launch_packed(prm, nullptr, plan); break;
+    case PATH_HORNER: e = qw_launch_horner(prm, nullptr, plan); break;
     case PATH_STREAM: e = qw_stream_plan(prm, plan); break;
     default: {
         int blocks; size_t bytes;

@@ -1,0 +1,413 @@
+// Register-resident RK4 in nested (Horner) form, one (T, gamma) point per thread block.
+//
+// Same integrator as qw_resident.cu -- fixed-step RK4 of QW_Search.py:149-164 over the
+// implicit H(t) = a(t) L + d(t)|w><w| of BCB.py:28-99 -- evaluated with fewer FP64
+// instructions.  With M = -iL and Q = -i|w><w| a step is
+//     y+ = y + sum_s b_s F_s u_s,  u_1 = y,  u_{s+1} = y + c_s F_s u_s,  F_s = a_s M + d_s Q.
+// Without Q every F_s is a multiple of M and the step operator is the polynomial
+// I + b1 M + b2 M^2 + b3 M^3 + b4 M^4, evaluated as four nested axpy's
+//     z4 = y + r4 M y,  z3 = y + r3 M z4,  z2 = y + r2 M z3,  y+ = y + r1 M z2
+// (r1 = b1, r2 = b2/b1, r3 = b3/b2, r4 = b4/b3): per site and level one DADD and two DFMA per
+// real component, 24 FP64 instructions per site-update instead of 30, and no accumulator
+// vector (two complex vectors in registers instead of three).
+// The oracle term does not commute with L, but every word of the step operator that
+// contains a Q ends in a multiple of M^k |w>, k = 0..3.  Adding a complex scalar sigma_l to
+// the marked vertex of z4, z3, z2 and y+ (the outer M's spread it over w-3..w+3) therefore
+// restores the RK4 step exactly.  The four scalars are linear in
+// (y_w, (Ly)_w, (L^2 y)_w, (L^3 y)_w) with coefficients that depend on the step's operator
+// scalars only; they are tabulated per step next to r1..r4 by the block's own threads
+// (one thread per step of a 32-step chunk).  tests/horner_model.py is the numpy statement of
+// this algebra, checked against the oracle on the CPU.
+//
+// Layout: the ring is relabelled so that the marked vertex is slot HW0 = 3 of thread 0, i.e.
+// thread 0 holds w-3..w+R-4 and all the oracle work is local to it.  Halo values cross
+// threads through a double-buffered shared-memory mailbox, one __syncthreads() per level;
+// edge slots are updated and published first.
+#include "qw_common.cuh"
+
+namespace {
+
+constexpr int HW0 = 3;               // slot of the marked vertex in thread 0
+
+struct HornerStep {                  // 24 doubles per RK4 step
+    double rho[4];                   // r1 (outermost) .. r4 (innermost)
+    double2 c[10];                   // sigma_4: c[0]; sigma_3: c[1..2]; sigma_2: c[3..5];
+                                     // sigma_1: c[6..9]  (basis y_w, Ly_w, L^2y_w, L^3y_w)
+};
+
+struct HornerShared {
+    HornerStep st[QW_CHUNK];
+    double red[2 * 32];
+    int owner;
+};
+
+__device__ __forceinline__ double2 mul_mi(const double s, const double2 v)   // (-i s) v
+{
+    return make_double2(s * v.y, -s * v.x);
+}
+
+__device__ __forceinline__ double2 axpy2(const double s, const double2 v, const double2 acc)
+{
+    return make_double2(fma(s, v.x, acc.x), fma(s, v.y, acc.y));
+}
+
+__device__ __forceinline__ double safe_inv(const double x) { return x != 0.0 ? 1.0 / x : 0.0; }
+
+// Coefficients of one step.  ad1, ad2, ad4 = (a, d) at t_n, t_n + h/2, t_n + h;
+// lww = L_ww, l2ww = (L^2)_ww.
+__device__ void horner_coefficients(HornerStep &o, const double h, const double2 ad1,
+                                    const double2 ad2, const double2 ad4, const double lww,
+                                    const double l2ww)
+{
+    const double A1 = 0.5 * h * ad1.x, A2 = 0.5 * h * ad2.x, A3 = h * ad2.x;
+    const double B1 = h / 6.0 * ad1.x, B2 = h / 3.0 * ad2.x, B4 = h / 6.0 * ad4.x;
+    const double DA1 = 0.5 * h * ad1.y, DA2 = 0.5 * h * ad2.y, DA3 = h * ad2.y;
+    const double DB1 = h / 6.0 * ad1.y, DB2 = h / 3.0 * ad2.y, DB4 = h / 6.0 * ad4.y;
+    const double b1 = B1 + 2.0 * B2 + B4;
+    const double b2 = B2 * A1 + B2 * A2 + B4 * A3;
+    const double b3 = B2 * A2 * A1 + B4 * A3 * A2;
+    const double b4 = B4 * A3 * A2 * A1;
+    const double i1 = safe_inv(b1), i2 = safe_inv(b2), i3 = safe_inv(b3);
+    o.rho[0] = b1; o.rho[1] = b2 * i1; o.rho[2] = b3 * i2; o.rho[3] = b4 * i3;
+
+    const double2 zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
+    // q_s = true stage value at the marked vertex, al_s = -i c_s d_s q_s, as coefficient
+    // vectors over (y_w, Ly_w, L^2y_w, L^3y_w)
+    double2 q2[4], q3[4], q4[4], al1[4], al2[4], al3[4];
+    al1[0] = make_double2(0.0, -DA1); al1[1] = zero; al1[2] = zero; al1[3] = zero;
+    q2[0] = make_double2(1.0, -DA1); q2[1] = make_double2(0.0, -A1); q2[2] = zero; q2[3] = zero;
+    const double2 u3[4] = {one, make_double2(0.0, -A2), make_double2(-A2 * A1, 0.0), zero};
+    const double2 u4[4] = {one, make_double2(0.0, -A3), make_double2(-A3 * A2, 0.0),
+                           make_double2(0.0, A3 * A2 * A1)};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        al2[j] = mul_mi(DA2, q2[j]);
+        const double2 t3 = mul_mi(A2 * lww, al1[j]);
+        q3[j] = make_double2(u3[j].x + t3.x + al2[j].x, u3[j].y + t3.y + al2[j].y);
+        al3[j] = mul_mi(DA3, q3[j]);
+        const double2 t4 = mul_mi(A3 * lww, al2[j]);
+        q4[j] = make_double2(u4[j].x - A3 * A2 * l2ww * al1[j].x + t4.x + al3[j].x,
+                             u4[j].y - A3 * A2 * l2ww * al1[j].y + t4.y + al3[j].y);
+    }
+    double2 k0[4], k1[4], k2[4], k3[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        double2 s = (j == 0) ? make_double2(DB1, 0.0) : zero;          // DB1 q1
+        s = axpy2(DB2, q2[j], s);
+        s = axpy2(DB2, q3[j], s);
+        s = axpy2(DB4, q4[j], s);
+        k0[j] = make_double2(s.y, -s.x);                               // -i s
+        k1[j] = axpy2(B4, al3[j], axpy2(B2, al2[j], make_double2(B2 * al1[j].x, B2 * al1[j].y)));
+        k2[j] = axpy2(B4 * A3, al2[j], make_double2(B2 * A2 * al1[j].x, B2 * A2 * al1[j].y));
+        k3[j] = make_double2(B4 * A3 * A2 * al1[j].x, B4 * A3 * A2 * al1[j].y);
+    }
+    o.c[0] = make_double2(k3[0].x * i3, k3[0].y * i3);
+    o.c[1] = make_double2(k2[0].x * i2, k2[0].y * i2);
+    o.c[2] = make_double2(k2[1].x * i2, k2[1].y * i2);
+    o.c[3] = make_double2(k1[0].x * i1, k1[0].y * i1);
+    o.c[4] = make_double2(k1[1].x * i1, k1[1].y * i1);
+    o.c[5] = make_double2(k1[2].x * i1, k1[2].y * i1);
+    o.c[6] = k0[0]; o.c[7] = k0[1]; o.c[8] = k0[2]; o.c[9] = k0[3];
+}
+
+// One thread per step of the chunk; stage times as in qw_fill_table (t_n = n h by
+// multiplication, tau = t / T by division).  Caller synchronises before and after.
+template <bool CYCLE>
+__device__ __forceinline__ void horner_fill_table(HornerStep *tab, const QwPoint &pt,
+                                                  const int64_t n0, const int cnt,
+                                                  const int schedule, const int gamma_on,
+                                                  const double lww, const double l2ww)
+{
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const double t0 = (double)(n0 + i) * pt.h;
+        const double2 ad1 = qw_operator_scalars(t0 / pt.T, pt.gamma, schedule, gamma_on);
+        const double2 ad2 = qw_operator_scalars((t0 + 0.5 * pt.h) / pt.T, pt.gamma, schedule,
+                                                gamma_on);
+        const double2 ad4 = qw_operator_scalars((t0 + pt.h) / pt.T, pt.gamma, schedule, gamma_on);
+        horner_coefficients(tab[i], pt.h, ad1, ad2, ad4, lww, l2ww);
+        if (CYCLE) {            // basis (y_w, s1, s2, s3), s_k = y_{w-k} + y_{w+k}:
+            // Ly_w = 2y - s1, L^2y_w = 6y - 4s1 + s2, L^3y_w = 20y - 15s1 + 6s2 - s3
+            double2 *c = tab[i].c;
+            c[1] = axpy2(2.0, c[2], c[1]);
+            c[2] = make_double2(-c[2].x, -c[2].y);
+            c[3] = axpy2(6.0, c[5], axpy2(2.0, c[4], c[3]));
+            c[4] = make_double2(-c[4].x - 4.0 * c[5].x, -c[4].y - 4.0 * c[5].y);
+            c[6] = axpy2(20.0, c[9], axpy2(6.0, c[8], axpy2(2.0, c[7], c[6])));
+            c[7] = make_double2(-c[7].x - 4.0 * c[8].x - 15.0 * c[9].x,
+                                -c[7].y - 4.0 * c[8].y - 15.0 * c[9].y);
+            c[8] = axpy2(6.0, c[9], c[8]);
+            c[9] = make_double2(-c[9].x, -c[9].y);
+        }
+    }
+}
+
+__device__ __forceinline__ double2 cmul_acc(const double2 c, const double2 v, const double2 acc)
+{
+    return make_double2(fma(c.x, v.x, fma(-c.y, v.y, acc.x)), fma(c.x, v.y, fma(c.y, v.x, acc.y)));
+}
+
+__device__ __forceinline__ double2 cmul(const double2 c, const double2 v)
+{
+    return make_double2(fma(c.x, v.x, -c.y * v.y), fma(c.x, v.y, c.y * v.x));
+}
+
+// out = y - i rho (2 c - l - r)
+__device__ __forceinline__ void hsite(const double lr, const double li, const double cr,
+                                      const double ci, const double rr, const double ri,
+                                      const double rho, const double y_r, const double y_i,
+                                      double &o_r, double &o_i)
+{
+    const double vr = fma(2.0, cr, -(lr + rr));
+    const double vi = fma(2.0, ci, -(li + ri));
+    o_r = fma(rho, vi, y_r);
+    o_i = fma(-rho, vr, y_i);
+}
+
+template <int R>
+struct HState {
+    double yr[R], yi[R];   // psi_n
+    double zr[R], zi[R];   // nested intermediate
+};
+
+// LEVEL 4: x = y, out = z.  LEVEL 3, 2: x = z, out = z (in place).  LEVEL 1: x = z, out = y.
+#define HX_R(r) ((LEVEL == 4) ? s.yr[r] : s.zr[r])
+#define HX_I(r) ((LEVEL == 4) ? s.yi[r] : s.zi[r])
+#define HO_R(r) ((LEVEL == 1) ? s.yr[r] : s.zr[r])
+#define HO_I(r) ((LEVEL == 1) ? s.yi[r] : s.zi[r])
+
+template <int R, int LEVEL>
+__device__ __forceinline__ void hedges(HState<R> &s, const double rho, const double2 hl,
+                                       const double2 hr, double2 &o0, double2 &oL)
+{
+    o0 = make_double2(HX_R(0), HX_I(0));
+    oL = make_double2(HX_R(R - 1), HX_I(R - 1));
+    hsite(hl.x, hl.y, o0.x, o0.y, HX_R(1), HX_I(1), rho, s.yr[0], s.yi[0], HO_R(0), HO_I(0));
+    hsite(HX_R(R - 2), HX_I(R - 2), oL.x, oL.y, hr.x, hr.y, rho, s.yr[R - 1], s.yi[R - 1],
+          HO_R(R - 1), HO_I(R - 1));
+}
+
+template <int R, int LEVEL>
+__device__ __forceinline__ void hinterior(HState<R> &s, const double rho, const double2 o0,
+                                          const double2 oL)
+{
+    double pr = o0.x, pi = o0.y;
+#pragma unroll
+    for (int r = 1; r < R - 1; ++r) {
+        const double cr = HX_R(r), ci = HX_I(r);
+        const double nr = (r + 1 < R - 1) ? HX_R(r + 1 < R ? r + 1 : r) : oL.x;
+        const double ni = (r + 1 < R - 1) ? HX_I(r + 1 < R ? r + 1 : r) : oL.y;
+        hsite(pr, pi, cr, ci, nr, ni, rho, s.yr[r], s.yi[r], HO_R(r), HO_I(r));
+        pr = cr;
+        pi = ci;
+    }
+}
+
+__device__ __forceinline__ double2 hblock_sum(double2 v, double *red)
+{
+    v.x = qw_warp_sum(v.x);
+    v.y = qw_warp_sum(v.y);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    if (lane == 0) { red[2 * warp] = v.x; red[2 * warp + 1] = v.y; }
+    __syncthreads();
+    double2 w = make_double2(0.0, 0.0);
+    if (lane < nwarps) w = make_double2(red[2 * lane], red[2 * lane + 1]);
+    w.x = qw_warp_sum(w.x);
+    w.y = qw_warp_sum(w.y);
+    return w;
+}
+
+// Physical warp slot of the calling warp.  Warps are assigned to the four SM sub-partitions
+// (each with its own FP64 lanes) by slot number modulo 4.
+__device__ __forceinline__ unsigned warp_slot()
+{
+    unsigned w;
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(w));
+    return w;
+}
+
+// `cnt` RK4 steps with the table in shared memory.  OWN: this warp holds the marked vertex.
+// Its correction arithmetic is issued by all lanes of the warp (an FP64 instruction costs the
+// same pipe time whatever its mask) and masked by msk = 1 in the owner thread, 0 elsewhere,
+// so that it is straight-line code the compiler interleaves with the interior sites.
+template <int R, bool OWN>
+__device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab, double2 *first,
+                                             double2 *last, const int nt, const int t,
+                                             const int tl, const int tr, const int cnt, int &par,
+                                             const double msk)
+{
+    for (int sidx = 0; sidx < cnt; ++sidx) {
+        const HornerStep &hs = tab[sidx];
+        double2 b0, b1, b2, b3;                    // y_w and the neighbour sums at distance 1..3
+#define QW_HORNER_LEVEL(LEVEL, CBASE, NTERMS)                                               \
+        {                                                                                   \
+            __syncthreads();                                                                \
+            const double2 hl = last[par * nt + tl];                                         \
+            const double2 hr = first[par * nt + tr];                                        \
+            const double rho = hs.rho[LEVEL - 1];                                           \
+            double2 o0, oL;                                                                 \
+            if (OWN && LEVEL == 4) {                                                        \
+                b0 = make_double2(s.yr[HW0], s.yi[HW0]);                                    \
+                b1 = make_double2(s.yr[HW0 - 1] + s.yr[HW0 + 1], s.yi[HW0 - 1] + s.yi[HW0 + 1]); \
+                b2 = make_double2(s.yr[HW0 - 2] + s.yr[HW0 + 2], s.yi[HW0 - 2] + s.yi[HW0 + 2]); \
+                b3 = make_double2(s.yr[HW0 - 3] + s.yr[HW0 + 3], s.yi[HW0 - 3] + s.yi[HW0 + 3]); \
+            }                                                                               \
+            hedges<R, LEVEL>(s, rho, hl, hr, o0, oL);                                       \
+            par ^= 1;                                                                       \
+            if (LEVEL > 1) {                                                                \
+                first[par * nt + t] = make_double2(s.zr[0], s.zi[0]);                       \
+                last[par * nt + t] = make_double2(s.zr[R - 1], s.zi[R - 1]);                \
+            } else {                                                                        \
+                first[par * nt + t] = make_double2(s.yr[0], s.yi[0]);                       \
+                last[par * nt + t] = make_double2(s.yr[R - 1], s.yi[R - 1]);                \
+            }                                                                               \
+            hinterior<R, LEVEL>(s, rho, o0, oL);                                            \
+            if (OWN) {                                  /* oracle correction sigma_LEVEL */ \
+                double2 sg = cmul(hs.c[CBASE], b0);                                         \
+                if (NTERMS > 1) sg = cmul_acc(hs.c[CBASE + 1], b1, sg);                     \
+                if (NTERMS > 2) sg = cmul_acc(hs.c[CBASE + 2], b2, sg);                     \
+                if (NTERMS > 3) sg = cmul_acc(hs.c[CBASE + 3], b3, sg);                     \
+                if (LEVEL > 1) {                                                            \
+                    s.zr[HW0] = fma(msk, sg.x, s.zr[HW0]);                                  \
+                    s.zi[HW0] = fma(msk, sg.y, s.zi[HW0]);                                  \
+                } else {                                                                    \
+                    s.yr[HW0] = fma(msk, sg.x, s.yr[HW0]);                                  \
+                    s.yi[HW0] = fma(msk, sg.y, s.yi[HW0]);                                  \
+                }                                                                           \
+            }                                                                               \
+        }
+        QW_HORNER_LEVEL(4, 0, 1)
+        QW_HORNER_LEVEL(3, 1, 2)
+        QW_HORNER_LEVEL(2, 3, 3)
+        QW_HORNER_LEVEL(1, 6, 4)
+#undef QW_HORNER_LEVEL
+    }
+}
+
+template <int R, int MAXNT, int MINB>
+__global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams prm)
+{
+    static_assert(R >= 2 * HW0 + 1, "the window w-3..w+3 must sit in one thread");
+    extern __shared__ double2 mbox[];         // [2][2][blockDim.x]: parity, first/last
+    __shared__ HornerShared sh;
+    const int t = threadIdx.x, nt = blockDim.x, nact = prm.nact;
+    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const bool active = t < nact;
+    // ring neighbours among the active threads; idle threads talk to themselves (zeros)
+    const int tl = active ? (t == 0 ? nact - 1 : t - 1) : t;
+    const int tr = active ? (t == nact - 1 ? 0 : t + 1) : t;
+    // The owner of the marked vertex is lane 0 of warp 0 -- or of another warp, rotating with
+    // the block's physical warp slots: the owner warp issues ~14 % more FP64 instructions, and
+    // warps go to the four SM sub-partitions by slot number modulo 4, so without the rotation
+    // all owner warps of an SM would share one (4-warp blocks) or two (2-warp blocks) of them.
+    int ht = 0;
+    if ((nt == 64 || nt == 128) && nact == nt && !(prm.flags & QW_FLAG_NO_ROTATE)) {
+        if (t == 0) sh.owner = 32 * (int)((warp_slot() >> 2) & (nt == 64 ? 1u : 3u));
+        __syncthreads();
+        ht = sh.owner;
+    }
+    const bool own = (t == ht);
+
+    HState<R> s;
+    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.zr[r] = 0.0; s.zi[r] = 0.0;
+    }
+    int par = 0;
+    double2 *first = mbox, *last = mbox + 2 * nt;      // [parity][thread]
+    first[t] = make_double2(s.yr[0], s.yi[0]);
+    last[t] = make_double2(s.yr[R - 1], s.yi[R - 1]);
+
+    for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
+        const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
+        __syncthreads();                               // the last chunk's table is no longer read
+        horner_fill_table<true>(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, 2.0, 6.0);
+        if ((t >> 5) == (ht >> 5))
+            horner_steps<R, true>(s, sh.st, first, last, nt, t, tl, tr, cnt, par, own ? 1.0 : 0.0);
+        else
+            horner_steps<R, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, par, 0.0);
+    }
+
+    // p = |psi_w|^2 / ||psi||^2, ||psi||^2 (BCB.py:189-199, Runge_Kutta_Error.py:103)
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    const double pw = own ? fma(s.yr[HW0], s.yr[HW0], s.yi[HW0] * s.yi[HW0]) : 0.0;
+    __syncthreads();
+    const double2 tot = hblock_sum(make_double2(nrm, pw), sh.red);
+    if (t == 0) {
+        prm.p[pt.q] = tot.y / tot.x;
+        if (prm.norm) prm.norm[pt.q] = tot.x;
+    }
+    if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + l,
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;   // l = (t - ht) R + r - HW0
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t j = (int64_t)(t - ht) * R + r - HW0 + prm.target;
+            if (j < 0) j += prm.n;
+            if (j >= prm.n) j -= prm.n;
+            out[j] = make_double2(s.yr[r], s.yi[r]);
+        }
+    }
+}
+
+template <typename K>
+cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cudaStream_t st,
+                    qw_plan *plan)
+{
+    if (plan) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem);
+        if (e != cudaSuccess) return e;
+        plan->threads_per_block = threads;
+        plan->blocks_per_sm = nb;
+        plan->regs_per_thread = fa.numRegs;
+        plan->smem_bytes = (int)(fa.sharedSizeBytes + smem);
+        return cudaSuccess;
+    }
+    kernel<<<(unsigned)prm.n_points, threads, smem, st>>>(prm);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Sites per thread of the nested-form kernels, or 0 when n does not fit them: n = R * threads
+// with R in {16, 8} (the window w-3..w+3 has to sit in one thread) and at least one full warp.
+int qw_horner_sites_per_thread(const QwParams &prm)
+{
+    if (prm.topology != QW_TOPO_CYCLE) return 0;
+    const int64_t n = prm.n;
+    if (!(prm.flags & QW_FLAG_R8) && n % 16 == 0 && n / 16 >= 32 && n / 16 <= 256) return 16;
+    if (n % 8 == 0 && n / 8 >= 32 && n / 8 <= 512) return 8;
+    return 0;
+}
+
+cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
+{
+    const int R = qw_horner_sites_per_thread(prm);
+    if (R == 0) return cudaErrorInvalidConfiguration;
+    prm.nact = (int)(prm.n / R);
+    const int threads = ((prm.nact + 31) / 32) * 32;
+    const size_t smem = (size_t)threads * 4 * sizeof(double2);
+    if (plan) {
+        plan->path = 5;
+        plan->sites_per_thread = R;
+    }
+    if (R == 16) {
+        // register file = 16 K per SM sub-partition: 2 / 3 warps there allow 255 / 168 registers
+        if (threads <= 64 && (prm.flags & QW_FLAG_OCC4))
+            return hlaunch(rk4_cycle_horner<16, 64, 4>, prm, threads, smem, st, plan);
+        if (threads <= 64) return hlaunch(rk4_cycle_horner<16, 64, 6>, prm, threads, smem, st, plan);
+        if (threads <= 128) return hlaunch(rk4_cycle_horner<16, 128, 2>, prm, threads, smem, st, plan);
+        return hlaunch(rk4_cycle_horner<16, 256, 1>, prm, threads, smem, st, plan);
+    }
+    if (threads <= 64) return hlaunch(rk4_cycle_horner<8, 64, 8>, prm, threads, smem, st, plan);
+    if (threads <= 128) return hlaunch(rk4_cycle_horner<8, 128, 4>, prm, threads, smem, st, plan);
+    if (threads <= 256) return hlaunch(rk4_cycle_horner<8, 256, 2>, prm, threads, smem, st, plan);
+    return hlaunch(rk4_cycle_horner<8, 512, 1>, prm, threads, smem, st, plan);
+}

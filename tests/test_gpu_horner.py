@@ -1,0 +1,75 @@
+"""GPU parity of the nested-form (Horner) resident kernels (csrc/qw_horner.cu) against the
+oracle and against the classic stage-form kernels (QW_FLAG_NO_HORNER = 2048).
+
+Tolerances as everywhere: |dp| <= 1e-10, |dpsi| <= 1e-11, identical argmax."""
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+P_TOL = 1e-10
+PSI_TOL = 1e-11
+NO_HORNER, R8, OCC4, NO_PACK, NO_ROT = 2048, 256, 128, 512, 4096
+
+
+@pytest.mark.parametrize("n,flags", [(256, NO_PACK), (264, 0), (512, 0), (520, 0), (1024, 0),
+                                     (1024, OCC4), (1024, R8), (1024, NO_ROT), (1024, R8 | NO_ROT), (2048, NO_ROT), (1040, 0), (2048, 0), (2048, R8),
+                                     (3072, 0), (4096, 0), (4096, R8), (4088, 0)])
+def test_cycle_all_schedules_vs_oracle(qw, n, flags):
+    pl = qw.plan(qw.Problem(n=n, topology="circular", step_size=0.1, flags=flags))
+    assert pl["path"] == "horner-cycle", pl
+    rng = np.random.default_rng(n + flags)
+    for sched in ["lin", "sqrt", "cbrt", "cerf_3", "cerf_5", "cerf_7", "static"]:
+        for gamma_on in ("oracle", "laplacian"):
+            P = 4
+            T = rng.uniform(0.0, 12.0, P)
+            g = rng.uniform(0.0, 2.5, P)
+            T[0] = 0.0
+            g[1] = 0.0                 # gamma = 0: no oracle (or no Laplacian) at all
+            S = 100                    # > 3 coefficient-table chunks, ragged tail
+            prob = qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S,
+                              gamma_on=gamma_on, flags=flags)
+            p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+            po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, n_steps=S,
+                                                 gamma_on=gamma_on, return_psi=True)
+            assert np.abs(p - po).max() <= P_TOL, (n, sched, gamma_on)
+            assert np.abs(norm - no).max() <= P_TOL, (n, sched, gamma_on)
+            assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched, gamma_on)
+
+
+def test_targets_step_size_rule_and_long_runs(qw):
+    n = 1024
+    for target in (0, 1, 2, 3, 4, 511, 1020, 1023):
+        prob = qw.Problem(n=n, topology="circular", schedule="lin", target=target, n_steps=64)
+        p, norm, psi = qw.rk4_batch(prob, [9.0], [1.3], return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "circular", "lin", [9.0], [1.3], n_steps=64,
+                                             target=target, return_psi=True)
+        assert abs(p[0] - po[0]) <= P_TOL and np.abs(psi - psio).max() <= PSI_TOL, target
+    T = np.array([0.0, 0.05, 3.3, 7.77, 12.0])
+    g = np.array([1.0, 0.3, 2.2, 1.1, 0.7])
+    prob = qw.Problem(n=512, topology="circular", schedule="cerf_3", step_size=0.1)
+    p, norm = qw.rk4_batch(prob, T, g)
+    po, no, _ = c_oracle.rk4_batch(512, "circular", "cerf_3", T, g, step_size=0.1)
+    assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+    # the C5 step count on a few points: rounding must not accumulate over 4096 steps
+    T, g = np.array([1024.0, 333.3, 51.14]), np.array([0.2102, 1.7, 0.9213])
+    prob = qw.Problem(n=1024, topology="circular", schedule="lin", n_steps=4096)
+    p, norm = qw.rk4_batch(prob, T, g)
+    po, no, _ = c_oracle.rk4_batch(1024, "circular", "lin", T, g, n_steps=4096)
+    assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+
+
+def test_heatmap_matches_the_stage_form_kernel_and_keeps_the_argmax(qw):
+    t, b = np.linspace(0.1, 300.0, 24), np.linspace(0.0, 2.5, 16)
+    res = {}
+    for flags in (0, NO_HORNER):
+        prob = qw.Problem(n=1024, topology="circular", schedule="lin", n_steps=1200, flags=flags)
+        res[flags] = qw.rk4_heatmap(prob, t, b)
+    assert np.abs(res[0][0] - res[NO_HORNER][0]).max() <= 1e-12
+    assert np.abs(res[0][1] - res[NO_HORNER][1]).max() <= 1e-12
+    assert np.argmax(res[0][0]) == np.argmax(res[NO_HORNER][0])
+    ho, _ = c_oracle.heatmap(1024, "circular", "lin", t, b, n_steps=1200)
+    assert np.abs(res[0][0] - ho).max() <= P_TOL and np.argmax(res[0][0]) == np.argmax(ho)

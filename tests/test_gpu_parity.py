@@ -261,8 +261,10 @@ def test_error_behaviour(qw):
 
 def test_plan_reports_native_kernels(qw):
     pl = qw.plan(qw.Problem(n=1024, topology="circular", n_steps=1))
-    assert pl["path"] == "resident-cycle" and pl["sites_per_thread"] == 16
+    assert pl["path"] == "horner-cycle" and pl["sites_per_thread"] == 16
     assert pl["threads_per_block"] == 64 and pl["sm_count"] >= 100
+    pl = qw.plan(qw.Problem(n=1024, topology="circular", n_steps=1, flags=2048))
+    assert pl["path"] == "resident-cycle" and pl["sites_per_thread"] == 16
     pl = qw.plan(qw.Problem(n=1024, topology="circular", n_steps=1, flags=256))
     assert pl["sites_per_thread"] == 8 and pl["threads_per_block"] == 128
     pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1))

@@ -17,7 +17,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import qwtdh_b200 as qw  # noqa: E402
 
 VARIANTS = {
-    "c5": [("v2 R=16 (default)", 0), ("v2 R=8 occ3", 256), ("v2 R=8 occ4", 256 | 128),
+    "c5": [("horner R=16 occ6 (default)", 0), ("horner R=16 occ4", 128), ("horner R=8", 256),
+           ("horner R=16 occ6 no-rotate", 4096), ("horner R=16 occ4 no-rotate", 4096 | 128),
+           ("horner R=8 no-rotate", 4096 | 256),
+           ("v2 R=16", 2048), ("v2 R=8 occ3", 2048 | 256), ("v2 R=8 occ4", 2048 | 256 | 128),
            ("v2 R=8 mbarrier occ3", 256 | 64), ("v1 R=8 legacy occ3", 256 | 32),
            ("v1 R=8 legacy occ4", 256 | 32 | 128)],
     "c4": [("packed (default)", 0), ("v2 occ3", 512), ("v2 occ4", 128), ("v1 legacy occ3", 32),
