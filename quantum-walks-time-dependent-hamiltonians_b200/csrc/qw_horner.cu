@@ -29,10 +29,20 @@ namespace {
 
 constexpr int HW0 = 3;               // slot of the marked vertex in thread 0
 
-struct HornerStep {                  // 24 doubles per RK4 step
+struct HornerCoef {                  // coefficients of one RK4 step
     double rho[4];                   // r1 (outermost) .. r4 (innermost)
     double2 c[10];                   // sigma_4: c[0]; sigma_3: c[1..2]; sigma_2: c[3..5];
                                      // sigma_1: c[6..9]  (basis y_w, Ly_w, L^2y_w, L^3y_w)
+};
+
+// Shared-memory form for the cycle kernel.  The four corrections are evaluated by eight lanes
+// of the owner warp at once: lane 2m + c holds component c (0 re, 1 im) of sigma_{4-m} as a
+// real dot product of length 8 with (re, im) of (y_w, s1, s2, s3), s_k = y_{w-k} + y_{w+k}.
+// coef[k][lane]: conflict-free for the lanes' loads; 69 doubles: conflict-free fill.
+struct HornerStep {
+    double rho[4];
+    double coef[8][8];
+    double pad;
 };
 
 struct HornerShared {
@@ -55,7 +65,7 @@ __device__ __forceinline__ double safe_inv(const double x) { return x != 0.0 ? 1
 
 // Coefficients of one step.  ad1, ad2, ad4 = (a, d) at t_n, t_n + h/2, t_n + h;
 // lww = L_ww, l2ww = (L^2)_ww.
-__device__ void horner_coefficients(HornerStep &o, const double h, const double2 ad1,
+__device__ void horner_coefficients(HornerCoef &o, const double h, const double2 ad1,
                                     const double2 ad2, const double2 ad4, const double lww,
                                     const double l2ww)
 {
@@ -112,11 +122,9 @@ __device__ void horner_coefficients(HornerStep &o, const double h, const double2
 
 // One thread per step of the chunk; stage times as in qw_fill_table (t_n = n h by
 // multiplication, tau = t / T by division).  Caller synchronises before and after.
-template <bool CYCLE>
-__device__ __forceinline__ void horner_fill_table(HornerStep *tab, const QwPoint &pt,
+__device__ __forceinline__ void horner_fill_cycle(HornerStep *tab, const QwPoint &pt,
                                                   const int64_t n0, const int cnt,
-                                                  const int schedule, const int gamma_on,
-                                                  const double lww, const double l2ww)
+                                                  const int schedule, const int gamma_on)
 {
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
         const double t0 = (double)(n0 + i) * pt.h;
@@ -124,31 +132,34 @@ __device__ __forceinline__ void horner_fill_table(HornerStep *tab, const QwPoint
         const double2 ad2 = qw_operator_scalars((t0 + 0.5 * pt.h) / pt.T, pt.gamma, schedule,
                                                 gamma_on);
         const double2 ad4 = qw_operator_scalars((t0 + pt.h) / pt.T, pt.gamma, schedule, gamma_on);
-        horner_coefficients(tab[i], pt.h, ad1, ad2, ad4, lww, l2ww);
-        if (CYCLE) {            // basis (y_w, s1, s2, s3), s_k = y_{w-k} + y_{w+k}:
-            // Ly_w = 2y - s1, L^2y_w = 6y - 4s1 + s2, L^3y_w = 20y - 15s1 + 6s2 - s3
-            double2 *c = tab[i].c;
-            c[1] = axpy2(2.0, c[2], c[1]);
-            c[2] = make_double2(-c[2].x, -c[2].y);
-            c[3] = axpy2(6.0, c[5], axpy2(2.0, c[4], c[3]));
-            c[4] = make_double2(-c[4].x - 4.0 * c[5].x, -c[4].y - 4.0 * c[5].y);
-            c[6] = axpy2(20.0, c[9], axpy2(6.0, c[8], axpy2(2.0, c[7], c[6])));
-            c[7] = make_double2(-c[7].x - 4.0 * c[8].x - 15.0 * c[9].x,
-                                -c[7].y - 4.0 * c[8].y - 15.0 * c[9].y);
-            c[8] = axpy2(6.0, c[9], c[8]);
-            c[9] = make_double2(-c[9].x, -c[9].y);
+        HornerCoef hc;
+        horner_coefficients(hc, pt.h, ad1, ad2, ad4, 2.0, 6.0);     // L_ww = 2, (L^2)_ww = 6
+        // basis (y_w, s1, s2, s3):  Ly_w = 2y - s1,  L^2y_w = 6y - 4s1 + s2,
+        //                           L^3y_w = 20y - 15s1 + 6s2 - s3
+        double2 *c = hc.c;
+        c[1] = axpy2(2.0, c[2], c[1]);
+        c[2] = make_double2(-c[2].x, -c[2].y);
+        c[3] = axpy2(6.0, c[5], axpy2(2.0, c[4], c[3]));
+        c[4] = make_double2(-c[4].x - 4.0 * c[5].x, -c[4].y - 4.0 * c[5].y);
+        c[6] = axpy2(20.0, c[9], axpy2(6.0, c[8], axpy2(2.0, c[7], c[6])));
+        c[7] = make_double2(-c[7].x - 4.0 * c[8].x - 15.0 * c[9].x,
+                            -c[7].y - 4.0 * c[8].y - 15.0 * c[9].y);
+        c[8] = axpy2(6.0, c[9], c[8]);
+        c[9] = make_double2(-c[9].x, -c[9].y);
+        HornerStep &o = tab[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
+        const int base[4] = {0, 1, 3, 6};              // first coefficient of sigma_4 .. sigma_1
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {              // term k multiplies (b_k.re, b_k.im)
+                const double2 ck = (k <= m) ? c[base[m] + k] : make_double2(0.0, 0.0);
+                o.coef[2 * k][2 * m] = ck.x;      o.coef[2 * k + 1][2 * m] = -ck.y;      // re
+                o.coef[2 * k][2 * m + 1] = ck.y;  o.coef[2 * k + 1][2 * m + 1] = ck.x;   // im
+            }
         }
     }
-}
-
-__device__ __forceinline__ double2 cmul_acc(const double2 c, const double2 v, const double2 acc)
-{
-    return make_double2(fma(c.x, v.x, fma(-c.y, v.y, acc.x)), fma(c.x, v.y, fma(c.y, v.x, acc.y)));
-}
-
-__device__ __forceinline__ double2 cmul(const double2 c, const double2 v)
-{
-    return make_double2(fma(c.x, v.x, -c.y * v.y), fma(c.x, v.y, c.y * v.x));
 }
 
 // out = y - i rho (2 c - l - r)
@@ -230,56 +241,66 @@ __device__ __forceinline__ unsigned warp_slot()
 // Its correction arithmetic is issued by all lanes of the warp (an FP64 instruction costs the
 // same pipe time whatever its mask) and masked by msk = 1 in the owner thread, 0 elsewhere,
 // so that it is straight-line code the compiler interleaves with the interior sites.
+// A step has four levels, so the mailbox parity of a level is a compile-time constant: level 4
+// and 2 read buffer 0 and write buffer 1, level 3 and 1 the other way round.
+// (A pairwise bar.arrive / bar.sync handshake between the two warps of a block instead of the
+// block barrier was measured: equal at best, -6 % once the publication was pinned early --
+// ptxas places the arithmetic around the barriers as it likes)
 template <int R, bool OWN>
 __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab, double2 *first,
                                              double2 *last, const int nt, const int t,
-                                             const int tl, const int tr, const int cnt, int &par,
+                                             const int tl, const int tr, const int cnt,
                                              const double msk)
 {
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const HornerStep &hs = tab[sidx];
-        double2 b0, b1, b2, b3;                    // y_w and the neighbour sums at distance 1..3
-#define QW_HORNER_LEVEL(LEVEL, CBASE, NTERMS)                                               \
+        double sgl = 0.0;                          // this lane's component of its sigma
+#define QW_HORNER_LEVEL(LEVEL)                                                              \
         {                                                                                   \
+            constexpr int par = (4 - LEVEL) & 1;                                            \
             __syncthreads();                                                                \
             const double2 hl = last[par * nt + tl];                                         \
             const double2 hr = first[par * nt + tr];                                        \
             const double rho = hs.rho[LEVEL - 1];                                           \
             double2 o0, oL;                                                                 \
             if (OWN && LEVEL == 4) {                                                        \
-                b0 = make_double2(s.yr[HW0], s.yi[HW0]);                                    \
-                b1 = make_double2(s.yr[HW0 - 1] + s.yr[HW0 + 1], s.yi[HW0 - 1] + s.yi[HW0 + 1]); \
-                b2 = make_double2(s.yr[HW0 - 2] + s.yr[HW0 + 2], s.yi[HW0 - 2] + s.yi[HW0 + 2]); \
-                b3 = make_double2(s.yr[HW0 - 3] + s.yr[HW0 + 3], s.yi[HW0 - 3] + s.yi[HW0 + 3]); \
+                /* y_w and the neighbour sums at distance 1..3 (meaningful in the owner */  \
+                /* lane), broadcast; every lane then forms its own dot product          */  \
+                double b[8];                                                                \
+                b[0] = s.yr[HW0];                     b[1] = s.yi[HW0];                     \
+                b[2] = s.yr[HW0 - 1] + s.yr[HW0 + 1]; b[3] = s.yi[HW0 - 1] + s.yi[HW0 + 1]; \
+                b[4] = s.yr[HW0 - 2] + s.yr[HW0 + 2]; b[5] = s.yi[HW0 - 2] + s.yi[HW0 + 2]; \
+                b[6] = s.yr[HW0 - 3] + s.yr[HW0 + 3]; b[7] = s.yi[HW0 - 3] + s.yi[HW0 + 3]; \
+                sgl = hs.coef[0][t & 7] * __shfl_sync(0xffffffffu, b[0], 0);                \
+                _Pragma("unroll")                                                           \
+                for (int k = 1; k < 8; ++k)                                                 \
+                    sgl = fma(hs.coef[k][t & 7], __shfl_sync(0xffffffffu, b[k], 0), sgl);   \
             }                                                                               \
             hedges<R, LEVEL>(s, rho, hl, hr, o0, oL);                                       \
-            par ^= 1;                                                                       \
             if (LEVEL > 1) {                                                                \
-                first[par * nt + t] = make_double2(s.zr[0], s.zi[0]);                       \
-                last[par * nt + t] = make_double2(s.zr[R - 1], s.zi[R - 1]);                \
+                first[(par ^ 1) * nt + t] = make_double2(s.zr[0], s.zi[0]);                 \
+                last[(par ^ 1) * nt + t] = make_double2(s.zr[R - 1], s.zi[R - 1]);          \
             } else {                                                                        \
-                first[par * nt + t] = make_double2(s.yr[0], s.yi[0]);                       \
-                last[par * nt + t] = make_double2(s.yr[R - 1], s.yi[R - 1]);                \
+                first[(par ^ 1) * nt + t] = make_double2(s.yr[0], s.yi[0]);                 \
+                last[(par ^ 1) * nt + t] = make_double2(s.yr[R - 1], s.yi[R - 1]);          \
             }                                                                               \
             hinterior<R, LEVEL>(s, rho, o0, oL);                                            \
             if (OWN) {                                  /* oracle correction sigma_LEVEL */ \
-                double2 sg = cmul(hs.c[CBASE], b0);                                         \
-                if (NTERMS > 1) sg = cmul_acc(hs.c[CBASE + 1], b1, sg);                     \
-                if (NTERMS > 2) sg = cmul_acc(hs.c[CBASE + 2], b2, sg);                     \
-                if (NTERMS > 3) sg = cmul_acc(hs.c[CBASE + 3], b3, sg);                     \
+                const double sgr = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));          \
+                const double sgi = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);      \
                 if (LEVEL > 1) {                                                            \
-                    s.zr[HW0] = fma(msk, sg.x, s.zr[HW0]);                                  \
-                    s.zi[HW0] = fma(msk, sg.y, s.zi[HW0]);                                  \
+                    s.zr[HW0] = fma(msk, sgr, s.zr[HW0]);                                   \
+                    s.zi[HW0] = fma(msk, sgi, s.zi[HW0]);                                   \
                 } else {                                                                    \
-                    s.yr[HW0] = fma(msk, sg.x, s.yr[HW0]);                                  \
-                    s.yi[HW0] = fma(msk, sg.y, s.yi[HW0]);                                  \
+                    s.yr[HW0] = fma(msk, sgr, s.yr[HW0]);                                   \
+                    s.yi[HW0] = fma(msk, sgi, s.yi[HW0]);                                   \
                 }                                                                           \
             }                                                                               \
         }
-        QW_HORNER_LEVEL(4, 0, 1)
-        QW_HORNER_LEVEL(3, 1, 2)
-        QW_HORNER_LEVEL(2, 3, 3)
-        QW_HORNER_LEVEL(1, 6, 4)
+        QW_HORNER_LEVEL(4)
+        QW_HORNER_LEVEL(3)
+        QW_HORNER_LEVEL(2)
+        QW_HORNER_LEVEL(1)
 #undef QW_HORNER_LEVEL
     }
 }
@@ -315,19 +336,21 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
         s.yr[r] = amp; s.yi[r] = 0.0;
         s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
-    int par = 0;
-    double2 *first = mbox, *last = mbox + 2 * nt;      // [parity][thread]
+    double2 *first = mbox, *last = mbox + 2 * nt;      // [parity][thread]; a step starts at 0
     first[t] = make_double2(s.yr[0], s.yi[0]);
     last[t] = make_double2(s.yr[R - 1], s.yi[R - 1]);
 
+    const int warp = t >> 5;
     for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
         const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
         __syncthreads();                               // the last chunk's table is no longer read
-        horner_fill_table<true>(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, 2.0, 6.0);
-        if ((t >> 5) == (ht >> 5))
-            horner_steps<R, true>(s, sh.st, first, last, nt, t, tl, tr, cnt, par, own ? 1.0 : 0.0);
+        horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on);
+        __syncthreads();
+        const double msk = own ? 1.0 : 0.0;
+        if (warp == (ht >> 5))
+            horner_steps<R, true>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk);
         else
-            horner_steps<R, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, par, 0.0);
+            horner_steps<R, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk);
     }
 
     // p = |psi_w|^2 / ||psi||^2, ||psi||^2 (BCB.py:189-199, Runge_Kutta_Error.py:103)
@@ -369,6 +392,11 @@ cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cud
         plan->regs_per_thread = fa.numRegs;
         plan->smem_bytes = (int)(fa.sharedSizeBytes + smem);
         return cudaSuccess;
+    }
+    if (smem + sizeof(HornerShared) > 48 * 1024) {     // static + dynamic above the default cap
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
     }
     kernel<<<(unsigned)prm.n_points, threads, smem, st>>>(prm);
     return cudaGetLastError();

@@ -16,7 +16,7 @@ NO_HORNER, R8, OCC4, NO_PACK, NO_ROT = 2048, 256, 128, 512, 4096
 
 
 @pytest.mark.parametrize("n,flags", [(256, NO_PACK), (264, 0), (512, 0), (520, 0), (1024, 0),
-                                     (1024, OCC4), (1024, R8), (1024, NO_ROT), (1024, R8 | NO_ROT), (2048, NO_ROT), (1040, 0), (2048, 0), (2048, R8),
+                                     (1024, OCC4), (1024, R8), (1536, 0), (1792, 0), (1024, NO_ROT), (1024, R8 | NO_ROT), (2048, NO_ROT), (1040, 0), (2048, 0), (2048, R8),
                                      (3072, 0), (4096, 0), (4096, R8), (4088, 0)])
 def test_cycle_all_schedules_vs_oracle(qw, n, flags):
     pl = qw.plan(qw.Problem(n=n, topology="circular", step_size=0.1, flags=flags))
