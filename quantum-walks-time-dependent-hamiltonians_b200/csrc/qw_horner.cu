@@ -376,6 +376,192 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Complete graph: (L x)_j = N x_j - sum(x).  A nested level z' = y - i rho (N z - S_z) touches no
+// other site, and the sum of every level input follows from the marked vertex alone because
+// the column sums of L vanish: S(z_l) = S(y) + sigma_l, S(y+) = S(y) + sigma_1.  The sigmas are
+// linear in (y_w, (Ly)_w) here ((L^2 y)_w = N (Ly)_w, (L^3 y)_w = N^2 (Ly)_w), so the owner of
+// the marked vertex (lane 0 of warp 0) produces all four level sums of step n+1 while step n
+// runs, and the block meets at ONE barrier per step instead of one per stage.  16 FP64
+// instructions per site-update (classic stage form: 22).  S(y) is re-anchored to a direct block
+// sum at every coefficient-table refill (32 steps).
+struct CHStep {
+    double rho[4];
+    double coef[4][8];       // lane 2m + c: component c of sigma_{4-m} over (re, im)(y_w, Ly_w)
+    double pad;
+};
+
+struct CHShared {
+    CHStep st[QW_CHUNK];
+    double2 sums[2][4];      // [buffer][S(y), S(z4), S(z3), S(z2)] of a step
+    double red[2 * 2 * 32];
+};
+
+__device__ __forceinline__ void horner_fill_complete(CHStep *tab, const QwPoint &pt,
+                                                     const int64_t n0, const int cnt,
+                                                     const int schedule, const int gamma_on,
+                                                     const double n)
+{
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const double t0 = (double)(n0 + i) * pt.h;
+        const double2 ad1 = qw_operator_scalars(t0 / pt.T, pt.gamma, schedule, gamma_on);
+        const double2 ad2 = qw_operator_scalars((t0 + 0.5 * pt.h) / pt.T, pt.gamma, schedule,
+                                                gamma_on);
+        const double2 ad4 = qw_operator_scalars((t0 + pt.h) / pt.T, pt.gamma, schedule, gamma_on);
+        HornerCoef hc;
+        horner_coefficients(hc, pt.h, ad1, ad2, ad4, n - 1.0, n * (n - 1.0));
+        // basis (y_w, Ly_w): L^2y_w = N Ly_w, L^3y_w = N^2 Ly_w
+        double2 *c = hc.c;
+        c[4] = axpy2(n, c[5], c[4]);
+        c[7] = axpy2(n * n, c[9], axpy2(n, c[8], c[7]));
+        CHStep &o = tab[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
+        const double2 zero = make_double2(0.0, 0.0);
+        const double2 c0[4] = {c[0], c[1], c[3], c[6]};       // coefficient of y_w in sigma_4..1
+        const double2 c1[4] = {zero, c[2], c[4], c[7]};       // coefficient of Ly_w
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            o.coef[0][2 * m] = c0[m].x;     o.coef[1][2 * m] = -c0[m].y;
+            o.coef[2][2 * m] = c1[m].x;     o.coef[3][2 * m] = -c1[m].y;
+            o.coef[0][2 * m + 1] = c0[m].y; o.coef[1][2 * m + 1] = c0[m].x;
+            o.coef[2][2 * m + 1] = c1[m].y; o.coef[3][2 * m + 1] = c1[m].x;
+        }
+    }
+}
+
+// one level on all R sites of a thread: out = y - i rho (N x - S)
+template <int R, int LEVEL>
+__device__ __forceinline__ void clevel(HState<R> &s, const double rho, const double nd,
+                                       const double2 S)
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double tr_ = fma(nd, HX_R(r), -S.x);
+        const double ti_ = fma(nd, HX_I(r), -S.y);
+        HO_R(r) = fma(rho, ti_, s.yr[r]);
+        HO_I(r) = fma(-rho, tr_, s.yi[r]);
+    }
+}
+
+// Owner warp: level sums and corrections of the step whose coefficients are `hs`, from the
+// marked vertex value yw and S(y) held by lane 0.  Writes the four sums to `out`, returns this
+// lane's component of its sigma (lane 2m + c: sigma_{4-m}) and advances Sy to S(y+).
+__device__ __forceinline__ double complete_duty(const CHStep &hs, const double2 yw, double2 &Sy,
+                                                const double nd, double2 *out, const int t)
+{
+    const double m1r = fma(nd, yw.x, -Sy.x), m1i = fma(nd, yw.y, -Sy.y);     // (Ly)_w
+    const int l8 = t & 7;
+    double sgl = hs.coef[0][l8] * __shfl_sync(0xffffffffu, yw.x, 0);
+    sgl = fma(hs.coef[1][l8], __shfl_sync(0xffffffffu, yw.y, 0), sgl);
+    sgl = fma(hs.coef[2][l8], __shfl_sync(0xffffffffu, m1r, 0), sgl);
+    sgl = fma(hs.coef[3][l8], __shfl_sync(0xffffffffu, m1i, 0), sgl);
+    // S(z4), S(z3), S(z2), S(y+) = S(y) + sigma_4 .. sigma_1: lanes 0..7 add their component
+    const double bx = __shfl_sync(0xffffffffu, Sy.x, 0), by = __shfl_sync(0xffffffffu, Sy.y, 0);
+    const double sum = ((l8 & 1) ? by : bx) + sgl;
+    if (t < 6) ((double *)out)[2 + t] = sum;               // S(z4), S(z3), S(z2) as (re, im)
+    if (t == 0) out[0] = make_double2(bx, by);
+    Sy.x = __shfl_sync(0xffffffffu, sum, 6);               // S(y+): the next step's S(y)
+    Sy.y = __shfl_sync(0xffffffffu, sum, 7);
+    return sgl;
+}
+
+template <int R, bool OWN>
+__device__ __forceinline__ void complete_steps(HState<R> &s, CHShared &sh, const int cnt,
+                                               const double nd, const double msk, double2 &Sy,
+                                               double &sgl, const int t)
+{
+    for (int sidx = 0; sidx < cnt; ++sidx) {
+        const CHStep &hs = sh.st[sidx];
+        const double2 *sm = sh.sums[sidx & 1];
+        const double act = (nd != 0.0) ? 1.0 : 0.0;        // idle threads stay at zero
+#define QW_CH_LEVEL(LEVEL)                                                                  \
+        {                                                                                   \
+            double2 S = sm[4 - LEVEL];                                                      \
+            S.x *= act; S.y *= act;                                                         \
+            clevel<R, LEVEL>(s, hs.rho[LEVEL - 1], nd, S);                                  \
+            if (OWN) {                                                                      \
+                const double sgr = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));          \
+                const double sgi = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);      \
+                if (LEVEL > 1) {                                                            \
+                    s.zr[0] = fma(msk, sgr, s.zr[0]); s.zi[0] = fma(msk, sgi, s.zi[0]);     \
+                } else {                                                                    \
+                    s.yr[0] = fma(msk, sgr, s.yr[0]); s.yi[0] = fma(msk, sgi, s.yi[0]);     \
+                }                                                                           \
+            }                                                                               \
+        }
+        QW_CH_LEVEL(4)
+        QW_CH_LEVEL(3)
+        QW_CH_LEVEL(2)
+        QW_CH_LEVEL(1)
+#undef QW_CH_LEVEL
+        if (OWN && sidx + 1 < cnt)                         // scalars of the next step
+            sgl = complete_duty(sh.st[sidx + 1], make_double2(s.yr[0], s.yi[0]), Sy, nd,
+                                sh.sums[(sidx + 1) & 1], t);
+        __syncthreads();
+    }
+}
+
+template <int R, int MAXNT, int MINB>
+__global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_horner(const QwParams prm)
+{
+    __shared__ CHShared sh;
+    const int t = threadIdx.x, nact = prm.nact;
+    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const bool active = t < nact;
+    const double nd = active ? (double)prm.n : 0.0;
+
+    HState<R> s;
+    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.zr[r] = 0.0; s.zi[r] = 0.0;
+    }
+    const double msk = (t == 0) ? 1.0 : 0.0;
+    double sgl = 0.0;
+
+    for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
+        const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
+        __syncthreads();                               // the last chunk's table is no longer read
+        horner_fill_complete(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, (double)prm.n);
+        // re-anchor S(y) to a direct summation of the state
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) { a += s.yr[r]; b += s.yi[r]; }
+        double2 Sy = hblock_sum(make_double2(a, b), sh.red + (int)((n0 / QW_CHUNK) & 1) * 64);
+        __syncthreads();                               // table complete
+        if (t < 32) {
+            sgl = complete_duty(sh.st[0], make_double2(s.yr[0], s.yi[0]), Sy, nd, sh.sums[0], t);
+            __syncthreads();
+            complete_steps<R, true>(s, sh, cnt, nd, msk, Sy, sgl, t);
+        } else {
+            __syncthreads();
+            complete_steps<R, false>(s, sh, cnt, nd, msk, Sy, sgl, t);
+        }
+    }
+
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    const double pw = (t == 0) ? fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]) : 0.0;
+    __syncthreads();
+    const double2 tot = hblock_sum(make_double2(nrm, pw), sh.red);
+    if (t == 0) {
+        prm.p[pt.q] = tot.y / tot.x;
+        if (prm.norm) prm.norm[pt.q] = tot.x;
+    }
+    if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + t R + r
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t j = (int64_t)t * R + r + prm.target;
+            if (j >= prm.n) j -= prm.n;
+            out[j] = make_double2(s.yr[r], s.yi[r]);
+        }
+    }
+}
+
 template <typename K>
 cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cudaStream_t st,
                     qw_plan *plan)
@@ -408,8 +594,13 @@ cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cud
 // with R in {16, 8} (the window w-3..w+3 has to sit in one thread) and at least one full warp.
 int qw_horner_sites_per_thread(const QwParams &prm)
 {
-    if (prm.topology != QW_TOPO_CYCLE) return 0;
     const int64_t n = prm.n;
+    if (prm.topology != QW_TOPO_CYCLE) {
+        if (prm.flags & QW_FLAG_EXACT_SUM) return 0;
+        if (!(prm.flags & QW_FLAG_R8) && n % 16 == 0 && n / 16 >= 32 && n / 16 <= 256) return 16;
+        if (n % 8 == 0 && n / 8 >= 32 && n / 8 <= 512) return 8;
+        return 0;
+    }
     if (!(prm.flags & QW_FLAG_R8) && n % 16 == 0 && n / 16 >= 32 && n / 16 <= 256) return 16;
     if (n % 8 == 0 && n / 8 >= 32 && n / 8 <= 512) return 8;
     return 0;
@@ -421,17 +612,28 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
     if (R == 0) return cudaErrorInvalidConfiguration;
     prm.nact = (int)(prm.n / R);
     const int threads = ((prm.nact + 31) / 32) * 32;
-    const size_t smem = (size_t)threads * 4 * sizeof(double2);
+    const bool cyc = prm.topology == QW_TOPO_CYCLE;
+    const size_t smem = cyc ? (size_t)threads * 4 * sizeof(double2) : 0;
     if (plan) {
-        plan->path = 5;
+        plan->path = cyc ? 5 : 6;
         plan->sites_per_thread = R;
+    }
+    if (!cyc) {
+        if (R == 16) {
+            if (threads <= 64) return hlaunch(rk4_complete_horner<16, 64, 6>, prm, threads, smem, st, plan);
+            if (threads <= 128) return hlaunch(rk4_complete_horner<16, 128, 3>, prm, threads, smem, st, plan);
+            return hlaunch(rk4_complete_horner<16, 256, 1>, prm, threads, smem, st, plan);
+        }
+        if (threads <= 128) return hlaunch(rk4_complete_horner<8, 128, 4>, prm, threads, smem, st, plan);
+        if (threads <= 256) return hlaunch(rk4_complete_horner<8, 256, 2>, prm, threads, smem, st, plan);
+        return hlaunch(rk4_complete_horner<8, 512, 1>, prm, threads, smem, st, plan);
     }
     if (R == 16) {
         // register file = 16 K per SM sub-partition: 2 / 3 warps there allow 255 / 168 registers
         if (threads <= 64 && (prm.flags & QW_FLAG_OCC4))
             return hlaunch(rk4_cycle_horner<16, 64, 4>, prm, threads, smem, st, plan);
         if (threads <= 64) return hlaunch(rk4_cycle_horner<16, 64, 6>, prm, threads, smem, st, plan);
-        if (threads <= 128) return hlaunch(rk4_cycle_horner<16, 128, 2>, prm, threads, smem, st, plan);
+        if (threads <= 128) return hlaunch(rk4_cycle_horner<16, 128, 3>, prm, threads, smem, st, plan);
         return hlaunch(rk4_cycle_horner<16, 256, 1>, prm, threads, smem, st, plan);
     }
     if (threads <= 64) return hlaunch(rk4_cycle_horner<8, 64, 8>, prm, threads, smem, st, plan);

@@ -73,3 +73,47 @@ def test_heatmap_matches_the_stage_form_kernel_and_keeps_the_argmax(qw):
     assert np.argmax(res[0][0]) == np.argmax(res[NO_HORNER][0])
     ho, _ = c_oracle.heatmap(1024, "circular", "lin", t, b, n_steps=1200)
     assert np.abs(res[0][0] - ho).max() <= P_TOL and np.argmax(res[0][0]) == np.argmax(ho)
+
+
+@pytest.mark.parametrize("n,flags", [(256, 0), (264, 0), (512, 0), (520, 0), (1024, 0), (1024, R8),
+                                     (2048, 0), (2048, R8), (3072, 0), (4096, 0), (4096, R8),
+                                     (4088, 0)])
+def test_complete_all_schedules_vs_oracle(qw, n, flags):
+    pl = qw.plan(qw.Problem(n=n, topology="complete", n_steps=1, flags=flags))
+    assert pl["path"] == "horner-complete", pl
+    rng = np.random.default_rng(7 * n + flags)
+    for sched in ["lin", "sqrt", "cbrt", "cerf_3", "cerf_5", "cerf_7", "static"]:
+        for gamma_on in ("oracle", "laplacian"):
+            P = 4
+            T = rng.uniform(0.0, 40.0 / n, P) if gamma_on == "oracle" else rng.uniform(0.0, 30.0, P)
+            g = rng.uniform(0.0, 2.0 * n, P) if gamma_on == "oracle" else rng.uniform(0.2, 1.6, P) / n
+            T[0] = 0.0
+            g[1] = 0.0
+            S = 100
+            prob = qw.Problem(n=n, topology="complete", schedule=sched, n_steps=S,
+                              gamma_on=gamma_on, flags=flags)
+            p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+            po, no, psio, _ = c_oracle.rk4_batch(n, "complete", sched, T, g, n_steps=S,
+                                                 gamma_on=gamma_on, return_psi=True)
+            assert np.abs(p - po).max() <= P_TOL, (n, sched, gamma_on)
+            assert np.abs(norm - no).max() <= P_TOL, (n, sched, gamma_on)
+            assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched, gamma_on)
+
+
+def test_complete_config3_sample_and_targets(qw):
+    n = 4096
+    T = np.array([512.0, 333.3, 102.5, 20.0])
+    g = np.array([0.0002446, 0.0004897, 0.0005108, 0.0003])
+    for sched in ("cerf_3", "lin"):
+        prob = qw.Problem(n=n, topology="complete", schedule=sched, gamma_on="laplacian",
+                          n_steps=2048)
+        p, norm = qw.rk4_batch(prob, T, g)
+        po, no, _ = c_oracle.rk4_batch(n, "complete", sched, T, g, n_steps=2048,
+                                       gamma_on="laplacian")
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+    for target in (0, 5, 1000, 1023):
+        prob = qw.Problem(n=1024, topology="complete", schedule="lin", target=target, n_steps=50)
+        p, norm, psi = qw.rk4_batch(prob, [0.03], [700.0], return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(1024, "complete", "lin", [0.03], [700.0], n_steps=50,
+                                             target=target, return_psi=True)
+        assert abs(p[0] - po[0]) <= P_TOL and np.abs(psi - psio).max() <= PSI_TOL, target
