@@ -32,8 +32,24 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FLOPS_PER_SITE_UPDATE = 52          # SURVEY.md section 8d (22 DFMA + 8 DADD)
+FLOPS_PER_SITE_UPDATE = 52          # SURVEY.md section 8d (22 DFMA + 8 DADD): ALGORITHMIC flops
 METRIC = "rk4_site_updates_per_sec"
+
+
+def executed_fp64_per_site_update(plan):
+    """FP64 instructions the selected kernel issues per site-update (per lane), from the
+    kernel sources: classic stage form 30 (cycle) / 22 (complete); nested (Horner) form
+    24 (cycle) / 16 (complete) plus the owner warp's oracle corrections (22 warp-instructions
+    per step and block, i.e. 22 * 32 lane-slots over the block's n sites)."""
+    path, r, thr = plan["path"], plan["sites_per_thread"], plan["threads_per_block"]
+    n_block = max(1, r * thr)
+    if path == "horner-cycle":
+        return 24.0 + 22.0 * 32.0 / n_block
+    if path == "horner-complete":
+        return 16.0 + 22.0 * 32.0 / n_block
+    if path == "resident-complete":
+        return 22.0
+    return 30.0
 
 WORKLOADS = {
     # name: n, topology, schedule, gamma_on, n_steps, n_time, T range, gamma range, rows/GPU
@@ -314,6 +330,9 @@ def run_b200(args):
     if rank == 0:
         kernel_s = ms_per_step * 1e-3                 # one launch per step and per GPU
         achieved = FLOPS_PER_SITE_UPDATE * pts_local * w["site_updates_per_point"] / kernel_s / 1e12
+        ex = executed_fp64_per_site_update(plan)
+        lane_rate = plan["sm_count"] * 64 * (clocks["sm_mhz"] or 1965.0) * 1e6    # FP64 lanes/s
+        pipe_util = ex * pts_local * w["site_updates_per_point"] / kernel_s / lane_rate
         line = {
             "metric": METRIC, "value": value, "unit": "site-updates/s",
             "grid_points_per_sec": pts_total / (ms_per_step * 1e-3),
@@ -339,7 +358,13 @@ def run_b200(args):
                          "frac_of_nominal": achieved / (148 * 64 * 2 * 1.965e-3),
                          "probe_clocks": probe_clock,
                          "algorithmic_flops_per_site_update": FLOPS_PER_SITE_UPDATE,
-                         "max_frac_of_fma_peak": 52.0 / 60.0},
+                         "executed_fp64_instructions_per_site_update": ex,
+                         "fp64_pipe_utilisation": pipe_util,
+                         "note": "achieved counts the ALGORITHMIC 52 flops of classic RK4 per "
+                                 "site-update (SURVEY.md 8d); the nested-form kernels issue "
+                                 "fewer FP64 instructions for the same step, so frac = 1 is "
+                                 "not the ceiling: frac <= 52 / (2 * executed instructions)",
+                         "max_frac_of_fma_peak": 52.0 / (2.0 * ex)},
             "e2e": {"value": e2e_value, "unit": "site-updates/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "grid_points_per_sec": pts_total / (e2e_ms * 1e-3)},

@@ -379,30 +379,39 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 // ---------------------------------------------------------------------------------------------
 // Complete graph: (L x)_j = N x_j - sum(x).  A nested level z' = y - i rho (N z - S_z) touches no
 // other site, and the sum of every level input follows from the marked vertex alone because
-// the column sums of L vanish: S(z_l) = S(y) + sigma_l, S(y+) = S(y) + sigma_1.  The sigmas are
-// linear in (y_w, (Ly)_w) here ((L^2 y)_w = N (Ly)_w, (L^3 y)_w = N^2 (Ly)_w), so the owner of
-// the marked vertex (lane 0 of warp 0) produces all four level sums of step n+1 while step n
-// runs, and the block meets at ONE barrier per step instead of one per stage.  16 FP64
-// instructions per site-update (classic stage form: 22).  S(y) is re-anchored to a direct block
-// sum at every coefficient-table refill (32 steps).
+// the column sums of L vanish: S(z_l) = S(y) + sigma_l, S(y+) = S(y) + sigma_1, with sigmas that
+// are linear in (y_w, (Ly)_w) ((L^2 y)_w = N (Ly)_w, (L^3 y)_w = N^2 (Ly)_w).  The pair
+// (y_w, S(y)) is therefore a closed two-variable system.  One warp integrates it a whole
+// 32-step chunk AHEAD of the vector work (interleaved with its own share of that work) and
+// leaves the level sums and corrections of the coming chunk in shared memory; another warp
+// refills the coefficient table two chunks ahead.  Both duties rotate over the warps.  The
+// warps of a block then meet at ONE barrier per chunk and never wait for each other inside
+// it.  16 FP64 instructions per site-update (classic stage form: 22, one barrier per stage).
+// The tracked S(y) is never re-anchored to a direct sum of the state: the difference e between
+// the two obeys e+ = Phi0 e with the step polynomial at the top eigenvalue of L, |Phi0| <= 1
+// inside the stability region of RK4, so rounding noise does not grow -- while a correction
+// that arrives a chunk late has rotated by 32 steps' worth of phase and DOES grow (measured).
 struct CHStep {
     double rho[4];
     double coef[4][8];       // lane 2m + c: component c of sigma_{4-m} over (re, im)(y_w, Ly_w)
     double pad;
 };
 
-struct CHShared {
-    CHStep st[QW_CHUNK];
-    double2 sums[2][4];      // [buffer][S(y), S(z4), S(z3), S(z2)] of a step
-    double red[2 * 2 * 32];
+struct CFShared {
+    CHStep tab[3][QW_CHUNK];             // coefficients of chunk c in tab[c % 3]
+    double2 sums[2][QW_CHUNK][4];        // chunk c in [c & 1]: S(y), S(z4), S(z3), S(z2) per step
+    double2 sig[2][QW_CHUNK][4];         // sigma_4 .. sigma_1 per step (owner thread)
+    double2 xw[2], xs[2];                // tracked y_w, S(y) at the start of chunk c in [c & 1]
+    double red[2 * 32];
 };
 
+// executed by ONE warp: coefficient sets of `cnt` steps starting at step n0
 __device__ __forceinline__ void horner_fill_complete(CHStep *tab, const QwPoint &pt,
                                                      const int64_t n0, const int cnt,
                                                      const int schedule, const int gamma_on,
-                                                     const double n)
+                                                     const double n, const int lane)
 {
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+    for (int i = lane; i < cnt; i += 32) {
         const double t0 = (double)(n0 + i) * pt.h;
         const double2 ad1 = qw_operator_scalars(t0 / pt.T, pt.gamma, schedule, gamma_on);
         const double2 ad2 = qw_operator_scalars((t0 + 0.5 * pt.h) / pt.T, pt.gamma, schedule,
@@ -430,6 +439,42 @@ __device__ __forceinline__ void horner_fill_complete(CHStep *tab, const QwPoint 
     }
 }
 
+// One step of the marked-vertex subsystem.  Every lane of the warp holds the same (yw, Sy);
+// the four corrections are one dot product of length 4 per lane (lane 2m + c: component c of
+// sigma_{4-m}).  Leaves the level sums and corrections of the step in shared memory.
+__device__ __forceinline__ void scalar_step(const CHStep &hs, double2 &yw, double2 &Sy,
+                                            const double nd, double2 *sums4, double2 *sig4,
+                                            const int lane)
+{
+    const unsigned full = 0xffffffffu;
+    const double2 m1 = make_double2(fma(nd, yw.x, -Sy.x), fma(nd, yw.y, -Sy.y));    // (Ly)_w
+    const int l8 = lane & 7;
+    double sgl = hs.coef[0][l8] * yw.x;
+    sgl = fma(hs.coef[1][l8], yw.y, sgl);
+    sgl = fma(hs.coef[2][l8], m1.x, sgl);
+    sgl = fma(hs.coef[3][l8], m1.y, sgl);
+    const double2 g4 = make_double2(__shfl_sync(full, sgl, 0), __shfl_sync(full, sgl, 1));
+    const double2 g3 = make_double2(__shfl_sync(full, sgl, 2), __shfl_sync(full, sgl, 3));
+    const double2 g2 = make_double2(__shfl_sync(full, sgl, 4), __shfl_sync(full, sgl, 5));
+    const double2 g1 = make_double2(__shfl_sync(full, sgl, 6), __shfl_sync(full, sgl, 7));
+    const double2 S4 = make_double2(Sy.x + g4.x, Sy.y + g4.y);
+    const double2 S3 = make_double2(Sy.x + g3.x, Sy.y + g3.y);
+    const double2 S2 = make_double2(Sy.x + g2.x, Sy.y + g2.y);
+    if (lane == 0) {
+        sums4[0] = Sy; sums4[1] = S4; sums4[2] = S3; sums4[3] = S2;
+        sig4[0] = g4; sig4[1] = g3; sig4[2] = g2; sig4[3] = g1;
+    }
+    // the marked vertex through the four levels (same operations as the vector code)
+    double2 z = make_double2(fma(hs.rho[3], m1.y, yw.x) + g4.x, fma(-hs.rho[3], m1.x, yw.y) + g4.y);
+    double2 v = make_double2(fma(nd, z.x, -S4.x), fma(nd, z.y, -S4.y));
+    z = make_double2(fma(hs.rho[2], v.y, yw.x) + g3.x, fma(-hs.rho[2], v.x, yw.y) + g3.y);
+    v = make_double2(fma(nd, z.x, -S3.x), fma(nd, z.y, -S3.y));
+    z = make_double2(fma(hs.rho[1], v.y, yw.x) + g2.x, fma(-hs.rho[1], v.x, yw.y) + g2.y);
+    v = make_double2(fma(nd, z.x, -S2.x), fma(nd, z.y, -S2.y));
+    yw = make_double2(fma(hs.rho[0], v.y, yw.x) + g1.x, fma(-hs.rho[0], v.x, yw.y) + g1.y);
+    Sy = make_double2(Sy.x + g1.x, Sy.y + g1.y);
+}
+
 // one level on all R sites of a thread: out = y - i rho (N x - S)
 template <int R, int LEVEL>
 __device__ __forceinline__ void clevel(HState<R> &s, const double rho, const double nd,
@@ -444,49 +489,43 @@ __device__ __forceinline__ void clevel(HState<R> &s, const double rho, const dou
     }
 }
 
-// Owner warp: level sums and corrections of the step whose coefficients are `hs`, from the
-// marked vertex value yw and S(y) held by lane 0.  Writes the four sums to `out`, returns this
-// lane's component of its sigma (lane 2m + c: sigma_{4-m}) and advances Sy to S(y+).
-__device__ __forceinline__ double complete_duty(const CHStep &hs, const double2 yw, double2 &Sy,
-                                                const double nd, double2 *out, const int t)
+// Vector work of chunk c (cnt steps) and, in the duty warp, the scalar subsystem of chunk c+1
+// (cnt_next steps).  No barrier inside.
+template <int R, bool OWN, bool DUTY>
+__device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const int64_t c,
+                                               const int cnt, const int cnt_next,
+                                               const double nd, const double nfull,
+                                               const double msk, const int lane, const int nwarps)
 {
-    const double m1r = fma(nd, yw.x, -Sy.x), m1i = fma(nd, yw.y, -Sy.y);     // (Ly)_w
-    const int l8 = t & 7;
-    double sgl = hs.coef[0][l8] * __shfl_sync(0xffffffffu, yw.x, 0);
-    sgl = fma(hs.coef[1][l8], __shfl_sync(0xffffffffu, yw.y, 0), sgl);
-    sgl = fma(hs.coef[2][l8], __shfl_sync(0xffffffffu, m1r, 0), sgl);
-    sgl = fma(hs.coef[3][l8], __shfl_sync(0xffffffffu, m1i, 0), sgl);
-    // S(z4), S(z3), S(z2), S(y+) = S(y) + sigma_4 .. sigma_1: lanes 0..7 add their component
-    const double bx = __shfl_sync(0xffffffffu, Sy.x, 0), by = __shfl_sync(0xffffffffu, Sy.y, 0);
-    const double sum = ((l8 & 1) ? by : bx) + sgl;
-    if (t < 6) ((double *)out)[2 + t] = sum;               // S(z4), S(z3), S(z2) as (re, im)
-    if (t == 0) out[0] = make_double2(bx, by);
-    Sy.x = __shfl_sync(0xffffffffu, sum, 6);               // S(y+): the next step's S(y)
-    Sy.y = __shfl_sync(0xffffffffu, sum, 7);
-    return sgl;
-}
-
-template <int R, bool OWN>
-__device__ __forceinline__ void complete_steps(HState<R> &s, CHShared &sh, const int cnt,
-                                               const double nd, const double msk, double2 &Sy,
-                                               double &sgl, const int t)
-{
+    const CHStep *tab = sh.tab[c % 3];
+    const CHStep *tab_next = sh.tab[(c + 1) % 3];
+    const int cur = (int)(c & 1), nxt = cur ^ 1;
+    const double act = (nd != 0.0) ? 1.0 : 0.0;            // idle threads stay at zero
+    double2 yw = make_double2(0.0, 0.0), Sy = yw;
+    if (DUTY) {
+        yw = sh.xw[nxt];                                   // tracked state at the start of c+1
+        Sy = sh.xs[nxt];
+    }
     for (int sidx = 0; sidx < cnt; ++sidx) {
-        const CHStep &hs = sh.st[sidx];
-        const double2 *sm = sh.sums[sidx & 1];
-        const double act = (nd != 0.0) ? 1.0 : 0.0;        // idle threads stay at zero
+        const CHStep &hs = tab[sidx];
+        // all scalars of the step up front: nothing inside the step waits for shared memory
+        double2 Sl[4];
+        double rl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            Sl[k] = sh.sums[cur][sidx][k];
+            Sl[k].x *= act; Sl[k].y *= act;
+            rl[k] = hs.rho[k];
+        }
 #define QW_CH_LEVEL(LEVEL)                                                                  \
         {                                                                                   \
-            double2 S = sm[4 - LEVEL];                                                      \
-            S.x *= act; S.y *= act;                                                         \
-            clevel<R, LEVEL>(s, hs.rho[LEVEL - 1], nd, S);                                  \
+            clevel<R, LEVEL>(s, rl[LEVEL - 1], nd, Sl[4 - LEVEL]);                          \
             if (OWN) {                                                                      \
-                const double sgr = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));          \
-                const double sgi = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);      \
+                const double2 sg = sh.sig[cur][sidx][4 - LEVEL];                            \
                 if (LEVEL > 1) {                                                            \
-                    s.zr[0] = fma(msk, sgr, s.zr[0]); s.zi[0] = fma(msk, sgi, s.zi[0]);     \
+                    s.zr[0] = fma(msk, sg.x, s.zr[0]); s.zi[0] = fma(msk, sg.y, s.zi[0]);   \
                 } else {                                                                    \
-                    s.yr[0] = fma(msk, sgr, s.yr[0]); s.yi[0] = fma(msk, sgi, s.yi[0]);     \
+                    s.yr[0] = fma(msk, sg.x, s.yr[0]); s.yi[0] = fma(msk, sg.y, s.yi[0]);   \
                 }                                                                           \
             }                                                                               \
         }
@@ -495,51 +534,75 @@ __device__ __forceinline__ void complete_steps(HState<R> &s, CHShared &sh, const
         QW_CH_LEVEL(2)
         QW_CH_LEVEL(1)
 #undef QW_CH_LEVEL
-        if (OWN && sidx + 1 < cnt)                         // scalars of the next step
-            sgl = complete_duty(sh.st[sidx + 1], make_double2(s.yr[0], s.yi[0]), Sy, nd,
-                                sh.sums[(sidx + 1) & 1], t);
-        __syncthreads();
+        if (DUTY && sidx < cnt_next)
+            scalar_step(tab_next[sidx], yw, Sy, nfull, sh.sums[nxt][sidx], sh.sig[nxt][sidx], lane);
+    }
+    if (DUTY && lane == 0) {                               // start of chunk c+2
+        sh.xw[cur] = yw;
+        sh.xs[cur] = Sy;
     }
 }
 
 template <int R, int MAXNT, int MINB>
 __global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_horner(const QwParams prm)
 {
-    __shared__ CHShared sh;
+    __shared__ CFShared sh;
     const int t = threadIdx.x, nact = prm.nact;
+    const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
     const QwPoint pt = qw_point(prm, blockIdx.x);
     const bool active = t < nact;
-    const double nd = active ? (double)prm.n : 0.0;
+    const double nfull = (double)prm.n;
+    const double nd = active ? nfull : 0.0;
 
     HState<R> s;
-    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+    const double amp = active ? 1.0 / sqrt(nfull) : 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         s.yr[r] = amp; s.yi[r] = 0.0;
         s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
     const double msk = (t == 0) ? 1.0 : 0.0;
-    double sgl = 0.0;
+    const int64_t nchunks = (pt.steps + QW_CHUNK - 1) / QW_CHUNK;
+#define QW_CNT(C) ((int)((pt.steps - (C) * QW_CHUNK) < QW_CHUNK ? (pt.steps - (C) * QW_CHUNK) : QW_CHUNK))
 
-    for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
-        const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
-        __syncthreads();                               // the last chunk's table is no longer read
-        horner_fill_complete(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, (double)prm.n);
-        // re-anchor S(y) to a direct summation of the state
+    if (nchunks > 0) {
+        // prologue: tables of chunks 0 and 1, scalar subsystem of chunk 0
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) { a += s.yr[r]; b += s.yi[r]; }
-        double2 Sy = hblock_sum(make_double2(a, b), sh.red + (int)((n0 / QW_CHUNK) & 1) * 64);
-        __syncthreads();                               // table complete
-        if (t < 32) {
-            sgl = complete_duty(sh.st[0], make_double2(s.yr[0], s.yi[0]), Sy, nd, sh.sums[0], t);
-            __syncthreads();
-            complete_steps<R, true>(s, sh, cnt, nd, msk, Sy, sgl, t);
-        } else {
-            __syncthreads();
-            complete_steps<R, false>(s, sh, cnt, nd, msk, Sy, sgl, t);
+        const double2 S0 = hblock_sum(make_double2(a, b), sh.red);
+        if (warp == 0)
+            horner_fill_complete(sh.tab[0], pt, 0, QW_CNT(0), prm.schedule, prm.gamma_on, nfull, lane);
+        if (nchunks > 1 && warp == (nwarps > 1 ? 1 : 0))
+            horner_fill_complete(sh.tab[1], pt, QW_CHUNK, QW_CNT(1), prm.schedule, prm.gamma_on,
+                                 nfull, lane);
+        __syncthreads();
+        if (warp == 0) {
+            double2 yw = make_double2(1.0 / sqrt(nfull), 0.0), Sy = S0;
+            if (lane == 0) sh.xs[0] = S0;
+            const int cnt0 = QW_CNT(0);
+            for (int sidx = 0; sidx < cnt0; ++sidx)
+                scalar_step(sh.tab[0][sidx], yw, Sy, nfull, sh.sums[0][sidx], sh.sig[0][sidx], lane);
+            if (lane == 0) { sh.xw[1] = yw; sh.xs[1] = Sy; }
         }
     }
+    for (int64_t c = 0; c < nchunks; ++c) {
+        __syncthreads();
+        const int cnt = QW_CNT(c);
+        const bool duty = (c + 1 < nchunks) && warp == (int)(c % nwarps);
+        const int cnt_next = duty ? QW_CNT(c + 1) : 0;
+        if (c + 2 < nchunks && warp == (int)((c + 1) % nwarps))
+            horner_fill_complete(sh.tab[(c + 2) % 3], pt, (c + 2) * QW_CHUNK, QW_CNT(c + 2),
+                                 prm.schedule, prm.gamma_on, nfull, lane);
+        if (warp == 0) {
+            if (duty) complete_chunk<R, true, true>(s, sh, c, cnt, cnt_next, nd, nfull, msk, lane, nwarps);
+            else complete_chunk<R, true, false>(s, sh, c, cnt, cnt_next, nd, nfull, msk, lane, nwarps);
+        } else {
+            if (duty) complete_chunk<R, false, true>(s, sh, c, cnt, cnt_next, nd, nfull, msk, lane, nwarps);
+            else complete_chunk<R, false, false>(s, sh, c, cnt, cnt_next, nd, nfull, msk, lane, nwarps);
+        }
+    }
+#undef QW_CNT
 
     double nrm = 0.0;
 #pragma unroll
