@@ -381,12 +381,13 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 // other site, and the sum of every level input follows from the marked vertex alone because
 // the column sums of L vanish: S(z_l) = S(y) + sigma_l, S(y+) = S(y) + sigma_1, with sigmas that
 // are linear in (y_w, (Ly)_w) ((L^2 y)_w = N (Ly)_w, (L^3 y)_w = N^2 (Ly)_w).  The pair
-// (y_w, S(y)) is therefore a closed two-variable system.  One warp integrates it a whole
-// 32-step chunk AHEAD of the vector work (interleaved with its own share of that work) and
-// leaves the level sums and corrections of the coming chunk in shared memory; another warp
-// refills the coefficient table two chunks ahead.  Both duties rotate over the warps.  The
-// warps of a block then meet at ONE barrier per chunk and never wait for each other inside
-// it.  16 FP64 instructions per site-update (classic stage form: 22, one barrier per stage).
+// (y_w, S(y)) is therefore a closed two-variable system.  One extra warp of the block (the
+// "scalar warp", no sites of its own) integrates it a whole 32-step chunk AHEAD of the vector
+// work and leaves the level sums and corrections of the coming chunk in shared memory; it also
+// refills the coefficient table two chunks ahead.  The worker warps meet at ONE barrier per
+// chunk and never wait inside it.  16 FP64 instructions per site-update (classic stage form:
+// 22, one barrier per stage).  (Rotating the two duties over the worker warps instead was
+// measured 19 % barrier stall: the duty warp finishes its chunk last and alone.)
 // The tracked S(y) is never re-anchored to a direct sum of the state: the difference e between
 // the two obeys e+ = Phi0 e with the step polynomial at the top eigenvalue of L, |Phi0| <= 1
 // inside the stability region of RK4, so rounding noise does not grow -- while a correction
@@ -401,7 +402,6 @@ struct CFShared {
     CHStep tab[3][QW_CHUNK];             // coefficients of chunk c in tab[c % 3]
     double2 sums[2][QW_CHUNK][4];        // chunk c in [c & 1]: S(y), S(z4), S(z3), S(z2) per step
     double2 sig[2][QW_CHUNK][4];         // sigma_4 .. sigma_1 per step (owner thread)
-    double2 xw[2], xs[2];                // tracked y_w, S(y) at the start of chunk c in [c & 1]
     double red[2 * 32];
 };
 
@@ -489,23 +489,14 @@ __device__ __forceinline__ void clevel(HState<R> &s, const double rho, const dou
     }
 }
 
-// Vector work of chunk c (cnt steps) and, in the duty warp, the scalar subsystem of chunk c+1
-// (cnt_next steps).  No barrier inside.
-template <int R, bool OWN, bool DUTY>
+// Vector work of chunk c (cnt steps).  No barrier inside.
+template <int R, bool OWN>
 __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const int64_t c,
-                                               const int cnt, const int cnt_next,
-                                               const double nd, const double nfull,
-                                               const double msk, const int lane, const int nwarps)
+                                               const int cnt, const double nd, const double msk)
 {
     const CHStep *tab = sh.tab[c % 3];
-    const CHStep *tab_next = sh.tab[(c + 1) % 3];
-    const int cur = (int)(c & 1), nxt = cur ^ 1;
+    const int cur = (int)(c & 1);
     const double act = (nd != 0.0) ? 1.0 : 0.0;            // idle threads stay at zero
-    double2 yw = make_double2(0.0, 0.0), Sy = yw;
-    if (DUTY) {
-        yw = sh.xw[nxt];                                   // tracked state at the start of c+1
-        Sy = sh.xs[nxt];
-    }
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const CHStep &hs = tab[sidx];
         // all scalars of the step up front: nothing inside the step waits for shared memory
@@ -534,21 +525,16 @@ __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const
         QW_CH_LEVEL(2)
         QW_CH_LEVEL(1)
 #undef QW_CH_LEVEL
-        if (DUTY && sidx < cnt_next)
-            scalar_step(tab_next[sidx], yw, Sy, nfull, sh.sums[nxt][sidx], sh.sig[nxt][sidx], lane);
-    }
-    if (DUTY && lane == 0) {                               // start of chunk c+2
-        sh.xw[cur] = yw;
-        sh.xs[cur] = Sy;
     }
 }
 
+// blockDim = worker threads (n / R rounded up to warps) + 32: the last warp is the scalar warp
 template <int R, int MAXNT, int MINB>
-__global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_horner(const QwParams prm)
+__global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const QwParams prm)
 {
     __shared__ CFShared sh;
     const int t = threadIdx.x, nact = prm.nact;
-    const int lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+    const int lane = t & 31, warp = t >> 5, swarp = (blockDim.x >> 5) - 1;
     const QwPoint pt = qw_point(prm, blockIdx.x);
     const bool active = t < nact;
     const double nfull = (double)prm.n;
@@ -565,41 +551,41 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_horner(const QwParam
     const int64_t nchunks = (pt.steps + QW_CHUNK - 1) / QW_CHUNK;
 #define QW_CNT(C) ((int)((pt.steps - (C) * QW_CHUNK) < QW_CHUNK ? (pt.steps - (C) * QW_CHUNK) : QW_CHUNK))
 
+    double2 yw = make_double2(1.0 / sqrt(nfull), 0.0), Sy = make_double2(0.0, 0.0);
     if (nchunks > 0) {
-        // prologue: tables of chunks 0 and 1, scalar subsystem of chunk 0
+        // prologue: S(y) by direct summation; tables of chunks 0 and 1, scalars of chunk 0
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) { a += s.yr[r]; b += s.yi[r]; }
-        const double2 S0 = hblock_sum(make_double2(a, b), sh.red);
-        if (warp == 0)
+        Sy = hblock_sum(make_double2(a, b), sh.red);
+        if (warp == swarp) {
             horner_fill_complete(sh.tab[0], pt, 0, QW_CNT(0), prm.schedule, prm.gamma_on, nfull, lane);
-        if (nchunks > 1 && warp == (nwarps > 1 ? 1 : 0))
-            horner_fill_complete(sh.tab[1], pt, QW_CHUNK, QW_CNT(1), prm.schedule, prm.gamma_on,
-                                 nfull, lane);
-        __syncthreads();
-        if (warp == 0) {
-            double2 yw = make_double2(1.0 / sqrt(nfull), 0.0), Sy = S0;
-            if (lane == 0) sh.xs[0] = S0;
+            if (nchunks > 1)
+                horner_fill_complete(sh.tab[1], pt, QW_CHUNK, QW_CNT(1), prm.schedule,
+                                     prm.gamma_on, nfull, lane);
+            __syncwarp();
             const int cnt0 = QW_CNT(0);
             for (int sidx = 0; sidx < cnt0; ++sidx)
                 scalar_step(sh.tab[0][sidx], yw, Sy, nfull, sh.sums[0][sidx], sh.sig[0][sidx], lane);
-            if (lane == 0) { sh.xw[1] = yw; sh.xs[1] = Sy; }
         }
     }
     for (int64_t c = 0; c < nchunks; ++c) {
         __syncthreads();
-        const int cnt = QW_CNT(c);
-        const bool duty = (c + 1 < nchunks) && warp == (int)(c % nwarps);
-        const int cnt_next = duty ? QW_CNT(c + 1) : 0;
-        if (c + 2 < nchunks && warp == (int)((c + 1) % nwarps))
-            horner_fill_complete(sh.tab[(c + 2) % 3], pt, (c + 2) * QW_CHUNK, QW_CNT(c + 2),
-                                 prm.schedule, prm.gamma_on, nfull, lane);
-        if (warp == 0) {
-            if (duty) complete_chunk<R, true, true>(s, sh, c, cnt, cnt_next, nd, nfull, msk, lane, nwarps);
-            else complete_chunk<R, true, false>(s, sh, c, cnt, cnt_next, nd, nfull, msk, lane, nwarps);
+        if (warp == swarp) {
+            // two chunks ahead: coefficients; one chunk ahead: the (y_w, S) subsystem
+            if (c + 2 < nchunks)
+                horner_fill_complete(sh.tab[(c + 2) % 3], pt, (c + 2) * QW_CHUNK, QW_CNT(c + 2),
+                                     prm.schedule, prm.gamma_on, nfull, lane);
+            if (c + 1 < nchunks) {
+                const CHStep *tn = sh.tab[(c + 1) % 3];
+                const int cn = QW_CNT(c + 1), nxt = (int)((c + 1) & 1);
+                for (int sidx = 0; sidx < cn; ++sidx)
+                    scalar_step(tn[sidx], yw, Sy, nfull, sh.sums[nxt][sidx], sh.sig[nxt][sidx], lane);
+            }
+        } else if (warp == 0) {
+            complete_chunk<R, true>(s, sh, c, QW_CNT(c), nd, msk);
         } else {
-            if (duty) complete_chunk<R, false, true>(s, sh, c, cnt, cnt_next, nd, nfull, msk, lane, nwarps);
-            else complete_chunk<R, false, false>(s, sh, c, cnt, cnt_next, nd, nfull, msk, lane, nwarps);
+            complete_chunk<R, false>(s, sh, c, QW_CNT(c), nd, msk);
         }
     }
 #undef QW_CNT
@@ -682,14 +668,15 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
         plan->sites_per_thread = R;
     }
     if (!cyc) {
+        const int bt = threads + 32;              // + the scalar warp
         if (R == 16) {
-            if (threads <= 64) return hlaunch(rk4_complete_horner<16, 64, 6>, prm, threads, smem, st, plan);
-            if (threads <= 128) return hlaunch(rk4_complete_horner<16, 128, 3>, prm, threads, smem, st, plan);
-            return hlaunch(rk4_complete_horner<16, 256, 1>, prm, threads, smem, st, plan);
+            if (threads <= 64) return hlaunch(rk4_complete_horner<16, 64, 4>, prm, bt, smem, st, plan);
+            if (threads <= 128) return hlaunch(rk4_complete_horner<16, 128, 2>, prm, bt, smem, st, plan);
+            return hlaunch(rk4_complete_horner<16, 256, 1>, prm, bt, smem, st, plan);
         }
-        if (threads <= 128) return hlaunch(rk4_complete_horner<8, 128, 4>, prm, threads, smem, st, plan);
-        if (threads <= 256) return hlaunch(rk4_complete_horner<8, 256, 2>, prm, threads, smem, st, plan);
-        return hlaunch(rk4_complete_horner<8, 512, 1>, prm, threads, smem, st, plan);
+        if (threads <= 128) return hlaunch(rk4_complete_horner<8, 128, 3>, prm, bt, smem, st, plan);
+        if (threads <= 256) return hlaunch(rk4_complete_horner<8, 256, 1>, prm, bt, smem, st, plan);
+        return hlaunch(rk4_complete_horner<8, 512, 1>, prm, bt, smem, st, plan);
     }
     if (R == 16) {
         // register file = 16 K per SM sub-partition: 2 / 3 warps there allow 255 / 168 registers

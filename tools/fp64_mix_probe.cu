@@ -61,6 +61,45 @@ __global__ void __launch_bounds__(256) kC(int iters, double seed, double *sink)
     if (s == 123.456) sink[0] = s;
 }
 
+// F: two fresh operands and one reused: acc = fma(rho, acc, y[c])
+__global__ void __launch_bounds__(256) kF(int iters, double seed, double *sink)
+{
+    double acc[C], y[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { acc[c] = seed + c + threadIdx.x; y[c] = 1e-9 * (c + 1) * seed; }
+    const double rho = 1.0 - 1e-9 * seed;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = fma(rho, acc[c], y[c]);
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s += acc[c];
+    if (s == 123.456) sink[0] = s;
+}
+
+// H: the complete-graph level: t = fma(nd, z, -S) (1 fresh), z = fma(rho, t, y) (2 fresh)
+__global__ void __launch_bounds__(256) kH(int iters, double seed, double *sink)
+{
+    double z[C], y[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { z[c] = seed + c + threadIdx.x; y[c] = 1e-9 * (c + 1) * seed; }
+    const double rho = 1e-3 * seed, nd = 1.0 + 1e-9 * seed, mS = 1e-9 * seed;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const double t = fma(nd, z[c], mS);
+                z[c] = fma(rho, t, y[c]);
+            }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s += z[c];
+    if (s == 123.456) sink[0] = s;
+}
+
 // D / E: the nested-form level on R = 16 sites per thread (ring closed inside the thread),
 // 24 FP64 instructions per site and step; SYNC adds one block barrier per level
 // RHO: 0 = kernel-parameter derived (uniform register), 1 = loaded from shared memory per level
@@ -144,6 +183,10 @@ int main()
     run("B dfma 3 varying operands", kB, 1, 256, 4000, 256.0);
     run("C dadd 2 varying operands", kC, 2, 256, 4000, 256.0);
     run("C dadd 2 varying operands", kC, 1, 256, 4000, 256.0);
+    run("F dfma 2 fresh + 1 reused", kF, 2, 256, 4000, 256.0);
+    run("F dfma 2 fresh + 1 reused", kF, 1, 256, 4000, 256.0);
+    run("H complete-graph level pattern", kH, 2, 256, 4000, 256.0);
+    run("H complete-graph level pattern", kH, 1, 256, 4000, 256.0);
     run("D nested level, no barrier", kD<false, 4>, 4, 64, 20000, 16 * 24.0);
     run("D nested level, no barrier", kD<false, 6>, 6, 64, 20000, 16 * 24.0);
     run("D nested level, no barrier", kD<false, 4>, 2, 64, 20000, 16 * 24.0);
