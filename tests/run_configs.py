@@ -168,7 +168,9 @@ def main():
     ms, (p, nrm) = timed(lambda: qw.rk4_batch(prob, dT, dg), reps=3)
     st = qw.ensemble_stats(p)
     po, _, _ = c_oracle.rk4_batch(n, "circular", "lin", T[:8], g[:8], n_steps=512)
-    print("| C4 cycle N=256 1e5 noisy (T,gamma), sigma=5%%, S=512 | resident-cycle R=8 x 32 thr | "
+    pl = qw.plan(prob)
+    kname = "%s R=%d x %d thr" % (pl["path"], pl["sites_per_thread"], pl["threads_per_block"])
+    print("| C4 cycle N=256 1e5 noisy (T,gamma), sigma=5%%, S=512 | " + kname + " | "
           "100000 | %.1f | %.3e | %.3e | centre (T0=%.4f, gamma0=%.3f, p0=%.6f); mean %.6f std "
           "%.6f, R=p0-mean=%.6f, frac>=0.8/0.9/0.95/0.99 = %s | %.1e |"
           % (ms, 1e5 * n * 512 / (ms * 1e-3), 1e5 / (ms * 1e-3), T0, g0, p0, st["mean"], st["std"],
@@ -184,7 +186,7 @@ def main():
         ms, (p, nrm) = timed(lambda: qw.rk4_batch(probl, dT, dg))
         st = qw.ensemble_stats(p)
         print("| C4 localization: cycle N=256, T0=N^2/2=32768, S=131072, 2e4 realisations | "
-              "resident-cycle R=8 x 32 thr | 20000 | %.1f | %.3e | %.3e | mean %.6f std %.6f, "
+              + kname + " | 20000 | %.1f | %.3e | %.3e | mean %.6f std %.6f, "
               "frac>=0.8/0.9/0.95/0.99 = %s | n/a |"
               % (ms, 2e4 * n * 131072 / (ms * 1e-3), 2e4 / (ms * 1e-3), st["mean"], st["std"],
                  "/".join("%.4f" % v for v in st["fraction_ge"].values())), flush=True)

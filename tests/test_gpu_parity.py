@@ -268,6 +268,8 @@ def test_plan_reports_native_kernels(qw):
     pl = qw.plan(qw.Problem(n=1024, topology="circular", n_steps=1, flags=256))
     assert pl["sites_per_thread"] == 8 and pl["threads_per_block"] == 128
     pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1))
+    assert pl["path"] == "horner-complete" and pl["threads_per_block"] == 288   # + scalar warp
+    pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1, flags=2048))
     assert pl["path"] == "resident-complete" and pl["threads_per_block"] == 256
     before = qw.launch_count()
     qw.rk4_batch(qw.Problem(n=16, n_steps=4), [1.0], [1.0])
