@@ -88,12 +88,14 @@ int choose_path(const QwParams &prm)
 {
     if (prm.flags & QW_FLAG_FORCE_GENERIC) return PATH_GENERIC;
     if ((prm.flags & QW_FLAG_FORCE_STREAM) && qw_stream_supported(prm)) return PATH_STREAM;
+    const bool horner = !(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_CYCLE_SPLIT |
+                                       QW_FLAG_NO_HORNER | QW_FLAG_COMPLETE_FREE)) &&
+                        qw_horner_sites_per_thread(prm) > 0;
+    // from 512 sites on a point fills a warp of the packed kernel anyway: nested form first
+    if (horner && prm.n >= 512) return PATH_HORNER;
     if (!(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_NO_PACK)) && qw_packed_supported(prm))
         return PATH_PACKED;
-    if (!(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_CYCLE_SPLIT | QW_FLAG_NO_HORNER |
-                       QW_FLAG_COMPLETE_FREE)) &&
-        qw_horner_sites_per_thread(prm) > 0)
-        return PATH_HORNER;
+    if (horner) return PATH_HORNER;
     if (qw_resident_sites_per_thread(prm.n) > 0) return PATH_RESIDENT;
     if (qw_stream_supported(prm)) return PATH_STREAM;
     return PATH_GENERIC;

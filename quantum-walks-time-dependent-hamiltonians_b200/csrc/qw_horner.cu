@@ -23,17 +23,9 @@
 // thread 0 holds w-3..w+R-4 and all the oracle work is local to it.  Halo values cross
 // threads through a double-buffered shared-memory mailbox, one __syncthreads() per level;
 // edge slots are updated and published first.
-#include "qw_common.cuh"
+#include "qw_horner_level.cuh"
 
 namespace {
-
-constexpr int HW0 = 3;               // slot of the marked vertex in thread 0
-
-struct HornerCoef {                  // coefficients of one RK4 step
-    double rho[4];                   // r1 (outermost) .. r4 (innermost)
-    double2 c[10];                   // sigma_4: c[0]; sigma_3: c[1..2]; sigma_2: c[3..5];
-                                     // sigma_1: c[6..9]  (basis y_w, Ly_w, L^2y_w, L^3y_w)
-};
 
 // Shared-memory form for the cycle kernel.  The four corrections are evaluated by eight lanes
 // of the owner warp at once: lane 2m + c holds component c (0 re, 1 im) of sigma_{4-m} as a
@@ -51,75 +43,6 @@ struct HornerShared {
     int owner;
 };
 
-__device__ __forceinline__ double2 mul_mi(const double s, const double2 v)   // (-i s) v
-{
-    return make_double2(s * v.y, -s * v.x);
-}
-
-__device__ __forceinline__ double2 axpy2(const double s, const double2 v, const double2 acc)
-{
-    return make_double2(fma(s, v.x, acc.x), fma(s, v.y, acc.y));
-}
-
-__device__ __forceinline__ double safe_inv(const double x) { return x != 0.0 ? 1.0 / x : 0.0; }
-
-// Coefficients of one step.  ad1, ad2, ad4 = (a, d) at t_n, t_n + h/2, t_n + h;
-// lww = L_ww, l2ww = (L^2)_ww.
-__device__ void horner_coefficients(HornerCoef &o, const double h, const double2 ad1,
-                                    const double2 ad2, const double2 ad4, const double lww,
-                                    const double l2ww)
-{
-    const double A1 = 0.5 * h * ad1.x, A2 = 0.5 * h * ad2.x, A3 = h * ad2.x;
-    const double B1 = h / 6.0 * ad1.x, B2 = h / 3.0 * ad2.x, B4 = h / 6.0 * ad4.x;
-    const double DA1 = 0.5 * h * ad1.y, DA2 = 0.5 * h * ad2.y, DA3 = h * ad2.y;
-    const double DB1 = h / 6.0 * ad1.y, DB2 = h / 3.0 * ad2.y, DB4 = h / 6.0 * ad4.y;
-    const double b1 = B1 + 2.0 * B2 + B4;
-    const double b2 = B2 * A1 + B2 * A2 + B4 * A3;
-    const double b3 = B2 * A2 * A1 + B4 * A3 * A2;
-    const double b4 = B4 * A3 * A2 * A1;
-    const double i1 = safe_inv(b1), i2 = safe_inv(b2), i3 = safe_inv(b3);
-    o.rho[0] = b1; o.rho[1] = b2 * i1; o.rho[2] = b3 * i2; o.rho[3] = b4 * i3;
-
-    const double2 zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
-    // q_s = true stage value at the marked vertex, al_s = -i c_s d_s q_s, as coefficient
-    // vectors over (y_w, Ly_w, L^2y_w, L^3y_w)
-    double2 q2[4], q3[4], q4[4], al1[4], al2[4], al3[4];
-    al1[0] = make_double2(0.0, -DA1); al1[1] = zero; al1[2] = zero; al1[3] = zero;
-    q2[0] = make_double2(1.0, -DA1); q2[1] = make_double2(0.0, -A1); q2[2] = zero; q2[3] = zero;
-    const double2 u3[4] = {one, make_double2(0.0, -A2), make_double2(-A2 * A1, 0.0), zero};
-    const double2 u4[4] = {one, make_double2(0.0, -A3), make_double2(-A3 * A2, 0.0),
-                           make_double2(0.0, A3 * A2 * A1)};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        al2[j] = mul_mi(DA2, q2[j]);
-        const double2 t3 = mul_mi(A2 * lww, al1[j]);
-        q3[j] = make_double2(u3[j].x + t3.x + al2[j].x, u3[j].y + t3.y + al2[j].y);
-        al3[j] = mul_mi(DA3, q3[j]);
-        const double2 t4 = mul_mi(A3 * lww, al2[j]);
-        q4[j] = make_double2(u4[j].x - A3 * A2 * l2ww * al1[j].x + t4.x + al3[j].x,
-                             u4[j].y - A3 * A2 * l2ww * al1[j].y + t4.y + al3[j].y);
-    }
-    double2 k0[4], k1[4], k2[4], k3[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        double2 s = (j == 0) ? make_double2(DB1, 0.0) : zero;          // DB1 q1
-        s = axpy2(DB2, q2[j], s);
-        s = axpy2(DB2, q3[j], s);
-        s = axpy2(DB4, q4[j], s);
-        k0[j] = make_double2(s.y, -s.x);                               // -i s
-        k1[j] = axpy2(B4, al3[j], axpy2(B2, al2[j], make_double2(B2 * al1[j].x, B2 * al1[j].y)));
-        k2[j] = axpy2(B4 * A3, al2[j], make_double2(B2 * A2 * al1[j].x, B2 * A2 * al1[j].y));
-        k3[j] = make_double2(B4 * A3 * A2 * al1[j].x, B4 * A3 * A2 * al1[j].y);
-    }
-    o.c[0] = make_double2(k3[0].x * i3, k3[0].y * i3);
-    o.c[1] = make_double2(k2[0].x * i2, k2[0].y * i2);
-    o.c[2] = make_double2(k2[1].x * i2, k2[1].y * i2);
-    o.c[3] = make_double2(k1[0].x * i1, k1[0].y * i1);
-    o.c[4] = make_double2(k1[1].x * i1, k1[1].y * i1);
-    o.c[5] = make_double2(k1[2].x * i1, k1[2].y * i1);
-    o.c[6] = k0[0]; o.c[7] = k0[1]; o.c[8] = k0[2]; o.c[9] = k0[3];
-}
-
 // One thread per step of the chunk; stage times as in qw_fill_table (t_n = n h by
 // multiplication, tau = t / T by division).  Caller synchronises before and after.
 __device__ __forceinline__ void horner_fill_cycle(HornerStep *tab, const QwPoint &pt,
@@ -134,18 +57,8 @@ __device__ __forceinline__ void horner_fill_cycle(HornerStep *tab, const QwPoint
         const double2 ad4 = qw_operator_scalars((t0 + pt.h) / pt.T, pt.gamma, schedule, gamma_on);
         HornerCoef hc;
         horner_coefficients(hc, pt.h, ad1, ad2, ad4, 2.0, 6.0);     // L_ww = 2, (L^2)_ww = 6
-        // basis (y_w, s1, s2, s3):  Ly_w = 2y - s1,  L^2y_w = 6y - 4s1 + s2,
-        //                           L^3y_w = 20y - 15s1 + 6s2 - s3
-        double2 *c = hc.c;
-        c[1] = axpy2(2.0, c[2], c[1]);
-        c[2] = make_double2(-c[2].x, -c[2].y);
-        c[3] = axpy2(6.0, c[5], axpy2(2.0, c[4], c[3]));
-        c[4] = make_double2(-c[4].x - 4.0 * c[5].x, -c[4].y - 4.0 * c[5].y);
-        c[6] = axpy2(20.0, c[9], axpy2(6.0, c[8], axpy2(2.0, c[7], c[6])));
-        c[7] = make_double2(-c[7].x - 4.0 * c[8].x - 15.0 * c[9].x,
-                            -c[7].y - 4.0 * c[8].y - 15.0 * c[9].y);
-        c[8] = axpy2(6.0, c[9], c[8]);
-        c[9] = make_double2(-c[9].x, -c[9].y);
+        horner_cycle_sum_basis(hc.c);
+        const double2 *c = hc.c;
         HornerStep &o = tab[i];
 #pragma unroll
         for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
@@ -159,57 +72,6 @@ __device__ __forceinline__ void horner_fill_cycle(HornerStep *tab, const QwPoint
                 o.coef[2 * k][2 * m + 1] = ck.y;  o.coef[2 * k + 1][2 * m + 1] = ck.x;   // im
             }
         }
-    }
-}
-
-// out = y - i rho (2 c - l - r)
-__device__ __forceinline__ void hsite(const double lr, const double li, const double cr,
-                                      const double ci, const double rr, const double ri,
-                                      const double rho, const double y_r, const double y_i,
-                                      double &o_r, double &o_i)
-{
-    const double vr = fma(2.0, cr, -(lr + rr));
-    const double vi = fma(2.0, ci, -(li + ri));
-    o_r = fma(rho, vi, y_r);
-    o_i = fma(-rho, vr, y_i);
-}
-
-template <int R>
-struct HState {
-    double yr[R], yi[R];   // psi_n
-    double zr[R], zi[R];   // nested intermediate
-};
-
-// LEVEL 4: x = y, out = z.  LEVEL 3, 2: x = z, out = z (in place).  LEVEL 1: x = z, out = y.
-#define HX_R(r) ((LEVEL == 4) ? s.yr[r] : s.zr[r])
-#define HX_I(r) ((LEVEL == 4) ? s.yi[r] : s.zi[r])
-#define HO_R(r) ((LEVEL == 1) ? s.yr[r] : s.zr[r])
-#define HO_I(r) ((LEVEL == 1) ? s.yi[r] : s.zi[r])
-
-template <int R, int LEVEL>
-__device__ __forceinline__ void hedges(HState<R> &s, const double rho, const double2 hl,
-                                       const double2 hr, double2 &o0, double2 &oL)
-{
-    o0 = make_double2(HX_R(0), HX_I(0));
-    oL = make_double2(HX_R(R - 1), HX_I(R - 1));
-    hsite(hl.x, hl.y, o0.x, o0.y, HX_R(1), HX_I(1), rho, s.yr[0], s.yi[0], HO_R(0), HO_I(0));
-    hsite(HX_R(R - 2), HX_I(R - 2), oL.x, oL.y, hr.x, hr.y, rho, s.yr[R - 1], s.yi[R - 1],
-          HO_R(R - 1), HO_I(R - 1));
-}
-
-template <int R, int LEVEL>
-__device__ __forceinline__ void hinterior(HState<R> &s, const double rho, const double2 o0,
-                                          const double2 oL)
-{
-    double pr = o0.x, pi = o0.y;
-#pragma unroll
-    for (int r = 1; r < R - 1; ++r) {
-        const double cr = HX_R(r), ci = HX_I(r);
-        const double nr = (r + 1 < R - 1) ? HX_R(r + 1 < R ? r + 1 : r) : oL.x;
-        const double ni = (r + 1 < R - 1) ? HX_I(r + 1 < R ? r + 1 : r) : oL.y;
-        hsite(pr, pi, cr, ci, nr, ni, rho, s.yr[r], s.yi[r], HO_R(r), HO_I(r));
-        pr = cr;
-        pi = ci;
     }
 }
 
@@ -615,6 +477,11 @@ template <typename K>
 cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cudaStream_t st,
                     qw_plan *plan)
 {
+    if (smem + sizeof(HornerShared) > 48 * 1024) {     // static + dynamic above the default cap
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     if (plan) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
@@ -627,11 +494,6 @@ cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cud
         plan->regs_per_thread = fa.numRegs;
         plan->smem_bytes = (int)(fa.sharedSizeBytes + smem);
         return cudaSuccess;
-    }
-    if (smem + sizeof(HornerShared) > 48 * 1024) {     // static + dynamic above the default cap
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return e;
     }
     kernel<<<(unsigned)prm.n_points, threads, smem, st>>>(prm);
     return cudaGetLastError();

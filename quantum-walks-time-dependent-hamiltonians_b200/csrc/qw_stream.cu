@@ -19,7 +19,10 @@
 // Replaces the same reference path as the resident kernels (BCB.py:163-203 with the step
 // rule of QW_Search.py:149-164); vertices keep their physical labels, so the marked vertex
 // can sit in any slot of any window (including the redundant halo copies).
+#include <type_traits>
+
 #include "qw_stage.cuh"
+#include "qw_horner_level.cuh"
 
 namespace {
 
@@ -60,12 +63,48 @@ struct PassEntry {
     int32_t pad[3];
 };
 
-template <int SR>
+// The same for the nested (Horner) form of the step (qw_horner_level.cuh): r1..r4 and the ten
+// correction coefficients over (y_w, s1, s2, s3) per step.
+struct HPassEntry {
+    double rho[4 * 4];
+    double2 c[4 * 10];
+    int32_t kb;
+    int32_t pad[3];
+};
+
+template <int SR, bool HORNER>
 struct StreamShared {
+    using Entry = typename std::conditional<HORNER, HPassEntry, PassEntry>::type;
     double2 xbuf[Geo<SR>::DEPTH][Geo<SR>::PAD];   // window ring (load target, store staging)
-    PassEntry tab[Geo<SR>::DEPTH];        // the point's pass entry travels with its window
+    Entry tab[Geo<SR>::DEPTH];            // the point's pass entry travels with its window
     double2 mbox[4 * Geo<SR>::NT];        // [parity][first/last][thread]
 };
+
+__global__ void stream_pass_tables_horner(const QwParams prm, int64_t count, int64_t step0,
+                                          int kbmax, HPassEntry *__restrict__ tab)
+{
+    const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= count) return;
+    const QwPoint pt = qw_point(prm, prm.point_offset + local);
+    const int64_t todo = pt.steps - step0;
+    const int kb = todo < 0 ? 0 : (todo > kbmax ? kbmax : (int)todo);
+    HPassEntry &e = tab[local];
+    e.kb = kb;
+    const double h = pt.h;
+    for (int s = 0; s < kb; ++s) {
+        const double t0 = (double)(step0 + s) * h;
+        const double2 c0 = qw_operator_scalars(t0 / pt.T, pt.gamma, prm.schedule, prm.gamma_on);
+        const double2 c1 = qw_operator_scalars((t0 + 0.5 * h) / pt.T, pt.gamma, prm.schedule,
+                                               prm.gamma_on);
+        const double2 c2 = qw_operator_scalars((t0 + h) / pt.T, pt.gamma, prm.schedule,
+                                               prm.gamma_on);
+        HornerCoef hc;
+        horner_coefficients(hc, h, c0, c1, c2, 2.0, 6.0);
+        horner_cycle_sum_basis(hc.c);
+        for (int k = 0; k < 4; ++k) e.rho[4 * s + k] = hc.rho[k];
+        for (int k = 0; k < 10; ++k) e.c[10 * s + k] = hc.c[k];
+    }
+}
 
 __global__ void stream_pass_tables(const QwParams prm, int64_t count, int64_t step0, int kbmax,
                                    PassEntry *__restrict__ tab)
@@ -152,11 +191,14 @@ struct Win {
     static constexpr int TILE = Geo<SR>::W - 2 * HALO;
 };
 
-template <int KB, int SR, bool ALIGNED>
-__device__ __forceinline__ void prefetch_window(StreamShared<SR> &sh, int slot, const double2 *in,
-                                                const PassEntry *tab, int64_t n, uint32_t idx,
-                                                uint32_t tiles, int t)
+template <int KB, int SR, bool ALIGNED, bool HORNER>
+__device__ __forceinline__ void prefetch_window(StreamShared<SR, HORNER> &sh, int slot,
+                                                const double2 *in,
+                                                const typename StreamShared<SR, HORNER>::Entry *tab,
+                                                int64_t n, uint32_t idx, uint32_t tiles, int t)
 {
+    using Entry = typename StreamShared<SR, HORNER>::Entry;
+    static_assert(sizeof(Entry) % 16 == 0 && sizeof(Entry) / 16 <= Geo<SR>::NT, "entry copy");
     constexpr int HALO = Win<KB, SR, ALIGNED>::HALO, TILE = Win<KB, SR, ALIGNED>::TILE,
                   SNT = Geo<SR>::NT;
     const uint32_t local = idx / tiles, tile = idx - local * tiles;
@@ -171,23 +213,31 @@ __device__ __forceinline__ void prefetch_window(StreamShared<SR> &sh, int slot, 
         if (j >= n) { j -= n; if (j >= n) j %= n; }
         cp_async16(&xb[Geo<SR>::pad(e)], &src[j]);
     }
-    if (t < (int)(sizeof(PassEntry) / 16))
+    if (t < (int)(sizeof(Entry) / 16))
         cp_async16(reinterpret_cast<char *>(&sh.tab[slot]) + 16 * t,
                    reinterpret_cast<const char *>(tab + local) + 16 * t);
     cp_async_commit();
 }
 
-template <int KB, int SR, bool ALIGNED>
+// HORNER (ALIGNED only): the nested form of the step, 24 instead of 30 FP64 instructions per
+// site-update; the ring is then rotated so that the marked vertex is logical site 3, i.e. slot
+// 3 of a thread whose segment holds the whole window w-3..w+3 of the oracle corrections.
+template <int KB, int SR, bool ALIGNED, bool HORNER>
 __global__ void __launch_bounds__(Geo<SR>::NT, Geo<SR>::BLOCKS_PER_SM)
 rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__restrict__ out,
-                 const PassEntry *__restrict__ tab, uint32_t tiles, uint32_t total)
+                 const typename StreamShared<SR, HORNER>::Entry *__restrict__ tab, uint32_t tiles,
+                 uint32_t total)
 {
+    static_assert(!HORNER || (ALIGNED && SR >= 2 * HW0 + 1), "nested form needs the aligned layout");
+    using Shared = StreamShared<SR, HORNER>;
+    using Entry = typename Shared::Entry;
+    using Regs = typename std::conditional<HORNER, HState<SR>, State<SR>>::type;
     constexpr int HALO = Win<KB, SR, ALIGNED>::HALO;
     constexpr int TILE = Win<KB, SR, ALIGNED>::TILE;
     constexpr int SNT = Geo<SR>::NT;
     constexpr int SDEPTH = Geo<SR>::DEPTH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    StreamShared<SR> &sh = *reinterpret_cast<StreamShared<SR> *>(smem_raw);
+    Shared &sh = *reinterpret_cast<Shared *>(smem_raw);
 
     const int t = threadIdx.x;
     const int64_t n = prm.n;
@@ -203,7 +253,7 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
 #pragma unroll
     for (int k = 0; k < SDEPTH - 1; ++k) {
         const uint64_t w = (uint64_t)idx + (uint64_t)k * stride;
-        if (w < total) prefetch_window<KB, SR, ALIGNED>(sh, k, in, tab, n, (uint32_t)w, tiles, t);
+        if (w < total) prefetch_window<KB, SR, ALIGNED, HORNER>(sh, k, in, tab, n, (uint32_t)w, tiles, t);
         else cp_async_commit();
     }
 
@@ -214,19 +264,20 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
 
         cp_async_wait_pending<SDEPTH - 2>();
         __syncthreads();               // window idx has landed; the slot freed last round is free
-        const PassEntry &pe = sh.tab[slot];
+        const Entry &pe = sh.tab[slot];
         const int kb = pe.kb;
-        State<SR> s;
+        Regs s;
 #pragma unroll
         for (int r = 0; r < SR; ++r) {
             const double2 v = sh.xbuf[slot][Geo<SR>::pad(t * SR + r)];
             s.yr[r] = v.x; s.yi[r] = v.y;
-            s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+            if constexpr (HORNER) { s.zr[r] = 0.0; s.zi[r] = 0.0; }
+            else { s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0; }
         }
         {
             const uint64_t w = (uint64_t)idx + (uint64_t)(SDEPTH - 1) * stride;
             const int ps = (slot + SDEPTH - 1) % SDEPTH;
-            if (w < total) prefetch_window<KB, SR, ALIGNED>(sh, ps, in, tab, n, (uint32_t)w, tiles, t);
+            if (w < total) prefetch_window<KB, SR, ALIGNED, HORNER>(sh, ps, in, tab, n, (uint32_t)w, tiles, t);
             else cp_async_commit();
         }
 
@@ -242,6 +293,50 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
             fst[t] = make_double2(s.yr[0], s.yi[0]);
             lst[t] = make_double2(s.yr[SR - 1], s.yi[SR - 1]);
             __syncthreads();                   // edge values published
+            if constexpr (HORNER) {
+              const bool own = own_slot == HW0;
+              double2 b0 = zero2, b1 = zero2, b2 = zero2, b3 = zero2;
+              for (int sidx = 0; sidx < kb; ++sidx) {
+#define QW_STREAM_LEVEL(LEVEL, CBASE, NTERMS)                                           \
+                {                                                                       \
+                    if (LEVEL < 4 || sidx > 0) __syncthreads();                         \
+                    const double2 hl = lst[par * SNT + tl];                             \
+                    const double2 hr = fst[par * SNT + tr];                             \
+                    const double rho = pe.rho[4 * sidx + LEVEL - 1];                    \
+                    double2 o0, oL;                                                     \
+                    if (LEVEL == 4 && warp_owns && own) {                               \
+                        b0 = make_double2(s.yr[HW0], s.yi[HW0]);                        \
+                        b1 = make_double2(s.yr[HW0 - 1] + s.yr[HW0 + 1], s.yi[HW0 - 1] + s.yi[HW0 + 1]); \
+                        b2 = make_double2(s.yr[HW0 - 2] + s.yr[HW0 + 2], s.yi[HW0 - 2] + s.yi[HW0 + 2]); \
+                        b3 = make_double2(s.yr[HW0 - 3] + s.yr[HW0 + 3], s.yi[HW0 - 3] + s.yi[HW0 + 3]); \
+                    }                                                                   \
+                    hedges<SR, LEVEL>(s, rho, hl, hr, o0, oL);                          \
+                    hinterior<SR, LEVEL>(s, rho, o0, oL);                               \
+                    if (warp_owns && own) {        /* oracle correction sigma_LEVEL */  \
+                        const double2 *c = pe.c + 10 * sidx + CBASE;                    \
+                        double2 sg = cmul2(c[0], b0);                                   \
+                        if (NTERMS > 1) sg = cmul2_acc(c[1], b1, sg);                   \
+                        if (NTERMS > 2) sg = cmul2_acc(c[2], b2, sg);                   \
+                        if (NTERMS > 3) sg = cmul2_acc(c[3], b3, sg);                   \
+                        if (LEVEL > 1) { s.zr[HW0] += sg.x; s.zi[HW0] += sg.y; }        \
+                        else { s.yr[HW0] += sg.x; s.yi[HW0] += sg.y; }                  \
+                    }                                                                   \
+                    par ^= 1;                                                           \
+                    if (LEVEL > 1) {                                                    \
+                        fst[par * SNT + t] = make_double2(s.zr[0], s.zi[0]);            \
+                        lst[par * SNT + t] = make_double2(s.zr[SR - 1], s.zi[SR - 1]);  \
+                    } else {                                                            \
+                        fst[par * SNT + t] = make_double2(s.yr[0], s.yi[0]);            \
+                        lst[par * SNT + t] = make_double2(s.yr[SR - 1], s.yi[SR - 1]);  \
+                    }                                                                   \
+                }
+                QW_STREAM_LEVEL(4, 0, 1)
+                QW_STREAM_LEVEL(3, 1, 2)
+                QW_STREAM_LEVEL(2, 3, 3)
+                QW_STREAM_LEVEL(1, 6, 4)
+#undef QW_STREAM_LEVEL
+              }
+            } else {
             for (int sidx = 0; sidx < kb; ++sidx) {
 #define QW_STREAM_STAGE(K)                                                              \
                 {                                                                       \
@@ -274,6 +369,7 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
                 QW_STREAM_STAGE(2)
                 QW_STREAM_STAGE(3)
 #undef QW_STREAM_STAGE
+            }
             }
         }
 
@@ -331,7 +427,9 @@ __global__ void __launch_bounds__(512) stream_finish(const QwParams prm, const d
     }
     const double2 tot = qw_block_sum2(nrm, 0.0, red);
     if (threadIdx.x == 0) {
-        const double2 v = src[prm.target - prm.stream_rot];
+        int64_t lw = prm.target - prm.stream_rot;          // logical site of the marked vertex
+        if (lw < 0) lw += n;
+        const double2 v = src[lw];
         prm.p[pt.q] = fma(v.x, v.x, v.y * v.y) / tot.x;
         if (prm.norm) prm.norm[pt.q] = tot.x;
     }
@@ -364,60 +462,88 @@ int sm_count()
     return g_sm_count;
 }
 
-template <int KB, int SR, bool ALIGNED>
+template <int KB, int SR, bool ALIGNED, bool HORNER>
 cudaError_t configure()
 {
     static bool configured = false;
     if (configured) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(rk4_cycle_stream<KB, SR, ALIGNED>,
+    cudaError_t e = cudaFuncSetAttribute(rk4_cycle_stream<KB, SR, ALIGNED, HORNER>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(StreamShared<SR>));
+                                         (int)sizeof(StreamShared<SR, HORNER>));
     if (e == cudaSuccess) configured = true;
     return e;
 }
 
-template <int KB, int SR, bool ALIGNED>
-cudaError_t launch_pass_a(const QwParams &prm, const double2 *in, double2 *out, PassEntry *tab,
+template <int KB, int SR, bool ALIGNED, bool HORNER>
+cudaError_t launch_pass_a(const QwParams &prm, const double2 *in, double2 *out, void *tab,
                           int64_t step0, int64_t points, cudaStream_t st)
 {
+    using Entry = typename StreamShared<SR, HORNER>::Entry;
     constexpr int TILE = Win<KB, SR, ALIGNED>::TILE;
-    stream_pass_tables<<<(unsigned)((points + 127) / 128), 128, 0, st>>>(prm, points, step0, KB,
-                                                                         tab);
+    Entry *etab = static_cast<Entry *>(tab);
+    if constexpr (HORNER)
+        stream_pass_tables_horner<<<(unsigned)((points + 127) / 128), 128, 0, st>>>(
+            prm, points, step0, KB, etab);
+    else
+        stream_pass_tables<<<(unsigned)((points + 127) / 128), 128, 0, st>>>(prm, points, step0,
+                                                                             KB, etab);
     const uint32_t tiles = (uint32_t)((prm.n + TILE - 1) / TILE);
     const uint64_t total = (uint64_t)points * tiles;
     uint32_t grid = (uint32_t)(sm_count() * Geo<SR>::BLOCKS_PER_SM);       // persistent blocks
     if (total < grid) grid = (uint32_t)total;
-    cudaError_t e = configure<KB, SR, ALIGNED>();
+    cudaError_t e = configure<KB, SR, ALIGNED, HORNER>();
     if (e != cudaSuccess) return e;
-    rk4_cycle_stream<KB, SR, ALIGNED><<<grid, Geo<SR>::NT, sizeof(StreamShared<SR>), st>>>(
-        prm, in, out, tab, tiles, (uint32_t)total);
+    rk4_cycle_stream<KB, SR, ALIGNED, HORNER>
+        <<<grid, Geo<SR>::NT, sizeof(StreamShared<SR, HORNER>), st>>>(prm, in, out, etab, tiles,
+                                                                      (uint32_t)total);
     return cudaGetLastError();
 }
 
-template <int KB, int SR>
-cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, PassEntry *tab,
-                        int64_t step0, int64_t points, cudaStream_t st)
+// nested form wherever the aligned layout applies (n a multiple of the sites per thread)
+bool stream_horner(const QwParams &prm, int sr)
 {
-    return prm.n % SR == 0 ? launch_pass_a<KB, SR, true>(prm, in, out, tab, step0, points, st)
-                           : launch_pass_a<KB, SR, false>(prm, in, out, tab, step0, points, st);
+    return prm.n % sr == 0 && !(prm.flags & QW_FLAG_NO_HORNER);
 }
 
 template <int KB, int SR>
-cudaError_t plan_of(qw_plan *plan)
+cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, void *tab,
+                        int64_t step0, int64_t points, cudaStream_t st)
+{
+    if (stream_horner(prm, SR))
+        return launch_pass_a<KB, SR, true, true>(prm, in, out, tab, step0, points, st);
+    return prm.n % SR == 0
+               ? launch_pass_a<KB, SR, true, false>(prm, in, out, tab, step0, points, st)
+               : launch_pass_a<KB, SR, false, false>(prm, in, out, tab, step0, points, st);
+}
+
+template <int KB, int SR>
+cudaError_t plan_of(qw_plan *plan, bool horner)
 {
     cudaFuncAttributes fa;
     int occ = 0;
-    cudaError_t e = configure<KB, SR, true>();
-    if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB, SR, true>);
-    if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rk4_cycle_stream<KB, SR, true>,
-                                                          Geo<SR>::NT, sizeof(StreamShared<SR>));
+    cudaError_t e;
+    size_t smem;
+    if (horner) {
+        smem = sizeof(StreamShared<SR, true>);
+        e = configure<KB, SR, true, true>();
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB, SR, true, true>);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &occ, rk4_cycle_stream<KB, SR, true, true>, Geo<SR>::NT, smem);
+    } else {
+        smem = sizeof(StreamShared<SR, false>);
+        e = configure<KB, SR, true, false>();
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB, SR, true, false>);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &occ, rk4_cycle_stream<KB, SR, true, false>, Geo<SR>::NT, smem);
+    }
     if (e != cudaSuccess) return e;
     plan->sites_per_thread = SR;
     plan->threads_per_block = Geo<SR>::NT;
     plan->blocks_per_sm = occ;
     plan->regs_per_thread = fa.numRegs;
-    plan->smem_bytes = (int)(fa.sharedSizeBytes + sizeof(StreamShared<SR>));
+    plan->smem_bytes = (int)(fa.sharedSizeBytes + smem);
     plan->steps_per_pass = KB;
     return cudaSuccess;
 }
@@ -439,7 +565,7 @@ cudaError_t qw_stream_plan(const QwParams &prm, qw_plan *plan)
 {
     plan->path = 3;
     const int kb = stream_kb(prm), sr = stream_sr(prm);
-    return QW_STREAM_DISPATCH(plan_of, plan);
+    return QW_STREAM_DISPATCH(plan_of, plan, stream_horner(prm, sr));
 }
 
 cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *launches)
@@ -447,7 +573,12 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     QwParams prm = prm_in;
     const int kb = stream_kb(prm), sr = stream_sr(prm);
     const int64_t n = prm.n;
-    prm.stream_rot = (n % sr == 0) ? prm.target : 0;     // aligned layout: marked vertex first
+    // aligned layout: the marked vertex is logical site 0 (stage form) or HW0 (nested form)
+    prm.stream_rot = 0;
+    if (n % sr == 0) {
+        prm.stream_rot = prm.target - (stream_horner(prm, sr) ? HW0 : 0);
+        if (prm.stream_rot < 0) prm.stream_rot += n;
+    }
     // points in flight: bounded by ~8 GiB of ping-pong scratch and by 32-bit window indices
     int64_t chunk = (int64_t)(8ull << 30) / (2 * n * (int64_t)sizeof(double2));
     const int64_t tiles_max = n / (1024 - 32) + 2;
@@ -459,8 +590,9 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     cudaError_t e = cudaMallocAsync((void **)&bufA, (size_t)chunk * 2 * n * sizeof(double2), st);
     if (e != cudaSuccess) return e;
     double2 *bufB = bufA + chunk * n;
-    PassEntry *tab = nullptr;
-    e = cudaMallocAsync((void **)&tab, (size_t)chunk * sizeof(PassEntry), st);
+    void *tab = nullptr;
+    const size_t entry = sizeof(HPassEntry) > sizeof(PassEntry) ? sizeof(HPassEntry) : sizeof(PassEntry);
+    e = cudaMallocAsync(&tab, (size_t)chunk * entry, st);
     if (e != cudaSuccess) { cudaFreeAsync(bufA, st); return e; }
     const bool varying = prm.step_size > 0.0 || prm.n_steps != nullptr;
     if (varying) {

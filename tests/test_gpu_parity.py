@@ -277,11 +277,12 @@ def test_plan_reports_native_kernels(qw):
 
 
 @pytest.mark.parametrize("n", [8, 64, 1000, 1016, 1024, 2050, 4100, 9001])
-@pytest.mark.parametrize("kb_flag", [8, 16, 0, 256, 256 | 8])
+@pytest.mark.parametrize("kb_flag", [8, 16, 0, 256, 256 | 8, 2048, 2048 | 8, 2048 | 16])
 def test_streaming_kernel_vs_oracle(qw, n, kb_flag):
     """Tile-fused HBM-streaming kernel (flags: 2 = force it, 8 / 16 = 1 / 2 steps per pass,
-    default 4; 256 = 8 instead of 16 sites per thread for n >= 4096), windows that wrap,
-    ragged last tiles, marked vertex in a halo copy."""
+    default 4; 256 = 8 instead of 16 sites per thread for n >= 4096; 2048 = stage form instead
+    of the nested form, which is used whenever n is a multiple of the sites per thread),
+    windows that wrap, ragged last tiles, marked vertex in a halo copy."""
     rng = np.random.default_rng(n + kb_flag)
     T = np.concatenate([[0.0], rng.uniform(1.0, 9.0, 3)])
     g = rng.uniform(0.1, 2.4, 4)
@@ -299,7 +300,7 @@ def test_streaming_kernel_vs_oracle(qw, n, kb_flag):
 def test_streaming_kernel_step_size_rule_and_targets(qw):
     T = np.array([0.0, 0.31, 0.117, 0.25])
     g = np.array([1.0, 0.5, 2.0, 0.1])
-    for target in (None, 0, 1015, 1016, 2999):
+    for target in (None, 0, 1, 2, 3, 4, 1015, 1016, 2997, 2999):
         prob = qw.Problem(n=3000, topology="circular", schedule="sqrt", step_size=1e-2,
                           target=target, flags=2)
         p, norm = qw.rk4_batch(prob, T, g)

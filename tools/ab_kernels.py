@@ -45,13 +45,20 @@ def main():
     ap.add_argument("--rows", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--workload", default="c5")
+    ap.add_argument("--n", type=int, default=0, help="override the dimension of the shape")
+    ap.add_argument("--only", default="", help="comma-separated flag values to run")
     a = ap.parse_args()
-    sh = SHAPES[a.workload]
+    sh = dict(SHAPES[a.workload])
+    if a.n:
+        sh["n"] = a.n
     dev = torch.device("cuda")
     t = torch.linspace(sh["t"][0], sh["t"][1], sh["nT"], dtype=torch.float64, device=dev)
     b = torch.linspace(sh["g"][0], sh["g"][1], a.rows, dtype=torch.float64, device=dev)
     ref = None
+    only = [int(x) for x in a.only.split(",") if x]
     for name, flags in VARIANTS[a.workload]:
+        if only and flags not in only:
+            continue
         prob = qw.Problem(n=sh["n"], topology=sh["topology"], schedule=sh["schedule"],
                           n_steps=sh["n_steps"], gamma_on=sh.get("gamma_on", "oracle"),
                           flags=flags)
