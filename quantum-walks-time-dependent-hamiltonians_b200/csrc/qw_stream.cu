@@ -222,8 +222,14 @@ __device__ __forceinline__ void prefetch_window(StreamShared<SR, HORNER> &sh, in
 // HORNER (ALIGNED only): the nested form of the step, 24 instead of 30 FP64 instructions per
 // site-update; the ring is then rotated so that the marked vertex is logical site 3, i.e. slot
 // 3 of a thread whose segment holds the whole window w-3..w+3 of the oracle corrections.
+// resident blocks per SM.  (The nested form needs two instead of three complex vectors in
+// registers and would fit five blocks of the 64 x 16 geometry at 168 registers: measured
+// 3.64e11 vs 4.01e11 site-updates/s at KB = 4, so it stays at four.)
+template <int SR, bool HORNER>
+constexpr int stream_blocks_per_sm() { return Geo<SR>::BLOCKS_PER_SM; }
+
 template <int KB, int SR, bool ALIGNED, bool HORNER>
-__global__ void __launch_bounds__(Geo<SR>::NT, Geo<SR>::BLOCKS_PER_SM)
+__global__ void __launch_bounds__(Geo<SR>::NT, stream_blocks_per_sm<SR, HORNER>())
 rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__restrict__ out,
                  const typename StreamShared<SR, HORNER>::Entry *__restrict__ tab, uint32_t tiles,
                  uint32_t total)
@@ -489,7 +495,7 @@ cudaError_t launch_pass_a(const QwParams &prm, const double2 *in, double2 *out, 
                                                                              KB, etab);
     const uint32_t tiles = (uint32_t)((prm.n + TILE - 1) / TILE);
     const uint64_t total = (uint64_t)points * tiles;
-    uint32_t grid = (uint32_t)(sm_count() * Geo<SR>::BLOCKS_PER_SM);       // persistent blocks
+    uint32_t grid = (uint32_t)(sm_count() * stream_blocks_per_sm<SR, HORNER>());   // persistent
     if (total < grid) grid = (uint32_t)total;
     cudaError_t e = configure<KB, SR, ALIGNED, HORNER>();
     if (e != cudaSuccess) return e;
