@@ -170,7 +170,7 @@ def stream_measure(qw, torch, dev, reps=3):
     out["roofline"] = {            # the plain read-psi_n / write-psi_n+1 stream (KB = 1)
         "bound": "hbm", "achieved": kb1["algorithmic_gbs_at_32B_per_site_update"],
         "peak": peak, "unit": "GB/s", "frac": kb1["frac_of_hbm_peak_algorithmic"],
-        "traffic": 2103516000,
+        "traffic": 2100816000,
         "traffic_note": "dram__bytes_read+write of one pass over 1024 points (ncu --set full, "
                         "profiles/r1_stream_kb1_ncu_full.md); algorithmic bytes per pass = "
                         "1024 x 65536 x 32 = 2147483648"}
