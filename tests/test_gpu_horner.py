@@ -117,3 +117,28 @@ def test_complete_config3_sample_and_targets(qw):
         po, no, psio, _ = c_oracle.rk4_batch(1024, "complete", "lin", [0.03], [700.0], n_steps=50,
                                              target=target, return_psi=True)
         assert abs(p[0] - po[0]) <= P_TOL and np.abs(psi - psio).max() <= PSI_TOL, target
+
+
+@pytest.mark.parametrize("topo,n", [("circular", 1024), ("complete", 1024), ("complete", 4096),
+                                    ("circular", 65536)])
+def test_chunk_edges_per_point_steps_and_order(qw, topo, n):
+    """Step counts around the 32-step coefficient-table chunks (and the 3-deep table ring of
+    the complete-graph kernel), per-point n_steps arrays, a block order permutation and the
+    host-buffer C entry point."""
+    S = np.array([0, 1, 2, 31, 32, 33, 63, 64, 65, 95, 96, 97, 129], dtype=np.int64)
+    P = S.size
+    rng = np.random.default_rng(n)
+    if topo == "circular":                 # keep every step inside RK4's stability region
+        h, g = rng.uniform(0.05, 0.25, P), rng.uniform(0.0, 2.5, P)
+    else:
+        h, g = rng.uniform(0.2, 1.0, P) / n, rng.uniform(0.0, 2.0 * n, P)
+    T = np.where(S > 0, h * S, 1.0)
+    prob = qw.Problem(n=n, topology=topo, schedule="cerf_5")
+    order = rng.permutation(P)
+    p, norm, psi = qw.rk4_batch(prob, T, g, n_steps=S, order=order, return_psi=True)
+    po, no, psio, _ = c_oracle.rk4_batch(n, topo, "cerf_5", T, g, n_steps=S, return_psi=True)
+    assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+    assert np.abs(psi - psio).max() <= PSI_TOL
+    assert p[0] == pytest.approx(1.0 / n, abs=1e-15)
+    ph, nh = qw.rk4_batch_host(prob, T, g, n_steps=S)
+    assert np.array_equal(ph, p) and np.array_equal(nh, norm)
