@@ -106,8 +106,10 @@ __device__ __forceinline__ unsigned warp_slot()
 // A step has four levels, so the mailbox parity of a level is a compile-time constant: level 4
 // and 2 read buffer 0 and write buffer 1, level 3 and 1 the other way round.
 // (A pairwise bar.arrive / bar.sync handshake between the two warps of a block instead of the
-// block barrier was measured: equal at best, -6 % once the publication was pinned early --
-// ptxas places the arithmetic around the barriers as it likes)
+// block barrier was measured: equal at best, -6 % once the publication was pinned early.
+// ptxas moves arithmetic across BAR.ARV / BAR.SYNC freely: whatever the PTX order, the interior
+// arithmetic of a level ends up after the *next* wait, so an arrival is always followed at once
+// by the wait for the partner's arrival of the same level -- a plain barrier.  DESIGN.md 7.)
 template <int R, bool OWN>
 __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab, double2 *first,
                                              double2 *last, const int nt, const int t,
