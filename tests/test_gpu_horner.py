@@ -142,3 +142,43 @@ def test_chunk_edges_per_point_steps_and_order(qw, topo, n):
     assert p[0] == pytest.approx(1.0 / n, abs=1e-15)
     ph, nh = qw.rk4_batch_host(prob, T, g, n_steps=S)
     assert np.array_equal(ph, p) and np.array_equal(nh, norm)
+
+
+def test_randomised_nested_vs_stage_form(qw):
+    """Differential test: the nested-form kernels against the stage-form kernels
+    (QW_FLAG_NO_HORNER) on random problems -- dimension, graph, schedule, gamma placement, step
+    rule, marked vertex -- at 1e-12, far below the parity tolerance."""
+    rng = np.random.default_rng(20240607)
+    scheds = ["lin", "sqrt", "cbrt", "cerf_3", "cerf_5", "cerf_7", "static"]
+    for trial in range(40):
+        topo = "circular" if trial % 2 == 0 else "complete"
+        n = int(rng.choice([256, 264, 512, 776, 1024, 1536, 2048, 4096]))
+        sched = scheds[int(rng.integers(len(scheds)))]
+        gamma_on = "oracle" if rng.random() < 0.5 else "laplacian"
+        target = int(rng.integers(n))
+        P = 3
+        if topo == "circular":
+            h = rng.uniform(0.02, 0.25, P)      # h * 4 * gamma <= 2.5: inside RK4 stability
+            g = rng.uniform(0.0, 2.5, P)
+        else:
+            h = rng.uniform(0.1, 1.0, P) / n
+            g = rng.uniform(0.0, 2.0, P) * (n if gamma_on == "oracle" else 1.0 / n)
+            if gamma_on == "laplacian":
+                h = h * n * rng.uniform(0.3, 1.0)       # a = (1-g) gamma ~ 1/n: h up to ~1
+        steps = rng.integers(1, 200, P)
+        if rng.random() < 0.5:
+            kw, T = dict(n_steps=None), h * steps
+            extra = dict(n_steps=steps.astype(np.int64))
+        else:
+            hs = float(h[0])
+            kw, T = dict(step_size=hs), hs * steps + rng.uniform(0.0, 0.9, P) * hs
+            extra = {}
+        res = []
+        for flags in (0, NO_HORNER):
+            prob = qw.Problem(n=n, topology=topo, schedule=sched, gamma_on=gamma_on,
+                              target=target, flags=flags, **{k: v for k, v in kw.items() if v})
+            res.append(qw.rk4_batch(prob, T, g, return_psi=True, **extra))
+        ctx = (trial, topo, n, sched, gamma_on, target)
+        assert np.abs(res[0][0] - res[1][0]).max() <= 1e-12, ctx
+        assert np.abs(res[0][1] - res[1][1]).max() <= 1e-12, ctx
+        assert np.abs(res[0][2] - res[1][2]).max() <= 1e-12, ctx
