@@ -45,6 +45,8 @@ def executed_fp64_per_site_update(plan):
     n_block = max(1, r * thr)
     if path == "horner-cycle":
         return 24.0 + 22.0 * 32.0 / n_block
+    if path == "packed-horner-cycle":
+        return 24.0 + 22.0 * 32.0 / 512.0
     if path == "horner-complete":
         return 16.0 + 22.0 * 32.0 / n_block
     if path == "resident-complete":

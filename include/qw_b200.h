@@ -201,7 +201,8 @@ int qw_heatmap_summary_dev(const double *p, const double *time_array, int64_t n_
 
 typedef struct qw_plan {
     int32_t path;            /* 0 resident-cycle, 1 resident-complete, 2 generic, 3 stream,
-                                4 warp-packed cycle, 5 / 6 resident cycle / complete in nested form */
+                                4 warp-packed cycle, 5 / 6 resident cycle / complete in nested form,
+                                7 warp-packed cycle in nested form */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */

@@ -11,6 +11,7 @@
 // Same arithmetic as qw_resident.cu (reference path BCB.py:163-203, step rule
 // QW_Search.py:149-164).
 #include "qw_stage.cuh"
+#include "qw_horner_level.cuh"
 
 namespace {
 
@@ -106,6 +107,179 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Nested (Horner) form of the step for the packed layout (qw_horner_level.cuh):
+// N = 16 * TPP with TPP = 8 or 16 lanes per point (N = 128, 256; from 512 sites on the
+// block-per-point kernel of qw_horner.cu takes over).  24 instead of 30 FP64 instructions per
+// site-update and two instead of three complex vectors in registers (12 instead of 8 warps
+// per SM).  The step coefficients depend on the point (h, gamma), so every point of the warp
+// has its own table: a refill computes 32 coefficient sets -- 32 / G steps for each of the
+// G = 32 / TPP points -- one per lane.  The marked vertex is slot 3 of the first lane of a
+// point's group; eight lanes of the group evaluate its four corrections at once.
+struct PackedStep {                  // as HornerStep in qw_horner.cu
+    double rho[4];
+    double coef[8][8];
+    double pad;
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwParams prm,
+                                                                    const int tpp_log2)
+{
+    constexpr int R = 16;
+    __shared__ PackedStep tab[32];               // [group][step of the chunk]
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int tpp = 1 << tpp_log2, groups = 32 >> tpp_log2, ch = 32 / groups;   // ch = tpp
+    const int li = lane & (tpp - 1), grp = lane >> tpp_log2, gbase = grp << tpp_log2;
+    int64_t b = (int64_t)blockIdx.x * groups + grp;
+    const bool valid = b < prm.n_points;
+    if (!valid) b = prm.n_points - 1;            // idle groups shadow the last point
+    const QwPoint pt = qw_point(prm, b);
+    const int64_t S = prm.n_steps_uniform;
+    const int left = (li == 0) ? lane + tpp - 1 : lane - 1;
+    const int right = (li == tpp - 1) ? lane - tpp + 1 : lane + 1;
+    const double msk = (li == 0) ? 1.0 : 0.0;
+    // the lane's refill duty: step (lane % ch) of point (lane / ch) of this warp
+    const int fgrp = lane / ch, fstep = lane - fgrp * ch;
+    int64_t fb = (int64_t)blockIdx.x * groups + fgrp;
+    if (fb >= prm.n_points) fb = prm.n_points - 1;
+    const QwPoint fpt = qw_point(prm, fb);
+
+    HState<R> s;
+    const double amp = 1.0 / sqrt((double)prm.n);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.zr[r] = 0.0; s.zi[r] = 0.0;
+    }
+
+    for (int64_t n0 = 0; n0 < S; n0 += ch) {
+        __syncwarp();
+        if (n0 + fstep < S && fpt.steps == 0) {        // T == 0: identity step (BCB.py:72-73)
+            PackedStep &o = tab[lane];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o.rho[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int m = 0; m < 8; ++m) o.coef[k][m] = 0.0;
+        } else if (n0 + fstep < S) {
+            const double t0 = (double)(n0 + fstep) * fpt.h;
+            const double2 ad1 = qw_operator_scalars(t0 / fpt.T, fpt.gamma, prm.schedule, prm.gamma_on);
+            const double2 ad2 = qw_operator_scalars((t0 + 0.5 * fpt.h) / fpt.T, fpt.gamma,
+                                                    prm.schedule, prm.gamma_on);
+            const double2 ad4 = qw_operator_scalars((t0 + fpt.h) / fpt.T, fpt.gamma, prm.schedule,
+                                                    prm.gamma_on);
+            HornerCoef hc;
+            horner_coefficients(hc, fpt.h, ad1, ad2, ad4, 2.0, 6.0);
+            horner_cycle_sum_basis(hc.c);
+            PackedStep &o = tab[lane];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
+            const int base[4] = {0, 1, 3, 6};
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double2 ck = (k <= m) ? hc.c[base[m] + k] : make_double2(0.0, 0.0);
+                    o.coef[2 * k][2 * m] = ck.x;      o.coef[2 * k + 1][2 * m] = -ck.y;
+                    o.coef[2 * k][2 * m + 1] = ck.y;  o.coef[2 * k + 1][2 * m + 1] = ck.x;
+                }
+            }
+        }
+        __syncwarp();
+        const int cnt = (int)((S - n0 < ch) ? (S - n0) : ch);
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+            const PackedStep &hs = tab[grp * ch + sidx];
+            double sgl = 0.0;
+#define QW_PH_LEVEL(LEVEL)                                                                  \
+            {                                                                               \
+                const double xfr = (LEVEL == 4) ? s.yr[0] : s.zr[0];                        \
+                const double xfi = (LEVEL == 4) ? s.yi[0] : s.zi[0];                        \
+                const double xlr = (LEVEL == 4) ? s.yr[R - 1] : s.zr[R - 1];                \
+                const double xli = (LEVEL == 4) ? s.yi[R - 1] : s.zi[R - 1];                \
+                const double2 hl = make_double2(__shfl_sync(full, xlr, left),               \
+                                                __shfl_sync(full, xli, left));              \
+                const double2 hr = make_double2(__shfl_sync(full, xfr, right),              \
+                                                __shfl_sync(full, xfi, right));             \
+                const double rho = hs.rho[LEVEL - 1];                                       \
+                if (LEVEL == 4) {                                                           \
+                    double bb[8];                                                           \
+                    bb[0] = s.yr[HW0];                     bb[1] = s.yi[HW0];               \
+                    bb[2] = s.yr[HW0 - 1] + s.yr[HW0 + 1]; bb[3] = s.yi[HW0 - 1] + s.yi[HW0 + 1]; \
+                    bb[4] = s.yr[HW0 - 2] + s.yr[HW0 + 2]; bb[5] = s.yi[HW0 - 2] + s.yi[HW0 + 2]; \
+                    bb[6] = s.yr[HW0 - 3] + s.yr[HW0 + 3]; bb[7] = s.yi[HW0 - 3] + s.yi[HW0 + 3]; \
+                    sgl = hs.coef[0][li & 7] * __shfl_sync(full, bb[0], gbase);             \
+                    _Pragma("unroll")                                                       \
+                    for (int k = 1; k < 8; ++k)                                             \
+                        sgl = fma(hs.coef[k][li & 7], __shfl_sync(full, bb[k], gbase), sgl); \
+                }                                                                           \
+                double2 o0, oL;                                                             \
+                hedges<R, LEVEL>(s, rho, hl, hr, o0, oL);                                   \
+                hinterior<R, LEVEL>(s, rho, o0, oL);                                        \
+                const double sgr = __shfl_sync(full, sgl, gbase + 2 * (4 - LEVEL));         \
+                const double sgi = __shfl_sync(full, sgl, gbase + 2 * (4 - LEVEL) + 1);     \
+                if (LEVEL > 1) {                                                            \
+                    s.zr[HW0] = fma(msk, sgr, s.zr[HW0]); s.zi[HW0] = fma(msk, sgi, s.zi[HW0]); \
+                } else {                                                                    \
+                    s.yr[HW0] = fma(msk, sgr, s.yr[HW0]); s.yi[HW0] = fma(msk, sgi, s.yi[HW0]); \
+                }                                                                           \
+            }
+            QW_PH_LEVEL(4)
+            QW_PH_LEVEL(3)
+            QW_PH_LEVEL(2)
+            QW_PH_LEVEL(1)
+#undef QW_PH_LEVEL
+        }
+    }
+
+    // epilogue: segmented reductions over the tpp lanes of each point
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    for (int o = tpp >> 1; o > 0; o >>= 1) nrm += __shfl_xor_sync(full, nrm, o);
+    if (li == 0 && valid) {
+        prm.p[pt.q] = fma(s.yr[HW0], s.yr[HW0], s.yi[HW0] * s.yi[HW0]) / nrm;
+        if (prm.norm) prm.norm[pt.q] = nrm;
+    }
+    if (prm.psi && valid) {              // undo the relabelling: slot r of lane li -> w + li R + r - 3
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t j = (int64_t)li * R + r - HW0 + prm.target;
+            if (j < 0) j += prm.n;
+            if (j >= prm.n) j -= prm.n;
+            out[j] = make_double2(s.yr[r], s.yi[r]);
+        }
+    }
+}
+
+cudaError_t launch_packed_horner(const QwParams &prm, int tpp_log2, cudaStream_t st, qw_plan *plan)
+{
+    constexpr int MINB = 12;
+    const int groups = 32 >> tpp_log2;
+    if (plan) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_packed_horner<MINB>);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk4_cycle_packed_horner<MINB>, 32, 0);
+        if (e != cudaSuccess) return e;
+        plan->path = 7;
+        plan->sites_per_thread = 16;
+        plan->threads_per_block = 32;
+        plan->blocks_per_sm = nb;
+        plan->regs_per_thread = fa.numRegs;
+        plan->smem_bytes = (int)fa.sharedSizeBytes;
+        plan->steps_per_pass = groups;          // points per warp
+        return cudaSuccess;
+    }
+    const int64_t blocks = (prm.n_points + groups - 1) / groups;
+    rk4_cycle_packed_horner<MINB><<<(unsigned)blocks, 32, 0, st>>>(prm, tpp_log2);
+    return cudaGetLastError();
+}
+
 template <int R, int MINB>
 cudaError_t launch_packed(const QwParams &prm, int tpp_log2, cudaStream_t st, qw_plan *plan)
 {
@@ -182,9 +356,31 @@ bool qw_packed_supported(const QwParams &prm)
            qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l) > 0;
 }
 
+// nested form: N = 128 or 256 (16 sites per lane, 8 or 16 lanes per point), a batch that fills
+// the machine, the n_steps rule (qw_packed_supported)
+static bool packed_horner(const QwParams &prm, int *tpp_log2)
+{
+    if (prm.flags & (QW_FLAG_NO_HORNER | QW_FLAG_R8)) return false;
+    if (prm.n != 128 && prm.n != 256) return false;
+    *tpp_log2 = prm.n == 128 ? 3 : 4;
+    // enough warps to fill the machine twice, as for the throughput geometries above;
+    // smaller batches keep the latency-oriented stage-form geometries
+    const int64_t per_warp = 32 >> *tpp_log2;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            sms <= 0)
+            sms = 148;
+    }
+    return (prm.n_points + per_warp - 1) / per_warp >= 2 * (int64_t)sms;
+}
+
 cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan)
 {
     int l = 0;
+    if (packed_horner(prm, &l)) return launch_packed_horner(prm, l, st, plan);
     const int R = qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l);
     switch (R) {
     case 16: return launch_packed<16, 8>(prm, l, st, plan);

@@ -182,3 +182,34 @@ def test_randomised_nested_vs_stage_form(qw):
         assert np.abs(res[0][0] - res[1][0]).max() <= 1e-12, ctx
         assert np.abs(res[0][1] - res[1][1]).max() <= 1e-12, ctx
         assert np.abs(res[0][2] - res[1][2]).max() <= 1e-12, ctx
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_packed_nested_form_vs_oracle(qw, n):
+    """Warp-packed nested-form kernel (N = 128 / 256, batches that fill the machine): all
+    schedules, both gamma placements, T = 0 and gamma = 0 points, ragged last warp, chunk edges
+    of the per-point tables (8 / 16 steps), psi output, custom target."""
+    P = 1303
+    assert qw.plan(qw.Problem(n=n, n_steps=8))["path"] in ("packed-cycle", "packed-horner-cycle")
+    rng = np.random.default_rng(n)
+    for sched, gamma_on, S, target in [("lin", "oracle", 37, None), ("cerf_3", "laplacian", 16, 5),
+                                       ("sqrt", "oracle", 17, 0), ("cbrt", "laplacian", 33, n - 1),
+                                       ("cerf_7", "oracle", 8, 2), ("static", "oracle", 9, None),
+                                       ("cerf_5", "laplacian", 1, 77)]:
+        T = rng.uniform(0.1, 0.2 * S, P)
+        g = rng.uniform(0.0, 2.5, P)
+        T[::97] = 0.0
+        g[5::131] = 0.0
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, gamma_on=gamma_on,
+                          target=target, n_steps=S)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, n_steps=S,
+                                             gamma_on=gamma_on, target=target, return_psi=True)
+        assert np.abs(p - po).max() <= P_TOL, (n, sched)
+        assert np.abs(norm - no).max() <= P_TOL, (n, sched)
+        assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched)
+    # the same batch through the stage-form packed kernel
+    prob2 = qw.Problem(n=n, topology="circular", schedule="cerf_5", gamma_on="laplacian",
+                       target=77, n_steps=1, flags=NO_HORNER)
+    p2, _ = qw.rk4_batch(prob2, T, g)
+    assert np.abs(p2 - p).max() <= 1e-13
