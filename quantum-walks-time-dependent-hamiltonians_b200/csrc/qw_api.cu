@@ -91,10 +91,11 @@ int choose_path(const QwParams &prm)
     const bool horner = !(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_CYCLE_SPLIT |
                                        QW_FLAG_NO_HORNER | QW_FLAG_COMPLETE_FREE)) &&
                         qw_horner_sites_per_thread(prm) > 0;
-    // from 512 sites on a point fills a warp of the packed kernel anyway: nested form first
-    if (horner && prm.n >= 512) return PATH_HORNER;
-    if (!(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_NO_PACK)) && qw_packed_supported(prm))
-        return PATH_PACKED;
+    const bool packed = !(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_NO_PACK)) &&
+                        qw_packed_supported(prm);
+    // above 512 sites a point needs more than one warp: block-per-point nested form
+    if (horner && (prm.n > 512 || !packed)) return PATH_HORNER;
+    if (packed) return PATH_PACKED;
     if (horner) return PATH_HORNER;
     if (qw_resident_sites_per_thread(prm.n) > 0) return PATH_RESIDENT;
     if (qw_stream_supported(prm)) return PATH_STREAM;

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
 
 // ---------------------------------------------------------------------------------------------
 // Nested (Horner) form of the step for the packed layout (qw_horner_level.cuh):
-// N = 16 * TPP with TPP = 8 or 16 lanes per point (N = 128, 256; from 512 sites on the
+// N = 16 * TPP with TPP = 8, 16 or 32 lanes per point (N = 128, 256, 512; above that the
 // block-per-point kernel of qw_horner.cu takes over).  24 instead of 30 FP64 instructions per
 // site-update and two instead of three complex vectors in registers (12 instead of 8 warps
 // per SM).  The step coefficients depend on the point (h, gamma), so every point of the warp
@@ -361,8 +361,8 @@ bool qw_packed_supported(const QwParams &prm)
 static bool packed_horner(const QwParams &prm, int *tpp_log2)
 {
     if (prm.flags & (QW_FLAG_NO_HORNER | QW_FLAG_R8)) return false;
-    if (prm.n != 128 && prm.n != 256) return false;
-    *tpp_log2 = prm.n == 128 ? 3 : 4;
+    if (prm.n != 128 && prm.n != 256 && prm.n != 512) return false;
+    *tpp_log2 = prm.n == 128 ? 3 : (prm.n == 256 ? 4 : 5);
     // enough warps to fill the machine twice, as for the throughput geometries above;
     // smaller batches keep the latency-oriented stage-form geometries
     const int64_t per_warp = 32 >> *tpp_log2;
