@@ -350,9 +350,9 @@ def run_b200(args):
                        "kernel": plan, "results_sane_and_e2e_equals_device": ok},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": 46080,
+                         "traffic": 78592,
                          "traffic_note": "dram__bytes_read+write of an 8192-point launch (ncu "
-                                         "--set full, profiles/r1_cycle_resident_r16_ncu_full"
+                                         "--set full, profiles/r1_cycle_horner_r16_ncu_full"
                                          ".md): the kernel is register-resident, DRAM sees "
                                          "only T, gamma, p, norm",
                          "peak_source": "qw_fp64_peak_probe: dependent-free DFMA stream "
