@@ -197,6 +197,22 @@ int qw_heatmap_robustness_dev(const double *p, int64_t n_beta, int64_t n_time,
 int qw_heatmap_summary_dev(const double *p, const double *time_array, int64_t n_beta,
                            int64_t n_time, double t_min, double *out, void *stream);
 
+/* Adiabatic diagnostics of H(s) = (1-g(s)) L - g(s) gamma |w><w| (or the gamma-on-Laplacian
+ * form) for a batch of (s_q, gamma_q), s = t/T in [0, 1]: replaces compute_energy_diff(s, beta)
+ * and compute_gamma(s, beta) (Schroedinger_Solver.py:208-253; a dense scipy.linalg.eig of
+ * generate_hamiltonian_derivative(s, beta, 0) per call there), the two ingredients of
+ * adiabatic_theorem_check (Schroedinger_Solver.py:255-280).
+ *   gap[q]      = E_1 - E_0, the two lowest eigenvalues of H(s_q)
+ *   coupling[q] = |<phi_1| dH/ds |phi_0>| (nullable; NaN at s = 1 where H has no Laplacian part)
+ *   e0[q]       = E_0 (nullable)
+ * From the secular equation of the rank-one perturbation (cycle graph, dimension <= 4096) or
+ * the 2 x 2 symmetric subspace (complete graph); no matrix is built.  reference_derivative != 0
+ * reproduces the reference's cube-root slope 1/(3 cbrt(s)) (Schroedinger_Solver.py:204-206)
+ * instead of d/ds s^(1/3).  prob->schedule applies, the step rule is ignored. */
+int qw_adiabatic_batch_dev(const qw_problem *prob, const double *s, const double *gamma,
+                           int64_t n_points, int32_t reference_derivative, double *gap,
+                           double *coupling, double *e0, void *stream);
+
 /* ---- introspection ------------------------------------------------------------------- */
 
 typedef struct qw_plan {

@@ -3,8 +3,12 @@
 Same function names, argument meaning, return shapes and module globals
 (Schroedinger_Solver.py:16-18): set ``dimension``, ``step_function`` (1 = lin, 2 = sqrt,
 3 = cbrt) and call ``grid_probability_evaluation`` / ``evaluate_probability`` /
-``solve_schrodinger_equation`` / ``single_evaluation_benchmark``.  The SciPy optimisers,
-the adiabatic-theorem check and the plots of that script are outside the accelerated path.
+``solve_schrodinger_equation`` / ``single_evaluation_benchmark`` / ``optimization``.  The
+adiabatic-theorem diagnostics (``compute_energy_diff``, ``compute_gamma``,
+``adiabatic_theorem_check``; Schroedinger_Solver.py:146-280) run on the device too, from the
+secular equation of the rank-one perturbation instead of dense eigensolves;
+``reference_derivative = True`` keeps the reference's cube-root slope 1/(3 cbrt(s)).  The plots
+of that script are outside the accelerated path.
 """
 
 from . import _dropin
@@ -17,6 +21,7 @@ n_steps = None             # h = T / n_steps when set
 step_size = 1e-3           # else n = int(T / step_size) steps (QW_Search.py:153-154)
 gamma_on = "oracle"
 integrator = "rk4"           # 'rk45': SciPy's adaptive RK45 as the reference ships it
+reference_derivative = True  # dH/ds of the cube-root schedule as the reference codes it
 device = None
 
 _dropin.install(globals(), "SS")

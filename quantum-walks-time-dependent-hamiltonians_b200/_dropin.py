@@ -233,6 +233,64 @@ def install(g, flavor):
         print()
         return 1
 
+    # ---- adiabatic-theorem diagnostics (Schroedinger_Solver.py:146-280) -------------------
+    def _slope(s, name, reference):
+        """g'(s); the reference's cube-root slope is 1/(3 cbrt(s)) (SS:204-206)."""
+        if name == "lin":
+            return 1.0
+        if name == "sqrt":
+            return 1.0 / (2.0 * np.sqrt(s))
+        if name == "cbrt":
+            return 1.0 / (3.0 * np.cbrt(s)) if reference else 1.0 / (3.0 * np.cbrt(s) ** 2)
+        if name in ("cerf_3", "cerf_5", "cerf_7"):
+            k = int(name[-1])
+            return k * (2.0 * s - 1.0) ** (k - 1)
+        raise ValueError("step_function value not defined: %r" % (name,))
+
+    def generate_hamiltonian_derivative(s, beta, derivative):
+        """Dense H(s) (derivative = 0) or dH/ds (derivative = 1) with the reference's
+        conventions (SS:146-207).  Inspection helper; the diagnostics below never build it."""
+        n = int(g["dimension"])
+        lap = laplacian(n, _topology(g, flavor))
+        name = _schedule_name(g, flavor)
+        w = _marked_vertex(n)
+        if derivative == 0:
+            gs = schedule_value(s, name)
+            ham = (1 - gs) * lap
+            ham[w, w] += -gs * beta
+        elif derivative == 1:
+            sl = _slope(s, name, g.get("reference_derivative", True))
+            ham = -sl * lap
+            ham[w, w] += -sl * beta
+        else:
+            raise ValueError("derivative flag unknown: %r" % (derivative,))
+        return ham
+
+    def _adiabatic(s, beta):
+        gap, cpl, e0 = engine.adiabatic_batch(
+            _problem(g, flavor), np.atleast_1d(float(s)), np.atleast_1d(float(beta)),
+            reference_derivative=g.get("reference_derivative", True), device=g.get("device"))
+        return float(gap[0]), float(cpl[0])
+
+    def compute_energy_diff(s, beta):
+        """E1 - E0 of H(s) (SS:248-253) from the secular equation on the device."""
+        return _adiabatic(s, beta)[0]
+
+    def compute_gamma(s, beta):
+        """-|<phi1| dH/ds |phi0>| as a (1, 1) array (SS:225-246)."""
+        return -np.abs(np.array([[_adiabatic(s, beta)[1]]]))
+
+    def adiabatic_theorem_check(current_par):
+        """[adiabatic_time, gamma_max, energy_min, flag, minutes] (SS:255-280): the two shgo
+        runs over dense eigensolves become a few batched launches (engine.adiabatic_check)."""
+        tic = _time.perf_counter()
+        res = engine.adiabatic_check(_problem(g, flavor), float(current_par[2]),
+                                     reference_derivative=g.get("reference_derivative", True),
+                                     device=g.get("device"))
+        flag = "True" if res["energy_min"] > 0 else "False"
+        return [res["adiabatic_time"], res["gamma_max"], res["energy_min"], flag,
+                (tic - _time.perf_counter()) / 60]
+
     def optimization_precision(x, probability, context):
         """Callback of SS:125-130: stop once p >= 0.99."""
         return bool(probability <= -0.99)
@@ -345,7 +403,10 @@ def install(g, flavor):
         g.update(grid_probability_evaluation=grid_probability_evaluation,
                  single_evaluation_benchmark=single_evaluation_benchmark,
                  optimization=optimization, optimization_precision=optimization_precision,
-                 arrange_local_maxima=arrange_local_maxima)
+                 arrange_local_maxima=arrange_local_maxima,
+                 generate_hamiltonian_derivative=generate_hamiltonian_derivative,
+                 compute_energy_diff=compute_energy_diff, compute_gamma=compute_gamma,
+                 adiabatic_theorem_check=adiabatic_theorem_check)
     else:
         g.update(generate_time_independent_hamiltonian=generate_time_independent_hamiltonian,
                  evaluate_time_independent_probability=evaluate_time_independent_probability,

@@ -30,6 +30,10 @@ bool qw_rk45_supported(const QwParams &prm);
 cudaError_t qw_launch_rk45(QwParams prm, double rtol, double atol, int64_t *nfev, cudaStream_t st);
 int qw_horner_sites_per_thread(const QwParams &prm);
 cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan);
+cudaError_t qw_launch_adiabatic(int64_t n, int topology, int schedule, int gamma_on, int ref,
+                                const double *s, const double *gamma, int64_t n_points,
+                                double *gap, double *coupling, double *e0, cudaStream_t st);
+int qw_adiabatic_max_dimension();
 bool qw_cheb_supported(const QwParams &prm);
 cudaError_t qw_launch_cheb(QwParams prm, cudaStream_t st);
 
@@ -441,6 +445,31 @@ int qw_heatmap_summary_dev(const double *p, const double *time_array, int64_t n_
                                       (cudaStream_t)stream);
     g_launches += 1;
     if (e != cudaSuccess) return cuda_fail(e, "summary kernel launch");
+    return 0;
+}
+
+int qw_adiabatic_batch_dev(const qw_problem *prob, const double *s, const double *gamma,
+                           int64_t n_points, int32_t reference_derivative, double *gap,
+                           double *coupling, double *e0, void *stream)
+{
+    QwParams prm;
+    qw_problem tmp;
+    if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
+    tmp = *prob;
+    if (!(tmp.step_size > 0.0) && tmp.n_steps < 0) tmp.n_steps = 0;   // no step rule needed
+    int rc = validate(&tmp, &prm);
+    if (rc) return rc;
+    if (n_points < 0) return fail(QW_E_SIZE, "n_points < 0");
+    if (n_points == 0) return 0;
+    if (!s || !gamma || !gap) return fail(QW_E_NULL, "s, gamma and gap are required");
+    if (prm.topology == QW_TOPO_CYCLE && prm.n > qw_adiabatic_max_dimension())
+        return fail(QW_E_UNSUPPORTED, "adiabatic diagnostics: cycle graph up to dimension %d",
+                    qw_adiabatic_max_dimension());
+    cudaError_t e = qw_launch_adiabatic(prm.n, prm.topology, prm.schedule, prm.gamma_on,
+                                        reference_derivative != 0, s, gamma, n_points, gap,
+                                        coupling, e0, (cudaStream_t)stream);
+    g_launches += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "adiabatic kernel launch");
     return 0;
 }
 

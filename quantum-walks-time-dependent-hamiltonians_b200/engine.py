@@ -306,6 +306,65 @@ def rhs(problem, t, T, gamma, y, device=None):
         return out.cpu().numpy() if host else out
 
 
+def adiabatic_batch(problem, s, gamma, reference_derivative=False, device=None):
+    """Gap E1 - E0, coupling |<phi1|dH/ds|phi0>| and E0 of H(s) for (s_q, gamma_q) points:
+    compute_energy_diff / compute_gamma of Schroedinger_Solver.py:208-253, batched on the
+    device (secular equation of the rank-one perturbation; no dense eigensolve)."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ds, host = _as_dev(s, dev)
+        dg, _ = _as_dev(gamma, dev)
+        if dg.numel() == 1 and ds.numel() > 1:
+            dg = dg.expand(ds.numel()).contiguous()
+        if ds.numel() != dg.numel():
+            raise ValueError("s and gamma must have the same length")
+        P = ds.numel()
+        gap = torch.empty(P, dtype=torch.float64, device=dev)
+        cpl = torch.empty(P, dtype=torch.float64, device=dev)
+        e0 = torch.empty(P, dtype=torch.float64, device=dev)
+        prob = problem.c_struct(per_point_steps=True)
+        _lib.check(lib.qw_adiabatic_batch_dev(ctypes.byref(prob), _ptr(ds), _ptr(dg), P,
+                                              1 if reference_derivative else 0, _ptr(gap),
+                                              _ptr(cpl), _ptr(e0), _stream()))
+        out = (gap, cpl, e0)
+        if host:
+            out = tuple(t.cpu().numpy() for t in out)
+        return out
+
+
+def adiabatic_check(problem, gamma, samples=4097, rounds=4, reference_derivative=False,
+                    device=None):
+    """max_s |<phi1|dH/ds|phi0>| and min_s (E1 - E0) over s in (0, 1), the two numbers behind
+    adiabatic_theorem_check (Schroedinger_Solver.py:255-280: two shgo runs over dense
+    eigensolves there): one launch over a uniform grid of interior points, then `rounds`
+    launches that zoom into the best cell of each quantity (x 64 per round).  Returns
+    dict(gamma_max, s_gamma, energy_min, s_gap, adiabatic_time)."""
+    K = int(samples)
+    s = (np.arange(K) + 0.5) / K
+    gap, cpl, _ = adiabatic_batch(problem, s, np.full(K, float(gamma)),
+                                  reference_derivative=reference_derivative, device=device)
+    out = {}
+    for name, vals, best in (("gamma", cpl, np.nanargmax), ("gap", gap, np.nanargmin)):
+        i = int(best(vals))
+        lo, hi = max(s[i] - 1.0 / K, 0.0), min(s[i] + 1.0 / K, 1.0)
+        sb, vb = s[i], vals[i]
+        for _ in range(int(rounds)):
+            ss = np.linspace(lo, hi, 131)[1:-1]
+            g2, c2, _ = adiabatic_batch(problem, ss, np.full(ss.size, float(gamma)),
+                                        reference_derivative=reference_derivative,
+                                        device=device)
+            v2 = c2 if name == "gamma" else g2
+            j = int(best(v2))
+            sb, vb = ss[j], v2[j]
+            w = (hi - lo) / 130.0
+            lo, hi = max(sb - w, 0.0), min(sb + w, 1.0)
+        out[name] = (float(vb), float(sb))
+    gmax, emin = out["gamma"][0], out["gap"][0]
+    return {"gamma_max": gmax, "s_gamma": out["gamma"][1], "energy_min": emin,
+            "s_gap": out["gap"][1], "adiabatic_time": gmax / (emin * emin)}
+
+
 def ensemble_stats(p, thresholds=(0.8, 0.9, 0.95, 0.99), device=None):
     """mean / std / min / max / fraction >= threshold over an ensemble of probabilities
     (contour levels of SS:415; thesis section 2.3)."""
