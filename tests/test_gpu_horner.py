@@ -213,3 +213,26 @@ def test_packed_nested_form_vs_oracle(qw, n):
                        target=77, n_steps=1, flags=NO_HORNER)
     p2, _ = qw.rk4_batch(prob2, T, g)
     assert np.abs(p2 - p).max() <= 1e-13
+
+
+def test_runs_are_bitwise_reproducible(qw):
+    """Every nested-form kernel twice on the same inputs: bitwise identical p, norm and psi
+    (fixed summation orders; a shared-memory race would show up here as run-to-run noise)."""
+    rng = np.random.default_rng(99)
+    cases = [dict(n=1024, topology="circular", n_steps=200),
+             dict(n=2048, topology="circular", n_steps=90),
+             dict(n=4096, topology="circular", n_steps=70),
+             dict(n=1024, topology="complete", n_steps=200),
+             dict(n=4096, topology="complete", n_steps=130),
+             dict(n=256, topology="circular", n_steps=100),
+             dict(n=8192, topology="circular", n_steps=24)]
+    for kw in cases:
+        P = 700 if kw["n"] == 256 else 40
+        scale = 1.0 if kw["topology"] == "circular" else 1.0 / kw["n"]
+        T = rng.uniform(1.0, 9.0, P) * scale
+        g = rng.uniform(0.1, 2.4, P) / scale
+        prob = qw.Problem(schedule="cerf_3", **kw)
+        a = qw.rk4_batch(prob, T, g, return_psi=True)
+        for _ in range(3):
+            b = qw.rk4_batch(prob, T, g, return_psi=True)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), kw
