@@ -37,6 +37,8 @@ struct QwParams {
     double2 *psi;
     // geometry of the resident kernels
     int32_t nact;                 // active threads per point (n / sites_per_thread)
+    int32_t nfull;                // nested-form kernels: threads 0 .. nfull-1 hold R sites, threads
+                                  // nfull .. nact-1 hold R-1 (their last slot is a ghost)
     // scratch of the global-memory kernels (generic: 5 complex vectors per running block;
     // streaming: two psi buffers per point of the chunk in flight)
     double2 *scratch;

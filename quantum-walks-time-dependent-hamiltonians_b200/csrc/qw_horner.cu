@@ -19,6 +19,12 @@
 // (one thread per step of a 32-step chunk).  tests/horner_model.py is the numpy statement of
 // this algebra, checked against the oracle on the CPU.
 //
+// Any dimension: n = nact (R - 1) + nfull sites are dealt out as R sites to the first nfull
+// threads and R - 1 to the others (possible whenever n >= R^2).  The last slot of a short
+// thread is a ghost: before every level it is loaded with the right neighbour's first value,
+// so that the thread's last real site sees the correct neighbour in the unrolled stencil; a
+// short thread publishes slot R-2 as its last value.  Two selects per level, no FP64 work.
+//
 // Layout: the ring is relabelled so that the marked vertex is slot HW0 = 3 of thread 0, i.e.
 // thread 0 holds w-3..w+R-4 and all the oracle work is local to it.  Halo values cross
 // threads through a double-buffered shared-memory mailbox, one __syncthreads() per level;
@@ -114,7 +120,7 @@ template <int R, bool OWN>
 __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab, double2 *first,
                                              double2 *last, const int nt, const int t,
                                              const int tl, const int tr, const int cnt,
-                                             const double msk)
+                                             const double msk, const bool full)
 {
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const HornerStep &hs = tab[sidx];
@@ -127,6 +133,10 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
             const double2 hr = first[par * nt + tr];                                        \
             const double rho = hs.rho[LEVEL - 1];                                           \
             double2 o0, oL;                                                                 \
+            if (!full) {                      /* ghost slot := the right neighbour's value */ \
+                if (LEVEL == 4) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }                 \
+                else { s.zr[R - 1] = hr.x; s.zi[R - 1] = hr.y; }                            \
+            }                                                                               \
             if (OWN && LEVEL == 4) {                                                        \
                 /* y_w and the neighbour sums at distance 1..3 (meaningful in the owner */  \
                 /* lane), broadcast; every lane then forms its own dot product          */  \
@@ -141,14 +151,16 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
                     sgl = fma(hs.coef[k][t & 7], __shfl_sync(0xffffffffu, b[k], 0), sgl);   \
             }                                                                               \
             hedges<R, LEVEL>(s, rho, hl, hr, o0, oL);                                       \
-            if (LEVEL > 1) {                                                                \
-                first[(par ^ 1) * nt + t] = make_double2(s.zr[0], s.zi[0]);                 \
-                last[(par ^ 1) * nt + t] = make_double2(s.zr[R - 1], s.zi[R - 1]);          \
-            } else {                                                                        \
-                first[(par ^ 1) * nt + t] = make_double2(s.yr[0], s.yi[0]);                 \
-                last[(par ^ 1) * nt + t] = make_double2(s.yr[R - 1], s.yi[R - 1]);          \
-            }                                                                               \
             hinterior<R, LEVEL>(s, rho, o0, oL);                                            \
+            {   /* publish: the last REAL site is slot R-1, or R-2 in a short thread */     \
+                const double lr = (LEVEL > 1) ? (full ? s.zr[R - 1] : s.zr[R - 2])          \
+                                              : (full ? s.yr[R - 1] : s.yr[R - 2]);         \
+                const double li = (LEVEL > 1) ? (full ? s.zi[R - 1] : s.zi[R - 2])          \
+                                              : (full ? s.yi[R - 1] : s.yi[R - 2]);         \
+                first[(par ^ 1) * nt + t] = (LEVEL > 1) ? make_double2(s.zr[0], s.zi[0])    \
+                                                        : make_double2(s.yr[0], s.yi[0]);   \
+                last[(par ^ 1) * nt + t] = make_double2(lr, li);                            \
+            }                                                                               \
             if (OWN) {                                  /* oracle correction sigma_LEVEL */ \
                 const double sgr = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));          \
                 const double sgi = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);      \
@@ -175,9 +187,10 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
     static_assert(R >= 2 * HW0 + 1, "the window w-3..w+3 must sit in one thread");
     extern __shared__ double2 mbox[];         // [2][2][blockDim.x]: parity, first/last
     __shared__ HornerShared sh;
-    const int t = threadIdx.x, nt = blockDim.x, nact = prm.nact;
+    const int t = threadIdx.x, nt = blockDim.x, nact = prm.nact, nfull = prm.nfull;
     const QwPoint pt = qw_point(prm, blockIdx.x);
     const bool active = t < nact;
+    const bool full = t < nfull || !active;           // R sites (idle threads: R zeros)
     // ring neighbours among the active threads; idle threads talk to themselves (zeros)
     const int tl = active ? (t == 0 ? nact - 1 : t - 1) : t;
     const int tr = active ? (t == nact - 1 ? 0 : t + 1) : t;
@@ -202,7 +215,7 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
     }
     double2 *first = mbox, *last = mbox + 2 * nt;      // [parity][thread]; a step starts at 0
     first[t] = make_double2(s.yr[0], s.yi[0]);
-    last[t] = make_double2(s.yr[R - 1], s.yi[R - 1]);
+    last[t] = make_double2(s.yr[R - 1], s.yi[R - 1]);  // uniform start: any slot will do
 
     const int warp = t >> 5;
     for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
@@ -212,15 +225,16 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
         __syncthreads();
         const double msk = own ? 1.0 : 0.0;
         if (warp == (ht >> 5))
-            horner_steps<R, true>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk);
+            horner_steps<R, true>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk, full);
         else
-            horner_steps<R, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk);
+            horner_steps<R, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk, full);
     }
 
     // p = |psi_w|^2 / ||psi||^2, ||psi||^2 (BCB.py:189-199, Runge_Kutta_Error.py:103)
     double nrm = 0.0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    for (int r = 0; r < R - 1; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    if (full) nrm = fma(s.yr[R - 1], s.yr[R - 1], fma(s.yi[R - 1], s.yi[R - 1], nrm));
     const double pw = own ? fma(s.yr[HW0], s.yr[HW0], s.yi[HW0] * s.yi[HW0]) : 0.0;
     __syncthreads();
     const double2 tot = hblock_sum(make_double2(nrm, pw), sh.red);
@@ -229,10 +243,13 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
         if (prm.norm) prm.norm[pt.q] = tot.x;
     }
     if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + l,
-        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;   // l = (t - ht) R + r - HW0
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;   // l = off(t) - off(ht) + r - HW0
+        const int64_t off_t = (int64_t)t * (R - 1) + (t < nfull ? t : nfull);
+        const int64_t off_h = (int64_t)ht * (R - 1) + (ht < nfull ? ht : nfull);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            int64_t j = (int64_t)(t - ht) * R + r - HW0 + prm.target;
+            if (r == R - 1 && !full) continue;                    // ghost
+            int64_t j = off_t - off_h + r - HW0 + prm.target;
             if (j < 0) j += prm.n;
             if (j >= prm.n) j -= prm.n;
             out[j] = make_double2(s.yr[r], s.yi[r]);
@@ -340,14 +357,15 @@ __device__ __forceinline__ void scalar_step(const CHStep &hs, double2 &yw, doubl
 }
 
 // one level on all R sites of a thread: out = y - i rho (N x - S)
+// (ndg, Sg): the same for the last slot -- zero in a short thread, whose last slot is a ghost
 template <int R, int LEVEL>
 __device__ __forceinline__ void clevel(HState<R> &s, const double rho, const double nd,
-                                       const double2 S)
+                                       const double2 S, const double ndg, const double2 Sg)
 {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const double tr_ = fma(nd, HX_R(r), -S.x);
-        const double ti_ = fma(nd, HX_I(r), -S.y);
+        const double tr_ = fma(r == R - 1 ? ndg : nd, HX_R(r), -(r == R - 1 ? Sg.x : S.x));
+        const double ti_ = fma(r == R - 1 ? ndg : nd, HX_I(r), -(r == R - 1 ? Sg.y : S.y));
         HO_R(r) = fma(rho, ti_, s.yr[r]);
         HO_I(r) = fma(-rho, tr_, s.yi[r]);
     }
@@ -356,25 +374,28 @@ __device__ __forceinline__ void clevel(HState<R> &s, const double rho, const dou
 // Vector work of chunk c (cnt steps).  No barrier inside.
 template <int R, bool OWN>
 __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const int64_t c,
-                                               const int cnt, const double nd, const double msk)
+                                               const int cnt, const double nd, const double msk,
+                                               const bool full)
 {
     const CHStep *tab = sh.tab[c % 3];
     const int cur = (int)(c & 1);
     const double act = (nd != 0.0) ? 1.0 : 0.0;            // idle threads stay at zero
+    const double actg = full ? act : 0.0, ndg = full ? nd : 0.0;   // ghost slot stays at zero
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const CHStep &hs = tab[sidx];
         // all scalars of the step up front: nothing inside the step waits for shared memory
-        double2 Sl[4];
+        double2 Sl[4], Sg[4];
         double rl[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            Sl[k] = sh.sums[cur][sidx][k];
-            Sl[k].x *= act; Sl[k].y *= act;
+            const double2 S = sh.sums[cur][sidx][k];
+            Sl[k] = make_double2(S.x * act, S.y * act);
+            Sg[k] = make_double2(S.x * actg, S.y * actg);
             rl[k] = hs.rho[k];
         }
 #define QW_CH_LEVEL(LEVEL)                                                                  \
         {                                                                                   \
-            clevel<R, LEVEL>(s, rl[LEVEL - 1], nd, Sl[4 - LEVEL]);                          \
+            clevel<R, LEVEL>(s, rl[LEVEL - 1], nd, Sl[4 - LEVEL], ndg, Sg[4 - LEVEL]);      \
             if (OWN) {                                                                      \
                 const double2 sg = sh.sig[cur][sidx][4 - LEVEL];                            \
                 if (LEVEL > 1) {                                                            \
@@ -401,6 +422,7 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
     const int lane = t & 31, warp = t >> 5, swarp = (blockDim.x >> 5) - 1;
     const QwPoint pt = qw_point(prm, blockIdx.x);
     const bool active = t < nact;
+    const bool full = t < prm.nfull;                   // R sites; else R-1 and a ghost slot
     const double nfull = (double)prm.n;
     const double nd = active ? nfull : 0.0;
 
@@ -408,7 +430,7 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
     const double amp = active ? 1.0 / sqrt(nfull) : 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.yr[r] = (r == R - 1 && !full) ? 0.0 : amp; s.yi[r] = 0.0;
         s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
     const double msk = (t == 0) ? 1.0 : 0.0;
@@ -447,9 +469,9 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
                     scalar_step(tn[sidx], yw, Sy, nfull, sh.sums[nxt][sidx], sh.sig[nxt][sidx], lane);
             }
         } else if (warp == 0) {
-            complete_chunk<R, true>(s, sh, c, QW_CNT(c), nd, msk);
+            complete_chunk<R, true>(s, sh, c, QW_CNT(c), nd, msk, full);
         } else {
-            complete_chunk<R, false>(s, sh, c, QW_CNT(c), nd, msk);
+            complete_chunk<R, false>(s, sh, c, QW_CNT(c), nd, msk, full);
         }
     }
 #undef QW_CNT
@@ -464,11 +486,13 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
         prm.p[pt.q] = tot.y / tot.x;
         if (prm.norm) prm.norm[pt.q] = tot.x;
     }
-    if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + t R + r
+    if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + off(t) + r
         double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
+        const int64_t off_t = (int64_t)t * (R - 1) + (t < prm.nfull ? t : prm.nfull);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            int64_t j = (int64_t)t * R + r + prm.target;
+            if (r == R - 1 && !full) continue;                    // ghost
+            int64_t j = off_t + r + prm.target;
             if (j >= prm.n) j -= prm.n;
             out[j] = make_double2(s.yr[r], s.yi[r]);
         }
@@ -503,19 +527,15 @@ cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cud
 
 }  // namespace
 
-// Sites per thread of the nested-form kernels, or 0 when n does not fit them: n = R * threads
-// with R in {16, 8} (the window w-3..w+3 has to sit in one thread) and at least one full warp.
+// Sites per thread of the nested-form kernels, or 0 when n does not fit them: R in {16, 8}
+// (the window w-3..w+3 has to sit in one thread), any n from 256 to 4096.
 int qw_horner_sites_per_thread(const QwParams &prm)
 {
     const int64_t n = prm.n;
-    if (prm.topology != QW_TOPO_CYCLE) {
-        if (prm.flags & QW_FLAG_EXACT_SUM) return 0;
-        if (!(prm.flags & QW_FLAG_R8) && n % 16 == 0 && n / 16 >= 32 && n / 16 <= 256) return 16;
-        if (n % 8 == 0 && n / 8 >= 32 && n / 8 <= 512) return 8;
-        return 0;
-    }
-    if (!(prm.flags & QW_FLAG_R8) && n % 16 == 0 && n / 16 >= 32 && n / 16 <= 256) return 16;
-    if (n % 8 == 0 && n / 8 >= 32 && n / 8 <= 512) return 8;
+    if (prm.topology != QW_TOPO_CYCLE && (prm.flags & QW_FLAG_EXACT_SUM)) return 0;
+    // n = nact (R - 1) + nfull with 1 <= nfull <= nact needs n >= R^2; at least one full warp
+    if (!(prm.flags & QW_FLAG_R8) && n >= 512 && (n + 15) / 16 <= 256) return 16;
+    if (n >= 256 && (n + 7) / 8 <= 512) return 8;
     return 0;
 }
 
@@ -523,7 +543,8 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
 {
     const int R = qw_horner_sites_per_thread(prm);
     if (R == 0) return cudaErrorInvalidConfiguration;
-    prm.nact = (int)(prm.n / R);
+    prm.nact = (int)((prm.n + R - 1) / R);
+    prm.nfull = (int)(prm.n - (int64_t)prm.nact * (R - 1));       // threads with R sites
     const int threads = ((prm.nact + 31) / 32) * 32;
     const bool cyc = prm.topology == QW_TOPO_CYCLE;
     const size_t smem = cyc ? (size_t)threads * 4 * sizeof(double2) : 0;

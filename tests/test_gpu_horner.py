@@ -17,7 +17,10 @@ NO_HORNER, R8, OCC4, NO_PACK, NO_ROT = 2048, 256, 128, 512, 4096
 
 @pytest.mark.parametrize("n,flags", [(256, NO_PACK), (264, 0), (512, 0), (520, 0), (1024, 0),
                                      (1024, OCC4), (1024, R8), (1536, 0), (1792, 0), (1024, NO_ROT), (1024, R8 | NO_ROT), (2048, NO_ROT), (1040, 0), (2048, 0), (2048, R8),
-                                     (3072, 0), (4096, 0), (4096, R8), (4088, 0)])
+                                     (3072, 0), (4096, 0), (4096, R8), (4088, 0),
+                                     # any dimension: R or R-1 sites per thread, ghost slots
+                                     (257, 0), (263, 0), (511, 0), (513, 0), (999, 0), (1001, 0),
+                                     (1023, R8), (1025, 0), (2049, 0), (3001, R8), (4095, 0)])
 def test_cycle_all_schedules_vs_oracle(qw, n, flags):
     pl = qw.plan(qw.Problem(n=n, topology="circular", step_size=0.1, flags=flags))
     assert pl["path"] == "horner-cycle", pl
@@ -77,7 +80,8 @@ def test_heatmap_matches_the_stage_form_kernel_and_keeps_the_argmax(qw):
 
 @pytest.mark.parametrize("n,flags", [(256, 0), (264, 0), (512, 0), (520, 0), (1024, 0), (1024, R8),
                                      (2048, 0), (2048, R8), (3072, 0), (4096, 0), (4096, R8),
-                                     (4088, 0)])
+                                     (4088, 0), (257, 0), (511, 0), (1001, 0), (1023, R8),
+                                     (2049, 0), (4095, 0)])
 def test_complete_all_schedules_vs_oracle(qw, n, flags):
     pl = qw.plan(qw.Problem(n=n, topology="complete", n_steps=1, flags=flags))
     assert pl["path"] == "horner-complete", pl
@@ -152,7 +156,7 @@ def test_randomised_nested_vs_stage_form(qw):
     scheds = ["lin", "sqrt", "cbrt", "cerf_3", "cerf_5", "cerf_7", "static"]
     for trial in range(40):
         topo = "circular" if trial % 2 == 0 else "complete"
-        n = int(rng.choice([256, 264, 512, 776, 1024, 1536, 2048, 4096]))
+        n = int(rng.choice([256, 264, 301, 512, 777, 1024, 1536, 2047, 2048, 4096]))
         sched = scheds[int(rng.integers(len(scheds)))]
         gamma_on = "oracle" if rng.random() < 0.5 else "laplacian"
         target = int(rng.integers(n))
