@@ -218,7 +218,8 @@ int qw_adiabatic_batch_dev(const qw_problem *prob, const double *s, const double
 typedef struct qw_plan {
     int32_t path;            /* 0 resident-cycle, 1 resident-complete, 2 generic, 3 stream,
                                 4 warp-packed cycle, 5 / 6 resident cycle / complete in nested form,
-                                7 warp-packed cycle in nested form */
+                                7 warp-packed cycle in nested form, 8 warp-packed cycle of any
+                                small dimension */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */

@@ -16,7 +16,7 @@ FLAG_FORCE_GENERIC, FLAG_FORCE_STREAM, FLAG_EXACT_SUM = 1, 2, 4
 FLAG_STREAM_KB1, FLAG_STREAM_KB2 = 8, 16
 PATH_NAMES = {0: "resident-cycle", 1: "resident-complete", 2: "generic", 3: "stream",
               4: "packed-cycle", 5: "horner-cycle", 6: "horner-complete",
-              7: "packed-horner-cycle"}
+              7: "packed-horner-cycle", 8: "packed-any-cycle"}
 
 
 class QwProblem(ctypes.Structure):

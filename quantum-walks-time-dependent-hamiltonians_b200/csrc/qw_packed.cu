@@ -108,6 +108,158 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Packed layout for ANY small ring (the reference's own runs use odd dimensions 3 .. 71):
+// n = L (R - 1) + nfull sites of a point are dealt out over L lanes, R sites to the first
+// nfull lanes and R - 1 to the others (possible whenever n >= R^2); a warp integrates
+// G = 32 / L points, lanes beyond G L idle.  The last slot of a short lane is a ghost that is
+// loaded with the right neighbour's first value before every stage, and a short lane hands
+// slot R-2 to its left neighbour: two selects per stage, no FP64 work.  Stage form.
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams prm, const int L,
+                                                                 const int nfull)
+{
+    static_assert(R >= 2, "a short lane needs at least one real site");
+    __shared__ PackedShared sh;
+    const unsigned full_mask = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int groups = 32 / L;
+    const int grp = lane / L, li = lane - grp * L;
+    const bool lane_used = grp < groups;
+    int64_t b = (int64_t)blockIdx.x * groups + (lane_used ? grp : groups - 1);
+    const bool valid = lane_used && b < prm.n_points;
+    if (b >= prm.n_points) b = prm.n_points - 1;   // idle groups shadow the last point
+    const QwPoint pt = qw_point(prm, b);
+    const int64_t S = prm.n_steps_uniform;
+    const bool own = lane_used && li == 0;
+    const bool full = !lane_used || li < nfull;        // R sites (idle lanes: R zeros)
+    const int left = !lane_used ? lane : (li == 0 ? lane + L - 1 : lane - 1);
+    const int right = !lane_used ? lane : (li == L - 1 ? lane - L + 1 : lane + 1);
+
+    const double h = pt.h;                       // 0 when T == 0: the state never moves
+    const double gl = prm.gamma_on == QW_GAMMA_ON_LAPLACIAN ? pt.gamma : 1.0;
+    const double gd = prm.gamma_on == QW_GAMMA_ON_ORACLE ? pt.gamma : 1.0;
+    const double a_half = 0.5 * h * gl, a_full = h * gl, a_6 = h / 6.0 * gl, a_3 = h / 3.0 * gl;
+    const double d_half = 0.5 * h * gd, d_full = h * gd, d_6 = h / 6.0 * gd, d_3 = h / 3.0 * gd;
+    const bool is_static = prm.schedule == QW_SCHED_STATIC;
+
+    State<R> s;
+    const double amp = lane_used ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+    }
+    const double2 zero2 = make_double2(0.0, 0.0);
+    const double inv_s = 1.0 / (double)S;
+
+    for (int64_t n0 = 0; n0 < S; n0 += QW_CHUNK) {
+        __syncwarp();
+        for (int i = lane; i < 3 * QW_CHUNK; i += 32) {
+            const int st = i / 3, k = i - 3 * st;
+            const double tau = ((double)(n0 + st) + 0.5 * (double)k) * inv_s;
+            const double g = is_static ? 1.0 : qw_schedule(tau, prm.schedule);
+            sh.fac[i] = is_static ? make_double2(1.0, -1.0) : make_double2(1.0 - g, -g);
+        }
+        __syncwarp();
+        const int cnt = (int)((S - n0 < QW_CHUNK) ? (S - n0) : QW_CHUNK);
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+#define QW_ANY_STAGE(K, TIDX, WA, WB, DWA, DWB)                                         \
+            {                                                                           \
+                const double2 f = sh.fac[3 * sidx + TIDX];                              \
+                const double xfr = (K == 0) ? s.yr[0] : s.ur[0];                        \
+                const double xfi = (K == 0) ? s.yi[0] : s.ui[0];                        \
+                const double xlr = (K == 0) ? (full ? s.yr[R - 1] : s.yr[R > 1 ? R - 2 : 0]) \
+                                            : (full ? s.ur[R - 1] : s.ur[R > 1 ? R - 2 : 0]); \
+                const double xli = (K == 0) ? (full ? s.yi[R - 1] : s.yi[R > 1 ? R - 2 : 0]) \
+                                            : (full ? s.ui[R - 1] : s.ui[R > 1 ? R - 2 : 0]); \
+                const double2 hl = make_double2(__shfl_sync(full_mask, xlr, left),      \
+                                                __shfl_sync(full_mask, xli, left));     \
+                const double2 hr = make_double2(__shfl_sync(full_mask, xfr, right),     \
+                                                __shfl_sync(full_mask, xfi, right));    \
+                if (!full) {                  /* ghost := the right neighbour's value */ \
+                    if (K == 0) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }             \
+                    else { s.ur[R - 1] = hr.x; s.ui[R - 1] = hr.y; }                    \
+                }                                                                       \
+                const double2 dd = make_double2((DWA) * f.y, (DWB) * f.y);              \
+                rk_stage<R, K, true>(s, (WA) * f.x, (WB) * f.x, hl, hr, zero2, 0.0, own, dd); \
+            }
+            QW_ANY_STAGE(0, 0, a_half, a_6, d_half, d_6)
+            QW_ANY_STAGE(1, 1, a_half, a_3, d_half, d_3)
+            QW_ANY_STAGE(2, 1, a_full, a_3, d_full, d_3)
+            QW_ANY_STAGE(3, 2, 0.0, a_6, 0.0, d_6)
+#undef QW_ANY_STAGE
+        }
+    }
+
+    // epilogue: ||psi||^2 over the real slots, summed over the L lanes of each point
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < R - 1; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    if (full) nrm = fma(s.yr[R - 1], s.yr[R - 1], fma(s.yi[R - 1], s.yi[R - 1], nrm));
+    double tot = nrm;
+    const int gbase = lane - li;
+    for (int k = 1; k < L; ++k) {
+        int src = li + k;
+        if (src >= L) src -= L;
+        tot += __shfl_sync(full_mask, nrm, lane_used ? gbase + src : lane);
+    }
+    if (own && valid) {
+        prm.p[pt.q] = fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]) / tot;
+        if (prm.norm) prm.norm[pt.q] = tot;
+    }
+    if (prm.psi && valid) {              // undo the relabelling: slot r of lane li -> w + off(li) + r
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
+        const int64_t off = (int64_t)li * (R - 1) + (li < nfull ? li : nfull);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r == R - 1 && !full) continue;
+            int64_t j = off + r + prm.target;
+            if (j >= prm.n) j -= prm.n;
+            out[j] = make_double2(s.yr[r], s.yi[r]);
+        }
+    }
+}
+
+template <int R, int MINB>
+cudaError_t launch_packed_any(const QwParams &prm, cudaStream_t st, qw_plan *plan)
+{
+    const int L = (int)((prm.n + R - 1) / R);
+    const int nfull = (int)(prm.n - (int64_t)L * (R - 1));
+    const int groups = 32 / L;
+    if (plan) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_packed_any<R, MINB>);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk4_cycle_packed_any<R, MINB>, 32, 0);
+        if (e != cudaSuccess) return e;
+        plan->path = 8;
+        plan->sites_per_thread = R;
+        plan->threads_per_block = 32;
+        plan->blocks_per_sm = nb;
+        plan->regs_per_thread = fa.numRegs;
+        plan->smem_bytes = (int)fa.sharedSizeBytes;
+        plan->steps_per_pass = groups;          // points per warp
+        return cudaSuccess;
+    }
+    const int64_t blocks = (prm.n_points + groups - 1) / groups;
+    rk4_cycle_packed_any<R, MINB><<<(unsigned)blocks, 32, 0, st>>>(prm, L, nfull);
+    return cudaGetLastError();
+}
+
+// sites per lane of the any-dimension packed kernel: the largest R in {8, 4, 2} with n >= R^2
+// whose ceil(n / R) lanes fit a warp; 0 if none (n < 4 or n > 256)
+static int packed_any_r(int64_t n)
+{
+    const int cand[3] = {8, 4, 2};
+    for (int i = 0; i < 3; ++i) {
+        const int R = cand[i];
+        if (n >= R * R && (n + R - 1) / R <= 32) return R;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Nested (Horner) form of the step for the packed layout (qw_horner_level.cuh):
 // N = 16 * TPP with TPP = 8, 16 or 32 lanes per point (N = 128, 256, 512; above that the
 // block-per-point kernel of qw_horner.cu takes over).  24 instead of 30 FP64 instructions per
@@ -351,9 +503,11 @@ int qw_packed_geometry(int64_t n, int64_t n_points, int max_r, int *tpp_log2)
 bool qw_packed_supported(const QwParams &prm)
 {
     int l;
-    return prm.topology == QW_TOPO_CYCLE && prm.step_size == 0.0 && prm.n_steps == nullptr &&
-           prm.n >= 3 &&
-           qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l) > 0;
+    if (!(prm.topology == QW_TOPO_CYCLE && prm.step_size == 0.0 && prm.n_steps == nullptr &&
+          prm.n >= 3))
+        return false;
+    return qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l) > 0 ||
+           packed_any_r(prm.n) > 0;
 }
 
 // nested form: N = 128 or 256 (16 sites per lane, 8 or 16 lanes per point), a batch that fills
@@ -382,6 +536,14 @@ cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan
     int l = 0;
     if (packed_horner(prm, &l)) return launch_packed_horner(prm, l, st, plan);
     const int R = qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l);
+    if (R == 0) {                    // not R * 2^k: R or R-1 sites per lane
+        switch (packed_any_r(prm.n)) {
+        case 8: return launch_packed_any<8, 12>(prm, st, plan);
+        case 4: return launch_packed_any<4, 16>(prm, st, plan);
+        case 2: return launch_packed_any<2, 16>(prm, st, plan);
+        default: return cudaErrorInvalidConfiguration;
+        }
+    }
     switch (R) {
     case 16: return launch_packed<16, 8>(prm, l, st, plan);
     case 8: return launch_packed<8, 12>(prm, l, st, plan);
