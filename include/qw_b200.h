@@ -230,7 +230,9 @@ typedef struct qw_plan {
                                 path: points per warp; else 0 */
 } qw_plan;
 
-/* Which kernel a problem would run on the current device. */
+/* Which kernel a large heatmap call (qw_rk4_grid_*) of this problem would run on the current
+ * device.  Batch calls with a fixed step size use the block-per-point kernels instead of the
+ * warp-packed ones (no common step count within a warp). */
 int qw_plan_query(const qw_problem *prob, qw_plan *plan);
 
 /* Sustained DFMA throughput of the current device in TFLOP/s (FMA = 2 flops), measured

@@ -485,6 +485,12 @@ int qw_plan_query(const qw_problem *prob, qw_plan *plan)
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return cuda_fail(e, "device query");
     prm.n_points = 1 << 20;
+    // the plan describes a large heatmap call (grid mode): with a fixed step size the packed
+    // kernels need the T columns of a grid (never dereferenced here)
+    static const double dummy_axis[1] = {1.0};
+    prm.time_array = dummy_axis;
+    prm.beta_array = dummy_axis;
+    prm.n_time = 1024;
     switch (choose_path(prm)) {
     case PATH_RESIDENT: e = qw_launch_resident(prm, nullptr, plan); break;
     case PATH_PACKED: e = qw_launch_packed(prm, nullptr, plan); break;

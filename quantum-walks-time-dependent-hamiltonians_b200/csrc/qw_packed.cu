@@ -19,6 +19,73 @@ struct PackedShared {
     double2 fac[3 * QW_CHUNK];       // (1 - g, -g) at tau_n, tau_n + 1/(2S), tau_n + 1/S
 };
 
+// Which point does group `grp` of warp `warp_id` integrate?  All points of a warp must share
+// the step count and the normalised stage times, so that one schedule table serves them:
+//  * n_steps rule: any points will do -- warp_id * groups + grp in launch order;
+//  * fixed step size on a heatmap (grid mode): the points of one T COLUMN share T, hence
+//    steps = int(T / h) and tau = t / T; a warp takes `groups` consecutive beta rows of one
+//    column, columns from the longest T to the shortest.
+__device__ __forceinline__ bool packed_column_mode(const QwParams &prm)
+{
+    return prm.step_size > 0.0;
+}
+
+__device__ __forceinline__ QwPoint packed_point(const QwParams &prm, const int64_t warp_id,
+                                                const int grp, const int groups, bool &valid)
+{
+    if (!packed_column_mode(prm)) {
+        int64_t b = warp_id * groups + grp;
+        valid = b < prm.n_points;
+        if (!valid) b = prm.n_points - 1;                // idle groups shadow the last point
+        return qw_point(prm, b);
+    }
+    const int64_t rows = prm.n_points / prm.n_time;
+    const int64_t wpc = (rows + groups - 1) / groups;     // warps per column
+    const int64_t slot = warp_id / wpc;
+    int64_t row = (warp_id - slot * wpc) * groups + grp;
+    valid = row < rows;
+    if (!valid) row = rows - 1;
+    const bool ascending = prm.time_array[0] <= prm.time_array[prm.n_time - 1];
+    const int64_t col = ascending ? prm.n_time - 1 - slot : slot;
+    QwPoint pt;
+    pt.q = row * prm.n_time + col;
+    pt.T = prm.time_array[col];
+    pt.gamma = prm.beta_array[prm.beta_begin + row];
+    pt.h = prm.step_size;
+    const double r = pt.T / pt.h;
+    pt.steps = (r > 0.0) ? (int64_t)r : 0;
+    return pt;
+}
+
+// warps needed for the whole batch
+static int64_t packed_warps(const QwParams &prm, int groups)
+{
+    if (prm.step_size > 0.0) {
+        const int64_t rows = prm.n_points / prm.n_time;
+        return prm.n_time * ((rows + groups - 1) / groups);
+    }
+    return (prm.n_points + groups - 1) / groups;
+}
+
+// (1 - g, -g) of the three stage times of step n: tau = (n + k/2) / S under the n_steps rule,
+// tau = t / T with t = n h (+ h/2, + h) under the fixed step size (as qw_fill_table)
+__device__ __forceinline__ double2 packed_factor(const QwParams &prm, const QwPoint &pt,
+                                                 const int64_t n, const int k, const double inv_s)
+{
+    if (prm.schedule == QW_SCHED_STATIC) return make_double2(1.0, -1.0);
+    double tau;
+    if (packed_column_mode(prm)) {
+        double t = (double)n * pt.h;
+        if (k == 1) t += 0.5 * pt.h;
+        if (k == 2) t += pt.h;
+        tau = t / pt.T;
+    } else {
+        tau = ((double)n + 0.5 * (double)k) * inv_s;
+    }
+    const double g = qw_schedule(tau, prm.schedule);
+    return make_double2(1.0 - g, -g);
+}
+
 template <int R, int MINB>
 __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm, const int tpp_log2)
 {
@@ -27,11 +94,9 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
     const int lane = threadIdx.x;
     const int tpp = 1 << tpp_log2, groups = 32 >> tpp_log2;
     const int li = lane & (tpp - 1), grp = lane >> tpp_log2;
-    int64_t b = (int64_t)blockIdx.x * groups + grp;
-    const bool valid = b < prm.n_points;
-    if (!valid) b = prm.n_points - 1;            // idle groups shadow the last point
-    const QwPoint pt = qw_point(prm, b);
-    const int64_t S = prm.n_steps_uniform;
+    bool valid;
+    const QwPoint pt = packed_point(prm, blockIdx.x, grp, groups, valid);
+    const int64_t S = packed_column_mode(prm) ? pt.steps : prm.n_steps_uniform;
     const bool own = (li == 0);
     const int left = (li == 0) ? lane + tpp - 1 : lane - 1;
     const int right = (li == tpp - 1) ? lane - tpp + 1 : lane + 1;
@@ -42,7 +107,6 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
     const double gd = prm.gamma_on == QW_GAMMA_ON_ORACLE ? pt.gamma : 1.0;
     const double a_half = 0.5 * h * gl, a_full = h * gl, a_6 = h / 6.0 * gl, a_3 = h / 3.0 * gl;
     const double d_half = 0.5 * h * gd, d_full = h * gd, d_6 = h / 6.0 * gd, d_3 = h / 3.0 * gd;
-    const bool is_static = prm.schedule == QW_SCHED_STATIC;
 
     State<R> s;
     const double amp = 1.0 / sqrt((double)prm.n);
@@ -58,9 +122,7 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
         __syncwarp();
         for (int i = lane; i < 3 * QW_CHUNK; i += 32) {
             const int st = i / 3, k = i - 3 * st;
-            const double tau = ((double)(n0 + st) + 0.5 * (double)k) * inv_s;
-            const double g = is_static ? 1.0 : qw_schedule(tau, prm.schedule);
-            sh.fac[i] = is_static ? make_double2(1.0, -1.0) : make_double2(1.0 - g, -g);
+            sh.fac[i] = packed_factor(prm, pt, n0 + st, k, inv_s);
         }
         __syncwarp();
         const int cnt = (int)((S - n0 < QW_CHUNK) ? (S - n0) : QW_CHUNK);
@@ -125,11 +187,10 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
     const int groups = 32 / L;
     const int grp = lane / L, li = lane - grp * L;
     const bool lane_used = grp < groups;
-    int64_t b = (int64_t)blockIdx.x * groups + (lane_used ? grp : groups - 1);
-    const bool valid = lane_used && b < prm.n_points;
-    if (b >= prm.n_points) b = prm.n_points - 1;   // idle groups shadow the last point
-    const QwPoint pt = qw_point(prm, b);
-    const int64_t S = prm.n_steps_uniform;
+    bool valid;
+    const QwPoint pt = packed_point(prm, blockIdx.x, lane_used ? grp : groups - 1, groups, valid);
+    valid = valid && lane_used;
+    const int64_t S = packed_column_mode(prm) ? pt.steps : prm.n_steps_uniform;
     const bool own = lane_used && li == 0;
     const bool full = !lane_used || li < nfull;        // R sites (idle lanes: R zeros)
     const int left = !lane_used ? lane : (li == 0 ? lane + L - 1 : lane - 1);
@@ -140,7 +201,6 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
     const double gd = prm.gamma_on == QW_GAMMA_ON_ORACLE ? pt.gamma : 1.0;
     const double a_half = 0.5 * h * gl, a_full = h * gl, a_6 = h / 6.0 * gl, a_3 = h / 3.0 * gl;
     const double d_half = 0.5 * h * gd, d_full = h * gd, d_6 = h / 6.0 * gd, d_3 = h / 3.0 * gd;
-    const bool is_static = prm.schedule == QW_SCHED_STATIC;
 
     State<R> s;
     const double amp = lane_used ? 1.0 / sqrt((double)prm.n) : 0.0;
@@ -156,9 +216,7 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
         __syncwarp();
         for (int i = lane; i < 3 * QW_CHUNK; i += 32) {
             const int st = i / 3, k = i - 3 * st;
-            const double tau = ((double)(n0 + st) + 0.5 * (double)k) * inv_s;
-            const double g = is_static ? 1.0 : qw_schedule(tau, prm.schedule);
-            sh.fac[i] = is_static ? make_double2(1.0, -1.0) : make_double2(1.0 - g, -g);
+            sh.fac[i] = packed_factor(prm, pt, n0 + st, k, inv_s);
         }
         __syncwarp();
         const int cnt = (int)((S - n0 < QW_CHUNK) ? (S - n0) : QW_CHUNK);
@@ -242,7 +300,7 @@ cudaError_t launch_packed_any(const QwParams &prm, cudaStream_t st, qw_plan *pla
         plan->steps_per_pass = groups;          // points per warp
         return cudaSuccess;
     }
-    const int64_t blocks = (prm.n_points + groups - 1) / groups;
+    const int64_t blocks = packed_warps(prm, groups);
     rk4_cycle_packed_any<R, MINB><<<(unsigned)blocks, 32, 0, st>>>(prm, L, nfull);
     return cudaGetLastError();
 }
@@ -284,19 +342,16 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
     const int lane = threadIdx.x;
     const int tpp = 1 << tpp_log2, groups = 32 >> tpp_log2, ch = 32 / groups;   // ch = tpp
     const int li = lane & (tpp - 1), grp = lane >> tpp_log2, gbase = grp << tpp_log2;
-    int64_t b = (int64_t)blockIdx.x * groups + grp;
-    const bool valid = b < prm.n_points;
-    if (!valid) b = prm.n_points - 1;            // idle groups shadow the last point
-    const QwPoint pt = qw_point(prm, b);
-    const int64_t S = prm.n_steps_uniform;
+    bool valid;
+    const QwPoint pt = packed_point(prm, blockIdx.x, grp, groups, valid);
+    const int64_t S = packed_column_mode(prm) ? pt.steps : prm.n_steps_uniform;
     const int left = (li == 0) ? lane + tpp - 1 : lane - 1;
     const int right = (li == tpp - 1) ? lane - tpp + 1 : lane + 1;
     const double msk = (li == 0) ? 1.0 : 0.0;
     // the lane's refill duty: step (lane % ch) of point (lane / ch) of this warp
     const int fgrp = lane / ch, fstep = lane - fgrp * ch;
-    int64_t fb = (int64_t)blockIdx.x * groups + fgrp;
-    if (fb >= prm.n_points) fb = prm.n_points - 1;
-    const QwPoint fpt = qw_point(prm, fb);
+    bool fvalid;
+    const QwPoint fpt = packed_point(prm, blockIdx.x, fgrp, groups, fvalid);
 
     HState<R> s;
     const double amp = 1.0 / sqrt((double)prm.n);
@@ -427,7 +482,7 @@ cudaError_t launch_packed_horner(const QwParams &prm, int tpp_log2, cudaStream_t
         plan->steps_per_pass = groups;          // points per warp
         return cudaSuccess;
     }
-    const int64_t blocks = (prm.n_points + groups - 1) / groups;
+    const int64_t blocks = packed_warps(prm, groups);
     rk4_cycle_packed_horner<MINB><<<(unsigned)blocks, 32, 0, st>>>(prm, tpp_log2);
     return cudaGetLastError();
 }
@@ -452,7 +507,7 @@ cudaError_t launch_packed(const QwParams &prm, int tpp_log2, cudaStream_t st, qw
         plan->steps_per_pass = groups;          // points per warp
         return cudaSuccess;
     }
-    const int64_t blocks = (prm.n_points + groups - 1) / groups;
+    const int64_t blocks = packed_warps(prm, groups);
     rk4_cycle_packed<R, MINB><<<(unsigned)blocks, 32, 0, st>>>(prm, tpp_log2);
     return cudaGetLastError();
 }
@@ -503,9 +558,12 @@ int qw_packed_geometry(int64_t n, int64_t n_points, int max_r, int *tpp_log2)
 bool qw_packed_supported(const QwParams &prm)
 {
     int l;
-    if (!(prm.topology == QW_TOPO_CYCLE && prm.step_size == 0.0 && prm.n_steps == nullptr &&
-          prm.n >= 3))
-        return false;
+    // one common step count per warp: the n_steps rule, or a fixed step size on a heatmap
+    // (grid mode), where a warp takes points of one T column
+    const bool uniform = prm.step_size == 0.0 && prm.n_steps == nullptr;
+    const bool columns = prm.step_size > 0.0 && prm.time_array != nullptr &&
+                         prm.order == nullptr && prm.n_time > 0;
+    if (!(prm.topology == QW_TOPO_CYCLE && (uniform || columns) && prm.n >= 3)) return false;
     return qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l) > 0 ||
            packed_any_r(prm.n) > 0;
 }

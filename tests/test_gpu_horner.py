@@ -22,7 +22,7 @@ NO_HORNER, R8, OCC4, NO_PACK, NO_ROT = 2048, 256, 128, 512, 4096
                                      (257, 0), (263, 0), (511, 0), (513, 0), (999, 0), (1001, 0),
                                      (1023, R8), (1025, 0), (2049, 0), (3001, R8), (4095, 0)])
 def test_cycle_all_schedules_vs_oracle(qw, n, flags):
-    pl = qw.plan(qw.Problem(n=n, topology="circular", step_size=0.1, flags=flags))
+    pl = qw.plan(qw.Problem(n=n, topology="circular", step_size=0.1, flags=flags | NO_PACK))
     assert pl["path"] == "horner-cycle", pl
     rng = np.random.default_rng(n + flags)
     for sched in ["lin", "sqrt", "cbrt", "cerf_3", "cerf_5", "cerf_7", "static"]:
@@ -240,3 +240,26 @@ def test_runs_are_bitwise_reproducible(qw):
         for _ in range(3):
             b = qw.rk4_batch(prob, T, g, return_psi=True)
             assert all(np.array_equal(x, y) for x, y in zip(a, b)), kw
+
+
+@pytest.mark.parametrize("n", [5, 16, 51, 64, 71, 100, 128, 255, 256, 512])
+def test_packed_kernels_fixed_step_size_on_heatmaps(qw, n):
+    """Fixed step size (the drop-in modules' default rule, QW_Search.py:153-154) on a heatmap:
+    the packed kernels take the points of one T column per warp (common step count and stage
+    times).  Ascending and descending T, T = 0, row shards, a batch large enough for the nested
+    packed kernel at N = 128 / 256 / 512."""
+    rng = np.random.default_rng(n)
+    nT, nB = 9, (160 if n >= 128 else 23)
+    t = np.sort(rng.uniform(0.3, 6.0, nT))
+    t[0] = 0.0
+    b = rng.uniform(0.0, 2.5, nB)
+    for sched, order in (("lin", 1), ("cbrt", -1)):
+        tt = t[::order].copy()
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, step_size=0.05)
+        assert qw.plan(prob)["path"].startswith("packed")
+        p, norm = qw.rk4_heatmap(prob, tt, b)
+        po, no = c_oracle.heatmap(n, "circular", sched, tt, b, step_size=0.05)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL, (n, sched)
+        assert np.argmax(p) == np.argmax(po)
+        p2, _ = qw.rk4_heatmap(prob, tt, b, rows=(3, 17))      # small batch: another geometry
+        assert np.abs(p2 - p[3:17]).max() <= 1e-13
