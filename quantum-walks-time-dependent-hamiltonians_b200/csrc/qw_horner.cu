@@ -116,12 +116,15 @@ __device__ __forceinline__ unsigned warp_slot()
 // ptxas moves arithmetic across BAR.ARV / BAR.SYNC freely: whatever the PTX order, the interior
 // arithmetic of a level ends up after the *next* wait, so an arrival is always followed at once
 // by the wait for the partner's arrival of the same level -- a plain barrier.  DESIGN.md 7.)
-template <int R, bool OWN>
+// RAGGED: some threads hold R-1 sites (`full` false); a compile-time switch, because even two
+// extra selects per level cost the exact-multiple sizes 5 % (register pressure at 168).
+template <int R, bool OWN, bool RAGGED>
 __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab, double2 *first,
                                              double2 *last, const int nt, const int t,
                                              const int tl, const int tr, const int cnt,
-                                             const double msk, const bool full)
+                                             const double msk, const bool full_in)
 {
+    const bool full = RAGGED ? full_in : true;
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const HornerStep &hs = tab[sidx];
         double sgl = 0.0;                          // this lane's component of its sigma
@@ -133,7 +136,7 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
             const double2 hr = first[par * nt + tr];                                        \
             const double rho = hs.rho[LEVEL - 1];                                           \
             double2 o0, oL;                                                                 \
-            if (!full) {                      /* ghost slot := the right neighbour's value */ \
+            if (RAGGED && !full) {            /* ghost slot := the right neighbour's value */ \
                 if (LEVEL == 4) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }                 \
                 else { s.zr[R - 1] = hr.x; s.zi[R - 1] = hr.y; }                            \
             }                                                                               \
@@ -181,7 +184,7 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
     }
 }
 
-template <int R, int MAXNT, int MINB>
+template <int R, int MAXNT, int MINB, bool RAGGED>
 __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams prm)
 {
     static_assert(R >= 2 * HW0 + 1, "the window w-3..w+3 must sit in one thread");
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
     const int t = threadIdx.x, nt = blockDim.x, nact = prm.nact, nfull = prm.nfull;
     const QwPoint pt = qw_point(prm, blockIdx.x);
     const bool active = t < nact;
-    const bool full = t < nfull || !active;           // R sites (idle threads: R zeros)
+    const bool full = !RAGGED || t < nfull || !active; // R sites (idle threads: R zeros)
     // ring neighbours among the active threads; idle threads talk to themselves (zeros)
     const int tl = active ? (t == 0 ? nact - 1 : t - 1) : t;
     const int tr = active ? (t == nact - 1 ? 0 : t + 1) : t;
@@ -225,9 +228,9 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
         __syncthreads();
         const double msk = own ? 1.0 : 0.0;
         if (warp == (ht >> 5))
-            horner_steps<R, true>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk, full);
+            horner_steps<R, true, RAGGED>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk, full);
         else
-            horner_steps<R, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk, full);
+            horner_steps<R, false, RAGGED>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk, full);
     }
 
     // p = |psi_w|^2 / ||psi||^2, ||psi||^2 (BCB.py:189-199, Runge_Kutta_Error.py:103)
@@ -358,21 +361,22 @@ __device__ __forceinline__ void scalar_step(const CHStep &hs, double2 &yw, doubl
 
 // one level on all R sites of a thread: out = y - i rho (N x - S)
 // (ndg, Sg): the same for the last slot -- zero in a short thread, whose last slot is a ghost
-template <int R, int LEVEL>
+template <int R, int LEVEL, bool RAGGED>
 __device__ __forceinline__ void clevel(HState<R> &s, const double rho, const double nd,
                                        const double2 S, const double ndg, const double2 Sg)
 {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const double tr_ = fma(r == R - 1 ? ndg : nd, HX_R(r), -(r == R - 1 ? Sg.x : S.x));
-        const double ti_ = fma(r == R - 1 ? ndg : nd, HX_I(r), -(r == R - 1 ? Sg.y : S.y));
+        const bool g = RAGGED && r == R - 1;
+        const double tr_ = fma(g ? ndg : nd, HX_R(r), -(g ? Sg.x : S.x));
+        const double ti_ = fma(g ? ndg : nd, HX_I(r), -(g ? Sg.y : S.y));
         HO_R(r) = fma(rho, ti_, s.yr[r]);
         HO_I(r) = fma(-rho, tr_, s.yi[r]);
     }
 }
 
 // Vector work of chunk c (cnt steps).  No barrier inside.
-template <int R, bool OWN>
+template <int R, bool OWN, bool RAGGED>
 __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const int64_t c,
                                                const int cnt, const double nd, const double msk,
                                                const bool full)
@@ -395,7 +399,7 @@ __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const
         }
 #define QW_CH_LEVEL(LEVEL)                                                                  \
         {                                                                                   \
-            clevel<R, LEVEL>(s, rl[LEVEL - 1], nd, Sl[4 - LEVEL], ndg, Sg[4 - LEVEL]);      \
+            clevel<R, LEVEL, RAGGED>(s, rl[LEVEL - 1], nd, Sl[4 - LEVEL], ndg, Sg[4 - LEVEL]); \
             if (OWN) {                                                                      \
                 const double2 sg = sh.sig[cur][sidx][4 - LEVEL];                            \
                 if (LEVEL > 1) {                                                            \
@@ -414,7 +418,7 @@ __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const
 }
 
 // blockDim = worker threads (n / R rounded up to warps) + 32: the last warp is the scalar warp
-template <int R, int MAXNT, int MINB>
+template <int R, int MAXNT, int MINB, bool RAGGED>
 __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const QwParams prm)
 {
     __shared__ CFShared sh;
@@ -422,7 +426,7 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
     const int lane = t & 31, warp = t >> 5, swarp = (blockDim.x >> 5) - 1;
     const QwPoint pt = qw_point(prm, blockIdx.x);
     const bool active = t < nact;
-    const bool full = t < prm.nfull;                   // R sites; else R-1 and a ghost slot
+    const bool full = !RAGGED || t < prm.nfull;        // R sites; else R-1 and a ghost slot
     const double nfull = (double)prm.n;
     const double nd = active ? nfull : 0.0;
 
@@ -469,9 +473,9 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
                     scalar_step(tn[sidx], yw, Sy, nfull, sh.sums[nxt][sidx], sh.sig[nxt][sidx], lane);
             }
         } else if (warp == 0) {
-            complete_chunk<R, true>(s, sh, c, QW_CNT(c), nd, msk, full);
+            complete_chunk<R, true, RAGGED>(s, sh, c, QW_CNT(c), nd, msk, full);
         } else {
-            complete_chunk<R, false>(s, sh, c, QW_CNT(c), nd, msk, full);
+            complete_chunk<R, false, RAGGED>(s, sh, c, QW_CNT(c), nd, msk, full);
         }
     }
 #undef QW_CNT
@@ -552,27 +556,32 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
         plan->path = cyc ? 5 : 6;
         plan->sites_per_thread = R;
     }
+    const bool ragged = prm.nfull != prm.nact;
+#define QW_HL(KERNEL, ...)                                                                  \
+    return ragged ? hlaunch(KERNEL<__VA_ARGS__, true>, prm, bthreads, smem, st, plan)      \
+                  : hlaunch(KERNEL<__VA_ARGS__, false>, prm, bthreads, smem, st, plan)
     if (!cyc) {
-        const int bt = threads + 32;              // + the scalar warp
+        const int bthreads = threads + 32;        // + the scalar warp
         if (R == 16) {
-            if (threads <= 64) return hlaunch(rk4_complete_horner<16, 64, 4>, prm, bt, smem, st, plan);
-            if (threads <= 128) return hlaunch(rk4_complete_horner<16, 128, 2>, prm, bt, smem, st, plan);
-            return hlaunch(rk4_complete_horner<16, 256, 1>, prm, bt, smem, st, plan);
+            if (threads <= 64) { QW_HL(rk4_complete_horner, 16, 64, 4); }
+            if (threads <= 128) { QW_HL(rk4_complete_horner, 16, 128, 2); }
+            QW_HL(rk4_complete_horner, 16, 256, 1);
         }
-        if (threads <= 128) return hlaunch(rk4_complete_horner<8, 128, 3>, prm, bt, smem, st, plan);
-        if (threads <= 256) return hlaunch(rk4_complete_horner<8, 256, 1>, prm, bt, smem, st, plan);
-        return hlaunch(rk4_complete_horner<8, 512, 1>, prm, bt, smem, st, plan);
+        if (threads <= 128) { QW_HL(rk4_complete_horner, 8, 128, 3); }
+        if (threads <= 256) { QW_HL(rk4_complete_horner, 8, 256, 1); }
+        QW_HL(rk4_complete_horner, 8, 512, 1);
     }
+    const int bthreads = threads;
     if (R == 16) {
         // register file = 16 K per SM sub-partition: 2 / 3 warps there allow 255 / 168 registers
-        if (threads <= 64 && (prm.flags & QW_FLAG_OCC4))
-            return hlaunch(rk4_cycle_horner<16, 64, 4>, prm, threads, smem, st, plan);
-        if (threads <= 64) return hlaunch(rk4_cycle_horner<16, 64, 6>, prm, threads, smem, st, plan);
-        if (threads <= 128) return hlaunch(rk4_cycle_horner<16, 128, 3>, prm, threads, smem, st, plan);
-        return hlaunch(rk4_cycle_horner<16, 256, 1>, prm, threads, smem, st, plan);
+        if (threads <= 64 && (prm.flags & QW_FLAG_OCC4)) { QW_HL(rk4_cycle_horner, 16, 64, 4); }
+        if (threads <= 64) { QW_HL(rk4_cycle_horner, 16, 64, 6); }
+        if (threads <= 128) { QW_HL(rk4_cycle_horner, 16, 128, 3); }
+        QW_HL(rk4_cycle_horner, 16, 256, 1);
     }
-    if (threads <= 64) return hlaunch(rk4_cycle_horner<8, 64, 8>, prm, threads, smem, st, plan);
-    if (threads <= 128) return hlaunch(rk4_cycle_horner<8, 128, 4>, prm, threads, smem, st, plan);
-    if (threads <= 256) return hlaunch(rk4_cycle_horner<8, 256, 2>, prm, threads, smem, st, plan);
-    return hlaunch(rk4_cycle_horner<8, 512, 1>, prm, threads, smem, st, plan);
+    if (threads <= 64) { QW_HL(rk4_cycle_horner, 8, 64, 8); }
+    if (threads <= 128) { QW_HL(rk4_cycle_horner, 8, 128, 4); }
+    if (threads <= 256) { QW_HL(rk4_cycle_horner, 8, 256, 2); }
+    QW_HL(rk4_cycle_horner, 8, 512, 1);
+#undef QW_HL
 }
