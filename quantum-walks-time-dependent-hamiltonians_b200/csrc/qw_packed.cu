@@ -57,6 +57,35 @@ __device__ __forceinline__ QwPoint packed_point(const QwParams &prm, const int64
     return pt;
 }
 
+// Step count of the warp.  It is the same in every lane, but in column mode it comes from a
+// load through a generic pointer, which the compiler counts as divergent -- and a possibly
+// divergent trip count puts divergence handling (BRA.DIV, two copies of every shuffle) into
+// the time loop (C1 latency 209 -> 258 us).  Passing the value through shared memory (`slot`)
+// makes it a load from a uniform shared address, which the compiler knows to be uniform.
+__device__ __forceinline__ int64_t packed_steps_raw(const QwParams &prm, const int64_t warp_id,
+                                                    const int groups);
+
+__device__ __forceinline__ int64_t packed_steps(const QwParams &prm, const int64_t warp_id,
+                                                const int groups, int64_t *slot)
+{
+    if (!packed_column_mode(prm)) return prm.n_steps_uniform;
+    const int64_t raw = packed_steps_raw(prm, warp_id, groups);
+    if (threadIdx.x == 0) *slot = raw;
+    __syncwarp();
+    return *slot;
+}
+
+__device__ __forceinline__ int64_t packed_steps_raw(const QwParams &prm, const int64_t warp_id,
+                                                    const int groups)
+{
+    const int64_t rows = prm.n_points / prm.n_time;
+    const int64_t wpc = (rows + groups - 1) / groups;
+    const int64_t slot = warp_id / wpc;
+    const bool ascending = prm.time_array[0] <= prm.time_array[prm.n_time - 1];
+    const double r = prm.time_array[ascending ? prm.n_time - 1 - slot : slot] / prm.step_size;
+    return (r > 0.0) ? (int64_t)r : 0;
+}
+
 // warps needed for the whole batch
 static int64_t packed_warps(const QwParams &prm, int groups)
 {
@@ -96,7 +125,8 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
     const int li = lane & (tpp - 1), grp = lane >> tpp_log2;
     bool valid;
     const QwPoint pt = packed_point(prm, blockIdx.x, grp, groups, valid);
-    const int64_t S = packed_column_mode(prm) ? pt.steps : prm.n_steps_uniform;
+    __shared__ int64_t steps_slot;
+    const int64_t S = packed_steps(prm, blockIdx.x, groups, &steps_slot);
     const bool own = (li == 0);
     const int left = (li == 0) ? lane + tpp - 1 : lane - 1;
     const int right = (li == tpp - 1) ? lane - tpp + 1 : lane + 1;
@@ -190,7 +220,8 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
     bool valid;
     const QwPoint pt = packed_point(prm, blockIdx.x, lane_used ? grp : groups - 1, groups, valid);
     valid = valid && lane_used;
-    const int64_t S = packed_column_mode(prm) ? pt.steps : prm.n_steps_uniform;
+    __shared__ int64_t steps_slot;
+    const int64_t S = packed_steps(prm, blockIdx.x, groups, &steps_slot);
     const bool own = lane_used && li == 0;
     const bool full = !lane_used || li < nfull;        // R sites (idle lanes: R zeros)
     const int left = !lane_used ? lane : (li == 0 ? lane + L - 1 : lane - 1);
@@ -344,7 +375,8 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
     const int li = lane & (tpp - 1), grp = lane >> tpp_log2, gbase = grp << tpp_log2;
     bool valid;
     const QwPoint pt = packed_point(prm, blockIdx.x, grp, groups, valid);
-    const int64_t S = packed_column_mode(prm) ? pt.steps : prm.n_steps_uniform;
+    __shared__ int64_t steps_slot;
+    const int64_t S = packed_steps(prm, blockIdx.x, groups, &steps_slot);
     const int left = (li == 0) ? lane + tpp - 1 : lane - 1;
     const int right = (li == tpp - 1) ? lane - tpp + 1 : lane + 1;
     const double msk = (li == 0) ? 1.0 : 0.0;
