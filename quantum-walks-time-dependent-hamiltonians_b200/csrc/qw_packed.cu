@@ -115,7 +115,10 @@ __device__ __forceinline__ double2 packed_factor(const QwParams &prm, const QwPo
     return make_double2(1.0 - g, -g);
 }
 
-template <int R, int MINB>
+// COLUMN: fixed step size on a heatmap (packed_point).  A template switch, because the step
+// count then comes from memory and lives in a vector register; with the n_steps rule it is a
+// kernel parameter and the loop control stays in the uniform datapath (C1: 5 % latency).
+template <int R, int MINB, bool COLUMN>
 __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm, const int tpp_log2)
 {
     __shared__ PackedShared sh;
@@ -126,7 +129,8 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
     bool valid;
     const QwPoint pt = packed_point(prm, blockIdx.x, grp, groups, valid);
     __shared__ int64_t steps_slot;
-    const int64_t S = packed_steps(prm, blockIdx.x, groups, &steps_slot);
+    const int64_t S = COLUMN ? packed_steps(prm, blockIdx.x, groups, &steps_slot)
+                             : prm.n_steps_uniform;
     const bool own = (li == 0);
     const int left = (li == 0) ? lane + tpp - 1 : lane - 1;
     const int right = (li == tpp - 1) ? lane - tpp + 1 : lane + 1;
@@ -525,10 +529,10 @@ cudaError_t launch_packed(const QwParams &prm, int tpp_log2, cudaStream_t st, qw
     const int groups = 32 >> tpp_log2;
     if (plan) {
         cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_packed<R, MINB>);
+        cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_packed<R, MINB, false>);
         if (e != cudaSuccess) return e;
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk4_cycle_packed<R, MINB>, 32, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk4_cycle_packed<R, MINB, false>, 32, 0);
         if (e != cudaSuccess) return e;
         plan->path = 4;
         plan->sites_per_thread = R;
@@ -540,7 +544,10 @@ cudaError_t launch_packed(const QwParams &prm, int tpp_log2, cudaStream_t st, qw
         return cudaSuccess;
     }
     const int64_t blocks = packed_warps(prm, groups);
-    rk4_cycle_packed<R, MINB><<<(unsigned)blocks, 32, 0, st>>>(prm, tpp_log2);
+    if (prm.step_size > 0.0)
+        rk4_cycle_packed<R, MINB, true><<<(unsigned)blocks, 32, 0, st>>>(prm, tpp_log2);
+    else
+        rk4_cycle_packed<R, MINB, false><<<(unsigned)blocks, 32, 0, st>>>(prm, tpp_log2);
     return cudaGetLastError();
 }
 
