@@ -26,11 +26,53 @@ _dropin.install(globals(), "BCBL")
 
 
 def production_sweep(step_functions=("lin", "sqrt", "cbrt", "cerf_3"),
-                     dims=tuple(np.arange(3, 71 + 1, 2))):
-    """The __main__ loop of BCB_latest.py:309-320."""
+                     dims=tuple(np.arange(3, 71 + 1, 2)), streams=8):
+    """The __main__ loop of BCB_latest.py:309-320.
+
+    A production heatmap is 300 points on a ring of at most 71 sites: one launch occupies a few
+    per cent of the GPU and runs for as long as its longest point (latency bound).  With
+    ``streams`` > 1 (one process, fixed-step RK4, time-dependent walk) the heatmaps are
+    therefore issued round-robin on that many CUDA streams and collected once at the end; the
+    files written are the same.  ``streams`` = 1, a process group, 'rk45' or the
+    time-independent comparator take the reference's sequential loop."""
     global step_function, dimension
+    import time as _time
+
+    import torch
+    import torch.distributed as dist
+
+    from . import engine
+
+    sequential = (streams <= 1 or integrator != "rk4" or type_of_qw != "dependent"
+                  or (dist.is_available() and dist.is_initialized()))
+    if sequential:
+        for step in step_functions:
+            step_function = step
+            for dim in dims:
+                dimension = int(dim)
+                parallel_routine()                         # noqa: F821 (installed above)
+        return
+    dev = engine._device(device)
+    pool = [torch.cuda.Stream(device=dev) for _ in range(int(streams))]
+    beta = np.asarray(PRODUCTION_BETA, dtype=np.float64)
+    d_beta = torch.from_numpy(beta).to(dev)
+    pending, tic = [], _time.perf_counter()
     for step in step_functions:
-        step_function = step
-        for dim in dims:
-            dimension = int(dim)
-            parallel_routine()                             # noqa: F821 (installed above)
+        for k, dim in enumerate(dims):
+            n = int(dim)
+            time_array = [(np.pi / 4) * np.sqrt(n), np.sqrt(n), (np.pi / 2) * np.sqrt(n),
+                          2 * np.sqrt(n)]
+            prob = engine.Problem(n=n, topology=topology, schedule=step, gamma_on=gamma_on,
+                                  n_steps=n_steps, step_size=None if n_steps else step_size)
+            d_time = torch.tensor(time_array, dtype=torch.float64, device=dev)
+            st = pool[len(pending) % len(pool)]
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                p, _ = engine.rk4_heatmap(prob, d_time, d_beta, device=dev)
+            pending.append((n, step, time_array, p))
+    torch.cuda.synchronize(dev)
+    for n, step, time_array, p in pending:
+        np.save(str(n) + '_probability_' + step + '.npy', p.cpu().numpy())
+        np.save(str(n) + '_circ_time.npy', time_array)
+        np.save(str(n) + '_circ_beta.npy', list(PRODUCTION_BETA))
+        print('Success: N ', n, ' in ', int((_time.perf_counter() - tic) / 60), ' min')

@@ -260,3 +260,23 @@ def test_runge_kutta_error_main_block():
         assert abs(defect - (1 - norm)) <= 1e-9, (atol, defect, 1 - norm)
         assert abs(defect) < 1e-3                    # "error in the order of <10^-4" (SS:112)
     rke.integrator, rke.rtolerance, rke.atolerance = "rk4", 1e-6, 1e-6
+
+
+def test_production_sweep_on_streams_writes_the_same_files(tmp_path, monkeypatch):
+    """BCB_latest.production_sweep: the multi-stream issue order must give the files of the
+    reference's sequential loop (names of BCB_latest.py:287-293), bit for bit."""
+    bl = _mod("BCB_latest")
+    out = {}
+    for streams in (1, 8):
+        d = tmp_path / ("s%d" % streams)
+        d.mkdir()
+        monkeypatch.chdir(d)
+        bl.integrator, bl.n_steps, bl.step_size, bl.type_of_qw = "rk4", None, 1e-2, "dependent"
+        bl.topology = "circular"
+        bl.production_sweep(step_functions=("lin", "cerf_3"), dims=(5, 21, 51, 64), streams=streams)
+        out[streams] = {f.name: np.load(f) for f in sorted(d.glob("*.npy"))}
+    bl.step_size = 1e-3
+    assert sorted(out[1]) == sorted(out[8]) and len(out[1]) == 2 * 4 + 2 * 4
+    for name in out[1]:
+        assert np.array_equal(out[1][name], out[8][name]), name
+    assert out[8]["51_probability_lin.npy"].shape == (75, 4)
