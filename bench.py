@@ -350,7 +350,7 @@ def run_b200(args):
                        "kernel": plan, "results_sane_and_e2e_equals_device": ok},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": 78592,
+                         "traffic": 626688,
                          "traffic_note": "dram__bytes_read+write of an 8192-point launch (ncu "
                                          "--set full, profiles/r1_cycle_horner_r16_ncu_full"
                                          ".md): the kernel is register-resident, DRAM sees "
