@@ -643,7 +643,9 @@ cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan
     }
     switch (R) {
     case 16: return launch_packed<16, 8>(prm, l, st, plan);
-    case 8: return launch_packed<8, 12>(prm, l, st, plan);
+    case 8:
+        if (prm.flags & QW_FLAG_OCC4) return launch_packed<8, 16>(prm, l, st, plan);   // A/B
+        return launch_packed<8, 12>(prm, l, st, plan);
     case 7: return launch_packed<7, 12>(prm, l, st, plan);
     case 6: return launch_packed<6, 12>(prm, l, st, plan);
     case 5: return launch_packed<5, 16>(prm, l, st, plan);
