@@ -95,9 +95,15 @@ enum {
                                     accumulator, 30 FP64 instructions per site-update) instead
                                     of the nested form with tabulated oracle corrections (24);
                                     A/B and cross-checks */
-    QW_FLAG_NO_ROTATE = 4096     /* nested-form kernels: keep the marked vertex in warp 0 of
+    QW_FLAG_NO_ROTATE = 4096,    /* nested-form kernels: keep the marked vertex in warp 0 of
                                     every block instead of alternating the owner warp with the
                                     physical warp slot (A/B) */
+    QW_FLAG_MIRROR = 8192        /* cycle graph, 160 <= n <= 1086: integrate only the half ring
+                                    w .. w + n/2 with reflecting ends (psi is mirror symmetric
+                                    about the marked vertex for the uniform initial state every
+                                    caller of the reference uses): same p, norm and psi with half
+                                    the arithmetic, one warp per point.  Opt-in; ignored where
+                                    it does not apply. */
 };
 
 /* ---- the hot path -------------------------------------------------------------------- */
@@ -219,7 +225,7 @@ typedef struct qw_plan {
     int32_t path;            /* 0 resident-cycle, 1 resident-complete, 2 generic, 3 stream,
                                 4 warp-packed cycle, 5 / 6 resident cycle / complete in nested form,
                                 7 warp-packed cycle in nested form, 8 warp-packed cycle of any
-                                small dimension */
+                                small dimension, 9 mirror-reduced cycle (QW_FLAG_MIRROR) */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */

@@ -14,9 +14,10 @@ SCHEDULES = {"cerf_3": 0, "lin": 1, "sqrt": 2, "cbrt": 3, "cerf_5": 4, "cerf_7":
 GAMMA_ON_ORACLE, GAMMA_ON_LAPLACIAN = 0, 1
 FLAG_FORCE_GENERIC, FLAG_FORCE_STREAM, FLAG_EXACT_SUM = 1, 2, 4
 FLAG_STREAM_KB1, FLAG_STREAM_KB2 = 8, 16
+FLAG_NO_HORNER, FLAG_MIRROR = 2048, 8192
 PATH_NAMES = {0: "resident-cycle", 1: "resident-complete", 2: "generic", 3: "stream",
               4: "packed-cycle", 5: "horner-cycle", 6: "horner-complete",
-              7: "packed-horner-cycle", 8: "packed-any-cycle"}
+              7: "packed-horner-cycle", 8: "packed-any-cycle", 9: "mirror-cycle"}
 
 
 class QwProblem(ctypes.Structure):

@@ -498,6 +498,185 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Mirror-reduced nested kernel (QW_FLAG_MIRROR, opt-in).  The reference always starts from the
+// uniform state (BCB.py:179-180) and H(t) is invariant under the reflection of the ring about
+// the marked vertex, so psi_{w+k} = psi_{w-k} at all times -- bit for bit in the full-ring
+// kernels, whose neighbour sums are commutative.  Integrating the half ring w .. w + n/2 with
+// reflecting ends (left of w: psi_{w+1}; right of the antipode: psi_{n/2-1} for even n, the
+// last site itself for odd n) gives the same numbers with half the arithmetic, and for
+// n <= 1086 the n/2 + 1 sites of a point fit the registers of ONE warp (17 sites per lane):
+// halo values travel by shuffles, there is no mailbox and no barrier.  s_k = 2 psi_{w+k} in the
+// correction basis; ||psi||^2 counts the interior sites twice.  One point per warp, any step
+// rule.  Not the default: the benchmark's unit is the full-ring site-update.
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) rk4_cycle_mirror(const QwParams prm, const int L,
+                                                             const int nfull)
+{
+    __shared__ PackedStep tab[32];
+    __shared__ int64_t steps_slot;
+    const unsigned fm = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const QwPoint pt = qw_point(prm, blockIdx.x);
+    if (lane == 0) steps_slot = pt.steps;         // uniform to the compiler (see packed_steps)
+    __syncwarp();
+    const int64_t S = steps_slot;
+    const bool active = lane < L;
+    const bool full = lane < nfull || !active;
+    const bool first = lane == 0, lastl = lane == L - 1;
+    const bool even = (prm.n & 1) == 0;
+    const int left = first ? lane : lane - 1, right = lane + 1 < 32 ? lane + 1 : lane;
+    const double msk = first ? 1.0 : 0.0;
+
+    HState<R> s;
+    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = (r == R - 1 && !full) ? 0.0 : amp; s.yi[r] = 0.0;
+        s.zr[r] = 0.0; s.zi[r] = 0.0;
+    }
+
+    for (int64_t n0 = 0; n0 < S; n0 += 32) {
+        __syncwarp();
+        if (n0 + lane < S) {
+            const double t0 = (double)(n0 + lane) * pt.h;
+            const double2 ad1 = qw_operator_scalars(t0 / pt.T, pt.gamma, prm.schedule, prm.gamma_on);
+            const double2 ad2 = qw_operator_scalars((t0 + 0.5 * pt.h) / pt.T, pt.gamma,
+                                                    prm.schedule, prm.gamma_on);
+            const double2 ad4 = qw_operator_scalars((t0 + pt.h) / pt.T, pt.gamma, prm.schedule,
+                                                    prm.gamma_on);
+            HornerCoef hc;
+            horner_coefficients(hc, pt.h, ad1, ad2, ad4, 2.0, 6.0);
+            horner_cycle_sum_basis(hc.c);
+            PackedStep &o = tab[lane];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
+            const int base[4] = {0, 1, 3, 6};
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double2 ck = (k <= m) ? hc.c[base[m] + k] : make_double2(0.0, 0.0);
+                    o.coef[2 * k][2 * m] = ck.x;      o.coef[2 * k + 1][2 * m] = -ck.y;
+                    o.coef[2 * k][2 * m + 1] = ck.y;  o.coef[2 * k + 1][2 * m + 1] = ck.x;
+                }
+            }
+        }
+        __syncwarp();
+        const int cnt = (int)((S - n0 < 32) ? (S - n0) : 32);
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+            const PackedStep &hs = tab[sidx];
+            double sgl = 0.0;
+#define QW_MX_R(LV, r) ((LV == 4) ? s.yr[r] : s.zr[r])
+#define QW_MX_I(LV, r) ((LV == 4) ? s.yi[r] : s.zi[r])
+#define QW_MIRROR_LEVEL(LEVEL)                                                              \
+            {                                                                               \
+                /* last real slot (a short lane's slot R-1 is a ghost) and the one before */ \
+                const double lr = full ? QW_MX_R(LEVEL, R - 1) : QW_MX_R(LEVEL, R - 2);                   \
+                const double li_ = full ? QW_MX_I(LEVEL, R - 1) : QW_MX_I(LEVEL, R - 2);                  \
+                const double br = full ? QW_MX_R(LEVEL, R - 2) : QW_MX_R(LEVEL, R - 3);                   \
+                const double bi = full ? QW_MX_I(LEVEL, R - 2) : QW_MX_I(LEVEL, R - 3);                   \
+                double2 hl = make_double2(__shfl_sync(fm, lr, left), __shfl_sync(fm, li_, left)); \
+                double2 hr = make_double2(__shfl_sync(fm, QW_MX_R(LEVEL, 0), right),               \
+                                          __shfl_sync(fm, QW_MX_I(LEVEL, 0), right));              \
+                if (first) hl = make_double2(QW_MX_R(LEVEL, 1), QW_MX_I(LEVEL, 1));     /* mirror about w */ \
+                if (lastl) hr = even ? make_double2(br, bi) : make_double2(lr, li_);        \
+                if (!full) {                                                                \
+                    if (LEVEL == 4) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }             \
+                    else { s.zr[R - 1] = hr.x; s.zi[R - 1] = hr.y; }                        \
+                }                                                                           \
+                const double rho = hs.rho[LEVEL - 1];                                       \
+                if (LEVEL == 4) {                                                           \
+                    double bb[8];                        /* y_w, s_k = 2 y_{w+k} */          \
+                    bb[0] = s.yr[0];           bb[1] = s.yi[0];                             \
+                    bb[2] = s.yr[1] + s.yr[1]; bb[3] = s.yi[1] + s.yi[1];                   \
+                    bb[4] = s.yr[2] + s.yr[2]; bb[5] = s.yi[2] + s.yi[2];                   \
+                    bb[6] = s.yr[3] + s.yr[3]; bb[7] = s.yi[3] + s.yi[3];                   \
+                    sgl = hs.coef[0][lane & 7] * __shfl_sync(fm, bb[0], 0);                 \
+                    _Pragma("unroll")                                                       \
+                    for (int k = 1; k < 8; ++k)                                             \
+                        sgl = fma(hs.coef[k][lane & 7], __shfl_sync(fm, bb[k], 0), sgl);    \
+                }                                                                           \
+                double2 o0, oL;                                                             \
+                hedges<R, LEVEL>(s, rho, hl, hr, o0, oL);                                   \
+                hinterior<R, LEVEL>(s, rho, o0, oL);                                        \
+                const double sgr = __shfl_sync(fm, sgl, 2 * (4 - LEVEL));                   \
+                const double sgi = __shfl_sync(fm, sgl, 2 * (4 - LEVEL) + 1);               \
+                if (LEVEL > 1) {                                                            \
+                    s.zr[0] = fma(msk, sgr, s.zr[0]); s.zi[0] = fma(msk, sgi, s.zi[0]);     \
+                } else {                                                                    \
+                    s.yr[0] = fma(msk, sgr, s.yr[0]); s.yi[0] = fma(msk, sgi, s.yi[0]);     \
+                }                                                                           \
+            }
+            QW_MIRROR_LEVEL(4)
+            QW_MIRROR_LEVEL(3)
+            QW_MIRROR_LEVEL(2)
+            QW_MIRROR_LEVEL(1)
+#undef QW_MIRROR_LEVEL
+#undef QW_MX_R
+#undef QW_MX_I
+        }
+    }
+
+    // ||psi||^2: every site of the half ring counts twice, except w and (even n) the antipode
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < R - 1; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    if (full) nrm = fma(s.yr[R - 1], s.yr[R - 1], fma(s.yi[R - 1], s.yi[R - 1], nrm));
+    nrm *= 2.0;
+    const double pw = fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]);
+    if (first) nrm -= pw;
+    if (lastl && even) {
+        const double ar = full ? s.yr[R - 1] : s.yr[R - 2], ai = full ? s.yi[R - 1] : s.yi[R - 2];
+        nrm -= fma(ar, ar, ai * ai);
+    }
+    if (!active) nrm = 0.0;
+    nrm = qw_warp_sum(nrm);
+    if (first) {
+        prm.p[pt.q] = pw / nrm;
+        if (prm.norm) prm.norm[pt.q] = nrm;
+    }
+    if (prm.psi && active) {              // both mirror images: w + l and w - l
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
+        const int64_t off = (int64_t)lane * (R - 1) + (lane < nfull ? lane : nfull);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r == R - 1 && !full) continue;
+            int64_t a = prm.target + off + r, b = prm.target - off - r;
+            if (a >= prm.n) a -= prm.n;
+            if (b < 0) b += prm.n;
+            out[a] = make_double2(s.yr[r], s.yi[r]);
+            out[b] = make_double2(s.yr[r], s.yi[r]);
+        }
+    }
+}
+
+template <int R, int MINB>
+cudaError_t launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan)
+{
+    const int64_t m = prm.n / 2 + 1;                 // sites of the half ring
+    const int L = (int)((m + R - 1) / R);
+    const int nfull = (int)(m - (int64_t)L * (R - 1));
+    if (plan) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_mirror<R, MINB>);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk4_cycle_mirror<R, MINB>, 32, 0);
+        if (e != cudaSuccess) return e;
+        plan->path = 9;
+        plan->sites_per_thread = R;
+        plan->threads_per_block = 32;
+        plan->blocks_per_sm = nb;
+        plan->regs_per_thread = fa.numRegs;
+        plan->smem_bytes = (int)fa.sharedSizeBytes;
+        plan->steps_per_pass = 1;
+        return cudaSuccess;
+    }
+    rk4_cycle_mirror<R, MINB><<<(unsigned)prm.n_points, 32, 0, st>>>(prm, L, nfull);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_packed_horner(const QwParams &prm, int tpp_log2, cudaStream_t st, qw_plan *plan)
 {
     constexpr int MINB = 12;
@@ -592,6 +771,28 @@ int qw_packed_geometry(int64_t n, int64_t n_points, int max_r, int *tpp_log2)
     for (int i = 0; i < 9; ++i)
         if (small[i] <= max_r && packed_fits(n, small[i], 32, tpp_log2)) return small[i];
     return 0;
+}
+
+// sites per lane of the mirror-reduced kernel (one point per warp), or 0: the half ring
+// n/2 + 1 = L (R - 1) + nfull must fit 32 lanes with R in {17, 9} and n/2 + 1 >= R^2
+int qw_mirror_sites_per_lane(const QwParams &prm)
+{
+    if (!(prm.flags & QW_FLAG_MIRROR) || prm.topology != QW_TOPO_CYCLE) return 0;
+    const int64_t m = prm.n / 2 + 1;
+    if (m >= 81 && (m + 8) / 9 <= 32) return 9;
+    if (m >= 289 && (m + 16) / 17 <= 32) return 17;
+    return 0;
+}
+
+cudaError_t qw_launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan)
+{
+    switch (qw_mirror_sites_per_lane(prm)) {
+    case 17:
+        if (prm.flags & QW_FLAG_OCC4) return launch_mirror<17, 8>(prm, st, plan);   // A/B: 196 registers
+        return launch_mirror<17, 12>(prm, st, plan);
+    case 9: return launch_mirror<9, 12>(prm, st, plan);
+    default: return cudaErrorInvalidConfiguration;
+    }
 }
 
 bool qw_packed_supported(const QwParams &prm)

@@ -263,3 +263,50 @@ def test_packed_kernels_fixed_step_size_on_heatmaps(qw, n):
         assert np.argmax(p) == np.argmax(po)
         p2, _ = qw.rk4_heatmap(prob, tt, b, rows=(3, 17))      # small batch: another geometry
         assert np.abs(p2 - p[3:17]).max() <= 1e-13
+
+
+MIRROR = 8192
+
+
+@pytest.mark.parametrize("n", [160, 161, 255, 256, 511, 512, 574, 575, 777, 1000, 1023, 1024, 1085,
+                               1086])
+def test_mirror_reduced_kernel_vs_oracle(qw, n):
+    """QW_FLAG_MIRROR: the half ring with reflecting ends, one warp per point, against the
+    full-ring oracle -- even and odd n, both register geometries (9 / 17 sites per lane), all
+    schedules, both gamma placements, both step rules, custom targets, psi (both images)."""
+    pl = qw.plan(qw.Problem(n=n, topology="circular", n_steps=1, flags=MIRROR))
+    assert pl["path"] == "mirror-cycle", pl
+    rng = np.random.default_rng(n)
+    for sched, gamma_on, target, rule in [("lin", "oracle", None, dict(n_steps=100)),
+                                          ("cbrt", "laplacian", 0, dict(n_steps=37)),
+                                          ("cerf_5", "oracle", n - 1, dict(step_size=0.07)),
+                                          ("static", "laplacian", 7, dict(n_steps=64))]:
+        T = rng.uniform(0.0, 9.0, 5)
+        g = rng.uniform(0.0, 2.5, 5)
+        T[0], g[1] = 0.0, 0.0
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, gamma_on=gamma_on,
+                          target=target, flags=MIRROR, **rule)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, gamma_on=gamma_on,
+                                             target=target, return_psi=True, **rule)
+        assert np.abs(p - po).max() <= P_TOL, (n, sched)
+        assert np.abs(norm - no).max() <= P_TOL, (n, sched)
+        assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched)
+    # heatmap through the grid entry point, identical argmax
+    t, b = np.linspace(0.1, 40.0, 7), np.linspace(0.0, 2.5, 9)
+    prob = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=300, flags=MIRROR)
+    hp, _ = qw.rk4_heatmap(prob, t, b)
+    ho, _ = c_oracle.heatmap(n, "circular", "lin", t, b, n_steps=300)
+    assert np.abs(hp - ho).max() <= P_TOL and np.argmax(hp) == np.argmax(ho)
+
+
+def test_mirror_flag_is_ignored_where_it_does_not_apply(qw):
+    for kw in (dict(n=64, topology="circular"), dict(n=2048, topology="circular"),
+               dict(n=1024, topology="complete")):
+        prob = qw.Problem(n_steps=50, flags=MIRROR, **kw)
+        assert qw.plan(prob)["path"] != "mirror-cycle"
+        scale = 1.0 if kw["topology"] == "circular" else 1.0 / kw["n"]
+        p, norm = qw.rk4_batch(prob, [3.0 * scale], [1.2 / scale])
+        po, no, _ = c_oracle.rk4_batch(kw["n"], kw["topology"], "lin", [3.0 * scale],
+                                       [1.2 / scale], n_steps=50)
+        assert abs(p[0] - po[0]) <= P_TOL

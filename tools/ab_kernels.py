@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import qwtdh_b200 as qw  # noqa: E402
 
 VARIANTS = {
-    "c5": [("horner R=16 occ6 (default)", 0), ("horner R=16 occ4", 128), ("horner R=8", 256),
+    "c5": [("horner R=16 occ6 (default)", 0), ("mirror-reduced, one warp per point", 8192), ("mirror-reduced, 8 warps/SM", 8192 | 128), ("horner R=16 occ4", 128), ("horner R=8", 256),
            ("horner R=16 occ6 no-rotate", 4096), ("horner R=16 occ4 no-rotate", 4096 | 128),
            ("horner R=8 no-rotate", 4096 | 256),
            ("v2 R=16", 2048), ("v2 R=8 occ3", 2048 | 256), ("v2 R=8 occ4", 2048 | 256 | 128),
