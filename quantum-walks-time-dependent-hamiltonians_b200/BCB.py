@@ -22,5 +22,6 @@ gamma_on = "oracle"
 integrator = "rk4"           # 'rk45': SciPy's adaptive RK45 as the reference ships it
 ti_method = "exact"         # time-independent comparator: 'exact' (Chebyshev) or 'rk4'
 device = None
+mirror = False               # True: integrate half the ring (QW_FLAG_MIRROR), same results
 
 _dropin.install(globals(), "BCB")

@@ -49,7 +49,8 @@ def _problem(g, flavor, schedule=None, topology=None, dimension=None):
     return engine.Problem(
         n=int(dim), topology=_topology(g, flavor) if topology is None else topology,
         schedule=_schedule_name(g, flavor) if schedule is None else schedule,
-        gamma_on=g.get("gamma_on", "oracle"), n_steps=n_steps, step_size=step_size)
+        gamma_on=g.get("gamma_on", "oracle"), n_steps=n_steps, step_size=step_size,
+        flags=8192 if g.get("mirror", False) else 0)       # QW_FLAG_MIRROR (opt-in)
 
 
 def _marked_vertex(n):

@@ -280,3 +280,17 @@ def test_production_sweep_on_streams_writes_the_same_files(tmp_path, monkeypatch
     for name in out[1]:
         assert np.array_equal(out[1][name], out[8][name]), name
     assert out[8]["51_probability_lin.npy"].shape == (75, 4)
+
+
+def test_mirror_knob_of_the_drop_in_modules():
+    """BCB.mirror = True routes grid_eval through the mirror-reduced kernel: same heatmap."""
+    bcb = _mod("BCB")
+    bcb.dimension, bcb.step_function, bcb.topology = 256, "lin", "circular"
+    bcb.type_of_qw, bcb.n_steps, bcb.step_size = "dependent", 200, None
+    t, b = np.linspace(0.1, 30.0, 5), np.linspace(0.0, 2.0, 6)
+    bcb.mirror = False
+    full = bcb.grid_eval(t, b)
+    bcb.mirror = True
+    half = bcb.grid_eval(t, b)
+    bcb.mirror, bcb.n_steps, bcb.step_size = False, None, 1e-3
+    assert np.abs(full - half).max() <= 1e-13 and np.argmax(full) == np.argmax(half)
