@@ -310,3 +310,17 @@ def test_mirror_flag_is_ignored_where_it_does_not_apply(qw):
         po, no, _ = c_oracle.rk4_batch(kw["n"], kw["topology"], "lin", [3.0 * scale],
                                        [1.2 / scale], n_steps=50)
         assert abs(p[0] - po[0]) <= P_TOL
+
+
+def test_localization_run_131072_steps(qw):
+    """BASELINE config 4, localization ensemble: T ~ N^2/2 = 32768, 131072 steps.  Rounding must
+    not accumulate in the nested form, the stage form or the mirror reduction."""
+    rng = np.random.default_rng(5)
+    P = 700                                        # fills the machine: packed nested kernel
+    T = 32768.0 * (1 + 0.05 * rng.standard_normal(P))
+    g = 1.45 * (1 + 0.05 * rng.standard_normal(P))
+    po, no, _ = c_oracle.rk4_batch(256, "circular", "lin", T[:4], g[:4], n_steps=131072)
+    for flags in (0, NO_HORNER, MIRROR):
+        prob = qw.Problem(n=256, topology="circular", schedule="lin", n_steps=131072, flags=flags)
+        p, nrm = qw.rk4_batch(prob, T, g)
+        assert np.abs(p[:4] - po).max() <= 1e-11 and np.abs(nrm[:4] - no).max() <= 1e-11, flags
