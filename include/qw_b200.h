@@ -98,12 +98,13 @@ enum {
     QW_FLAG_NO_ROTATE = 4096,    /* nested-form kernels: keep the marked vertex in warp 0 of
                                     every block instead of alternating the owner warp with the
                                     physical warp slot (A/B) */
-    QW_FLAG_MIRROR = 8192        /* cycle graph, 160 <= n <= 1086: integrate only the half ring
-                                    w .. w + n/2 with reflecting ends (psi is mirror symmetric
-                                    about the marked vertex for the uniform initial state every
-                                    caller of the reference uses): same p, norm and psi with half
-                                    the arithmetic, one warp per point.  Opt-in; ignored where
-                                    it does not apply. */
+    QW_FLAG_MIRROR = 8192        /* cycle graph: integrate only the half ring w .. w + n/2 with
+                                    reflecting ends (psi is mirror symmetric about the marked
+                                    vertex for the uniform initial state every caller of the
+                                    reference uses): same p, norm and psi with half the
+                                    arithmetic.  160 <= n <= 1086: one warp per point;
+                                    n >= 8192: streaming kernel with half the HBM traffic.
+                                    Opt-in; ignored where it does not apply. */
 };
 
 /* ---- the hot path -------------------------------------------------------------------- */

@@ -44,6 +44,8 @@ struct QwParams {
     double2 *scratch;
     int64_t point_offset;         // streaming: first point of the chunk in flight
     int64_t stream_rot;           // streaming: psi is stored rotated, logical l = (j - rot) mod n
+    int64_t mirror_m;             // streaming, QW_FLAG_MIRROR: sites of the half ring (n/2 + 1),
+                                  // stored behind 3 mirrored ghost sites; 0 = full ring
 };
 
 struct QwPoint {

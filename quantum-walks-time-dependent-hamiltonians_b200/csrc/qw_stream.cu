@@ -195,7 +195,8 @@ template <int KB, int SR, bool ALIGNED, bool HORNER>
 __device__ __forceinline__ void prefetch_window(StreamShared<SR, HORNER> &sh, int slot,
                                                 const double2 *in,
                                                 const typename StreamShared<SR, HORNER>::Entry *tab,
-                                                int64_t n, uint32_t idx, uint32_t tiles, int t)
+                                                int64_t n, uint32_t idx, uint32_t tiles, int t,
+                                                int64_t mirror_m = 0, bool even = true)
 {
     using Entry = typename StreamShared<SR, HORNER>::Entry;
     static_assert(sizeof(Entry) % 16 == 0 && sizeof(Entry) / 16 <= Geo<SR>::NT, "entry copy");
@@ -204,6 +205,19 @@ __device__ __forceinline__ void prefetch_window(StreamShared<SR, HORNER> &sh, in
     const uint32_t local = idx / tiles, tile = idx - local * tiles;
     const double2 *src = in + (int64_t)local * n;
     double2 *xb = sh.xbuf[slot];
+    if (mirror_m) {
+        // half ring behind 3 ghost sites: stored index i <-> chain site c = i - 3; the halo
+        // beyond either end is the mirror image (c < 0 -> -c; c > M-1 -> about the antipode)
+        const int64_t first = (int64_t)tile * TILE - HALO;
+#pragma unroll
+        for (int i = 0; i < SR; ++i) {
+            const int e = i * SNT + t;
+            int64_t c = first + e - 3;
+            if (c < 0) c = -c;
+            if (c > mirror_m - 1) c = 2 * (mirror_m - 1) + (even ? 0 : 1) - c;
+            cp_async16(&xb[Geo<SR>::pad(e)], &src[c + 3]);
+        }
+    } else {
     int64_t base = ((int64_t)tile * TILE - HALO) % n;
     if (base < 0) base += n;
 #pragma unroll
@@ -212,6 +226,7 @@ __device__ __forceinline__ void prefetch_window(StreamShared<SR, HORNER> &sh, in
         int64_t j = base + e;
         if (j >= n) { j -= n; if (j >= n) j %= n; }
         cp_async16(&xb[Geo<SR>::pad(e)], &src[j]);
+    }
     }
     if (t < (int)(sizeof(Entry) / 16))
         cp_async16(reinterpret_cast<char *>(&sh.tab[slot]) + 16 * t,
@@ -246,7 +261,9 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
     Shared &sh = *reinterpret_cast<Shared *>(smem_raw);
 
     const int t = threadIdx.x;
-    const int64_t n = prm.n;
+    const int64_t mirror_m = HORNER ? prm.mirror_m : 0;
+    const bool even = (prm.n & 1) == 0;
+    const int64_t n = mirror_m ? mirror_m + 3 : prm.n;       // stored sites per point
     const int tl = t == 0 ? 0 : t - 1, tr = t == SNT - 1 ? SNT - 1 : t + 1;   // open ends
     const double2 zero2 = make_double2(0.0, 0.0);
     double2 *fst = sh.mbox, *lst = sh.mbox + 2 * SNT;
@@ -259,7 +276,7 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
 #pragma unroll
     for (int k = 0; k < SDEPTH - 1; ++k) {
         const uint64_t w = (uint64_t)idx + (uint64_t)k * stride;
-        if (w < total) prefetch_window<KB, SR, ALIGNED, HORNER>(sh, k, in, tab, n, (uint32_t)w, tiles, t);
+        if (w < total) prefetch_window<KB, SR, ALIGNED, HORNER>(sh, k, in, tab, n, (uint32_t)w, tiles, t, mirror_m, even);
         else cp_async_commit();
     }
 
@@ -283,7 +300,7 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
         {
             const uint64_t w = (uint64_t)idx + (uint64_t)(SDEPTH - 1) * stride;
             const int ps = (slot + SDEPTH - 1) % SDEPTH;
-            if (w < total) prefetch_window<KB, SR, ALIGNED, HORNER>(sh, ps, in, tab, n, (uint32_t)w, tiles, t);
+            if (w < total) prefetch_window<KB, SR, ALIGNED, HORNER>(sh, ps, in, tab, n, (uint32_t)w, tiles, t, mirror_m, even);
             else cp_async_commit();
         }
 
@@ -291,8 +308,13 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
             // slot of the marked vertex in this thread's segment, or -1 (windows repeat mod n)
             // (the marked vertex is logical site target - rot: 0 in the ALIGNED layout)
             int64_t wrel = (prm.target - prm.stream_rot) - first - (int64_t)t * SR;
-            if (wrel < 0) { wrel += n; if (wrel < 0) wrel = wrel % n + n; }
-            if (wrel >= n) wrel -= n;
+            if (mirror_m) {                      // the marked vertex is stored index 3, once
+                wrel = HW0 - first - (int64_t)t * SR;
+                if (wrel < 0) wrel = SR;
+            } else {
+                if (wrel < 0) { wrel += n; if (wrel < 0) wrel = wrel % n + n; }
+                if (wrel >= n) wrel -= n;
+            }
             const int own_slot = wrel < SR ? (int)wrel : -1;     // ALIGNED: 0 or -1
             const bool warp_owns = __ballot_sync(0xffffffffu, own_slot >= 0) != 0u;
             int par = 0;
@@ -420,6 +442,33 @@ __global__ void __launch_bounds__(512) stream_finish(const QwParams prm, const d
     __shared__ double red[64];
     const int64_t local = blockIdx.x, n = prm.n;
     const QwPoint pt = qw_point(prm, prm.point_offset + local);
+    if (prm.mirror_m) {
+        // half ring behind 3 ghosts: every chain site counts twice in the norm except the
+        // marked vertex and (even n) the antipode; psi is written with both mirror images
+        const int64_t m = prm.mirror_m;
+        const bool even = (n & 1) == 0;
+        const double2 *src = buf + local * (m + 3) + 3;
+        double nrm = 0.0;
+        for (int64_t c = threadIdx.x; c < m; c += blockDim.x) {
+            const double2 v = src[c];
+            const double wgt = (c == 0 || (even && c == m - 1)) ? 1.0 : 2.0;
+            nrm = fma(wgt * v.x, v.x, fma(wgt * v.y, v.y, nrm));
+            if (prm.psi) {
+                int64_t a = prm.target + c, b = prm.target - c;
+                if (a >= n) a -= n;
+                if (b < 0) b += n;
+                prm.psi[(size_t)pt.q * (size_t)n + a] = v;
+                prm.psi[(size_t)pt.q * (size_t)n + b] = v;
+            }
+        }
+        const double2 tot = qw_block_sum2(nrm, 0.0, red);
+        if (threadIdx.x == 0) {
+            const double2 v = src[0];
+            prm.p[pt.q] = fma(v.x, v.x, v.y * v.y) / tot.x;
+            if (prm.norm) prm.norm[pt.q] = tot.x;
+        }
+        return;
+    }
     const double2 *src = buf + local * n;
     double nrm = 0.0;
     for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
@@ -493,7 +542,8 @@ cudaError_t launch_pass_a(const QwParams &prm, const double2 *in, double2 *out, 
     else
         stream_pass_tables<<<(unsigned)((points + 127) / 128), 128, 0, st>>>(prm, points, step0,
                                                                              KB, etab);
-    const uint32_t tiles = (uint32_t)((prm.n + TILE - 1) / TILE);
+    const int64_t len = prm.mirror_m ? prm.mirror_m + 3 : prm.n;      // stored sites per point
+    const uint32_t tiles = (uint32_t)((len + TILE - 1) / TILE);
     const uint64_t total = (uint64_t)points * tiles;
     uint32_t grid = (uint32_t)(sm_count() * stream_blocks_per_sm<SR, HORNER>());   // persistent
     if (total < grid) grid = (uint32_t)total;
@@ -506,8 +556,15 @@ cudaError_t launch_pass_a(const QwParams &prm, const double2 *in, double2 *out, 
 }
 
 // nested form wherever the aligned layout applies (n a multiple of the sites per thread)
+bool stream_mirror(const QwParams &prm)
+{
+    // one reflection per window end must suffice: the half ring is longer than a window
+    return (prm.flags & QW_FLAG_MIRROR) && !(prm.flags & QW_FLAG_NO_HORNER) && prm.n >= 8192;
+}
+
 bool stream_horner(const QwParams &prm, int sr)
 {
+    if (stream_mirror(prm)) return true;         // no wrap: every window start is aligned
     return prm.n % sr == 0 && !(prm.flags & QW_FLAG_NO_HORNER);
 }
 
@@ -578,10 +635,13 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
 {
     QwParams prm = prm_in;
     const int kb = stream_kb(prm), sr = stream_sr(prm);
-    const int64_t n = prm.n;
+    // QW_FLAG_MIRROR: the half ring w .. w + n/2 behind 3 mirrored ghost sites (the marked
+    // vertex is stored index 3 = slot 3 of the first thread segment), reflecting window halos
+    prm.mirror_m = stream_mirror(prm) ? prm.n / 2 + 1 : 0;
+    const int64_t n = prm.mirror_m ? prm.mirror_m + 3 : prm.n;        // stored sites per point
     // aligned layout: the marked vertex is logical site 0 (stage form) or HW0 (nested form)
     prm.stream_rot = 0;
-    if (n % sr == 0) {
+    if (!prm.mirror_m && n % sr == 0) {
         prm.stream_rot = prm.target - (stream_horner(prm, sr) ? HW0 : 0);
         if (prm.stream_rot < 0) prm.stream_rot += n;
     }
@@ -605,7 +665,7 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
         e = cudaMallocAsync((void **)&dmax, sizeof(unsigned long long), st);
         if (e != cudaSuccess) { cudaFreeAsync(bufA, st); cudaFreeAsync(tab, st); return e; }
     }
-    const double amp = 1.0 / sqrt((double)n);
+    const double amp = 1.0 / sqrt((double)prm.n);
 
     for (int64_t p0 = 0; p0 < prm.n_points && e == cudaSuccess; p0 += chunk) {
         const int64_t cnt = (prm.n_points - p0 < chunk) ? (prm.n_points - p0) : chunk;

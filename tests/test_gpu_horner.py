@@ -324,3 +324,23 @@ def test_localization_run_131072_steps(qw):
         prob = qw.Problem(n=256, topology="circular", schedule="lin", n_steps=131072, flags=flags)
         p, nrm = qw.rk4_batch(prob, T, g)
         assert np.abs(p[:4] - po).max() <= 1e-11 and np.abs(nrm[:4] - no).max() <= 1e-11, flags
+
+
+@pytest.mark.parametrize("n", [8192, 9001, 10000, 20011])
+@pytest.mark.parametrize("kb_flag", [8, 16, 0, 256])
+def test_mirror_reduced_streaming_vs_oracle(qw, n, kb_flag):
+    """QW_FLAG_MIRROR in the HBM-streaming kernel: the half ring behind three ghost sites,
+    reflecting window halos; even and odd n, 1 / 2 / 4 steps per pass, both window geometries,
+    custom target, psi with both mirror images."""
+    rng = np.random.default_rng(n + kb_flag)
+    T = np.concatenate([[0.0], rng.uniform(1.0, 9.0, 3)])
+    g = rng.uniform(0.1, 2.4, 4)
+    for sched, S, target in (("lin", 37, None), ("cbrt", 24, 5)):
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S, target=target,
+                          flags=MIRROR | kb_flag)
+        assert qw.plan(prob)["path"] == "stream"
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, n_steps=S, target=target,
+                                             return_psi=True)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL, (n, sched)
+        assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched)

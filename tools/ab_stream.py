@@ -15,7 +15,7 @@ t = torch.linspace(0.1, 64.0, 32, dtype=torch.float64, device=dev)
 b = torch.linspace(0.0, 2.5, 32, dtype=torch.float64, device=dev)
 ref = {}
 for kb, kflag in ((1, 8), (2, 16), (4, 0)):
-    for name, hflag in (("nested", 0), ("stage", 2048)):
+    for name, hflag in (("nested", 0), ("stage", 2048), ("mirror", 8192)):
         for r8 in (0, 256):
             prob = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=S,
                               flags=kflag | hflag | r8)
