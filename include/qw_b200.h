@@ -102,8 +102,9 @@ enum {
                                     reflecting ends (psi is mirror symmetric about the marked
                                     vertex for the uniform initial state every caller of the
                                     reference uses): same p, norm and psi with half the
-                                    arithmetic.  160 <= n <= 1086: one warp per point;
-                                    n >= 8192: streaming kernel with half the HBM traffic.
+                                    arithmetic.  160 <= n <= 1087: one warp per point; up to
+                                    8702: block-per-point kernel on the half ring; above:
+                                    streaming kernel with half the HBM traffic.
                                     Opt-in; ignored where it does not apply. */
 };
 

@@ -118,24 +118,40 @@ __device__ __forceinline__ unsigned warp_slot()
 // by the wait for the partner's arrival of the same level -- a plain barrier.  DESIGN.md 7.)
 // RAGGED: some threads hold R-1 sites (`full` false); a compile-time switch, because even two
 // extra selects per level cost the exact-multiple sizes 5 % (register pressure at 168).
-template <int R, bool OWN, bool RAGGED>
+// MIRROR (QW_FLAG_MIRROR): the threads hold the half ring w .. w + n/2; the marked vertex is
+// slot 0 of thread 0, whose left neighbour is its own slot 1; the last thread's right neighbour
+// is the mirror image about the antipode (mend = 1: even n, the site before the last; mend = 2:
+// odd n, the last site itself; 0: not the last thread).
+template <int R, bool OWN, bool RAGGED, bool MIRROR>
 __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab, double2 *first,
                                              double2 *last, const int nt, const int t,
                                              const int tl, const int tr, const int cnt,
-                                             const double msk, const bool full_in)
+                                             const double msk, const bool full_in, const int mend)
 {
+    constexpr int W0 = MIRROR ? 0 : HW0;
     const bool full = RAGGED ? full_in : true;
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const HornerStep &hs = tab[sidx];
         double sgl = 0.0;                          // this lane's component of its sigma
+#define QW_LX_R(LV, r) ((LV == 4) ? s.yr[r] : s.zr[r])
+#define QW_LX_I(LV, r) ((LV == 4) ? s.yi[r] : s.zi[r])
 #define QW_HORNER_LEVEL(LEVEL)                                                              \
         {                                                                                   \
             constexpr int par = (4 - LEVEL) & 1;                                            \
             __syncthreads();                                                                \
-            const double2 hl = last[par * nt + tl];                                         \
-            const double2 hr = first[par * nt + tr];                                        \
+            double2 hl = last[par * nt + tl];                                               \
+            double2 hr = first[par * nt + tr];                                              \
             const double rho = hs.rho[LEVEL - 1];                                           \
             double2 o0, oL;                                                                 \
+            if (MIRROR) {                     /* reflecting ends of the half ring */        \
+                if (t == 0) hl = make_double2(QW_LX_R(LEVEL, 1), QW_LX_I(LEVEL, 1));                            \
+                if (mend == 1)                                                              \
+                    hr = full ? make_double2(QW_LX_R(LEVEL, R - 2), QW_LX_I(LEVEL, R - 2))                      \
+                              : make_double2(QW_LX_R(LEVEL, R - 3), QW_LX_I(LEVEL, R - 3));                     \
+                if (mend == 2)                                                              \
+                    hr = full ? make_double2(QW_LX_R(LEVEL, R - 1), QW_LX_I(LEVEL, R - 1))                      \
+                              : make_double2(QW_LX_R(LEVEL, R - 2), QW_LX_I(LEVEL, R - 2));                     \
+            }                                                                               \
             if (RAGGED && !full) {            /* ghost slot := the right neighbour's value */ \
                 if (LEVEL == 4) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }                 \
                 else { s.zr[R - 1] = hr.x; s.zi[R - 1] = hr.y; }                            \
@@ -143,11 +159,14 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
             if (OWN && LEVEL == 4) {                                                        \
                 /* y_w and the neighbour sums at distance 1..3 (meaningful in the owner */  \
                 /* lane), broadcast; every lane then forms its own dot product          */  \
-                double b[8];                                                                \
-                b[0] = s.yr[HW0];                     b[1] = s.yi[HW0];                     \
-                b[2] = s.yr[HW0 - 1] + s.yr[HW0 + 1]; b[3] = s.yi[HW0 - 1] + s.yi[HW0 + 1]; \
-                b[4] = s.yr[HW0 - 2] + s.yr[HW0 + 2]; b[5] = s.yi[HW0 - 2] + s.yi[HW0 + 2]; \
-                b[6] = s.yr[HW0 - 3] + s.yr[HW0 + 3]; b[7] = s.yi[HW0 - 3] + s.yi[HW0 + 3]; \
+                double b[8];                  /* MIRROR: y_{w-k} = y_{w+k} = slot k */       \
+                b[0] = s.yr[W0];                                  b[1] = s.yi[W0];          \
+                b[2] = s.yr[MIRROR ? 1 : W0 - 1] + s.yr[W0 + 1];                            \
+                b[3] = s.yi[MIRROR ? 1 : W0 - 1] + s.yi[W0 + 1];                            \
+                b[4] = s.yr[MIRROR ? 2 : W0 - 2] + s.yr[W0 + 2];                            \
+                b[5] = s.yi[MIRROR ? 2 : W0 - 2] + s.yi[W0 + 2];                            \
+                b[6] = s.yr[MIRROR ? 3 : W0 - 3] + s.yr[W0 + 3];                            \
+                b[7] = s.yi[MIRROR ? 3 : W0 - 3] + s.yi[W0 + 3];                            \
                 sgl = hs.coef[0][t & 7] * __shfl_sync(0xffffffffu, b[0], 0);                \
                 _Pragma("unroll")                                                           \
                 for (int k = 1; k < 8; ++k)                                                 \
@@ -168,11 +187,11 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
                 const double sgr = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));          \
                 const double sgi = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);      \
                 if (LEVEL > 1) {                                                            \
-                    s.zr[HW0] = fma(msk, sgr, s.zr[HW0]);                                   \
-                    s.zi[HW0] = fma(msk, sgi, s.zi[HW0]);                                   \
+                    s.zr[W0] = fma(msk, sgr, s.zr[W0]);                                     \
+                    s.zi[W0] = fma(msk, sgi, s.zi[W0]);                                     \
                 } else {                                                                    \
-                    s.yr[HW0] = fma(msk, sgr, s.yr[HW0]);                                   \
-                    s.yi[HW0] = fma(msk, sgi, s.yi[HW0]);                                   \
+                    s.yr[W0] = fma(msk, sgr, s.yr[W0]);                                     \
+                    s.yi[W0] = fma(msk, sgi, s.yi[W0]);                                     \
                 }                                                                           \
             }                                                                               \
         }
@@ -181,12 +200,16 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
         QW_HORNER_LEVEL(2)
         QW_HORNER_LEVEL(1)
 #undef QW_HORNER_LEVEL
+#undef QW_LX_R
+#undef QW_LX_I
     }
 }
 
-template <int R, int MAXNT, int MINB, bool RAGGED>
+template <int R, int MAXNT, int MINB, bool RAGGED, bool MIRROR = false>
 __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams prm)
 {
+    static_assert(!MIRROR || RAGGED, "the half ring has an arbitrary number of sites");
+    constexpr int W0 = MIRROR ? 0 : HW0;
     static_assert(R >= 2 * HW0 + 1, "the window w-3..w+3 must sit in one thread");
     extern __shared__ double2 mbox[];         // [2][2][blockDim.x]: parity, first/last
     __shared__ HornerShared sh;
@@ -202,7 +225,8 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
     // warps go to the four SM sub-partitions by slot number modulo 4, so without the rotation
     // all owner warps of an SM would share one (4-warp blocks) or two (2-warp blocks) of them.
     int ht = 0;
-    if ((nt == 64 || nt == 128) && nact == nt && !(prm.flags & QW_FLAG_NO_ROTATE)) {
+    const int mend = (MIRROR && t == nact - 1) ? ((prm.n & 1) ? 2 : 1) : 0;
+    if (!MIRROR && (nt == 64 || nt == 128) && nact == nt && !(prm.flags & QW_FLAG_NO_ROTATE)) {
         if (t == 0) sh.owner = 32 * (int)((warp_slot() >> 2) & (nt == 64 ? 1u : 3u));
         __syncthreads();
         ht = sh.owner;
@@ -228,9 +252,11 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
         __syncthreads();
         const double msk = own ? 1.0 : 0.0;
         if (warp == (ht >> 5))
-            horner_steps<R, true, RAGGED>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk, full);
+            horner_steps<R, true, RAGGED, MIRROR>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk,
+                                                  full, mend);
         else
-            horner_steps<R, false, RAGGED>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk, full);
+            horner_steps<R, false, RAGGED, MIRROR>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk,
+                                                   full, mend);
     }
 
     // p = |psi_w|^2 / ||psi||^2, ||psi||^2 (BCB.py:189-199, Runge_Kutta_Error.py:103)
@@ -238,7 +264,15 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 #pragma unroll
     for (int r = 0; r < R - 1; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
     if (full) nrm = fma(s.yr[R - 1], s.yr[R - 1], fma(s.yi[R - 1], s.yi[R - 1], nrm));
-    const double pw = own ? fma(s.yr[HW0], s.yr[HW0], s.yi[HW0] * s.yi[HW0]) : 0.0;
+    const double pw = own ? fma(s.yr[W0], s.yr[W0], s.yi[W0] * s.yi[W0]) : 0.0;
+    if (MIRROR) {          // interior sites of the half ring count twice; w and (even n) the
+        nrm *= 2.0;        // antipode once
+        nrm -= pw;
+        if (mend == 1) {
+            const double ar = full ? s.yr[R - 1] : s.yr[R - 2], ai = full ? s.yi[R - 1] : s.yi[R - 2];
+            nrm -= fma(ar, ar, ai * ai);
+        }
+    }
     __syncthreads();
     const double2 tot = hblock_sum(make_double2(nrm, pw), sh.red);
     if (t == 0) {
@@ -252,10 +286,15 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (r == R - 1 && !full) continue;                    // ghost
-            int64_t j = off_t - off_h + r - HW0 + prm.target;
+            int64_t j = off_t - off_h + r - W0 + prm.target;
             if (j < 0) j += prm.n;
             if (j >= prm.n) j -= prm.n;
             out[j] = make_double2(s.yr[r], s.yi[r]);
+            if (MIRROR) {                                         // the mirror image w - l
+                int64_t jm = prm.target - (off_t + r);
+                if (jm < 0) jm += prm.n;
+                out[jm] = make_double2(s.yr[r], s.yi[r]);
+            }
         }
     }
 }
@@ -533,8 +572,21 @@ cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cud
 
 // Sites per thread of the nested-form kernels, or 0 when n does not fit them: R in {16, 8}
 // (the window w-3..w+3 has to sit in one thread), any n from 256 to 4096.
+// QW_FLAG_MIRROR on rings that need more than one warp per point (above 1086 sites): the
+// block holds the half ring n/2 + 1
+static bool horner_mirror(const QwParams &prm)
+{
+    return (prm.flags & QW_FLAG_MIRROR) && prm.topology == QW_TOPO_CYCLE && prm.n > 1086;
+}
+
 int qw_horner_sites_per_thread(const QwParams &prm)
 {
+    if (horner_mirror(prm)) {
+        // the half ring has n/2 + 1 sites: 17 sites per thread keep the "+ 1" from costing a
+        // whole extra warp (n = 2048: 1025 = 61 threads x 17 instead of 65 x 16)
+        const int64_t m = prm.n / 2 + 1;
+        return (m + 16) / 17 <= 256 ? 17 : 0;
+    }
     const int64_t n = prm.n;
     if (prm.topology != QW_TOPO_CYCLE && (prm.flags & QW_FLAG_EXACT_SUM)) return 0;
     // n = nact (R - 1) + nfull with 1 <= nfull <= nact needs n >= R^2; at least one full warp
@@ -547,8 +599,10 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
 {
     const int R = qw_horner_sites_per_thread(prm);
     if (R == 0) return cudaErrorInvalidConfiguration;
-    prm.nact = (int)((prm.n + R - 1) / R);
-    prm.nfull = (int)(prm.n - (int64_t)prm.nact * (R - 1));       // threads with R sites
+    const bool mirror = horner_mirror(prm);
+    const int64_t sites = mirror ? prm.n / 2 + 1 : prm.n;
+    prm.nact = (int)((sites + R - 1) / R);
+    prm.nfull = (int)(sites - (int64_t)prm.nact * (R - 1));       // threads with R sites
     const int threads = ((prm.nact + 31) / 32) * 32;
     const bool cyc = prm.topology == QW_TOPO_CYCLE;
     const size_t smem = cyc ? (size_t)threads * 4 * sizeof(double2) : 0;
@@ -572,6 +626,13 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
         QW_HL(rk4_complete_horner, 8, 512, 1);
     }
     const int bthreads = threads;
+    if (mirror) {                                  // R = 17, up to 255 registers
+#define QW_HM(...) return hlaunch(rk4_cycle_horner<__VA_ARGS__, true, true>, prm, bthreads, smem, st, plan)
+        if (threads <= 64) { QW_HM(17, 64, 4); }
+        if (threads <= 128) { QW_HM(17, 128, 2); }
+        QW_HM(17, 256, 1);
+#undef QW_HM
+    }
     if (R == 16) {
         // register file = 16 K per SM sub-partition: 2 / 3 warps there allow 255 / 168 registers
         if (threads <= 64 && (prm.flags & QW_FLAG_OCC4)) { QW_HL(rk4_cycle_horner, 16, 64, 4); }

@@ -301,8 +301,7 @@ def test_mirror_reduced_kernel_vs_oracle(qw, n):
 
 
 def test_mirror_flag_is_ignored_where_it_does_not_apply(qw):
-    for kw in (dict(n=64, topology="circular"), dict(n=2048, topology="circular"),
-               dict(n=1024, topology="complete")):
+    for kw in (dict(n=64, topology="circular"), dict(n=1024, topology="complete")):
         prob = qw.Problem(n_steps=50, flags=MIRROR, **kw)
         assert qw.plan(prob)["path"] != "mirror-cycle"
         scale = 1.0 if kw["topology"] == "circular" else 1.0 / kw["n"]
@@ -326,7 +325,7 @@ def test_localization_run_131072_steps(qw):
         assert np.abs(p[:4] - po).max() <= 1e-11 and np.abs(nrm[:4] - no).max() <= 1e-11, flags
 
 
-@pytest.mark.parametrize("n", [8192, 9001, 10000, 20011])
+@pytest.mark.parametrize("n", [8704, 9001, 10000, 20011])
 @pytest.mark.parametrize("kb_flag", [8, 16, 0, 256])
 def test_mirror_reduced_streaming_vs_oracle(qw, n, kb_flag):
     """QW_FLAG_MIRROR in the HBM-streaming kernel: the half ring behind three ghost sites,
@@ -343,4 +342,29 @@ def test_mirror_reduced_streaming_vs_oracle(qw, n, kb_flag):
         po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, n_steps=S, target=target,
                                              return_psi=True)
         assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL, (n, sched)
+        assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched)
+
+
+@pytest.mark.parametrize("n,flags", [(1087, 0), (1088, 0), (2048, 0), (3000, 0),
+                                     (4096, 0), (4097, 0), (8190, 0), (8191, 0), (8702, 0)])
+def test_mirror_reduced_block_kernel_vs_oracle(qw, n, flags):
+    """QW_FLAG_MIRROR between 1087 and 8191 sites: the half ring in the block-per-point nested
+    kernel (reflecting ends in thread 0 and in the last thread)."""
+    pl = qw.plan(qw.Problem(n=n, topology="circular", n_steps=1, flags=MIRROR | flags))
+    assert pl["path"] == ("mirror-cycle" if n // 2 + 1 <= 544 else "horner-cycle"), pl
+    assert pl["sites_per_thread"] == 17
+    rng = np.random.default_rng(n)
+    for sched, gamma_on, target, rule in [("lin", "oracle", None, dict(n_steps=70)),
+                                          ("sqrt", "laplacian", 3, dict(n_steps=33)),
+                                          ("cerf_3", "oracle", n - 2, dict(step_size=0.11))]:
+        T = rng.uniform(0.0, 7.0, 4)
+        g = rng.uniform(0.0, 2.5, 4)
+        T[0], g[1] = 0.0, 0.0
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, gamma_on=gamma_on,
+                          target=target, flags=MIRROR | flags, **rule)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, gamma_on=gamma_on,
+                                             target=target, return_psi=True, **rule)
+        assert np.abs(p - po).max() <= P_TOL, (n, sched)
+        assert np.abs(norm - no).max() <= P_TOL, (n, sched)
         assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched)
