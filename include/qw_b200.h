@@ -105,6 +105,9 @@ enum {
                                     arithmetic.  160 <= n <= 1087: one warp per point; up to
                                     8702: block-per-point kernel on the half ring; above:
                                     streaming kernel with half the HBM traffic.
+                                    Complete graph: all unmarked vertices carry one common
+                                    amplitude, one thread integrates the pair (psi_w, psi_other)
+                                    of a point, any n, O(n_steps) work.
                                     Opt-in; ignored where it does not apply. */
 };
 
@@ -227,7 +230,8 @@ typedef struct qw_plan {
     int32_t path;            /* 0 resident-cycle, 1 resident-complete, 2 generic, 3 stream,
                                 4 warp-packed cycle, 5 / 6 resident cycle / complete in nested form,
                                 7 warp-packed cycle in nested form, 8 warp-packed cycle of any
-                                small dimension, 9 mirror-reduced cycle (QW_FLAG_MIRROR) */
+                                small dimension, 9 mirror-reduced cycle, 10 symmetry-reduced
+                                complete graph (both QW_FLAG_MIRROR) */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */

@@ -22,6 +22,7 @@ gamma_on = "oracle"
 integrator = "rk4"           # 'rk45': SciPy's adaptive RK45 as the reference ships it
 ti_method = "exact"         # time-independent comparator: 'exact' (Chebyshev) or 'rk4'
 device = None
-mirror = False               # True: integrate half the ring (QW_FLAG_MIRROR), same results
+mirror = False               # True: symmetry-reduced state (QW_FLAG_MIRROR): half the ring /
+                             # (psi_w, psi_other) on the complete graph; same results
 
 _dropin.install(globals(), "BCB")

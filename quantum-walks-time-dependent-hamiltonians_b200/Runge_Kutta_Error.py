@@ -13,7 +13,8 @@ step_size = 1e-3
 gamma_on = "oracle"
 integrator = "rk4"           # 'rk45': SciPy's adaptive RK45 as the reference ships it
 device = None
-mirror = False               # True: integrate half the ring (QW_FLAG_MIRROR), same results
+mirror = False               # True: symmetry-reduced state (QW_FLAG_MIRROR): half the ring /
+                             # (psi_w, psi_other) on the complete graph; same results
 
 _dropin.install(globals(), "RKE")
 

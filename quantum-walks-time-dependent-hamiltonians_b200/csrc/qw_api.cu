@@ -36,6 +36,8 @@ cudaError_t qw_launch_adiabatic(int64_t n, int topology, int schedule, int gamma
 int qw_adiabatic_max_dimension();
 int qw_mirror_sites_per_lane(const QwParams &prm);
 cudaError_t qw_launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan);
+bool qw_symmetric_supported(const QwParams &prm);
+cudaError_t qw_launch_symmetric(const QwParams &prm, cudaStream_t st, qw_plan *plan);
 bool qw_cheb_supported(const QwParams &prm);
 cudaError_t qw_launch_cheb(QwParams prm, cudaStream_t st);
 
@@ -89,13 +91,14 @@ int validate(const qw_problem *prob, QwParams *prm)
 }
 
 enum { PATH_RESIDENT = 0, PATH_GENERIC = 2, PATH_STREAM = 3, PATH_PACKED = 4, PATH_HORNER = 5,
-       PATH_MIRROR = 9 };
+       PATH_MIRROR = 9, PATH_SYMMETRIC = 10 };
 
 int choose_path(const QwParams &prm)
 {
     if (prm.flags & QW_FLAG_FORCE_GENERIC) return PATH_GENERIC;
     if ((prm.flags & QW_FLAG_FORCE_STREAM) && qw_stream_supported(prm)) return PATH_STREAM;
     if (qw_mirror_sites_per_lane(prm) > 0) return PATH_MIRROR;
+    if (qw_symmetric_supported(prm)) return PATH_SYMMETRIC;
     const bool horner = !(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_CYCLE_SPLIT |
                                        QW_FLAG_NO_HORNER | QW_FLAG_COMPLETE_FREE)) &&
                         qw_horner_sites_per_thread(prm) > 0;
@@ -142,6 +145,11 @@ int run(QwParams &prm, cudaStream_t st)
     case PATH_MIRROR:
         e = qw_launch_mirror(prm, st, nullptr);
         if (e != cudaSuccess) return cuda_fail(e, "mirror kernel launch");
+        g_launches += 1;
+        return 0;
+    case PATH_SYMMETRIC:
+        e = qw_launch_symmetric(prm, st, nullptr);
+        if (e != cudaSuccess) return cuda_fail(e, "symmetric complete-graph kernel launch");
         g_launches += 1;
         return 0;
     case PATH_HORNER:
@@ -505,6 +513,7 @@ int qw_plan_query(const qw_problem *prob, qw_plan *plan)
     case PATH_PACKED: e = qw_launch_packed(prm, nullptr, plan); break;
     case PATH_HORNER: e = qw_launch_horner(prm, nullptr, plan); break;
     case PATH_MIRROR: e = qw_launch_mirror(prm, nullptr, plan); break;
+    case PATH_SYMMETRIC: e = qw_launch_symmetric(prm, nullptr, plan); break;
     case PATH_STREAM: e = qw_stream_plan(prm, plan); break;
     default: {
         int blocks; size_t bytes;

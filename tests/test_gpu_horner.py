@@ -301,9 +301,9 @@ def test_mirror_reduced_kernel_vs_oracle(qw, n):
 
 
 def test_mirror_flag_is_ignored_where_it_does_not_apply(qw):
-    for kw in (dict(n=64, topology="circular"), dict(n=1024, topology="complete")):
+    for kw in (dict(n=64, topology="circular"), dict(n=159, topology="circular")):
         prob = qw.Problem(n_steps=50, flags=MIRROR, **kw)
-        assert qw.plan(prob)["path"] != "mirror-cycle"
+        assert qw.plan(prob)["path"] not in ("mirror-cycle", "symmetric-complete")
         scale = 1.0 if kw["topology"] == "circular" else 1.0 / kw["n"]
         p, norm = qw.rk4_batch(prob, [3.0 * scale], [1.2 / scale])
         po, no, _ = c_oracle.rk4_batch(kw["n"], kw["topology"], "lin", [3.0 * scale],
@@ -368,3 +368,69 @@ def test_mirror_reduced_block_kernel_vs_oracle(qw, n, flags):
         assert np.abs(p - po).max() <= P_TOL, (n, sched)
         assert np.abs(norm - no).max() <= P_TOL, (n, sched)
         assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 256, 1000, 4096, 5000])
+def test_symmetry_reduced_complete_graph_vs_oracle(qw, n):
+    """QW_FLAG_MIRROR on the complete graph: one thread integrates (psi_w, psi_other) of a point.
+    Against the full-vector oracle: all schedules, both gamma placements, both step rules, custom
+    targets, psi expanded to all vertices; then against the default block-per-point kernel on a
+    heatmap (identical argmax)."""
+    pl = qw.plan(qw.Problem(n=n, topology="complete", n_steps=1, flags=MIRROR))
+    assert pl["path"] == "symmetric-complete", pl
+    rng = np.random.default_rng(n)
+    for sched, gamma_on, target, rule in [("lin", "oracle", None, dict(n_steps=100)),
+                                          ("cbrt", "laplacian", 0, dict(n_steps=37)),
+                                          ("cerf_5", "oracle", n - 1, dict(step_size=0.07 / n)),
+                                          ("sqrt", "oracle", n // 3, dict(n_steps=45)),
+                                          ("static", "laplacian", n // 2, dict(n_steps=64))]:
+        T = rng.uniform(0.0, 9.0, 37) / n                 # h * N stays in the stable range
+        g = rng.uniform(0.0, 2.5, 37) * (n if gamma_on == "oracle" else 1.0 / n)
+        T[0], g[1] = 0.0, 0.0
+        prob = qw.Problem(n=n, topology="complete", schedule=sched, gamma_on=gamma_on,
+                          target=target, flags=MIRROR, **rule)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "complete", sched, T, g, gamma_on=gamma_on,
+                                             target=target, return_psi=True, **rule)
+        assert np.abs(p - po).max() <= P_TOL, (n, sched)
+        assert np.abs(norm - no).max() <= P_TOL, (n, sched)
+        assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched)
+    if n >= 256:
+        t, b = np.linspace(0.1, 80.0, 33) / n, np.linspace(0.0, 2.5, 41) * n
+        for rule in (dict(n_steps=400), dict(step_size=0.2 / n)):
+            full, nf = qw.rk4_heatmap(qw.Problem(n=n, topology="complete", schedule="lin", **rule),
+                                      t, b)
+            red, nr = qw.rk4_heatmap(qw.Problem(n=n, topology="complete", schedule="lin",
+                                                flags=MIRROR, **rule), t, b)
+            assert np.abs(full - red).max() <= 1e-12 and np.abs(nf - nr).max() <= 1e-12
+            assert np.argmax(full) == np.argmax(red)
+
+
+def test_symmetry_reduced_complete_graph_beyond_memory(qw):
+    """With the reduction the dimension is just a number: N = 10^9 vertices (the full vector
+    would be 16 GB per point).  Checked against the same 2x2 system integrated with the
+    reference's RK4 in numpy, relative to the size of p (which is O(1/N) here)."""
+    n, S = 10 ** 9, 4000
+    T, gam = np.array([3000.0, 5000.0]), np.array([1.0, 1.3])
+    prob = qw.Problem(n=n, topology="complete", schedule="lin", gamma_on="laplacian", n_steps=S,
+                      flags=MIRROR)
+    p, norm = qw.rk4_batch(prob, T, gam / n)
+    for q in range(2):
+        m, h = n - 1.0, T[q] / S
+        y = np.array([1.0, 1.0], dtype=complex) / np.sqrt(n)
+
+        def rhs(t, y):
+            s = t / T[q]
+            a, d = (1.0 - s) * gam[q] / n, -s
+            dlt = y[0] - y[1]
+            return -1j * np.array([a * m * dlt + d * y[0], -a * dlt])
+        for k in range(S):
+            t = k * h
+            k1 = rhs(t, y)
+            k2 = rhs(t + 0.5 * h, y + 0.5 * h * k1)
+            k3 = rhs(t + 0.5 * h, y + 0.5 * h * k2)
+            k4 = rhs(t + h, y + h * k3)
+            y = y + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        nrm = abs(y[0]) ** 2 + m * abs(y[1]) ** 2
+        pref = abs(y[0]) ** 2 / nrm
+        assert abs(p[q] - pref) <= 1e-9 * pref and abs(norm[q] - nrm) <= 1e-10
