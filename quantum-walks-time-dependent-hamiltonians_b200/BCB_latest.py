@@ -28,7 +28,7 @@ _dropin.install(globals(), "BCBL")
 
 
 def production_sweep(step_functions=("lin", "sqrt", "cbrt", "cerf_3"),
-                     dims=tuple(np.arange(3, 71 + 1, 2)), streams=8):
+                     dims=tuple(np.arange(3, 71 + 1, 2)), streams=16):
     """The __main__ loop of BCB_latest.py:309-320.
 
     A production heatmap is 300 points on a ring of at most 71 sites: one launch occupies a few

@@ -443,3 +443,28 @@ def test_odd_shapes_and_catch_all_paths(qw):
     p, nrm = qw.rk4_heatmap(prob, t, b)
     po, no = c_oracle.heatmap(n, "circular", "sqrt", t, b, step_size=0.02)
     assert np.abs(p - po).max() <= P_TOL and np.abs(nrm - no).max() <= P_TOL
+
+
+@pytest.mark.parametrize("n", [17, 33, 51, 71, 100, 200])
+def test_any_dimension_packed_kernel_large_and_small_batches(qw, n):
+    """Rings that are not R * 2^k in the warp-packed kernel: a batch of 2003 points (ragged last
+    warp, T = 0 points, psi) against the oracle, and slices of five points against the same
+    points of the big batch (a point's result does not depend on its neighbours in the warp)."""
+    P = 2003
+    rng = np.random.default_rng(7 * n)
+    T = rng.uniform(0.0, 10.0, P)
+    g = rng.uniform(0.0, 2.5, P)
+    T[::211] = 0.0
+    for sched, gamma_on, target, S in (("cbrt", "oracle", None, 70), ("cerf_7", "laplacian", 1, 33)):
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, gamma_on=gamma_on,
+                          target=target, n_steps=S)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        idx = np.r_[0:24, P - 24:P]
+        po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T[idx], g[idx], n_steps=S,
+                                             gamma_on=gamma_on, target=target, return_psi=True)
+        assert np.abs(p[idx] - po).max() <= P_TOL and np.abs(norm[idx] - no).max() <= P_TOL
+        assert np.abs(psi[idx] - psio).max() <= PSI_TOL
+        for lo in range(0, P, 97):
+            ps, ns = qw.rk4_batch(prob, T[lo:lo + 5], g[lo:lo + 5])
+            assert np.abs(ps - p[lo:lo + 5]).max() <= 1e-13
+            assert np.abs(ns - norm[lo:lo + 5]).max() <= 1e-13
