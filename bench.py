@@ -145,7 +145,7 @@ def stream_measure(qw, torch, dev, reps=3):
     peak, src = hbm_peak_gbs()
     out = {"workload": "cycle N=65536 n_steps=256 lin, 32x32 heatmap (1024 points, 2 GiB "
                        "working set > L2)", "peak_gbs": peak, "peak_source": src, "variants": []}
-    for kb, flag in ((1, 8), (2, 16), (4, 0)):
+    for kb, flag in ((1, 8), (2, 16), (4, 24), (8, 0)):
         prob = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=S, flags=flag)
         qw.rk4_heatmap(prob, t, b)
         best = 1e30

@@ -76,8 +76,8 @@ enum {
     QW_FLAG_EXACT_SUM = 4,       /* complete graph: block-reduce sum(u) in every stage
                                     instead of once per step (tests) */
     QW_FLAG_STREAM_KB1 = 8,      /* streaming kernel: 1 RK4 step per pass over HBM (the plain
-                                    32 B/site-update roofline) instead of the default 4 */
-    QW_FLAG_STREAM_KB2 = 16,     /* streaming kernel: 2 steps per pass */
+                                    32 B/site-update roofline) instead of the default 8 */
+    QW_FLAG_STREAM_KB2 = 16,     /* streaming kernel: 2 steps per pass; KB1 | KB2: 4 steps */
     QW_FLAG_CYCLE_LEGACY = 32,   /* first-generation resident kernels (cycle: stage code without
                                     edge-first ordering; complete: blocking reduction per
                                     step); kept for A/B measurements */

@@ -56,9 +56,10 @@ __device__ __forceinline__ void cp_async_wait_pending()
 
 // Per point and per pass, computed once by stream_pass_tables instead of once per window:
 // the step plan of the point and the stage-weighted operator scalars of the KB steps.
+constexpr int MAXKB = 8;               // most steps fused per pass
 struct PassEntry {
-    double2 ab[4 * 4];                 // (A, B) per stage
-    double2 d[4 * 4];                  // (DA, DB) per stage
+    double2 ab[4 * MAXKB];             // (A, B) per stage
+    double2 d[4 * MAXKB];              // (DA, DB) per stage
     int32_t kb;                        // steps this point still takes in this pass
     int32_t pad[3];
 };
@@ -66,8 +67,8 @@ struct PassEntry {
 // The same for the nested (Horner) form of the step (qw_horner_level.cuh): r1..r4 and the ten
 // correction coefficients over (y_w, s1, s2, s3) per step.
 struct HPassEntry {
-    double rho[4 * 4];
-    double2 c[4 * 10];
+    double rho[4 * MAXKB];
+    double2 c[10 * MAXKB];
     int32_t kb;
     int32_t pad[3];
 };
@@ -199,7 +200,7 @@ __device__ __forceinline__ void prefetch_window(StreamShared<SR, HORNER> &sh, in
                                                 int64_t mirror_m = 0, bool even = true)
 {
     using Entry = typename StreamShared<SR, HORNER>::Entry;
-    static_assert(sizeof(Entry) % 16 == 0 && sizeof(Entry) / 16 <= Geo<SR>::NT, "entry copy");
+    static_assert(sizeof(Entry) % 16 == 0 && KB <= MAXKB, "entry copy");
     constexpr int HALO = Win<KB, SR, ALIGNED>::HALO, TILE = Win<KB, SR, ALIGNED>::TILE,
                   SNT = Geo<SR>::NT;
     const uint32_t local = idx / tiles, tile = idx - local * tiles;
@@ -228,9 +229,10 @@ __device__ __forceinline__ void prefetch_window(StreamShared<SR, HORNER> &sh, in
         cp_async16(&xb[Geo<SR>::pad(e)], &src[j]);
     }
     }
-    if (t < (int)(sizeof(Entry) / 16))
-        cp_async16(reinterpret_cast<char *>(&sh.tab[slot]) + 16 * t,
-                   reinterpret_cast<const char *>(tab + local) + 16 * t);
+    // the part of the entry the KB steps of this pass use (kb and the tables' heads)
+    for (int i = t; i < (int)(sizeof(Entry) / 16); i += SNT)
+        cp_async16(reinterpret_cast<char *>(&sh.tab[slot]) + 16 * i,
+                   reinterpret_cast<const char *>(tab + local) + 16 * i);
     cp_async_commit();
 }
 
@@ -490,18 +492,24 @@ __global__ void __launch_bounds__(512) stream_finish(const QwParams prm, const d
     }
 }
 
-int stream_kb(const QwParams &prm)
-{
-    if (prm.flags & QW_FLAG_STREAM_KB1) return 1;
-    if (prm.flags & QW_FLAG_STREAM_KB2) return 2;
-    return 4;
-}
-
 // Temporal blocking (KB >= 2) is FP64-bound: 64 x 16 blocks.  KB = 1 is HBM-bound and wants
 // the deeper prefetch ring of the 128 x 8 geometry; so do QW_FLAG_R8 and short rings.
 int stream_sr(const QwParams &prm)
 {
-    return ((prm.flags & (QW_FLAG_R8 | QW_FLAG_STREAM_KB1)) || prm.n < 4096) ? 8 : 16;
+    const bool kb1 = (prm.flags & QW_FLAG_STREAM_KB1) && !(prm.flags & QW_FLAG_STREAM_KB2);
+    return ((prm.flags & QW_FLAG_R8) || kb1 || prm.n < 4096) ? 8 : 16;
+}
+
+// RK4 steps fused per pass.  The load / unload phases of a window cost about as much as 1.75
+// steps (measured, 64 x 16 geometry), so deeper temporal blocking keeps paying while the halo
+// (4 sites per step and side, rounded to the thread segment) stays a few per cent of the
+// window: 8 steps (halo 32 of 1024) by default, 4 in the 128 x 8 geometry.
+int stream_kb(const QwParams &prm)
+{
+    if ((prm.flags & QW_FLAG_STREAM_KB1) && (prm.flags & QW_FLAG_STREAM_KB2)) return 4;
+    if (prm.flags & QW_FLAG_STREAM_KB1) return 1;
+    if (prm.flags & QW_FLAG_STREAM_KB2) return 2;
+    return stream_sr(prm) == 16 ? 8 : 4;
 }
 
 int g_sm_count = 0;
@@ -613,7 +621,7 @@ cudaError_t plan_of(qw_plan *plan, bool horner)
 
 #define QW_STREAM_DISPATCH(FN, ...)                                                     \
     (sr == 16 ? (kb == 1 ? FN<1, 16>(__VA_ARGS__) : kb == 2 ? FN<2, 16>(__VA_ARGS__)    \
-                                                            : FN<4, 16>(__VA_ARGS__))   \
+                 : kb == 8 ? FN<8, 16>(__VA_ARGS__) : FN<4, 16>(__VA_ARGS__))           \
               : (kb == 1 ? FN<1, 8>(__VA_ARGS__) : kb == 2 ? FN<2, 8>(__VA_ARGS__)      \
                                                            : FN<4, 8>(__VA_ARGS__)))
 
@@ -647,7 +655,7 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     }
     // points in flight: bounded by ~8 GiB of ping-pong scratch and by 32-bit window indices
     int64_t chunk = (int64_t)(8ull << 30) / (2 * n * (int64_t)sizeof(double2));
-    const int64_t tiles_max = n / (1024 - 32) + 2;
+    const int64_t tiles_max = n / (1024 - 64) + 2;
     if (chunk > (int64_t)0x7fffffff / tiles_max) chunk = (int64_t)0x7fffffff / tiles_max;
     if (chunk < 1) chunk = 1;
     if (chunk > prm.n_points) chunk = prm.n_points;

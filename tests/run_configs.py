@@ -198,7 +198,7 @@ def main():
                 dict(n=1024, topology="circular", schedule="lin", n_steps=4096), t, b)
     # C5 streaming variant
     t, b = np.linspace(0.1, 64, 32), np.linspace(0, 2.5, 32)
-    for flag, kb in ((8, 1), (0, 4)):
+    for flag, kb in ((8, 1), (24, 4), (0, 8)):
         heatmap_row("C5-stream cycle N=65536 32x32 lin S=256, %d step(s)/pass" % kb,
                     dict(n=65536, topology="circular", schedule="lin", n_steps=256, flags=flag),
                     t, b, reps=2, check=True)

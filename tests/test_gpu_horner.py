@@ -326,10 +326,10 @@ def test_localization_run_131072_steps(qw):
 
 
 @pytest.mark.parametrize("n", [8704, 9001, 10000, 20011])
-@pytest.mark.parametrize("kb_flag", [8, 16, 0, 256])
+@pytest.mark.parametrize("kb_flag", [8, 16, 24, 0, 256])
 def test_mirror_reduced_streaming_vs_oracle(qw, n, kb_flag):
     """QW_FLAG_MIRROR in the HBM-streaming kernel: the half ring behind three ghost sites,
-    reflecting window halos; even and odd n, 1 / 2 / 4 steps per pass, both window geometries,
+    reflecting window halos; even and odd n, 1 / 2 / 4 / 8 steps per pass, both window geometries,
     custom target, psi with both mirror images."""
     rng = np.random.default_rng(n + kb_flag)
     T = np.concatenate([[0.0], rng.uniform(1.0, 9.0, 3)])

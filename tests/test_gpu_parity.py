@@ -277,10 +277,12 @@ def test_plan_reports_native_kernels(qw):
 
 
 @pytest.mark.parametrize("n", [8, 64, 1000, 1016, 1024, 2050, 4100, 9001])
-@pytest.mark.parametrize("kb_flag", [8, 16, 0, 256, 256 | 8, 2048, 2048 | 8, 2048 | 16])
+@pytest.mark.parametrize("kb_flag", [8, 16, 24, 0, 256, 256 | 8, 2048, 2048 | 8, 2048 | 16,
+                                     2048 | 24])
 def test_streaming_kernel_vs_oracle(qw, n, kb_flag):
-    """Tile-fused HBM-streaming kernel (flags: 2 = force it, 8 / 16 = 1 / 2 steps per pass,
-    default 4; 256 = 8 instead of 16 sites per thread for n >= 4096; 2048 = stage form instead
+    """Tile-fused HBM-streaming kernel (flags: 2 = force it, 8 / 16 / 24 = 1 / 2 / 4 steps per
+    pass, default 8 with 16 sites per thread and 4 with 8; 256 = 8 instead of 16 sites per thread
+    for n >= 4096; 2048 = stage form instead
     of the nested form, which is used whenever n is a multiple of the sites per thread),
     windows that wrap, ragged last tiles, marked vertex in a halo copy."""
     rng = np.random.default_rng(n + kb_flag)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the streaming kernel on the C5 streaming shape (cycle N=65536, 32x32 grid, S=256):
-steps per pass 1 / 2 / 4, nested form vs stage form (QW_FLAG_NO_HORNER = 2048)."""
+steps per pass 1 / 2 / 4 / 8, nested form vs stage form (QW_FLAG_NO_HORNER = 2048)."""
 import os
 import sys
 
@@ -14,9 +14,11 @@ n, S = 65536, 256
 t = torch.linspace(0.1, 64.0, 32, dtype=torch.float64, device=dev)
 b = torch.linspace(0.0, 2.5, 32, dtype=torch.float64, device=dev)
 ref = {}
-for kb, kflag in ((1, 8), (2, 16), (4, 0)):
+for kb, kflag in ((1, 8), (2, 16), (4, 24), (8, 0)):
     for name, hflag in (("nested", 0), ("stage", 2048), ("mirror", 8192)):
         for r8 in (0, 256):
+            if kb == 8 and r8:
+                continue
             prob = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=S,
                               flags=kflag | hflag | r8)
             pl = qw.plan(prob)

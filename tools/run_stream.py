@@ -11,7 +11,7 @@ import qwtdh_b200 as qw  # noqa: E402
 kb = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 points = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-flag = {1: 8, 2: 16, 4: 0}[kb] | (256 if len(sys.argv) > 4 and sys.argv[4] == "r8" else 0)
+flag = {1: 8, 2: 16, 4: 24, 8: 0}[kb] | (256 if len(sys.argv) > 4 and sys.argv[4] == "r8" else 0)
 dev = torch.device("cuda")
 T = torch.linspace(0.1, 64.0, points, dtype=torch.float64, device=dev)
 g = torch.linspace(0.0, 2.5, points, dtype=torch.float64, device=dev)
