@@ -89,6 +89,12 @@ def test_last_error_is_per_thread(qw):
 
     lib = _lib.load()
     seen = {}
+    try:                                  # give this thread a message of its own
+        qw.rk4_batch(qw.Problem(n=5, topology="circular", n_steps=-3), [1.0], [1.0])
+    except ValueError:
+        pass
+    mine = lib.qw_last_error().decode()
+    assert "step_size" in mine or "n_steps" in mine, mine
 
     def bad():
         try:
@@ -108,4 +114,4 @@ def test_last_error_is_per_thread(qw):
     assert "cycle graph needs dimension >= 3" in seen["bad"], seen
     assert "dimension" in seen["bad_msg"]
     assert 0.0 < seen["good"] < 1.0
-    assert "dimension" not in lib.qw_last_error().decode()       # this thread never failed
+    assert lib.qw_last_error().decode() == mine           # untouched by the other threads' errors
