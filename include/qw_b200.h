@@ -224,6 +224,17 @@ int qw_adiabatic_batch_dev(const qw_problem *prob, const double *s, const double
                            int64_t n_points, int32_t reference_derivative, double *gap,
                            double *coupling, double *e0, void *stream);
 
+/* The whole spectrum of H(s_q) in ascending order, eigenvalues[q][0 .. n-1], for a batch of
+ * (s_q, gamma_q): replaces compute_eigenvalues(dimension, gamma, time, TIME) of
+ * Eigenvalues_Crossing.py:59-71 (time_dependent_hamiltonian + scipy.linalg.eig + sort per call;
+ * its __main__, lines 88-112, samples s for the level-crossing figure).  s = time / TIME.
+ * All roots of the secular equation of the rank-one perturbation, one thread per root (cycle
+ * graph, dimension <= 4096), or the 2 x 2 symmetric block plus the (n-2)-fold level a n
+ * (complete graph).  gamma >= 0 with the gamma-on-Laplacian placement (NaN otherwise).
+ * prob->schedule applies, the step rule is ignored. */
+int qw_spectrum_batch_dev(const qw_problem *prob, const double *s, const double *gamma,
+                          int64_t n_points, double *eigenvalues, void *stream);
+
 /* ---- introspection ------------------------------------------------------------------- */
 
 typedef struct qw_plan {

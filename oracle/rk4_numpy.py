@@ -314,3 +314,16 @@ def rk45_scipy(n, topology, schedule, T, gamma, rtol=1e-6, atol=1e-6, gamma_on=G
     psi = sol.y[:, -1]
     p, norm = _finish(psi, w)
     return p, norm, psi, sol.nfev
+
+
+def spectrum_dense(n, topology, schedule, s, gamma, gamma_on=GAMMA_ON_ORACLE, target=None):
+    """Sorted eigenvalues of H(s) = a L + d |w><w| by dense diagonalisation, restating
+    compute_eigenvalues of Eigenvalues_Crossing.py:59-71 (time_dependent_hamiltonian, lines
+    58-63, + scipy.linalg.eig + np.sort; H is real symmetric, so eigvalsh returns the same
+    numbers).  The reference's file is Python 2 (``hamiltonian[(dimension-1)/2]``) and cannot be
+    executed here: parity for this row is pinned to this restatement only."""
+    w = (n - 1) // 2 if target is None else target
+    a, d = (float(x) for x in operator_scalars(s, gamma, schedule, gamma_on))
+    H = a * laplacian_dense(n, topology)
+    H[w, w] += d
+    return np.linalg.eigvalsh(H)

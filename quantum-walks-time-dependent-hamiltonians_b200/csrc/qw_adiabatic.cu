@@ -126,6 +126,110 @@ adiabatic_kernel(int64_t n, int topology, int schedule, int gamma_on, int ref, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The whole sorted spectrum of H(s) = a L + d |w><w| for a batch of (s, gamma) points
+// (Eigenvalues_Crossing.py:59-71, compute_eigenvalues: a dense scipy.linalg.eig + sort per call;
+// its __main__ samples 100 values of s for the level-crossing figure).
+//
+// Cycle graph: L has the distinct eigenvalues mu_m = 2 - 2 cos(2 pi m / N), m = 0 .. M = N/2;
+// m = 1 .. D = (N-1)/2 are doubly degenerate.  Of each degenerate pair the combination that
+// vanishes on w is untouched by the oracle and stays at a mu_m; the other one, like the two
+// singlets, has weight omega_m = |<w|v_m>|^2 = 2/N (1/N) on w and moves to a root of
+//     f(E) = 1 + d sum_m omega_m / (a mu_m - E) = 0,
+// exactly one per interval between consecutive poles plus one beyond the end the perturbation
+// pushes towards (below a mu_0 - |d| .. a mu_0 for d < 0, above for d > 0).  f is monotonic
+// between poles: bisection to the last bit, one thread per root.  The interlacing also fixes the
+// sorted order, so the output needs no sort.  Complete graph: two roots of the 2 x 2 problem
+// above plus N - 2 copies of a N.
+constexpr int SP_THREADS = 128;
+constexpr int SP_MAXM = AD_MAXN / 2 + 1;
+
+__device__ __forceinline__ double secular_f(const double *pole, int m1, int dbl, double d,
+                                            double inv_n, double E)
+{
+    double acc = 0.0;
+    for (int m = 0; m < m1; ++m) {
+        const double w = (m >= 1 && m <= dbl) ? 2.0 : 1.0;
+        acc += w / (pole[m] - E);
+    }
+    return fma(d * inv_n, acc, 1.0);
+}
+
+__global__ void __launch_bounds__(SP_THREADS)
+spectrum_kernel(int64_t n, int topology, int schedule, int gamma_on, const double *s_arr,
+                const double *gamma_arr, int64_t n_points, double *out)
+{
+    __shared__ double pole[SP_MAXM];
+    const int64_t q = blockIdx.x;
+    const double s = s_arr[q], gamma = gamma_arr[q];
+    const double2 ad = qw_operator_scalars(s, gamma, schedule, gamma_on);
+    const double a = ad.x, d = ad.y, nn = (double)n;
+    double *o = out + q * n;
+    const int t = threadIdx.x;
+    if (!(a >= 0.0)) {                                 // gamma < 0 on the Laplacian: not ordered
+        for (int64_t i = t; i < n; i += SP_THREADS) o[i] = NAN;
+        return;
+    }
+    if (topology == QW_TOPO_COMPLETE) {
+        double E0 = d, E1 = d;
+        if (n >= 2) {
+            const double h11 = a * (nn - 1.0) + d, h22 = a, off = a * sqrt(nn - 1.0);
+            const double m = 0.5 * (h11 + h22), del = 0.5 * (h11 - h22);
+            const double r = sqrt(del * del + off * off);
+            E0 = m - r;
+            E1 = m + r;
+        }
+        const double mid = a * nn;                     // N - 2 fold
+        const int64_t below = (n >= 2 ? (E0 <= mid) + (E1 <= mid) : 1);   // roots placed first
+        for (int64_t i = t; i < n; i += SP_THREADS) {
+            double v;
+            if (n == 1) v = d;
+            else if (i < below) v = i == 0 ? E0 : E1;
+            else if (i < below + (n - 2)) v = mid;
+            else v = (i - (n - 2)) == 0 ? E0 : E1;
+            o[i] = v;
+        }
+        return;
+    }
+    const int M = (int)(n / 2), D = (int)((n - 1) / 2);
+    for (int m = t; m <= M; m += SP_THREADS)
+        pole[m] = a * (2.0 - 2.0 * cospi(2.0 * (double)m / nn));
+    __syncthreads();
+    if (a == 0.0) {                                    // no Laplacian: {d, 0 x (N - 1)}
+        for (int64_t i = t; i < n; i += SP_THREADS)
+            o[i] = d < 0.0 ? (i == 0 ? d : 0.0) : (i == n - 1 ? d : 0.0);
+        return;
+    }
+    const double inv_n = 1.0 / nn;
+    for (int j = t; j <= M; j += SP_THREADS) {
+        double root;
+        if (d == 0.0) root = pole[j];
+        else {
+            double lo, hi;
+            if (d < 0.0) { lo = j == 0 ? pole[0] + d : pole[j - 1]; hi = pole[j]; }
+            else { lo = pole[j]; hi = j == M ? pole[M] + d : pole[j + 1]; }
+            for (int it = 0; it < 1100; ++it) {        // until the bracket is two neighbours
+                const double mid = 0.5 * (lo + hi);
+                if (!(mid > lo && mid < hi)) break;
+                const double f = secular_f(pole, M + 1, D, d, inv_n, mid);
+                // d < 0: f falls from +inf to -inf across the interval; d > 0: it rises
+                if ((f > 0.0) == (d < 0.0)) lo = mid; else hi = mid;
+            }
+            root = 0.5 * (lo + hi);
+        }
+        const bool dbl = j >= 1 && j <= D;
+        if (d <= 0.0) {                                // r_0, then (r_j, a mu_j) pairs
+            const int pos = j == 0 ? 0 : j + (j - 1 < D ? j - 1 : D);
+            o[pos] = root;
+            if (dbl) o[pos + 1] = pole[j];
+        } else {                                       // (a mu_j, r_j)
+            const int pos = j + (j < D ? j : D);
+            o[pos] = root;
+            if (dbl) o[pos - 1] = pole[j];
+        }
+    }
+}
+
 }  // namespace
 
 cudaError_t qw_launch_adiabatic(int64_t n, int topology, int schedule, int gamma_on, int ref,
@@ -139,3 +243,11 @@ cudaError_t qw_launch_adiabatic(int64_t n, int topology, int schedule, int gamma
 }
 
 int qw_adiabatic_max_dimension() { return AD_MAXN; }
+
+cudaError_t qw_launch_spectrum(int64_t n, int topology, int schedule, int gamma_on, const double *s,
+                               const double *gamma, int64_t n_points, double *out, cudaStream_t st)
+{
+    spectrum_kernel<<<(unsigned)n_points, SP_THREADS, 0, st>>>(n, topology, schedule, gamma_on, s,
+                                                               gamma, n_points, out);
+    return cudaGetLastError();
+}

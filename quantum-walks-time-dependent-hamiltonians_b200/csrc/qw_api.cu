@@ -34,6 +34,8 @@ cudaError_t qw_launch_adiabatic(int64_t n, int topology, int schedule, int gamma
                                 const double *s, const double *gamma, int64_t n_points,
                                 double *gap, double *coupling, double *e0, cudaStream_t st);
 int qw_adiabatic_max_dimension();
+cudaError_t qw_launch_spectrum(int64_t n, int topology, int schedule, int gamma_on, const double *s,
+                               const double *gamma, int64_t n_points, double *out, cudaStream_t st);
 int qw_mirror_sites_per_lane(const QwParams &prm);
 cudaError_t qw_launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan);
 bool qw_symmetric_supported(const QwParams &prm);
@@ -487,6 +489,29 @@ int qw_adiabatic_batch_dev(const qw_problem *prob, const double *s, const double
                                         coupling, e0, (cudaStream_t)stream);
     g_launches += 1;
     if (e != cudaSuccess) return cuda_fail(e, "adiabatic kernel launch");
+    return 0;
+}
+
+int qw_spectrum_batch_dev(const qw_problem *prob, const double *s, const double *gamma,
+                          int64_t n_points, double *eigenvalues, void *stream)
+{
+    QwParams prm;
+    qw_problem tmp;
+    if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
+    tmp = *prob;
+    if (!(tmp.step_size > 0.0) && tmp.n_steps < 0) tmp.n_steps = 0;   // no step rule needed
+    int rc = validate(&tmp, &prm);
+    if (rc) return rc;
+    if (n_points < 0) return fail(QW_E_SIZE, "n_points < 0");
+    if (n_points == 0) return 0;
+    if (!s || !gamma || !eigenvalues) return fail(QW_E_NULL, "s, gamma and eigenvalues are required");
+    if (prm.topology == QW_TOPO_CYCLE && prm.n > qw_adiabatic_max_dimension())
+        return fail(QW_E_UNSUPPORTED, "spectrum: cycle graph up to dimension %d",
+                    qw_adiabatic_max_dimension());
+    cudaError_t e = qw_launch_spectrum(prm.n, prm.topology, prm.schedule, prm.gamma_on, s, gamma,
+                                       n_points, eigenvalues, (cudaStream_t)stream);
+    g_launches += 1;
+    if (e != cudaSuccess) return cuda_fail(e, "spectrum kernel launch");
     return 0;
 }
 

@@ -333,6 +333,27 @@ def adiabatic_batch(problem, s, gamma, reference_derivative=False, device=None):
         return out
 
 
+def spectrum_batch(problem, s, gamma, device=None):
+    """All eigenvalues of H(s_q), ascending, for (s_q, gamma_q) points -> float64[P, n]:
+    compute_eigenvalues of Eigenvalues_Crossing.py:59-71 (s = time / TIME), batched on the
+    device (every root of the secular equation; no dense eigensolve)."""
+    dev = _device(device)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        ds, host = _as_dev(s, dev)
+        dg, _ = _as_dev(gamma, dev)
+        if dg.numel() == 1 and ds.numel() > 1:
+            dg = dg.expand(ds.numel()).contiguous()
+        if ds.numel() != dg.numel():
+            raise ValueError("s and gamma must have the same length")
+        P = ds.numel()
+        eig = torch.empty((P, int(problem.n)), dtype=torch.float64, device=dev)
+        prob = problem.c_struct(per_point_steps=True)
+        _lib.check(lib.qw_spectrum_batch_dev(ctypes.byref(prob), _ptr(ds), _ptr(dg), P, _ptr(eig),
+                                             _stream()))
+        return eig.cpu().numpy() if host else eig
+
+
 def adiabatic_check(problem, gamma, samples=4097, rounds=4, reference_derivative=False,
                     device=None):
     """max_s |<phi1|dH/ds|phi0>| and min_s (E1 - E0) over s in (0, 1), the two numbers behind
