@@ -175,13 +175,13 @@ template <int R, int MAXNT, int MINB>
 cudaError_t launch_cheb(const QwParams &prm, int threads, cudaStream_t st)
 {
     const size_t smem = (size_t)threads * 4 * sizeof(double);
-    static bool configured = false;          // static + dynamic shared memory can pass 48 KB
-    if (!configured) {
+    static QwOncePerDevice configured;       // static + dynamic shared memory can pass 48 KB
+    if (configured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(cheb_cycle_resident<R, MAXNT, MINB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              MAXNT * 4 * (int)sizeof(double));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark();
     }
     cheb_cycle_resident<R, MAXNT, MINB><<<(unsigned)prm.n_points, threads, smem, st>>>(prm);
     return cudaGetLastError();

@@ -10,9 +10,33 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/qw_b200.h"
 
 #define QW_CHUNK 32               // RK4 steps per coefficient-table refill
+
+// Function attributes (cudaFuncSetAttribute) belong to a device: remember on which devices of
+// this process a kernel has been configured.  Setting one twice is harmless, so a benign race
+// between host threads only repeats the call.
+struct QwOncePerDevice {
+    std::atomic<uint64_t> mask{0};
+    static int device()
+    {
+        int d = 0;
+        return cudaGetDevice(&d) == cudaSuccess ? d : -1;
+    }
+    bool needed() const
+    {
+        const int d = device();
+        return d < 0 || d >= 64 || !((mask.load(std::memory_order_acquire) >> d) & 1ull);
+    }
+    void mark()
+    {
+        const int d = device();
+        if (d >= 0 && d < 64) mask.fetch_or(1ull << d, std::memory_order_release);
+    }
+};
 
 struct QwParams {
     int64_t n;

@@ -275,13 +275,13 @@ cudaError_t launch_rk45(const QwParams &prm, int threads, double rtol, double at
                         int64_t *nfev, cudaStream_t st)
 {
     const size_t smem = (size_t)threads * 4 * sizeof(double2);
-    static bool configured = false;
-    if (!configured) {
+    static QwOncePerDevice configured;
+    if (configured.needed()) {
         cudaError_t e = cudaFuncSetAttribute(rk45_resident<R, 1024>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              1024 * 4 * (int)sizeof(double2));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured.mark();
     }
     rk45_resident<R, 1024><<<(unsigned)prm.n_points, threads, smem, st>>>(prm, rtol, atol, nfev);
     return cudaGetLastError();

@@ -528,12 +528,12 @@ int sm_count()
 template <int KB, int SR, bool ALIGNED, bool HORNER>
 cudaError_t configure()
 {
-    static bool configured = false;
-    if (configured) return cudaSuccess;
+    static QwOncePerDevice configured;
+    if (!configured.needed()) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(rk4_cycle_stream<KB, SR, ALIGNED, HORNER>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(StreamShared<SR, HORNER>));
-    if (e == cudaSuccess) configured = true;
+    if (e == cudaSuccess) configured.mark();
     return e;
 }
 

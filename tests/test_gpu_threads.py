@@ -115,3 +115,25 @@ def test_last_error_is_per_thread(qw):
     assert "dimension" in seen["bad_msg"]
     assert 0.0 < seen["good"] < 1.0
     assert lib.qw_last_error().decode() == mine           # untouched by the other threads' errors
+
+
+def test_two_devices_in_one_process(qw):
+    """One process driving two GPUs (the `device=` argument): kernels that need more than 48 KB
+    of shared memory are configured per device (cudaFuncSetAttribute is per device).  Same
+    inputs on cuda:0 and cuda:1 -> bitwise the same results."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    for i, kw in enumerate(CASES):
+        T, g = _inputs(kw, 300 + i)
+        res = [qw.rk4_batch(qw.Problem(**kw), T, g, device=d) for d in (0, 1, 0)]
+        for r in res[1:]:
+            assert np.array_equal(r[0], res[0][0]) and np.array_equal(r[1], res[0][1]), kw
+    T, g = np.array([3.0, 7.5]), np.array([1.1, 0.4])
+    prob = qw.Problem(n=1024, topology="circular", schedule="lin")
+    a = [qw.rk45_batch(prob, T, g, device=d) for d in (0, 1)]
+    assert np.array_equal(a[0][0], a[1][0])
+    prob = qw.Problem(n=1024, topology="circular", schedule="static")
+    b = [qw.ti_exact_batch(prob, T, g, device=d) for d in (0, 1)]
+    assert np.array_equal(b[0][0], b[1][0])
