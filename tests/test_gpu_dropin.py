@@ -292,5 +292,14 @@ def test_mirror_knob_of_the_drop_in_modules():
     full = bcb.grid_eval(t, b)
     bcb.mirror = True
     half = bcb.grid_eval(t, b)
-    bcb.mirror, bcb.n_steps, bcb.step_size = False, None, 1e-3
     assert np.abs(full - half).max() <= 1e-13 and np.argmax(full) == np.argmax(half)
+    # complete graph (BCB.py:30-37): the (psi_w, psi_other) pair instead of 512 amplitudes
+    bcb.dimension, bcb.topology, bcb.n_steps = 512, "complete", 600
+    t, b = np.linspace(0.01, 0.3, 5), np.linspace(0.0, 900.0, 6)
+    bcb.mirror = False
+    full = bcb.grid_eval(t, b)
+    bcb.mirror = True
+    pair = bcb.grid_eval(t, b)
+    bcb.mirror, bcb.n_steps, bcb.step_size, bcb.topology = False, None, 1e-3, "circular"
+    assert np.isfinite(full).all() and full.max() > 0.1
+    assert np.abs(full - pair).max() <= 1e-12 and np.argmax(full) == np.argmax(pair)
