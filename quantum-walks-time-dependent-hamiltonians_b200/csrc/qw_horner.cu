@@ -323,7 +323,7 @@ struct CHStep {
 
 struct CFShared {
     CHStep tab[3][QW_CHUNK];             // coefficients of chunk c in tab[c % 3]
-    double2 sums[2][QW_CHUNK][4];        // chunk c in [c & 1]: S(y), S(z4), S(z3), S(z2) per step
+    double2 sums[2][QW_CHUNK][4];        // chunk c in [c & 1]: (S(y), S(z4), S(z3), S(z2)) / N per step
     double2 sig[2][QW_CHUNK][4];         // sigma_4 .. sigma_1 per step (owner thread)
     double red[2 * 32];
 };
@@ -366,8 +366,8 @@ __device__ __forceinline__ void horner_fill_complete(CHStep *tab, const QwPoint 
 // the four corrections are one dot product of length 4 per lane (lane 2m + c: component c of
 // sigma_{4-m}).  Leaves the level sums and corrections of the step in shared memory.
 __device__ __forceinline__ void scalar_step(const CHStep &hs, double2 &yw, double2 &Sy,
-                                            const double nd, double2 *sums4, double2 *sig4,
-                                            const int lane)
+                                            const double nd, const double invn, double2 *sums4,
+                                            double2 *sig4, const int lane)
 {
     const unsigned full = 0xffffffffu;
     const double2 m1 = make_double2(fma(nd, yw.x, -Sy.x), fma(nd, yw.y, -Sy.y));    // (Ly)_w
@@ -383,8 +383,11 @@ __device__ __forceinline__ void scalar_step(const CHStep &hs, double2 &yw, doubl
     const double2 S4 = make_double2(Sy.x + g4.x, Sy.y + g4.y);
     const double2 S3 = make_double2(Sy.x + g3.x, Sy.y + g3.y);
     const double2 S2 = make_double2(Sy.x + g2.x, Sy.y + g2.y);
-    if (lane == 0) {
-        sums4[0] = Sy; sums4[1] = S4; sums4[2] = S3; sums4[3] = S2;
+    if (lane == 0) {       // the workers use the level MEANS S / N (see clevel)
+        sums4[0] = make_double2(Sy.x * invn, Sy.y * invn);
+        sums4[1] = make_double2(S4.x * invn, S4.y * invn);
+        sums4[2] = make_double2(S3.x * invn, S3.y * invn);
+        sums4[3] = make_double2(S2.x * invn, S2.y * invn);
         sig4[0] = g4; sig4[1] = g3; sig4[2] = g2; sig4[3] = g1;
     }
     // the marked vertex through the four levels (same operations as the vector code)
@@ -398,19 +401,23 @@ __device__ __forceinline__ void scalar_step(const CHStep &hs, double2 &yw, doubl
     Sy = make_double2(Sy.x + g1.x, Sy.y + g1.y);
 }
 
-// one level on all R sites of a thread: out = y - i rho (N x - S)
-// (ndg, Sg): the same for the last slot -- zero in a short thread, whose last slot is a ghost
+// one level on all R sites of a thread: out = y - i rho (N x - S), evaluated as
+// y - i (rho N)(x - S/N): a two-operand DADD and a DFMA instead of two three-operand DFMAs
+// (the FP64 pipe is limited by register-operand delivery: 0.43 against 0.38 warp-instructions
+// per clock and sub-partition in tools/fp64_mix_probe.cu, patterns H3 / H).
+// rn = rho N in a working thread, 0 in an idle one (its sites stay at zero); rng: the same for
+// the last slot -- zero in a short thread, whose last slot is a ghost
 template <int R, int LEVEL, bool RAGGED>
-__device__ __forceinline__ void clevel(HState<R> &s, const double rho, const double nd,
-                                       const double2 S, const double ndg, const double2 Sg)
+__device__ __forceinline__ void clevel(HState<R> &s, const double rn, const double rng,
+                                       const double2 Sb)
 {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const bool g = RAGGED && r == R - 1;
-        const double tr_ = fma(g ? ndg : nd, HX_R(r), -(g ? Sg.x : S.x));
-        const double ti_ = fma(g ? ndg : nd, HX_I(r), -(g ? Sg.y : S.y));
-        HO_R(r) = fma(rho, ti_, s.yr[r]);
-        HO_I(r) = fma(-rho, tr_, s.yi[r]);
+        const double dr_ = HX_R(r) - Sb.x;
+        const double di_ = HX_I(r) - Sb.y;
+        HO_R(r) = fma(g ? rng : rn, di_, s.yr[r]);
+        HO_I(r) = fma(-(g ? rng : rn), dr_, s.yi[r]);
     }
 }
 
@@ -422,23 +429,21 @@ __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const
 {
     const CHStep *tab = sh.tab[c % 3];
     const int cur = (int)(c & 1);
-    const double act = (nd != 0.0) ? 1.0 : 0.0;            // idle threads stay at zero
-    const double actg = full ? act : 0.0, ndg = full ? nd : 0.0;   // ghost slot stays at zero
+    const double ndg = full ? nd : 0.0;                    // ghost slot stays at zero
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const CHStep &hs = tab[sidx];
         // all scalars of the step up front: nothing inside the step waits for shared memory
-        double2 Sl[4], Sg[4];
-        double rl[4];
+        double2 Sl[4];
+        double rl[4], rg[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const double2 S = sh.sums[cur][sidx][k];
-            Sl[k] = make_double2(S.x * act, S.y * act);
-            Sg[k] = make_double2(S.x * actg, S.y * actg);
-            rl[k] = hs.rho[k];
+            Sl[k] = sh.sums[cur][sidx][k];
+            rl[k] = hs.rho[k] * nd;                        // nd = 0 in an idle thread
+            rg[k] = hs.rho[k] * ndg;
         }
 #define QW_CH_LEVEL(LEVEL)                                                                  \
         {                                                                                   \
-            clevel<R, LEVEL, RAGGED>(s, rl[LEVEL - 1], nd, Sl[4 - LEVEL], ndg, Sg[4 - LEVEL]); \
+            clevel<R, LEVEL, RAGGED>(s, rl[LEVEL - 1], rg[LEVEL - 1], Sl[4 - LEVEL]);       \
             if (OWN) {                                                                      \
                 const double2 sg = sh.sig[cur][sidx][4 - LEVEL];                            \
                 if (LEVEL > 1) {                                                            \
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
     const bool active = t < nact;
     const bool full = !RAGGED || t < prm.nfull;        // R sites; else R-1 and a ghost slot
     const double nfull = (double)prm.n;
-    const double nd = active ? nfull : 0.0;
+    const double nd = active ? nfull : 0.0, invn = 1.0 / nfull;
 
     HState<R> s;
     const double amp = active ? 1.0 / sqrt(nfull) : 0.0;
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
             __syncwarp();
             const int cnt0 = QW_CNT(0);
             for (int sidx = 0; sidx < cnt0; ++sidx)
-                scalar_step(sh.tab[0][sidx], yw, Sy, nfull, sh.sums[0][sidx], sh.sig[0][sidx], lane);
+                scalar_step(sh.tab[0][sidx], yw, Sy, nfull, invn, sh.sums[0][sidx], sh.sig[0][sidx], lane);
         }
     }
     for (int64_t c = 0; c < nchunks; ++c) {
@@ -509,7 +514,8 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
                 const CHStep *tn = sh.tab[(c + 1) % 3];
                 const int cn = QW_CNT(c + 1), nxt = (int)((c + 1) & 1);
                 for (int sidx = 0; sidx < cn; ++sidx)
-                    scalar_step(tn[sidx], yw, Sy, nfull, sh.sums[nxt][sidx], sh.sig[nxt][sidx], lane);
+                    scalar_step(tn[sidx], yw, Sy, nfull, invn, sh.sums[nxt][sidx], sh.sig[nxt][sidx],
+                                lane);
             }
         } else if (warp == 0) {
             complete_chunk<R, true, RAGGED>(s, sh, c, QW_CNT(c), nd, msk, full);

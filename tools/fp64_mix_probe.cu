@@ -100,6 +100,55 @@ __global__ void __launch_bounds__(256) kH(int iters, double seed, double *sink)
     if (s == 123.456) sink[0] = s;
 }
 
+// H2: the same with the two instruction types grouped (all t first, then all z): does the
+// operand reuse cache (same register in the same operand slot of consecutive DFMAs) matter?
+template <int G>
+__global__ void __launch_bounds__(256) kH2(int iters, double seed, double *sink)
+{
+    double z[C], y[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { z[c] = seed + c + threadIdx.x; y[c] = 1e-9 * (c + 1) * seed; }
+    const double rho = 1e-3 * seed, nd = 1.0 + 1e-9 * seed, mS = 1e-9 * seed;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int g = 0; g < C; g += G) {
+                double t[G];
+#pragma unroll
+                for (int c = 0; c < G; ++c) t[c] = fma(nd, z[g + c], mS);
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < G; ++c) z[g + c] = fma(rho, t[c], y[g + c]);
+                asm volatile("" ::: "memory");
+            }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s += z[c];
+    if (s == 123.456) sink[0] = s;
+}
+
+// H3: d = z - zbar (DADD), z = fma(rhoN, d, y)
+__global__ void __launch_bounds__(256) kH3(int iters, double seed, double *sink)
+{
+    double z[C], y[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { z[c] = seed + c + threadIdx.x; y[c] = 1e-9 * (c + 1) * seed; }
+    const double rho = 1e-3 * seed, zbar = 1e-9 * seed;
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const double d = z[c] - zbar;
+                z[c] = fma(rho, d, y[c]);
+            }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s += z[c];
+    if (s == 123.456) sink[0] = s;
+}
+
 // D / E: the nested-form level on R = 16 sites per thread (ring closed inside the thread),
 // 24 FP64 instructions per site and step; SYNC adds one block barrier per level
 // RHO: 0 = kernel-parameter derived (uniform register), 1 = loaded from shared memory per level
@@ -187,6 +236,12 @@ int main()
     run("F dfma 2 fresh + 1 reused", kF, 1, 256, 4000, 256.0);
     run("H complete-graph level pattern", kH, 2, 256, 4000, 256.0);
     run("H complete-graph level pattern", kH, 1, 256, 4000, 256.0);
+    run("H2 grouped by type, groups of 16", kH2<16>, 2, 256, 4000, 256.0);
+    run("H2 grouped by type, groups of 16", kH2<16>, 1, 256, 4000, 256.0);
+    run("H2 grouped by type, groups of 8", kH2<8>, 2, 256, 4000, 256.0);
+    run("H2 grouped by type, groups of 4", kH2<4>, 2, 256, 4000, 256.0);
+    run("H3 dadd (z - zbar) + dfma", kH3, 2, 256, 4000, 256.0);
+    run("H3 dadd (z - zbar) + dfma", kH3, 1, 256, 4000, 256.0);
     run("D nested level, no barrier", kD<false, 4>, 4, 64, 20000, 16 * 24.0);
     run("D nested level, no barrier", kD<false, 6>, 6, 64, 20000, 16 * 24.0);
     run("D nested level, no barrier", kD<false, 4>, 2, 64, 20000, 16 * 24.0);
