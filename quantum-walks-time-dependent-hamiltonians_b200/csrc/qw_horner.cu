@@ -461,13 +461,19 @@ __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const
     }
 }
 
-// blockDim = worker threads (n / R rounded up to warps) + 32: the last warp is the scalar warp
-template <int R, int MAXNT, int MINB, bool RAGGED>
-__global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const QwParams prm)
+// blockDim = worker threads (n / R rounded up to warps) + 32 AUX: the last warp is the scalar
+// warp.  AUX = 2: the warp before it refills the coefficient tables instead (the "table warp").
+// Warps go to the four SM sub-partitions by slot number and the FP64 pipe is per sub-partition:
+// with eight worker warps and both duties in warp 8, sub-partition 0 issued 587 FP64
+// instructions per step against 520 on the others and everybody waited for it at the chunk
+// barrier (18 % of the warp samples); table warp 8 / scalar warp 9: 543 / 564 / 520 / 520.
+template <int R, int MAXNT, int MINB, int AUX, bool RAGGED>
+__global__ void __launch_bounds__(MAXNT + 32 * AUX, MINB) rk4_complete_horner(const QwParams prm)
 {
     __shared__ CFShared sh;
     const int t = threadIdx.x, nact = prm.nact;
     const int lane = t & 31, warp = t >> 5, swarp = (blockDim.x >> 5) - 1;
+    const int fwarp = swarp - (AUX - 1);
     const QwPoint pt = qw_point(prm, blockIdx.x);
     const bool active = t < nact;
     const bool full = !RAGGED || t < prm.nfull;        // R sites; else R-1 and a ghost slot
@@ -492,11 +498,11 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
 #pragma unroll
         for (int r = 0; r < R; ++r) { a += s.yr[r]; b += s.yi[r]; }
         Sy = hblock_sum(make_double2(a, b), sh.red);
+        if (warp == fwarp && nchunks > 1)
+            horner_fill_complete(sh.tab[1], pt, QW_CHUNK, QW_CNT(1), prm.schedule,
+                                 prm.gamma_on, nfull, lane);
         if (warp == swarp) {
             horner_fill_complete(sh.tab[0], pt, 0, QW_CNT(0), prm.schedule, prm.gamma_on, nfull, lane);
-            if (nchunks > 1)
-                horner_fill_complete(sh.tab[1], pt, QW_CHUNK, QW_CNT(1), prm.schedule,
-                                     prm.gamma_on, nfull, lane);
             __syncwarp();
             const int cnt0 = QW_CNT(0);
             for (int sidx = 0; sidx < cnt0; ++sidx)
@@ -505,12 +511,12 @@ __global__ void __launch_bounds__(MAXNT + 32, MINB) rk4_complete_horner(const Qw
     }
     for (int64_t c = 0; c < nchunks; ++c) {
         __syncthreads();
-        if (warp == swarp) {
+        if (warp >= fwarp) {
             // two chunks ahead: coefficients; one chunk ahead: the (y_w, S) subsystem
-            if (c + 2 < nchunks)
+            if (warp == fwarp && c + 2 < nchunks)
                 horner_fill_complete(sh.tab[(c + 2) % 3], pt, (c + 2) * QW_CHUNK, QW_CNT(c + 2),
                                      prm.schedule, prm.gamma_on, nfull, lane);
-            if (c + 1 < nchunks) {
+            if (warp == swarp && c + 1 < nchunks) {
                 const CHStep *tn = sh.tab[(c + 1) % 3];
                 const int cn = QW_CNT(c + 1), nxt = (int)((c + 1) & 1);
                 for (int sidx = 0; sidx < cn; ++sidx)
@@ -621,15 +627,19 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
     return ragged ? hlaunch(KERNEL<__VA_ARGS__, true>, prm, bthreads, smem, st, plan)      \
                   : hlaunch(KERNEL<__VA_ARGS__, false>, prm, bthreads, smem, st, plan)
     if (!cyc) {
-        const int bthreads = threads + 32;        // + the scalar warp
-        if (R == 16) {
-            if (threads <= 64) { QW_HL(rk4_complete_horner, 16, 64, 4); }
-            if (threads <= 128) { QW_HL(rk4_complete_horner, 16, 128, 2); }
-            QW_HL(rk4_complete_horner, 16, 256, 1);
+        if (R == 16 && threads > 128 && !(prm.flags & QW_FLAG_OCC4)) {
+            const int bthreads = threads + 64;    // + the table warp and the scalar warp
+            QW_HL(rk4_complete_horner, 16, 256, 1, 2);
         }
-        if (threads <= 128) { QW_HL(rk4_complete_horner, 8, 128, 3); }
-        if (threads <= 256) { QW_HL(rk4_complete_horner, 8, 256, 1); }
-        QW_HL(rk4_complete_horner, 8, 512, 1);
+        const int bthreads = threads + 32;        // + the scalar warp (both duties)
+        if (R == 16) {
+            if (threads <= 64) { QW_HL(rk4_complete_horner, 16, 64, 4, 1); }
+            if (threads <= 128) { QW_HL(rk4_complete_horner, 16, 128, 2, 1); }
+            QW_HL(rk4_complete_horner, 16, 256, 1, 1);        // QW_FLAG_OCC4: A/B only
+        }
+        if (threads <= 128) { QW_HL(rk4_complete_horner, 8, 128, 3, 1); }
+        if (threads <= 256) { QW_HL(rk4_complete_horner, 8, 256, 1, 1); }
+        QW_HL(rk4_complete_horner, 8, 512, 1, 1);
     }
     const int bthreads = threads;
     if (mirror) {                                  // R = 17, up to 255 registers

@@ -26,7 +26,8 @@ VARIANTS = {
     "c4": [("packed nested (default)", 0), ("packed stage form", 2048), ("horner R=8 one warp per point", 512), ("v2 occ3", 512 | 2048), ("v2 occ4", 128), ("v1 legacy occ3", 32),
            ("v1 legacy occ4", 32 | 128)],
     "c2": [("packed (default)", 0), ("packed 16 warps/SM at 128 regs", 128), ("packed R<=8", 256), ("v2 R=2 CTA-per-point", 512)],
-    "c3": [("complete horner R=16 (default)", 0), ("complete horner R=8", 256),
+    "c3": [("complete horner R=16 (default)", 0), ("complete horner R=16, one aux warp", 128),
+           ("complete horner R=8", 256),
            ("complete v2 R=16", 2048), ("complete barrier-free R=16", 1024),
            ("complete v2 R=8", 2048 | 256), ("complete v1 R=8 legacy", 256 | 32),
            ("complete R=8 exact-sum", 256 | 4)],
