@@ -315,21 +315,60 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 // the two obeys e+ = Phi0 e with the step polynomial at the top eigenvalue of L, |Phi0| <= 1
 // inside the stability region of RK4, so rounding noise does not grow -- while a correction
 // that arrives a chunk late has rotated by 32 steps' worth of phase and DOES grow (measured).
-struct CHStep {
+struct CHStep {                          // read by the workers
     double rho[4];
-    double coef[4][8];       // lane 2m + c: component c of sigma_{4-m} over (re, im)(y_w, Ly_w)
-    double pad;
+};
+
+// The marked-vertex subsystem is LINEAR in x = (y_w, S(y)): everything the scalar warp owes the
+// workers for a step, and the state after the step, is out_o = q[o][0] y_w + q[o][1] S(y).
+//   o = 0..3: (S(y), S(z4), S(z3), S(z2)) / N  -- the level means the workers subtract
+//   o = 4..7: sigma_4 .. sigma_1                -- the owner thread's corrections
+//   o = 8, 9: y_w and S(y) after the step
+// The maps are tabulated with the coefficients (lane-parallel over the steps of a chunk), so the
+// only sequential work per step is one 20 x 4 real matrix-vector product spread over 20 lanes:
+// 5 FP64 warp-instructions and one shuffle stage (the level-by-level form it replaces: 36
+// instructions in a dependent chain 16 deep, which under the workers' FP64 load took as long
+// as the workers' own step and made them wait at the chunk barrier).
+struct CSMap {
+    double2 q[10][2];
 };
 
 struct CFShared {
-    CHStep tab[3][QW_CHUNK];             // coefficients of chunk c in tab[c % 3]
+    CHStep tab[3][QW_CHUNK];             // chunk c in tab[c % 3]
+    CSMap map[2][QW_CHUNK];              // chunk c in map[c & 1]
     double2 sums[2][QW_CHUNK][4];        // chunk c in [c & 1]: (S(y), S(z4), S(z3), S(z2)) / N per step
     double2 sig[2][QW_CHUNK][4];         // sigma_4 .. sigma_1 per step (owner thread)
     double red[2 * 32];
 };
 
-// executed by ONE warp: coefficient sets of `cnt` steps starting at step n0
-__device__ __forceinline__ void horner_fill_complete(CHStep *tab, const QwPoint &pt,
+// one step of the subsystem in complex arithmetic (the operations of the vector code on the
+// marked vertex): the ten outputs listed at CSMap for the input (yw, Sy)
+__device__ __forceinline__ void cmap_eval(const double *rho, const double2 *c0, const double2 *c1,
+                                          const double n, const double invn, const double2 yw,
+                                          const double2 Sy, double2 *out)
+{
+    const double2 m1 = make_double2(fma(n, yw.x, -Sy.x), fma(n, yw.y, -Sy.y));      // (Ly)_w
+    double2 g[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) g[m] = cmul2_acc(c1[m], m1, cmul2(c0[m], yw));
+    out[0] = make_double2(Sy.x * invn, Sy.y * invn);
+    double2 v = m1;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {                       // levels 4, 3, 2
+        const double2 S = make_double2(Sy.x + g[m].x, Sy.y + g[m].y);
+        out[1 + m] = make_double2(S.x * invn, S.y * invn);
+        const double2 z = make_double2(fma(rho[3 - m], v.y, yw.x) + g[m].x,
+                                       fma(-rho[3 - m], v.x, yw.y) + g[m].y);
+        v = make_double2(fma(n, z.x, -S.x), fma(n, z.y, -S.y));
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) out[4 + m] = g[m];
+    out[8] = make_double2(fma(rho[0], v.y, yw.x) + g[3].x, fma(-rho[0], v.x, yw.y) + g[3].y);
+    out[9] = make_double2(Sy.x + g[3].x, Sy.y + g[3].y);
+}
+
+// executed by ONE warp: step-size ratios and subsystem maps of `cnt` steps starting at step n0
+__device__ __forceinline__ void horner_fill_complete(CHStep *tab, CSMap *map, const QwPoint &pt,
                                                      const int64_t n0, const int cnt,
                                                      const int schedule, const int gamma_on,
                                                      const double n, const int lane)
@@ -349,56 +388,40 @@ __device__ __forceinline__ void horner_fill_complete(CHStep *tab, const QwPoint 
         CHStep &o = tab[i];
 #pragma unroll
         for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
-        const double2 zero = make_double2(0.0, 0.0);
+        const double2 zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
         const double2 c0[4] = {c[0], c[1], c[3], c[6]};       // coefficient of y_w in sigma_4..1
         const double2 c1[4] = {zero, c[2], c[4], c[7]};       // coefficient of Ly_w
+        double2 qa[10], qb[10];
+        const double invn = 1.0 / n;
+        cmap_eval(hc.rho, c0, c1, n, invn, one, zero, qa);
+        cmap_eval(hc.rho, c0, c1, n, invn, zero, one, qb);
+        CSMap &mp = map[i];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            o.coef[0][2 * m] = c0[m].x;     o.coef[1][2 * m] = -c0[m].y;
-            o.coef[2][2 * m] = c1[m].x;     o.coef[3][2 * m] = -c1[m].y;
-            o.coef[0][2 * m + 1] = c0[m].y; o.coef[1][2 * m + 1] = c0[m].x;
-            o.coef[2][2 * m + 1] = c1[m].y; o.coef[3][2 * m + 1] = c1[m].x;
-        }
+        for (int k = 0; k < 10; ++k) { mp.q[k][0] = qa[k]; mp.q[k][1] = qb[k]; }
     }
 }
 
-// One step of the marked-vertex subsystem.  Every lane of the warp holds the same (yw, Sy);
-// the four corrections are one dot product of length 4 per lane (lane 2m + c: component c of
-// sigma_{4-m}).  Leaves the level sums and corrections of the step in shared memory.
-__device__ __forceinline__ void scalar_step(const CHStep &hs, double2 &yw, double2 &Sy,
-                                            const double nd, const double invn, double2 *sums4,
-                                            double2 *sig4, const int lane)
+// `cnt` steps of the subsystem.  x0..x3 = (re, im) y_w, (re, im) S(y), the same in every lane.
+// Lane l < 20 evaluates component l & 1 of output l >> 1; lanes 0..15 store theirs (the level
+// means and the corrections of the step), lanes 16..19 hold the next state.
+__device__ __forceinline__ void scalar_steps(const CSMap *map, const int cnt, double &x0,
+                                             double &x1, double &x2, double &x3,
+                                             double2 (*sums)[4], double2 (*sig)[4], const int lane)
 {
     const unsigned full = 0xffffffffu;
-    const double2 m1 = make_double2(fma(nd, yw.x, -Sy.x), fma(nd, yw.y, -Sy.y));    // (Ly)_w
-    const int l8 = lane & 7;
-    double sgl = hs.coef[0][l8] * yw.x;
-    sgl = fma(hs.coef[1][l8], yw.y, sgl);
-    sgl = fma(hs.coef[2][l8], m1.x, sgl);
-    sgl = fma(hs.coef[3][l8], m1.y, sgl);
-    const double2 g4 = make_double2(__shfl_sync(full, sgl, 0), __shfl_sync(full, sgl, 1));
-    const double2 g3 = make_double2(__shfl_sync(full, sgl, 2), __shfl_sync(full, sgl, 3));
-    const double2 g2 = make_double2(__shfl_sync(full, sgl, 4), __shfl_sync(full, sgl, 5));
-    const double2 g1 = make_double2(__shfl_sync(full, sgl, 6), __shfl_sync(full, sgl, 7));
-    const double2 S4 = make_double2(Sy.x + g4.x, Sy.y + g4.y);
-    const double2 S3 = make_double2(Sy.x + g3.x, Sy.y + g3.y);
-    const double2 S2 = make_double2(Sy.x + g2.x, Sy.y + g2.y);
-    if (lane == 0) {       // the workers use the level MEANS S / N (see clevel)
-        sums4[0] = make_double2(Sy.x * invn, Sy.y * invn);
-        sums4[1] = make_double2(S4.x * invn, S4.y * invn);
-        sums4[2] = make_double2(S3.x * invn, S3.y * invn);
-        sums4[3] = make_double2(S2.x * invn, S2.y * invn);
-        sig4[0] = g4; sig4[1] = g3; sig4[2] = g2; sig4[3] = g1;
+    const int o = lane < 20 ? (lane >> 1) : 9, c = lane & 1;
+#pragma unroll 4
+    for (int sidx = 0; sidx < cnt; ++sidx) {
+        const double2 P = map[sidx].q[o][0], Q = map[sidx].q[o][1];
+        // re: P.x x0 - P.y x1 + Q.x x2 - Q.y x3;  im: P.y x0 + P.x x1 + Q.y x2 + Q.x x3
+        const double a0 = c ? P.y : P.x, a1 = c ? P.x : -P.y;
+        const double a2 = c ? Q.y : Q.x, a3 = c ? Q.x : -Q.y;
+        const double r = fma(a0, x0, a1 * x1) + fma(a2, x2, a3 * x3);
+        if (lane < 8) reinterpret_cast<double *>(sums[sidx])[lane] = r;
+        else if (lane < 16) reinterpret_cast<double *>(sig[sidx])[lane - 8] = r;
+        x0 = __shfl_sync(full, r, 16); x1 = __shfl_sync(full, r, 17);
+        x2 = __shfl_sync(full, r, 18); x3 = __shfl_sync(full, r, 19);
     }
-    // the marked vertex through the four levels (same operations as the vector code)
-    double2 z = make_double2(fma(hs.rho[3], m1.y, yw.x) + g4.x, fma(-hs.rho[3], m1.x, yw.y) + g4.y);
-    double2 v = make_double2(fma(nd, z.x, -S4.x), fma(nd, z.y, -S4.y));
-    z = make_double2(fma(hs.rho[2], v.y, yw.x) + g3.x, fma(-hs.rho[2], v.x, yw.y) + g3.y);
-    v = make_double2(fma(nd, z.x, -S3.x), fma(nd, z.y, -S3.y));
-    z = make_double2(fma(hs.rho[1], v.y, yw.x) + g2.x, fma(-hs.rho[1], v.x, yw.y) + g2.y);
-    v = make_double2(fma(nd, z.x, -S2.x), fma(nd, z.y, -S2.y));
-    yw = make_double2(fma(hs.rho[0], v.y, yw.x) + g1.x, fma(-hs.rho[0], v.x, yw.y) + g1.y);
-    Sy = make_double2(Sy.x + g1.x, Sy.y + g1.y);
 }
 
 // one level on all R sites of a thread: out = y - i rho (N x - S), evaluated as
@@ -461,24 +484,25 @@ __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const
     }
 }
 
-// blockDim = worker threads (n / R rounded up to warps) + 32 AUX: the last warp is the scalar
-// warp.  AUX = 2: the warp before it refills the coefficient tables instead (the "table warp").
+// blockDim = worker threads (n / R rounded up to warps) + 32 AUX.  AUX = 1: the last warp is the
+// scalar warp and refills the tables too.  AUX = 2: the last warp only refills the tables (the
+// "table warp"), the one before it is the scalar warp.
 // Warps go to the four SM sub-partitions by slot number and the FP64 pipe is per sub-partition:
-// with eight worker warps and both duties in warp 8, sub-partition 0 issued 587 FP64
-// instructions per step against 520 on the others and everybody waited for it at the chunk
-// barrier (18 % of the warp samples); table warp 8 / scalar warp 9: 543 / 564 / 520 / 520.
+// with eight worker warps and both duties in warp 8 (level-by-level scalar step), sub-partition
+// 0 issued 587 FP64 instructions per step against 520 on the others and everybody waited for
+// it at the chunk barrier (18 % of the warp samples).
 template <int R, int MAXNT, int MINB, int AUX, bool RAGGED>
 __global__ void __launch_bounds__(MAXNT + 32 * AUX, MINB) rk4_complete_horner(const QwParams prm)
 {
     __shared__ CFShared sh;
     const int t = threadIdx.x, nact = prm.nact;
-    const int lane = t & 31, warp = t >> 5, swarp = (blockDim.x >> 5) - 1;
-    const int fwarp = swarp - (AUX - 1);
+    const int lane = t & 31, warp = t >> 5, fwarp = (blockDim.x >> 5) - 1;
+    const int swarp = fwarp - (AUX - 1);
     const QwPoint pt = qw_point(prm, blockIdx.x);
     const bool active = t < nact;
     const bool full = !RAGGED || t < prm.nfull;        // R sites; else R-1 and a ghost slot
     const double nfull = (double)prm.n;
-    const double nd = active ? nfull : 0.0, invn = 1.0 / nfull;
+    const double nd = active ? nfull : 0.0;
 
     HState<R> s;
     const double amp = active ? 1.0 / sqrt(nfull) : 0.0;
@@ -491,37 +515,38 @@ __global__ void __launch_bounds__(MAXNT + 32 * AUX, MINB) rk4_complete_horner(co
     const int64_t nchunks = (pt.steps + QW_CHUNK - 1) / QW_CHUNK;
 #define QW_CNT(C) ((int)((pt.steps - (C) * QW_CHUNK) < QW_CHUNK ? (pt.steps - (C) * QW_CHUNK) : QW_CHUNK))
 
-    double2 yw = make_double2(1.0 / sqrt(nfull), 0.0), Sy = make_double2(0.0, 0.0);
+    double x0 = 1.0 / sqrt(nfull), x1 = 0.0, x2 = 0.0, x3 = 0.0;    // y_w, S(y) (scalar warp)
     if (nchunks > 0) {
         // prologue: S(y) by direct summation; tables of chunks 0 and 1, scalars of chunk 0
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) { a += s.yr[r]; b += s.yi[r]; }
-        Sy = hblock_sum(make_double2(a, b), sh.red);
-        if (warp == fwarp && nchunks > 1)
-            horner_fill_complete(sh.tab[1], pt, QW_CHUNK, QW_CNT(1), prm.schedule,
+        const double2 Sy = hblock_sum(make_double2(a, b), sh.red);
+        x2 = Sy.x; x3 = Sy.y;
+        if (AUX == 2 && warp == fwarp && nchunks > 1)
+            horner_fill_complete(sh.tab[1], sh.map[1], pt, QW_CHUNK, QW_CNT(1), prm.schedule,
                                  prm.gamma_on, nfull, lane);
         if (warp == swarp) {
-            horner_fill_complete(sh.tab[0], pt, 0, QW_CNT(0), prm.schedule, prm.gamma_on, nfull, lane);
+            horner_fill_complete(sh.tab[0], sh.map[0], pt, 0, QW_CNT(0), prm.schedule,
+                                 prm.gamma_on, nfull, lane);
+            if (AUX == 1 && nchunks > 1)
+                horner_fill_complete(sh.tab[1], sh.map[1], pt, QW_CHUNK, QW_CNT(1), prm.schedule,
+                                     prm.gamma_on, nfull, lane);
             __syncwarp();
-            const int cnt0 = QW_CNT(0);
-            for (int sidx = 0; sidx < cnt0; ++sidx)
-                scalar_step(sh.tab[0][sidx], yw, Sy, nfull, invn, sh.sums[0][sidx], sh.sig[0][sidx], lane);
+            scalar_steps(sh.map[0], QW_CNT(0), x0, x1, x2, x3, sh.sums[0], sh.sig[0], lane);
         }
     }
     for (int64_t c = 0; c < nchunks; ++c) {
         __syncthreads();
-        if (warp >= fwarp) {
-            // two chunks ahead: coefficients; one chunk ahead: the (y_w, S) subsystem
+        if (warp >= swarp) {
+            // two chunks ahead: tables; one chunk ahead: the (y_w, S) subsystem
             if (warp == fwarp && c + 2 < nchunks)
-                horner_fill_complete(sh.tab[(c + 2) % 3], pt, (c + 2) * QW_CHUNK, QW_CNT(c + 2),
-                                     prm.schedule, prm.gamma_on, nfull, lane);
+                horner_fill_complete(sh.tab[(c + 2) % 3], sh.map[c & 1], pt, (c + 2) * QW_CHUNK,
+                                     QW_CNT(c + 2), prm.schedule, prm.gamma_on, nfull, lane);
             if (warp == swarp && c + 1 < nchunks) {
-                const CHStep *tn = sh.tab[(c + 1) % 3];
-                const int cn = QW_CNT(c + 1), nxt = (int)((c + 1) & 1);
-                for (int sidx = 0; sidx < cn; ++sidx)
-                    scalar_step(tn[sidx], yw, Sy, nfull, invn, sh.sums[nxt][sidx], sh.sig[nxt][sidx],
-                                lane);
+                const int nxt = (int)((c + 1) & 1);
+                scalar_steps(sh.map[nxt], QW_CNT(c + 1), x0, x1, x2, x3, sh.sums[nxt],
+                             sh.sig[nxt], lane);
             }
         } else if (warp == 0) {
             complete_chunk<R, true, RAGGED>(s, sh, c, QW_CNT(c), nd, msk, full);
@@ -628,7 +653,7 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
                   : hlaunch(KERNEL<__VA_ARGS__, false>, prm, bthreads, smem, st, plan)
     if (!cyc) {
         if (R == 16 && threads > 128 && !(prm.flags & QW_FLAG_OCC4)) {
-            const int bthreads = threads + 64;    // + the table warp and the scalar warp
+            const int bthreads = threads + 64;    // + the scalar warp and the table warp
             QW_HL(rk4_complete_horner, 16, 256, 1, 2);
         }
         const int bthreads = threads + 32;        // + the scalar warp (both duties)
