@@ -268,7 +268,12 @@ def test_plan_reports_native_kernels(qw):
     pl = qw.plan(qw.Problem(n=1024, topology="circular", n_steps=1, flags=256))
     assert pl["sites_per_thread"] == 8 and pl["threads_per_block"] == 128
     pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1))
-    assert pl["path"] == "horner-complete" and pl["threads_per_block"] == 288   # + scalar warp
+    assert pl["path"] == "horner-complete"
+    assert pl["threads_per_block"] == 320            # 8 worker warps + scalar warp + table warp
+    pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1, flags=128))
+    assert pl["threads_per_block"] == 288            # A/B: one auxiliary warp with both duties
+    pl = qw.plan(qw.Problem(n=2048, topology="complete", n_steps=1))
+    assert pl["threads_per_block"] == 160            # 4 worker warps + one auxiliary warp
     pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1, flags=2048))
     assert pl["path"] == "resident-complete" and pl["threads_per_block"] == 256
     before = qw.launch_count()
