@@ -85,8 +85,9 @@ enum {
                                     __syncthreads per stage (measured slower; A/B only) */
     QW_FLAG_OCC4 = 128,          /* resident kernels, <= 128 threads: 4 blocks/SM at 128
                                     registers instead of the default 3 at 168 (A/B only);
-                                    complete graph above 2048 sites: one auxiliary warp with
-                                    both duties instead of scalar warp + table warp (A/B) */
+                                    complete graph: one auxiliary warp with both duties
+                                    instead of scalar warp + table warp (above 2048 sites) or
+                                    of duties folded into the worker warps (up to 2048) (A/B) */
     QW_FLAG_R8 = 256,            /* resident kernels: at most 8 sites per thread (default: 16
                                     where n % 16 == 0 and n/16 >= 32; A/B only) */
     QW_FLAG_NO_PACK = 512,       /* do not use the warp-packed kernel for small rings (A/B) */

@@ -333,13 +333,15 @@ struct CSMap {
     double2 q[10][2];
 };
 
-struct CFShared {
+template <int MB>                        // MB = 1: one warp does both duties, scalar steps first
+struct CFSharedT {
     CHStep tab[3][QW_CHUNK];             // chunk c in tab[c % 3]
-    CSMap map[2][QW_CHUNK];              // chunk c in map[c & 1]
+    CSMap map[MB][QW_CHUNK];             // chunk c in map[c & (MB - 1)]
     double2 sums[2][QW_CHUNK][4];        // chunk c in [c & 1]: (S(y), S(z4), S(z3), S(z2)) / N per step
     double2 sig[2][QW_CHUNK][4];         // sigma_4 .. sigma_1 per step (owner thread)
     double red[2 * 32];
 };
+using CFShared = CFSharedT<2>;
 
 // one step of the subsystem in complex arithmetic (the operations of the vector code on the
 // marked vertex): the ten outputs listed at CSMap for the input (yw, Sy)
@@ -445,8 +447,8 @@ __device__ __forceinline__ void clevel(HState<R> &s, const double rn, const doub
 }
 
 // Vector work of chunk c (cnt steps).  No barrier inside.
-template <int R, bool OWN, bool RAGGED>
-__device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const int64_t c,
+template <int R, bool OWN, bool RAGGED, typename SH>
+__device__ __forceinline__ void complete_chunk(HState<R> &s, SH &sh, const int64_t c,
                                                const int cnt, const double nd, const double msk,
                                                const bool full)
 {
@@ -481,6 +483,35 @@ __device__ __forceinline__ void complete_chunk(HState<R> &s, CFShared &sh, const
         QW_CH_LEVEL(2)
         QW_CH_LEVEL(1)
 #undef QW_CH_LEVEL
+    }
+}
+
+// p, norm and psi(T) of a point from the workers' registers
+template <int R, typename SH>
+__device__ __forceinline__ void complete_epilogue(const HState<R> &s, SH &sh,
+                                                  const QwParams &prm, const QwPoint &pt,
+                                                  const int t, const bool active, const bool full)
+{
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    const double pw = (t == 0) ? fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]) : 0.0;
+    __syncthreads();
+    const double2 tot = hblock_sum(make_double2(nrm, pw), sh.red);
+    if (t == 0) {
+        prm.p[pt.q] = tot.y / tot.x;
+        if (prm.norm) prm.norm[pt.q] = tot.x;
+    }
+    if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + off(t) + r
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
+        const int64_t off_t = (int64_t)t * (R - 1) + (t < prm.nfull ? t : prm.nfull);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r == R - 1 && !full) continue;                    // ghost
+            int64_t j = off_t + r + prm.target;
+            if (j >= prm.n) j -= prm.n;
+            out[j] = make_double2(s.yr[r], s.yi[r]);
+        }
     }
 }
 
@@ -556,27 +587,96 @@ __global__ void __launch_bounds__(MAXNT + 32 * AUX, MINB) rk4_complete_horner(co
     }
 #undef QW_CNT
 
-    double nrm = 0.0;
+    complete_epilogue<R>(s, sh, prm, pt, t, active, full);
+}
+
+// Blocks of at most four worker warps: no auxiliary warp.  168 registers allow three warps per
+// SM sub-partition, and a dedicated scalar warp would hold a third (N <= 1024: up to a half) of
+// them while doing 5 FP64 instructions per step.  Here the last worker warp advances the
+// subsystem one chunk ahead before its own chunk, and another worker warp refills the tables
+// (both out of line, so the register allocation of the vector loop is not affected; the
+// worker's state is parked on the stack for the duration of the call, once per 32 steps).
+__device__ __noinline__ void fill_complete_call(CHStep *tab, CSMap *map, const QwPoint *pt,
+                                                const int64_t n0, const int cnt, const int schedule,
+                                                const int gamma_on, const double n, const int lane)
+{
+    horner_fill_complete(tab, map, *pt, n0, cnt, schedule, gamma_on, n, lane);
+}
+
+__device__ __noinline__ void scalar_steps_call(const CSMap *map, const int cnt, double *x,
+                                               double2 (*sums)[4], double2 (*sig)[4], const int lane)
+{
+    double x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3];
+    scalar_steps(map, cnt, x0, x1, x2, x3, sums, sig, lane);
+    x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3;
+}
+
+template <int R, int MAXNT, int MINB, int MB, bool RAGGED>
+__global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_folded(const QwParams prm)
+{
+    __shared__ CFSharedT<MB> sh;
+    const int t = threadIdx.x, nact = prm.nact;
+    const int lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    const int swarp = nw - 1, fwarp = nw >= 4 ? 1 : 0;      // warp 0 carries the marked vertex
+    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const bool active = t < nact;
+    const bool full = !RAGGED || t < prm.nfull;        // R sites; else R-1 and a ghost slot
+    const double nfull = (double)prm.n;
+    const double nd = active ? nfull : 0.0;
+
+    HState<R> s;
+    const double amp = active ? 1.0 / sqrt(nfull) : 0.0;
 #pragma unroll
-    for (int r = 0; r < R; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
-    const double pw = (t == 0) ? fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]) : 0.0;
-    __syncthreads();
-    const double2 tot = hblock_sum(make_double2(nrm, pw), sh.red);
-    if (t == 0) {
-        prm.p[pt.q] = tot.y / tot.x;
-        if (prm.norm) prm.norm[pt.q] = tot.x;
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = (r == R - 1 && !full) ? 0.0 : amp; s.yi[r] = 0.0;
+        s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
-    if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + off(t) + r
-        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
-        const int64_t off_t = (int64_t)t * (R - 1) + (t < prm.nfull ? t : prm.nfull);
+    const double msk = (t == 0) ? 1.0 : 0.0;
+    const int64_t nchunks = (pt.steps + QW_CHUNK - 1) / QW_CHUNK;
+#define QW_CNT(C) ((int)((pt.steps - (C) * QW_CHUNK) < QW_CHUNK ? (pt.steps - (C) * QW_CHUNK) : QW_CHUNK))
+
+    double x[4] = {1.0 / sqrt(nfull), 0.0, 0.0, 0.0};       // y_w, S(y) (warp `swarp`)
+    if (nchunks > 0) {
+        double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r == R - 1 && !full) continue;                    // ghost
-            int64_t j = off_t + r + prm.target;
-            if (j >= prm.n) j -= prm.n;
-            out[j] = make_double2(s.yr[r], s.yi[r]);
+        for (int r = 0; r < R; ++r) { a += s.yr[r]; b += s.yi[r]; }
+        const double2 Sy = hblock_sum(make_double2(a, b), sh.red);
+        x[2] = Sy.x; x[3] = Sy.y;
+        if (warp == fwarp && fwarp != swarp && nchunks > 1)
+            fill_complete_call(sh.tab[1], sh.map[MB - 1], &pt, QW_CHUNK, QW_CNT(1), prm.schedule,
+                               prm.gamma_on, nfull, lane);
+        if (warp == swarp) {
+            fill_complete_call(sh.tab[0], sh.map[0], &pt, 0, QW_CNT(0), prm.schedule,
+                               prm.gamma_on, nfull, lane);
+            __syncwarp();
+            scalar_steps_call(sh.map[0], QW_CNT(0), x, sh.sums[0], sh.sig[0], lane);
+            if (fwarp == swarp && nchunks > 1) {
+                __syncwarp();
+                fill_complete_call(sh.tab[1], sh.map[MB - 1], &pt, QW_CHUNK, QW_CNT(1),
+                                   prm.schedule, prm.gamma_on, nfull, lane);
+            }
         }
     }
+    for (int64_t c = 0; c < nchunks; ++c) {
+        __syncthreads();
+        // one chunk ahead: the (y_w, S) subsystem; two chunks ahead: tables
+        if (warp == swarp && c + 1 < nchunks) {
+            const int nxt = (int)((c + 1) & 1);
+            scalar_steps_call(sh.map[nxt & (MB - 1)], QW_CNT(c + 1), x, sh.sums[nxt], sh.sig[nxt],
+                              lane);
+            if (MB == 1) __syncwarp();           // the refill below reuses the only map buffer
+        }
+        if (warp == fwarp && c + 2 < nchunks)
+            fill_complete_call(sh.tab[(c + 2) % 3], sh.map[c & (MB - 1)], &pt, (c + 2) * QW_CHUNK,
+                               QW_CNT(c + 2), prm.schedule, prm.gamma_on, nfull, lane);
+        if (warp == 0) {
+            complete_chunk<R, true, RAGGED>(s, sh, c, QW_CNT(c), nd, msk, full);
+        } else {
+            complete_chunk<R, false, RAGGED>(s, sh, c, QW_CNT(c), nd, msk, full);
+        }
+    }
+#undef QW_CNT
+    complete_epilogue<R>(s, sh, prm, pt, t, active, full);
 }
 
 template <typename K>
@@ -655,6 +755,12 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
         if (R == 16 && threads > 128 && !(prm.flags & QW_FLAG_OCC4)) {
             const int bthreads = threads + 64;    // + the scalar warp and the table warp
             QW_HL(rk4_complete_horner, 16, 256, 1, 2);
+        }
+        if (R == 16 && threads <= 128 && !(prm.flags & QW_FLAG_OCC4)) {
+            const int bthreads = threads;         // duties folded into the worker warps
+            if (threads <= 32) { QW_HL(rk4_complete_folded, 16, 32, 12, 1); }
+            if (threads <= 64) { QW_HL(rk4_complete_folded, 16, 64, 6, 2); }
+            QW_HL(rk4_complete_folded, 16, 128, 3, 2);
         }
         const int bthreads = threads + 32;        // + the scalar warp (both duties)
         if (R == 16) {

@@ -81,9 +81,12 @@ def test_heatmap_matches_the_stage_form_kernel_and_keeps_the_argmax(qw):
 @pytest.mark.parametrize("n,flags", [(256, 0), (264, 0), (512, 0), (520, 0), (1024, 0), (1024, R8),
                                      (2048, 0), (2048, R8), (3072, 0), (4096, 0), (4096, R8),
                                      (4088, 0), (257, 0), (511, 0), (1001, 0), (1023, R8),
-                                     (2049, 0), (4095, 0), (4096, 128), (3000, 128), (3000, 0)])
+                                     (2049, 0), (4095, 0), (4096, 128), (3000, 128), (3000, 0),
+                                     (512, 128), (1001, 128), (1024, 128), (2048, 128), (1536, 0),
+                                     (1500, 0), (600, 0)])
 def test_complete_all_schedules_vs_oracle(qw, n, flags):
-    # flags 128 above 2048 sites: one auxiliary warp instead of scalar warp + table warp
+    # flags 128: one auxiliary warp with both duties (default: scalar warp + table warp above
+    # 2048 sites, duties folded into the worker warps up to 2048)
     pl = qw.plan(qw.Problem(n=n, topology="complete", n_steps=1, flags=flags))
     assert pl["path"] == "horner-complete", pl
     rng = np.random.default_rng(7 * n + flags)

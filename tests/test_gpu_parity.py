@@ -273,7 +273,11 @@ def test_plan_reports_native_kernels(qw):
     pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1, flags=128))
     assert pl["threads_per_block"] == 288            # A/B: one auxiliary warp with both duties
     pl = qw.plan(qw.Problem(n=2048, topology="complete", n_steps=1))
-    assert pl["threads_per_block"] == 160            # 4 worker warps + one auxiliary warp
+    assert pl["threads_per_block"] == 128            # 4 worker warps, duties folded into them
+    pl = qw.plan(qw.Problem(n=2048, topology="complete", n_steps=1, flags=128))
+    assert pl["threads_per_block"] == 160            # A/B: 4 worker warps + one auxiliary warp
+    pl = qw.plan(qw.Problem(n=512, topology="complete", n_steps=1))
+    assert pl["threads_per_block"] == 32 and pl["blocks_per_sm"] >= 9
     pl = qw.plan(qw.Problem(n=4096, topology="complete", n_steps=1, flags=2048))
     assert pl["path"] == "resident-complete" and pl["threads_per_block"] == 256
     before = qw.launch_count()
