@@ -333,6 +333,17 @@ def run_b200(args):
 
     if rank == 0:
         kernel_s = ms_per_step * 1e-3                 # one launch per step and per GPU
+        # DRAM bytes of one launch from the committed ncu --set full captures (not per-launch of
+        # this run: the resident kernels touch DRAM only for T, gamma, p, norm and their image)
+        traffic = {
+            "horner-cycle": (626688, "dram__bytes_read+write of an 8192-point launch (ncu --set "
+                             "full, profiles/r1_cycle_horner_r16_ncu_full.md): the kernel is "
+                             "register-resident, DRAM sees only T, gamma, p, norm"),
+            "horner-complete": (90112, "dram__bytes_read+write of a 2048-point launch (ncu --set "
+                                "full, profiles/r1_complete_horner_r16_final_ncu_full.md): the "
+                                "kernel is register-resident, DRAM sees only T, gamma, p, norm"),
+        }.get(plan["path"], (None, "no ncu --set full capture of this kernel at this workload; "
+                             "register-resident, DRAM sees only T, gamma, p, norm"))
         achieved = FLOPS_PER_SITE_UPDATE * pts_local * w["site_updates_per_point"] / kernel_s / 1e12
         ex = executed_fp64_per_site_update(plan)
         lane_rate = plan["sm_count"] * 64 * (clocks["sm_mhz"] or 1965.0) * 1e6    # FP64 lanes/s
@@ -350,11 +361,8 @@ def run_b200(args):
                        "kernel": plan, "results_sane_and_e2e_equals_device": ok},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": 626688,
-                         "traffic_note": "dram__bytes_read+write of an 8192-point launch (ncu "
-                                         "--set full, profiles/r1_cycle_horner_r16_ncu_full"
-                                         ".md): the kernel is register-resident, DRAM sees "
-                                         "only T, gamma, p, norm",
+                         "traffic": traffic[0],
+                         "traffic_note": traffic[1],
                          "peak_source": "qw_fp64_peak_probe: dependent-free DFMA stream "
                                         "measured in this process, best of 8/16/24 warps per "
                                         "SM (MEASURED_PEAKS.json has no FP64 entry)",
