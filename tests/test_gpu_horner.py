@@ -438,3 +438,34 @@ def test_symmetry_reduced_complete_graph_beyond_memory(qw):
         nrm = abs(y[0]) ** 2 + m * abs(y[1]) ** 2
         pref = abs(y[0]) ** 2 / nrm
         assert abs(p[q] - pref) <= 1e-9 * pref and abs(norm[q] - nrm) <= 1e-10
+
+
+@pytest.mark.parametrize("n", [512, 600, 1000, 1024, 2048, 3000, 4096])
+def test_complete_kernels_repeatable_and_variants_agree(qw, n):
+    """The chunk-ahead scheme of the complete-graph kernels (tables two chunks ahead, scalar steps
+    one chunk ahead, one barrier per chunk; folded into the worker warps up to 2048 sites, one
+    map buffer in one-warp blocks) has no ordering left to chance: a full machine of blocks gives
+    bitwise the same heatmap every time, and the one-auxiliary-warp variant (flags 128) agrees to
+    rounding.  235 steps = 7 full chunks and a ragged one."""
+    import torch
+
+    t = torch.linspace(0.5, 40.0, 96, dtype=torch.float64, device="cuda")
+    b = torch.linspace(0.3 / n, 2.2 / n, 32, dtype=torch.float64, device="cuda")
+    out = {}
+    for flags in (0, 128):
+        prob = qw.Problem(n=n, topology="complete", schedule="cerf_3", gamma_on="laplacian",
+                          n_steps=235, flags=flags)
+        assert qw.plan(prob)["path"] == "horner-complete"
+        runs = [qw.rk4_heatmap(prob, t, b) for _ in range(4)]
+        p0, n0 = runs[0][0].cpu().numpy(), runs[0][1].cpu().numpy()
+        for p, nrm in runs[1:]:
+            assert np.array_equal(p.cpu().numpy(), p0) and np.array_equal(nrm.cpu().numpy(), n0)
+        out[flags] = (p0, n0)
+    assert np.abs(out[0][0] - out[128][0]).max() <= 1e-13
+    assert np.abs(out[0][1] - out[128][1]).max() <= 1e-13
+    sel = [(0, 0), (31, 95), (17, 40)]
+    po, no, _ = c_oracle.rk4_batch(n, "complete", "cerf_3", [float(t[j]) for _, j in sel],
+                                   [float(b[i]) for i, _ in sel], n_steps=235,
+                                   gamma_on="laplacian")
+    for k, (i, j) in enumerate(sel):
+        assert abs(out[0][0][i, j] - po[k]) <= P_TOL and abs(out[0][1][i, j] - no[k]) <= P_TOL

@@ -14,8 +14,14 @@ g = np.array([1.1, 0.4, 2.0, 0.0])
 for kw in (dict(n=1024, topology="circular", n_steps=70),                 # cycle, 2 warps
            dict(n=2048, topology="circular", n_steps=40),                 # cycle, 4 warps
            dict(n=264, topology="circular", step_size=0.1),               # idle threads
-           dict(n=1024, topology="complete", n_steps=100),                # scalar warp, 4 chunks
-           dict(n=4096, topology="complete", n_steps=70),
+           dict(n=1024, topology="complete", n_steps=100),                # folded, 2 warps, 4 chunks
+           dict(n=512, topology="complete", n_steps=100),                 # folded, 1 warp, one map buffer
+           dict(n=2048, topology="complete", n_steps=70),                 # folded, 4 warps
+           dict(n=1000, topology="complete", n_steps=70),                 # folded, ragged
+           dict(n=1024, topology="complete", n_steps=100, flags=128),     # one auxiliary warp
+           dict(n=4096, topology="complete", n_steps=70),                 # scalar warp + table warp
+           dict(n=3000, topology="complete", n_steps=70),                 # same, ragged
+           dict(n=4096, topology="complete", n_steps=70, flags=128),
            dict(n=8192, topology="circular", n_steps=9, flags=0),         # stream, nested
            dict(n=8192, topology="circular", n_steps=5, flags=8)):
     scale = 1.0 if kw["topology"] == "circular" else 1.0 / kw["n"]
