@@ -85,6 +85,8 @@ enum {
                                     __syncthreads per stage (measured slower; A/B only) */
     QW_FLAG_OCC4 = 128,          /* resident kernels, <= 128 threads: 4 blocks/SM at 128
                                     registers instead of the default 3 at 168 (A/B only);
+                                    nested cycle kernel, 5 or 6 warps: one block per SM at 200
+                                    registers instead of two at 168 (A/B);
                                     complete graph: one auxiliary warp with both duties
                                     instead of scalar warp + table warp (above 2048 sites) or
                                     of duties folded into the worker warps (up to 2048) (A/B) */

@@ -752,15 +752,16 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
     return ragged ? hlaunch(KERNEL<__VA_ARGS__, true>, prm, bthreads, smem, st, plan)      \
                   : hlaunch(KERNEL<__VA_ARGS__, false>, prm, bthreads, smem, st, plan)
     if (!cyc) {
-        if (R == 16 && threads > 128 && !(prm.flags & QW_FLAG_OCC4)) {
+        if (R == 16 && threads > 192 && !(prm.flags & QW_FLAG_OCC4)) {
             const int bthreads = threads + 64;    // + the scalar warp and the table warp
             QW_HL(rk4_complete_horner, 16, 256, 1, 2);
         }
-        if (R == 16 && threads <= 128 && !(prm.flags & QW_FLAG_OCC4)) {
+        if (R == 16 && threads <= 192 && !(prm.flags & QW_FLAG_OCC4)) {
             const int bthreads = threads;         // duties folded into the worker warps
             if (threads <= 32) { QW_HL(rk4_complete_folded, 16, 32, 12, 1); }
             if (threads <= 64) { QW_HL(rk4_complete_folded, 16, 64, 6, 2); }
-            QW_HL(rk4_complete_folded, 16, 128, 3, 2);
+            if (threads <= 128) { QW_HL(rk4_complete_folded, 16, 128, 3, 2); }
+            QW_HL(rk4_complete_folded, 16, 192, 2, 2);        // 5 or 6 warps: two blocks per SM
         }
         const int bthreads = threads + 32;        // + the scalar warp (both duties)
         if (R == 16) {
@@ -784,6 +785,10 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
         // register file = 16 K per SM sub-partition: 2 / 3 warps there allow 255 / 168 registers
         if (threads <= 64 && (prm.flags & QW_FLAG_OCC4)) { QW_HL(rk4_cycle_horner, 16, 64, 4); }
         if (threads <= 64) { QW_HL(rk4_cycle_horner, 16, 64, 6); }
+        // 5 or 6 warps: two blocks per SM at 168 registers (one block at 200: QW_FLAG_OCC4, A/B)
+        if (threads > 128 && threads <= 192 && !(prm.flags & QW_FLAG_OCC4)) {
+            QW_HL(rk4_cycle_horner, 16, 192, 2);
+        }
         if (threads <= 128) { QW_HL(rk4_cycle_horner, 16, 128, 3); }
         QW_HL(rk4_cycle_horner, 16, 256, 1);
     }
