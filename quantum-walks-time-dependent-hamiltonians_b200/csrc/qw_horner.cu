@@ -304,13 +304,12 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 // other site, and the sum of every level input follows from the marked vertex alone because
 // the column sums of L vanish: S(z_l) = S(y) + sigma_l, S(y+) = S(y) + sigma_1, with sigmas that
 // are linear in (y_w, (Ly)_w) ((L^2 y)_w = N (Ly)_w, (L^3 y)_w = N^2 (Ly)_w).  The pair
-// (y_w, S(y)) is therefore a closed two-variable system.  One extra warp of the block (the
-// "scalar warp", no sites of its own) integrates it a whole 32-step chunk AHEAD of the vector
-// work and leaves the level sums and corrections of the coming chunk in shared memory; it also
-// refills the coefficient table two chunks ahead.  The worker warps meet at ONE barrier per
-// chunk and never wait inside it.  16 FP64 instructions per site-update (classic stage form:
-// 22, one barrier per stage).  (Rotating the two duties over the worker warps instead was
-// measured 19 % barrier stall: the duty warp finishes its chunk last and alone.)
+// (y_w, S(y)) is therefore a closed two-variable system.  It is integrated a whole 32-step chunk
+// AHEAD of the vector work (by the "scalar warp": a warp of its own above 3072 sites, the last
+// worker warp below, see the two kernels) and the level means and corrections of the coming
+// chunk are left in shared memory; the tables are refilled two chunks ahead.  The worker warps
+// meet at ONE barrier per chunk and never wait inside it.  16 FP64 instructions per site-update
+// (classic stage form: 22, one barrier per stage).
 // The tracked S(y) is never re-anchored to a direct sum of the state: the difference e between
 // the two obeys e+ = Phi0 e with the step polynomial at the top eigenvalue of L, |Phi0| <= 1
 // inside the stability region of RK4, so rounding noise does not grow -- while a correction
