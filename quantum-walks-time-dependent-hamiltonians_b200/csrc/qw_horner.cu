@@ -762,6 +762,11 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
             if (threads <= 128) { QW_HL(rk4_complete_folded, 16, 128, 3, 2); }
             QW_HL(rk4_complete_folded, 16, 192, 2, 2);        // 5 or 6 warps: two blocks per SM
         }
+        if (R == 8 && threads <= 64 && !(prm.flags & QW_FLAG_OCC4)) {      // 256 <= n < 512
+            const int bthreads = threads;
+            if (threads <= 32) { QW_HL(rk4_complete_folded, 8, 32, 12, 1); }
+            QW_HL(rk4_complete_folded, 8, 64, 7, 2);         // 7 blocks: shared memory
+        }
         const int bthreads = threads + 32;        // + the scalar warp (both duties)
         if (R == 16) {
             if (threads <= 64) { QW_HL(rk4_complete_horner, 16, 64, 4, 1); }

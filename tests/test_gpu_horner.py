@@ -83,7 +83,7 @@ def test_heatmap_matches_the_stage_form_kernel_and_keeps_the_argmax(qw):
                                      (4088, 0), (257, 0), (511, 0), (1001, 0), (1023, R8),
                                      (2049, 0), (4095, 0), (4096, 128), (3000, 128), (3000, 0),
                                      (512, 128), (1001, 128), (1024, 128), (2048, 128), (1536, 0),
-                                     (1500, 0), (600, 0)])
+                                     (1500, 0), (600, 0), (256, 128), (300, 128), (300, 0), (400, 0)])
 def test_complete_all_schedules_vs_oracle(qw, n, flags):
     # flags 128: one auxiliary warp with both duties (default: scalar warp + table warp above
     # 2048 sites, duties folded into the worker warps up to 2048)
@@ -440,7 +440,7 @@ def test_symmetry_reduced_complete_graph_beyond_memory(qw):
         assert abs(p[q] - pref) <= 1e-9 * pref and abs(norm[q] - nrm) <= 1e-10
 
 
-@pytest.mark.parametrize("n", [512, 600, 1000, 1024, 2048, 3000, 4096])
+@pytest.mark.parametrize("n", [256, 300, 512, 600, 1000, 1024, 2048, 2560, 3000, 4096])
 def test_complete_kernels_repeatable_and_variants_agree(qw, n):
     """The chunk-ahead scheme of the complete-graph kernels (tables two chunks ahead, scalar steps
     one chunk ahead, one barrier per chunk; folded into the worker warps up to 2048 sites, one
