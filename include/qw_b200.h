@@ -247,7 +247,8 @@ typedef struct qw_plan {
                                 4 warp-packed cycle, 5 / 6 resident cycle / complete in nested form,
                                 7 warp-packed cycle in nested form, 8 warp-packed cycle of any
                                 small dimension, 9 mirror-reduced cycle, 10 symmetry-reduced
-                                complete graph (both QW_FLAG_MIRROR) */
+                                complete graph (both QW_FLAG_MIRROR), 11 warp-packed complete
+                                graph of any small dimension */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */

@@ -313,6 +313,143 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same packed layout for small COMPLETE graphs (4 <= n < 256; the block-per-point kernels
+// need a block per point there and leave most lanes of it idle).  (L x)_j = n x_j - sum(x); the
+// sum of a stage input is never reduced over the lanes: the column sums of L vanish, so only
+// the oracle term changes it,
+//   S(u_{k+1}) = S(y) - i DA_k x_w^(k),   S(y+) = S(y) - i sum_k DB_k x_w^(k),
+// two FMAs per stage and sum in the lane that owns the marked vertex, broadcast to the lanes of
+// the point by one shuffle per component.  S(y) starts at n / sqrt(n) and is not re-anchored:
+// the difference between the tracked and the true sum is multiplied by the step polynomial at
+// the top eigenvalue of L in every step, |.| <= 1 inside the stability region (qw_horner.cu).
+// The ghost slot of a short lane evolves like a site of its own and is never read.
+template <int R, int MINB>
+__global__ void __launch_bounds__(32, MINB) rk4_complete_packed_any(const QwParams prm, const int L,
+                                                                    const int nfull)
+{
+    __shared__ PackedShared sh;
+    const unsigned full_mask = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int groups = 32 / L;
+    const int grp = lane / L, li = lane - grp * L;
+    const bool lane_used = grp < groups;
+    bool valid;
+    const QwPoint pt = packed_point(prm, blockIdx.x, lane_used ? grp : groups - 1, groups, valid);
+    valid = valid && lane_used;
+    __shared__ int64_t steps_slot;
+    const int64_t S = packed_steps(prm, blockIdx.x, groups, &steps_slot);
+    const bool own = lane_used && li == 0;
+    const bool full = !lane_used || li < nfull;        // R sites (idle lanes: R zeros)
+    const int gbase = lane_used ? lane - li : lane;    // the lane that owns the marked vertex
+
+    const double h = pt.h;                       // 0 when T == 0: the state never moves
+    const double gl = prm.gamma_on == QW_GAMMA_ON_LAPLACIAN ? pt.gamma : 1.0;
+    const double gd = prm.gamma_on == QW_GAMMA_ON_ORACLE ? pt.gamma : 1.0;
+    const double a_half = 0.5 * h * gl, a_full = h * gl, a_6 = h / 6.0 * gl, a_3 = h / 3.0 * gl;
+    const double d_half = 0.5 * h * gd, d_full = h * gd, d_6 = h / 6.0 * gd, d_3 = h / 3.0 * gd;
+    const double nd = lane_used ? (double)prm.n : 0.0;
+
+    State<R> s;
+    const double amp = lane_used ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = amp; s.yi[r] = 0.0;
+        s.ur[r] = 0.0; s.ui[r] = 0.0; s.ar[r] = 0.0; s.ai[r] = 0.0;
+    }
+    double2 Sy = make_double2(nd * amp, 0.0);    // sum of psi_n over the point's sites
+    double2 Sx = Sy, Sa = Sy;                    // sum of the stage input, of the accumulator
+    const double2 zero2 = make_double2(0.0, 0.0);
+    const double inv_s = 1.0 / (double)S;
+
+    for (int64_t n0 = 0; n0 < S; n0 += QW_CHUNK) {
+        __syncwarp();
+        for (int i = lane; i < 3 * QW_CHUNK; i += 32) {
+            const int st = i / 3, k = i - 3 * st;
+            sh.fac[i] = packed_factor(prm, pt, n0 + st, k, inv_s);
+        }
+        __syncwarp();
+        const int cnt = (int)((S - n0 < QW_CHUNK) ? (S - n0) : QW_CHUNK);
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+#define QW_CPL_STAGE(K, TIDX, WA, WB, DWA, DWB)                                         \
+            {                                                                           \
+                const double2 f = sh.fac[3 * sidx + TIDX];                              \
+                const double x0r = (K == 0) ? s.yr[0] : s.ur[0];                        \
+                const double x0i = (K == 0) ? s.yi[0] : s.ui[0];                        \
+                const double2 dd = make_double2((DWA) * f.y, (DWB) * f.y);              \
+                rk_stage<R, K, false>(s, (WA) * f.x, (WB) * f.x, zero2, zero2, Sx, nd, own, dd); \
+                const double bx = (K == 0) ? Sy.x : Sa.x, by = (K == 0) ? Sy.y : Sa.y;  \
+                Sa = make_double2(fma(dd.y, x0i, bx), fma(-dd.y, x0r, by));             \
+                const double2 nx = (K < 3) ? make_double2(fma(dd.x, x0i, Sy.x),         \
+                                                          fma(-dd.x, x0r, Sy.y)) : Sa;  \
+                Sx = make_double2(__shfl_sync(full_mask, nx.x, gbase),                  \
+                                  __shfl_sync(full_mask, nx.y, gbase));                 \
+                if (K == 3) Sy = Sx;                                                    \
+            }
+            QW_CPL_STAGE(0, 0, a_half, a_6, d_half, d_6)
+            QW_CPL_STAGE(1, 1, a_half, a_3, d_half, d_3)
+            QW_CPL_STAGE(2, 1, a_full, a_3, d_full, d_3)
+            QW_CPL_STAGE(3, 2, 0.0, a_6, 0.0, d_6)
+#undef QW_CPL_STAGE
+        }
+    }
+
+    // epilogue: ||psi||^2 over the real slots, summed over the L lanes of each point
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < R - 1; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    if (full) nrm = fma(s.yr[R - 1], s.yr[R - 1], fma(s.yi[R - 1], s.yi[R - 1], nrm));
+    double tot = nrm;
+    for (int k = 1; k < L; ++k) {
+        int src = li + k;
+        if (src >= L) src -= L;
+        tot += __shfl_sync(full_mask, nrm, lane_used ? gbase + src : lane);
+    }
+    if (own && valid) {
+        prm.p[pt.q] = fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]) / tot;
+        if (prm.norm) prm.norm[pt.q] = tot;
+    }
+    if (prm.psi && valid) {              // undo the relabelling: slot r of lane li -> w + off(li) + r
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
+        const int64_t off = (int64_t)li * (R - 1) + (li < nfull ? li : nfull);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r == R - 1 && !full) continue;
+            int64_t j = off + r + prm.target;
+            if (j >= prm.n) j -= prm.n;
+            out[j] = make_double2(s.yr[r], s.yi[r]);
+        }
+    }
+}
+
+template <int R, int MINB>
+cudaError_t launch_packed_complete(const QwParams &prm, cudaStream_t st, qw_plan *plan)
+{
+    const int L = (int)((prm.n + R - 1) / R);
+    const int nfull = (int)(prm.n - (int64_t)L * (R - 1));
+    const int groups = 32 / L;
+    if (plan) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, rk4_complete_packed_any<R, MINB>);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk4_complete_packed_any<R, MINB>, 32,
+                                                          0);
+        if (e != cudaSuccess) return e;
+        plan->path = 11;
+        plan->sites_per_thread = R;
+        plan->threads_per_block = 32;
+        plan->blocks_per_sm = nb;
+        plan->regs_per_thread = fa.numRegs;
+        plan->smem_bytes = (int)fa.sharedSizeBytes;
+        plan->steps_per_pass = groups;          // points per warp
+        return cudaSuccess;
+    }
+    const int64_t blocks = packed_warps(prm, groups);
+    rk4_complete_packed_any<R, MINB><<<(unsigned)blocks, 32, 0, st>>>(prm, L, nfull);
+    return cudaGetLastError();
+}
+
 template <int R, int MINB>
 cudaError_t launch_packed_any(const QwParams &prm, cudaStream_t st, qw_plan *plan)
 {
@@ -803,7 +940,10 @@ bool qw_packed_supported(const QwParams &prm)
     const bool uniform = prm.step_size == 0.0 && prm.n_steps == nullptr;
     const bool columns = prm.step_size > 0.0 && prm.time_array != nullptr &&
                          prm.order == nullptr && prm.n_time > 0;
-    if (!(prm.topology == QW_TOPO_CYCLE && (uniform || columns) && prm.n >= 3)) return false;
+    if (!(uniform || columns)) return false;
+    if (prm.topology == QW_TOPO_COMPLETE)      // small complete graphs: any-dimension layout only
+        return prm.n < 256 && packed_any_r(prm.n) > 0 && !(prm.flags & QW_FLAG_EXACT_SUM);
+    if (!(prm.topology == QW_TOPO_CYCLE && prm.n >= 3)) return false;
     return qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l) > 0 ||
            packed_any_r(prm.n) > 0;
 }
@@ -832,6 +972,14 @@ static bool packed_horner(const QwParams &prm, int *tpp_log2)
 cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan)
 {
     int l = 0;
+    if (prm.topology == QW_TOPO_COMPLETE) {
+        switch (packed_any_r(prm.n)) {
+        case 8: return launch_packed_complete<8, 12>(prm, st, plan);
+        case 4: return launch_packed_complete<4, 16>(prm, st, plan);
+        case 2: return launch_packed_complete<2, 16>(prm, st, plan);
+        default: return cudaErrorInvalidConfiguration;
+        }
+    }
     if (packed_horner(prm, &l)) return launch_packed_horner(prm, l, st, plan);
     const int R = qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l);
     if (R == 0) {                    // not R * 2^k: R or R-1 sites per lane

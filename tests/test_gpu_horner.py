@@ -469,3 +469,61 @@ def test_complete_kernels_repeatable_and_variants_agree(qw, n):
                                    gamma_on="laplacian")
     for k, (i, j) in enumerate(sel):
         assert abs(out[0][0][i, j] - po[k]) <= P_TOL and abs(out[0][1][i, j] - no[k]) <= P_TOL
+
+
+@pytest.mark.parametrize("n", [4, 5, 15, 16, 17, 51, 64, 71, 100, 128, 200, 255])
+def test_packed_complete_small_graphs_vs_oracle(qw, n):
+    """Warp-packed kernel for small complete graphs (4 <= n < 256; the sizes the reference runs):
+    R or R-1 sites per lane, several points per warp, stage sums tracked through the marked
+    vertex.  All schedules, both gamma placements, psi, ragged batches, custom targets."""
+    pl = qw.plan(qw.Problem(n=n, topology="complete", n_steps=1))
+    assert pl["path"] == "packed-complete", pl
+    assert qw.plan(qw.Problem(n=n, topology="complete", n_steps=1, flags=512))["path"] != \
+        "packed-complete"
+    rng = np.random.default_rng(11 * n)
+    for sched in ["lin", "sqrt", "cbrt", "cerf_3", "cerf_5", "cerf_7", "static"]:
+        for gamma_on in ("oracle", "laplacian"):
+            P = 37                                   # not a multiple of the points per warp
+            T = rng.uniform(0.0, 40.0 / n, P) if gamma_on == "oracle" else rng.uniform(0.0, 30.0, P)
+            g = rng.uniform(0.0, 2.0 * n, P) if gamma_on == "oracle" else rng.uniform(0.2, 1.6, P) / n
+            T[0] = 0.0
+            g[1] = 0.0
+            S = 100
+            prob = qw.Problem(n=n, topology="complete", schedule=sched, n_steps=S,
+                              gamma_on=gamma_on)
+            p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+            po, no, psio, _ = c_oracle.rk4_batch(n, "complete", sched, T, g, n_steps=S,
+                                                 gamma_on=gamma_on, return_psi=True)
+            assert np.abs(p - po).max() <= P_TOL, (n, sched, gamma_on)
+            assert np.abs(norm - no).max() <= P_TOL, (n, sched, gamma_on)
+            assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched, gamma_on)
+    for target in (0, n - 1, n // 3):
+        prob = qw.Problem(n=n, topology="complete", schedule="lin", target=target, n_steps=60)
+        p, norm, psi = qw.rk4_batch(prob, [0.7 / n, 3.0 / n], [0.9 * n, 1.4 * n], return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "complete", "lin", [0.7 / n, 3.0 / n],
+                                             [0.9 * n, 1.4 * n], n_steps=60, target=target,
+                                             return_psi=True)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(psi - psio).max() <= PSI_TOL
+
+
+def test_packed_complete_step_size_heatmap_and_long_run(qw):
+    """Fixed step size on a heatmap (a warp takes rows of one T column; the rule the drop-in
+    modules default to), and 60 000 steps without re-anchoring the tracked sums."""
+    n = 51
+    t = np.linspace(0.05, 9.0, 23)
+    b = np.linspace(0.2, 1.9, 13) / n
+    prob = qw.Problem(n=n, topology="complete", schedule="cerf_3", gamma_on="laplacian",
+                      step_size=0.01)
+    assert qw.plan(prob)["path"] == "packed-complete"
+    p, norm = qw.rk4_heatmap(prob, t, b)
+    ho, _ = c_oracle.heatmap(n, "complete", "cerf_3", t, b, step_size=0.01, gamma_on="laplacian")
+    assert np.abs(p - ho).max() <= P_TOL and np.argmax(p) == np.argmax(ho)
+    T = [600.0, 451.0]
+    g = [1.0 / n, 0.7 / n]
+    prob = qw.Problem(n=n, topology="complete", schedule="lin", gamma_on="laplacian",
+                      n_steps=60000)
+    pl, nl, psil = qw.rk4_batch(prob, T, g, return_psi=True)
+    po, no, psio, _ = c_oracle.rk4_batch(n, "complete", "lin", T, g, n_steps=60000,
+                                         gamma_on="laplacian", return_psi=True)
+    assert np.abs(pl - po).max() <= 1e-11 and np.abs(nl - no).max() <= 1e-11
+    assert np.abs(psil - psio).max() <= 1e-11

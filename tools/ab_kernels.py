@@ -27,6 +27,7 @@ VARIANTS = {
            ("v1 legacy occ4", 32 | 128)],
     "c2": [("packed (default)", 0), ("packed 16 warps/SM at 128 regs", 128), ("packed R<=8", 256), ("v2 R=2 CTA-per-point", 512)],
     "c3": [("complete horner R=16 (default)", 0), ("complete horner R=16, one aux warp", 128),
+           ("small complete graph: block per point (no packing)", 512),
            ("complete horner R=8", 256),
            ("complete v2 R=16", 2048), ("complete barrier-free R=16", 1024),
            ("complete v2 R=8", 2048 | 256), ("complete v1 R=8 legacy", 256 | 32),
