@@ -336,9 +336,11 @@ def run_b200(args):
         # DRAM bytes of one launch from the committed ncu --set full captures (not per-launch of
         # this run: the resident kernels touch DRAM only for T, gamma, p, norm and their image)
         traffic = {
-            "horner-cycle": (626688, "dram__bytes_read+write of an 8192-point launch (ncu --set "
-                             "full, profiles/r1_cycle_horner_r16_ncu_full.md): the kernel is "
-                             "register-resident, DRAM sees only T, gamma, p, norm"),
+            "horner-cycle": (253696, "dram__bytes_read+write of the launch this bench times by "
+                             "default (131072 points, 877.65 ms under ncu --set full, profiles/"
+                             "r1_cycle_horner_r16_bench_share_ncu_full.md): the kernel is register-"
+                             "resident, DRAM sees only T, gamma and the kernel image; the 2 MiB "
+                             "of p and norm stay in L2 until after the kernel"),
             "horner-complete": (90112, "dram__bytes_read+write of a 2048-point launch (ncu --set "
                                 "full, profiles/r1_complete_horner_r16_final_ncu_full.md): the "
                                 "kernel is register-resident, DRAM sees only T, gamma, p, norm"),
