@@ -88,8 +88,8 @@ enum {
                                     nested cycle kernel, 5 or 6 warps: one block per SM at 200
                                     registers instead of two at 168 (A/B);
                                     complete graph: one auxiliary warp with both duties
-                                    instead of scalar warp + table warp (above 2048 sites) or
-                                    of duties folded into the worker warps (up to 2048) (A/B) */
+                                    instead of scalar warp + table warp (above 3072 sites) or
+                                    of duties folded into the worker warps (up to 3072) (A/B) */
     QW_FLAG_R8 = 256,            /* resident kernels: at most 8 sites per thread (default: 16
                                     where n % 16 == 0 and n/16 >= 32; A/B only) */
     QW_FLAG_NO_PACK = 512,       /* do not use the warp-packed kernel for small rings (A/B) */

@@ -86,7 +86,7 @@ def test_heatmap_matches_the_stage_form_kernel_and_keeps_the_argmax(qw):
                                      (1500, 0), (600, 0), (256, 128), (300, 128), (300, 0), (400, 0)])
 def test_complete_all_schedules_vs_oracle(qw, n, flags):
     # flags 128: one auxiliary warp with both duties (default: scalar warp + table warp above
-    # 2048 sites, duties folded into the worker warps up to 2048)
+    # 3072 sites, duties folded into the worker warps up to 3072)
     pl = qw.plan(qw.Problem(n=n, topology="complete", n_steps=1, flags=flags))
     assert pl["path"] == "horner-complete", pl
     rng = np.random.default_rng(7 * n + flags)
@@ -443,7 +443,7 @@ def test_symmetry_reduced_complete_graph_beyond_memory(qw):
 @pytest.mark.parametrize("n", [256, 300, 512, 600, 1000, 1024, 2048, 2560, 3000, 4096])
 def test_complete_kernels_repeatable_and_variants_agree(qw, n):
     """The chunk-ahead scheme of the complete-graph kernels (tables two chunks ahead, scalar steps
-    one chunk ahead, one barrier per chunk; folded into the worker warps up to 2048 sites, one
+    one chunk ahead, one barrier per chunk; folded into the worker warps up to 3072 sites, one
     map buffer in one-warp blocks) has no ordering left to chance: a full machine of blocks gives
     bitwise the same heatmap every time, and the one-auxiliary-warp variant (flags 128) agrees to
     rounding.  235 steps = 7 full chunks and a ragged one."""
