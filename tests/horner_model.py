@@ -101,3 +101,82 @@ def rk4_horner(n, topology, schedule, T, gamma, n_steps, gamma_on, target=None):
         y = horner_step(y, w, topo, rho, C)
     norm = float(np.sum(np.abs(y) ** 2))
     return float(np.abs(y[w]) ** 2) / norm, norm, y
+
+
+# ---- complete graph: the marked-vertex subsystem as a linear map (csrc/qw_horner.cu, CSMap) ----
+
+def complete_subsystem_map(rho, C, n):
+    """Ten outputs of one step as out = qa * y_w + qb * S(y): the four level means
+    (S(y), S(z4), S(z3), S(z2)) / n, the corrections sigma_4..sigma_1, then y_w and S(y) after the
+    step.  Obtained as in the kernel: the two basis vectors go through the operations the
+    vector code applies to the marked vertex."""
+    def push(yw, sy):
+        m1 = n * yw - sy                                         # (L y)_w
+        g = {l: C[l][0] * yw + (C[l][1] + n * C[l][2] + n * n * C[l][3]) * m1
+             for l in (1, 2, 3, 4)}                              # L^2y_w = n Ly_w, L^3y_w = n^2 Ly_w
+        out = [sy / n]
+        v = m1
+        for l in (4, 3, 2):
+            s_l = sy + g[l]
+            out.append(s_l / n)
+            z = yw - 1j * rho[l - 1] * v + g[l]
+            v = n * z - s_l
+        out += [g[4], g[3], g[2], g[1]]
+        out += [yw - 1j * rho[0] * v + g[1], sy + g[1]]
+        return np.array(out)
+    return push(1.0 + 0j, 0j), push(0j, 1.0 + 0j)
+
+
+def rk4_complete_mapped(n, schedule, T, gamma, n_steps, gamma_on, target=None):
+    """The complete-graph kernels' scheme: the vector code never sums anything; x = (y_w, S(y)) is
+    advanced by the tabulated map, the levels subtract the level mean (y - i rho n (z - S/n)) and
+    the marked vertex receives sigma_l.  S(y) is never re-anchored."""
+    w = (n - 1) // 2 if target is None else target
+    y = np.full(n, 1 / np.sqrt(n), dtype=complex)
+    x = np.array([y[w], y.sum()])
+    h = T / n_steps
+    for s in range(n_steps):
+        t = s * h
+        a1, d1 = (float(v) for v in operator_scalars(t / T, gamma, schedule, gamma_on))
+        a2, d2 = (float(v) for v in operator_scalars((t + 0.5 * h) / T, gamma, schedule, gamma_on))
+        a4, d4 = (float(v) for v in operator_scalars((t + h) / T, gamma, schedule, gamma_on))
+        rho, C = step_coefficients(h, a1, a2, a4, d1, d2, d4, n - 1.0, n * (n - 1.0))
+        qa, qb = complete_subsystem_map(rho, C, n)
+        out = qa * x[0] + qb * x[1]
+        z = y
+        for idx, level in enumerate((4, 3, 2, 1)):
+            z = y - 1j * (rho[level - 1] * n) * (z - out[idx])
+            z[w] += out[4 + idx]
+        y = z
+        x = out[8:10]
+    norm = float(np.sum(np.abs(y) ** 2))
+    return float(np.abs(y[w]) ** 2) / norm, norm, y, x
+
+
+# ---- small complete graphs: stage form with tracked stage sums (csrc/qw_packed.cu) ------------
+
+def rk4_complete_tracked_sums(n, schedule, T, gamma, n_steps, gamma_on, target=None):
+    """Classic RK4 stages with (L x)_j = n x_j - S(x), where S of every stage input follows from
+    the marked vertex alone (the column sums of L vanish): S(k_s) = -i d_s x_w."""
+    w = (n - 1) // 2 if target is None else target
+    y = np.full(n, 1 / np.sqrt(n), dtype=complex)
+    sy = n * (1 / np.sqrt(n)) + 0j
+    h = T / n_steps
+    cs, bs = (0.5, 0.5, 1.0), (1 / 6, 1 / 3, 1 / 3, 1 / 6)
+    for s in range(n_steps):
+        t = s * h
+        ad = [tuple(float(v) for v in operator_scalars(tt / T, gamma, schedule, gamma_on))
+              for tt in (t, t + 0.5 * h, t + 0.5 * h, t + h)]
+        x, sx, acc, sa = y, sy, y.copy(), sy
+        for k in range(4):
+            a, d = ad[k]
+            kv = -1j * a * (n * x - sx)
+            kv[w] += -1j * d * x[w]
+            sk = -1j * d * x[w]
+            acc = acc + h * bs[k] * kv
+            sa = sa + h * bs[k] * sk
+            if k < 3:
+                x, sx = y + h * cs[k] * kv, sy + h * cs[k] * sk
+        y, sy = acc, sa
+    norm = float(np.sum(np.abs(y) ** 2))
+    return float(np.abs(y[w]) ** 2) / norm, norm, y, sy

@@ -38,3 +38,38 @@ def test_static_schedule_gives_the_autonomous_ratios():
 def test_config1_value():
     p, _, _ = rk4_horner(16, "circular", "lin", 16.0, 1.0, 1024, "oracle")
     assert abs(p - 0.42038739054526) < 1e-12
+
+
+COMPLETE_CASES = [
+    (64, "lin", 20.0, 1.0 / 64, 800, "laplacian"),
+    (51, "cerf_3", 30.0, 0.9 / 51, 1200, "laplacian"),
+    (17, "cbrt", 0.8, 12.0, 300, "oracle"),
+    (64, "sqrt", 2.0, 40.0, 600, "oracle"),
+    (40, "static", 25.0, 1.3 / 40, 500, "laplacian"),
+    (33, "lin", 400.0, 1.0 / 33, 20000, "laplacian"),      # long run: sums never re-anchored
+]
+
+
+@pytest.mark.parametrize("n,sched,T,g,S,go", COMPLETE_CASES)
+def test_complete_graph_subsystem_map_equals_rk4(n, sched, T, g, S, go):
+    """The scheme of rk4_complete_horner / rk4_complete_folded: tabulated linear map of
+    (y_w, S(y)), level means, corrections; the tracked pair stays on the true one."""
+    from horner_model import rk4_complete_mapped
+
+    p, norm, psi, x = rk4_complete_mapped(n, sched, T, g, S, go)
+    po, no, psio = rk4_L2(n, "complete", sched, [T], [g], n_steps=S, gamma_on=go, return_psi=True)
+    assert abs(p - po[0]) <= 1e-12 and abs(norm - no[0]) <= 1e-12
+    assert np.abs(psi - psio[0]).max() <= 1e-12
+    w = (n - 1) // 2
+    assert abs(x[0] - psio[0][w]) <= 1e-12 and abs(x[1] - psio[0].sum()) <= 1e-11
+
+
+@pytest.mark.parametrize("n,sched,T,g,S,go", COMPLETE_CASES)
+def test_complete_graph_tracked_stage_sums_equal_rk4(n, sched, T, g, S, go):
+    """The scheme of rk4_complete_packed_any: S(stage input) from the marked vertex alone."""
+    from horner_model import rk4_complete_tracked_sums
+
+    p, norm, psi, sy = rk4_complete_tracked_sums(n, sched, T, g, S, go)
+    po, no, psio = rk4_L2(n, "complete", sched, [T], [g], n_steps=S, gamma_on=go, return_psi=True)
+    assert abs(p - po[0]) <= 1e-12 and abs(norm - no[0]) <= 1e-12
+    assert np.abs(psi - psio[0]).max() <= 1e-12 and abs(sy - psio[0].sum()) <= 1e-11
