@@ -197,7 +197,7 @@ def cpu_port_rate(w, seconds, threads=0):
         return time.perf_counter() - t0
 
     run(nthr)                                         # warm the thread pool / caches
-    t1 = run(nthr)
+    t1 = run(4 * nthr) / 4.0                          # pilot: seconds per round of nthr points
     k = int(nthr * max(1, min(256, round(seconds / max(t1, 1e-3)))))
     dt = run(k)
     return {"value": k * w["site_updates_per_point"] / dt, "unit": "site-updates/s",
