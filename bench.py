@@ -2,14 +2,15 @@
 """bench.py -- RK4 site-updates/s and heatmap grid-points/s of the B200 path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload c5|c2|c3|c4] [--rows-per-gpu R]
+                    [--workload c5|c2|c3|c4] [--rows-per-gpu R] [--scaling weak|strong]
 
 One "step" is one pass of the hot path over the workload's (T, gamma) points.  The default
 workload is BASELINE config 5: cycle graph N=1024, n_steps=4096, schedule lin,
 T = linspace(0.1, 1024, 1024); every GPU integrates a block of 128 gamma rows of
 gamma = linspace(0, 2.5, 128*N_gpus), so that 8 GPUs compute exactly the named
 1024 x 1024 heatmap (weak scaling, no data-path collective; the e2e leg adds the final
-all_gather that replaces ray.get + np.concatenate of BCB.py:284-292).
+gather that replaces ray.get + np.concatenate of BCB.py:284-292).  `--scaling strong` keeps
+the TOTAL grid fixed instead (c5: the named 1024 x 1024 heatmap at every N).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in HBM,
 CUDA events, max over ranks); `e2e` goes through the public Python API with pinned host
@@ -36,15 +37,25 @@ FLOPS_PER_SITE_UPDATE = 52          # SURVEY.md section 8d (22 DFMA + 8 DADD): A
 METRIC = "rk4_site_updates_per_sec"
 
 
-def executed_fp64_per_site_update(plan):
-    """FP64 instructions the selected kernel issues per site-update (per lane), from the
-    kernel sources: classic stage form 30 (cycle) / 22 (complete); nested (Horner) form
-    24 (cycle) / 16 (complete) plus the owner warp's oracle corrections (22 warp-instructions
-    per step and block, i.e. 22 * 32 lane-slots over the block's n sites)."""
+def kernel_counters(plan):
+    """Hardware counters of the kernel the plan names, from committed ncu captures
+    (profiles/kernel_counters.json); {} when that kernel has none."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as fh:
+            table = json.load(fh)
+    except Exception:
+        return {}
+    key = "%s/R%d/T%d" % (plan["path"], plan["sites_per_thread"], plan["threads_per_block"])
+    return table.get(key, {})
+
+
+def source_fp64_per_site_update(plan):
+    """FP64 instructions per site-update counted in the kernel SOURCE / SASS (tools/sass_loops.py):
+    the fallback when no ncu opcode counters are committed for the kernel."""
     path, r, thr = plan["path"], plan["sites_per_thread"], plan["threads_per_block"]
     n_block = max(1, r * thr)
     if path == "horner-cycle":
-        return 24.0 + 22.0 * 32.0 / n_block
+        return 24.0 + 30.0 * 32.0 / n_block
     if path == "packed-horner-cycle":
         return 24.0 + 22.0 * 32.0 / 512.0
     if path == "horner-complete":
@@ -53,33 +64,49 @@ def executed_fp64_per_site_update(plan):
         return 22.0
     return 30.0
 
+
 WORKLOADS = {
     # name: n, topology, schedule, gamma_on, n_steps, n_time, T range, gamma range, rows/GPU
     "c5": dict(n=1024, topology="circular", schedule="lin", gamma_on="oracle", n_steps=4096,
-               n_time=1024, t=(0.1, 1024.0), g=(0.0, 2.5), rows=128,
+               n_time=1024, t=(0.1, 1024.0), g=(0.0, 2.5), rows=128, rows_total=1024,
                label="C5 cycle N=1024 n_steps=4096 lin, 1024 T x 128 gamma rows per GPU "
                      "(the full 1024x1024 heatmap at 8 GPUs)"),
     "c2": dict(n=64, topology="circular", schedule="lin", gamma_on="oracle", n_steps=1024,
-               n_time=100, t=(0.1, 64.0), g=(0.0, 2.5), rows=100,
+               n_time=100, t=(0.1, 64.0), g=(0.0, 2.5), rows=100, rows_total=100,
                label="C2 cycle N=64 n_steps=1024 lin, 100x100 heatmap per GPU"),
     "c3": dict(n=4096, topology="complete", schedule="cerf_3", gamma_on="laplacian",
                n_steps=2048, n_time=256, t=(0.1, 512.0), g=(0.5 / 4096, 2.5 / 4096), rows=32,
+               rows_total=256,
                label="C3 complete N=4096 n_steps=2048 cerf_3 gamma-on-Laplacian, "
                      "256 T x 32 gamma rows per GPU (256x256 at 8 GPUs)"),
     "c4": dict(n=256, topology="circular", schedule="lin", gamma_on="oracle", n_steps=512,
-               n_time=1000, t=(20.0, 30.0), g=(0.8, 1.2), rows=100,
+               n_time=1000, t=(20.0, 30.0), g=(0.8, 1.2), rows=100, rows_total=800,
                label="C4-shaped cycle N=256 n_steps=512 lin, 1e5 points per GPU"),
 }
 
 
-def _workload(name, n_gpus, rows_per_gpu=None):
+def _workload(name, n_gpus, rows_per_gpu=None, scaling="weak"):
     w = dict(WORKLOADS[name])
     if rows_per_gpu:
         w["rows"] = int(rows_per_gpu)
+    n_rows = w["rows_total"] if scaling == "strong" else w["rows"] * n_gpus
+    w["scaling"] = scaling
     w["time_array"] = np.linspace(w["t"][0], w["t"][1], w["n_time"])
-    w["beta_array"] = np.linspace(w["g"][0], w["g"][1], w["rows"] * n_gpus)
+    w["beta_array"] = np.linspace(w["g"][0], w["g"][1], n_rows)
     w["site_updates_per_point"] = w["n"] * w["n_steps"]
     return w
+
+
+def _config(w, n_gpus):
+    """The `config` object of the JSON line: the workload only, identical in both arms."""
+    return {"workload": w["label"] if w["scaling"] == "weak" else
+            w["label"].split(",")[0] + ", %d T x %d gamma rows in total (strong scaling)"
+            % (w["n_time"], w["beta_array"].size),
+            "n": w["n"], "topology": w["topology"], "schedule": w["schedule"],
+            "gamma_on": w["gamma_on"], "n_steps": w["n_steps"], "n_time": w["n_time"],
+            "n_gamma": int(w["beta_array"].size), "n_gpus": n_gpus, "scaling": w["scaling"],
+            "points_total": int(w["beta_array"].size * w["n_time"]),
+            "site_updates_per_point": w["site_updates_per_point"]}
 
 
 class ClockSampler(threading.Thread):
@@ -179,6 +206,29 @@ def stream_measure(qw, torch, dev, reps=3):
     return out
 
 
+def mirror_measure(qw, torch, w, d_time, d_beta, rows, flush, pts_local, p_dev, reps=2):
+    """The exact symmetry reductions the drop-in modules use by default (QW_FLAG_MIRROR: the
+    half ring / the (psi_w, psi_other) pair) on the same rows: the unit of `value` stays the
+    full-ring site-update, this reports what a user of the drop-in sees in grid points/s."""
+    prob = qw.Problem(n=w["n"], topology=w["topology"], schedule=w["schedule"],
+                      gamma_on=w["gamma_on"], n_steps=w["n_steps"], flags=8192)
+    qw.rk4_heatmap(prob, d_time, d_beta, rows=rows)
+    best, pm = 1e30, None
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pm, _ = qw.rk4_heatmap(prob, d_time, d_beta, rows=rows)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return {"kernel": qw.plan(prob), "ms_per_step_this_gpu": best,
+            "effective_grid_points_per_sec_this_gpu": pts_local / (best * 1e-3),
+            "effective_full_ring_site_updates_per_sec_this_gpu":
+                pts_local * w["site_updates_per_point"] / (best * 1e-3),
+            "max_abs_dp_vs_full_ring_kernel": float((pm - p_dev).abs().max())}
+
+
 def cpu_port_rate(w, seconds, threads=0):
     """C/OpenMP oracle port on a bounded sample of the workload's own points."""
     from oracle import c_oracle
@@ -206,11 +256,48 @@ def cpu_port_rate(w, seconds, threads=0):
                       "OpenMP over points, %.1f s" % (k, dt)}, k, dt
 
 
+def cpu_numpy_row(w, seconds=3.0):
+    """the numpy restatement of the oracle (stencil / rank-one, one
+    core) on a few points of the workload."""
+    from oracle import rk4_numpy as rk
+    t_arr, b_arr = w["time_array"], w["beta_array"]
+    rng = np.random.default_rng(6)
+    k, done, dt = 1, 0, 0.0
+    while dt < seconds and done < 64:
+        T, g = t_arr[rng.integers(0, t_arr.size, k)], b_arr[rng.integers(0, b_arr.size, k)]
+        t0 = time.perf_counter()
+        rk.rk4_L2(w["n"], w["topology"], w["schedule"], T, g, n_steps=w["n_steps"],
+                  gamma_on=w["gamma_on"])
+        dt += time.perf_counter() - t0
+        done += k
+    return {"value": done * w["site_updates_per_point"] / dt, "unit": "site-updates/s",
+            "cores": 1, "kind": "port-numpy",
+            "sample": "%d random points of the workload grid, oracle/rk4_numpy.py (L2 stencil "
+                      "restatement), one core, %.1f s" % (done, dt)}
+
+
+def literal_reference_row(w):
+    """SURVEY.md 8(d) row B1.  The unmodified reference (evaluate_probability, BCB.py:193-203:
+    SciPy RK45 over a dense H(t) rebuilt in Python loops on every right-hand side) cannot run
+    on the GPU box -- /root/reference does not travel -- so this row is an EXTRAPOLATION from
+    the survey's measurement in the build container: one RHS call
+    costs 0.66 us x N^2 on one core, and an RK4 step needs four of them."""
+    n = w["n"]
+    per_rhs = 0.66e-6 * n * n
+    return {"value": 1.0 / (4.0 * per_rhs / n), "unit": "site-updates/s", "cores": 1,
+            "kind": "literal-reference-extrapolated",
+            "sample": "not run here: 0.66 us x N^2 per schrodinger_equation call (measured on "
+                      "the unmodified reference in the build container, BASELINE.md section 2) "
+                      "x 4 calls per RK4 step, N = %d; the literal reference at this size is "
+                      "infeasible (%.2f s per right-hand side)" % (n, per_rhs)}
+
+
 def run_reference(args):
-    """CPU arm: rank 0 only."""
+    """CPU arm: rank 0 only.  A throughput measurement: every step integrates a bounded random
+    sample of the workload's own (T, gamma) points, not the whole grid."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    w = _workload(args.workload, args.gpus, args.rows_per_gpu)
+    w = _workload(args.workload, args.gpus, args.rows_per_gpu, args.scaling)
     per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_port_rate(w, per_step * 0.25)
@@ -221,12 +308,14 @@ def run_reference(args):
         tot_t += dt
     value = tot_pts * w["site_updates_per_point"] / tot_t
     info["value"] = value
+    info["sample"] = ("%d random points of the workload grid per step (%d in %d steps, %.1f s), "
+                      "oracle/rk4_oracle.c with OpenMP over points: a bounded sample, not the "
+                      "whole grid" % (tot_pts // max(1, args.steps), tot_pts, args.steps, tot_t))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "site-updates/s",
             "grid_points_per_sec": tot_pts / tot_t, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": w["label"],
-                                            "note": "bounded sample per step on host cores"},
+            "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": _config(w, args.gpus),
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": "site-updates/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -252,7 +341,7 @@ def run_b200(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
-    w = _workload(args.workload, world, args.rows_per_gpu)
+    w = _workload(args.workload, world, args.rows_per_gpu, args.scaling)
     prob = qw.Problem(n=w["n"], topology=w["topology"], schedule=w["schedule"],
                       gamma_on=w["gamma_on"], n_steps=w["n_steps"])
     rows = qw.shard_rows(w["beta_array"].size, world, rank)
@@ -312,8 +401,8 @@ def run_b200(args):
     def e2e_step():
         if world == 1:
             p, nrm = qw.rk4_heatmap(prob, h_time, h_beta, rows=rows)
-        else:
-            p, nrm = qw.heatmap_sharded(prob, h_time.numpy(), h_beta.numpy())
+        else:                       # one all_gather_into_tensor, one D2H on rank 0
+            p, nrm = qw.heatmap_sharded(prob, h_time.numpy(), h_beta.numpy(), dst=0)
         return p, nrm
 
     e2e_step()
@@ -324,47 +413,51 @@ def run_b200(args):
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     e2e_value = pts_total * w["site_updates_per_point"] / (e2e_ms * 1e-3)
-    h2d = (h_time.numel() + h_beta.numel()) * 8
-    d2h = 2 * pts_local * 8
+    # bytes over PCIe per step, summed over the ranks: every rank uploads both axes; the
+    # heatmap (p and norm, padded to equal row blocks) comes down once, on rank 0
+    h2d = world * (h_time.numel() + h_beta.numel()) * 8
+    d2h = sum(qw.sharded_d2h_bytes(w["beta_array"].size, w["n_time"], world, r, dst=0)
+              for r in range(world))
 
-    ok = bool(np.isfinite(p_host).all() and (p_host >= 0).all() and (p_host <= 1 + 1e-9).all()
-              and np.array_equal(p_host[rows[0] if world > 1 else 0:][:rows[1] - rows[0]],
-                                 p_dev.cpu().numpy()))
+    ok = True
+    if rank == 0:
+        ok = bool(np.isfinite(p_host).all() and (p_host >= 0).all()
+                  and (p_host <= 1 + 1e-9).all()
+                  and np.array_equal(p_host[rows[0]:rows[1]] if world > 1 else p_host,
+                                     p_dev.cpu().numpy()))
 
     if rank == 0:
         kernel_s = ms_per_step * 1e-3                 # one launch per step and per GPU
-        # DRAM bytes of one launch from the committed ncu --set full captures (not per-launch of
-        # this run: the resident kernels touch DRAM only for T, gamma, p, norm and their image)
-        traffic = {
-            "horner-cycle": (253696, "dram__bytes_read+write of the launch this bench times by "
-                             "default (131072 points, 877.65 ms under ncu --set full, profiles/"
-                             "r1_cycle_horner_r16_bench_share_ncu_full.md): the kernel is register-"
-                             "resident, DRAM sees only T, gamma and the kernel image; the 2 MiB "
-                             "of p and norm stay in L2 until after the kernel"),
-            "horner-complete": (90112, "dram__bytes_read+write of a 2048-point launch (ncu --set "
-                                "full, profiles/r1_complete_horner_r16_final_ncu_full.md): the "
-                                "kernel is register-resident, DRAM sees only T, gamma, p, norm"),
-        }.get(plan["path"], (None, "no ncu --set full capture of this kernel at this workload; "
-                             "register-resident, DRAM sees only T, gamma, p, norm"))
-        achieved = FLOPS_PER_SITE_UPDATE * pts_local * w["site_updates_per_point"] / kernel_s / 1e12
-        ex = executed_fp64_per_site_update(plan)
+        site_updates_local = pts_local * w["site_updates_per_point"]
+        achieved = FLOPS_PER_SITE_UPDATE * site_updates_local / kernel_s / 1e12
+        ctr = kernel_counters(plan)
+        if "fp64_thread_inst_per_site_update" in ctr:
+            ex, ex_src = ctr["fp64_thread_inst_per_site_update"], ctr["counters_source"]
+        else:
+            ex, ex_src = source_fp64_per_site_update(plan), (
+                "counted in the kernel source / SASS (tools/sass_loops.py); no ncu opcode "
+                "counters committed for this kernel")
+        traffic, traffic_note = None, ("no ncu --set full capture of this kernel at this launch "
+                                       "size in profiles/kernel_counters.json")
+        if ctr.get("dram_launch_points") == pts_local:
+            traffic, traffic_note = ctr["dram_bytes_per_launch"], ctr["dram_source"]
         lane_rate = plan["sm_count"] * 64 * (clocks["sm_mhz"] or 1965.0) * 1e6    # FP64 lanes/s
-        pipe_util = ex * pts_local * w["site_updates_per_point"] / kernel_s / lane_rate
+        pipe_util = ex * site_updates_local / kernel_s / lane_rate
         line = {
             "metric": METRIC, "value": value, "unit": "site-updates/s",
             "grid_points_per_sec": pts_total / (ms_per_step * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["label"], "points_per_gpu": pts_local,
-                       "points_total": pts_total, "site_updates_per_point":
-                       w["site_updates_per_point"], "l2": "flushed (256 MiB write) between "
-                       "timed iterations; state is register-resident",
-                       "kernel": plan, "results_sane_and_e2e_equals_device": ok},
+            "config": _config(w, world),
+            "kernel": plan, "points_per_gpu": pts_local,
+            "l2": "flushed (256 MiB write) between timed iterations; state is register-resident",
+            "results_sane_and_e2e_equals_device": ok,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": traffic[0],
-                         "traffic_note": traffic[1],
+                         "traffic": traffic, "traffic_note": traffic_note,
+                         "algorithmic_bytes_per_launch": 16 * pts_local + 8 * (
+                             w["n_time"] + int(w["beta_array"].size)),
                          "peak_source": "qw_fp64_peak_probe: dependent-free DFMA stream "
                                         "measured in this process, best of 8/16/24 warps per "
                                         "SM (MEASURED_PEAKS.json has no FP64 entry)",
@@ -373,6 +466,7 @@ def run_b200(args):
                          "probe_clocks": probe_clock,
                          "algorithmic_flops_per_site_update": FLOPS_PER_SITE_UPDATE,
                          "executed_fp64_instructions_per_site_update": ex,
+                         "executed_fp64_source": ex_src,
                          "fp64_pipe_utilisation": pipe_util,
                          "note": "achieved counts the ALGORITHMIC 52 flops of classic RK4 per "
                                  "site-update (SURVEY.md 8d); the nested-form kernels issue "
@@ -381,13 +475,19 @@ def run_b200(args):
                          "max_frac_of_fma_peak": 52.0 / (2.0 * ex)},
             "e2e": {"value": e2e_value, "unit": "site-updates/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "gather": "none (one GPU)" if world == 1 else
+                    "all_gather_into_tensor over NCCL, one device-to-host copy on rank 0",
                     "grid_points_per_sec": pts_total / (e2e_ms * 1e-3)},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if not args.no_mirror:
+            line["symmetry_reduced"] = mirror_measure(qw, torch, w, d_time, d_beta, rows, flush,
+                                                      pts_local, p_dev)
         if world == 1 and not args.no_stream:
             line["streaming"] = stream_measure(qw, torch, dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_port_rate(w, args.cpu_seconds)[0]
+            line["cpu_baseline"]["other_rows"] = [cpu_numpy_row(w), literal_reference_row(w)]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -401,6 +501,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--rows-per-gpu", type=int, default=None)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: fixed rows per GPU (default); strong: the workload's whole grid "
+                         "split over the GPUs (c5: 1024 x 1024 at every N)")
+    ap.add_argument("--no-mirror", action="store_true",
+                    help="skip the side measurement of the symmetry-reduced kernels")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream", action="store_true",

@@ -18,6 +18,7 @@ from . import _dropin, engine
 step_size = 1e-3           # QW_Search.py:153
 n_steps = None             # set to use h = time / n_steps instead
 device = None
+mirror = True              # exact symmetry reduction for the uniform start (QW_FLAG_MIRROR)
 
 _TOPOLOGY = {0: "complete", 1: "circular"}
 
@@ -62,7 +63,7 @@ class Hamiltonian:
         sched = "static" if self.type == 0 else self.step_func
         rule = dict(n_steps=n_steps) if n_steps is not None else dict(step_size=step_size)
         return engine.Problem(n=self.dim, topology=self.topology, schedule=sched,
-                              target=self.target, **rule)
+                              target=self.target, flags=8192 if mirror else 0, **rule)
 
 
 class State:
@@ -72,10 +73,12 @@ class State:
         self.dim = int(dim)
         self.ket = None
         self.H = None
+        self._elapsed = 0.0       # time already evolved since set_initial (static H only)
 
     def set_initial(self, type=0):
         if type == 0:
             self.ket = np.ones((self.dim), dtype=np.complex128) / np.sqrt(self.dim)
+            self._elapsed = 0.0
         else:
             print("Initial type missing or not yet implemented")
 
@@ -86,11 +89,25 @@ class State:
         return np.transpose(np.conjugate(self.ket))
 
     def evolve(self, time):
-        """psi(time) from the uniform initial state, by the RK4 kernel."""
+        """Advance ``ket`` by ``time`` with the RK4 kernel.  The kernels start from the uniform
+        state (the only initial state the reference defines, QW_Search.py:128-131), so a
+        repeated call re-integrates from it over the accumulated time: well defined for the
+        time-independent type (exp(-iH t2) exp(-iH t1) = exp(-iH (t1 + t2))); for the
+        time-dependent type the schedule g(t / T) belongs to ONE run of length T and a second
+        ``evolve`` raises."""
         if self.H.type not in (0, 1):
             print("Error, unknown evolution type")
             return
+        if self._elapsed > 0.0:
+            if self.H.type == 1:
+                raise ValueError("time-dependent evolution is one run of length T from the "
+                                 "uniform state: call set_initial(0) before evolving again")
+            total = self._elapsed + float(time)
+            self.ket = _runge_kutta(self.H, None, total)
+            self._elapsed = total
+            return
         self.ket = _runge_kutta(self.H, self.ket, time)
+        self._elapsed = float(time)
 
     def success_probability(self):
         """|<target|psi>|^2 / <psi|psi>."""

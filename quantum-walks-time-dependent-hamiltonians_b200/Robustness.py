@@ -43,6 +43,8 @@ def routine(dim, flag):
     probability, time, beta = load_data_file(dim, flag)
     R2, arg = robustness_map(probability, 2)
     max_index = int(arg[2])
+    if max_index < 0:        # no p > 0 in that column: the reference's scan leaves max_index unset
+        raise ValueError("no positive probability in time column 2 of the %s heatmap" % (dim,))
     out = (dim, robustness(probability, max_index, 2, 2), robustness(probability, max_index, 2, 4))
     print(*out)
     return out

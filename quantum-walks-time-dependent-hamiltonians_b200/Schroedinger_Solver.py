@@ -23,7 +23,8 @@ gamma_on = "oracle"
 integrator = "rk4"           # 'rk45': SciPy's adaptive RK45 as the reference ships it
 reference_derivative = True  # dH/ds of the cube-root schedule as the reference codes it
 device = None
-mirror = False               # True: symmetry-reduced state (QW_FLAG_MIRROR): half the ring /
-                             # (psi_w, psi_other) on the complete graph; same results
+mirror = True                # symmetry-reduced state (QW_FLAG_MIRROR), exact for the uniform start every
+                             # caller uses (BCB.py:179-180): half the ring / (psi_w, psi_other) on the
+                             # complete graph, same p, norm and psi; False integrates every site
 
 _dropin.install(globals(), "SS")

@@ -50,7 +50,8 @@ def _problem(g, flavor, schedule=None, topology=None, dimension=None):
         n=int(dim), topology=_topology(g, flavor) if topology is None else topology,
         schedule=_schedule_name(g, flavor) if schedule is None else schedule,
         gamma_on=g.get("gamma_on", "oracle"), n_steps=n_steps, step_size=step_size,
-        flags=8192 if g.get("mirror", False) else 0)       # QW_FLAG_MIRROR (opt-in)
+        flags=8192 if g.get("mirror", True) else 0)        # QW_FLAG_MIRROR: exact symmetry
+                                                           # reduction for the uniform start
 
 
 def _marked_vertex(n):
@@ -176,14 +177,9 @@ def install(g, flavor):
         return -np.array([[p[0] * norm[0]]])          # the reference does not renormalise
 
     def heatmap2d(*args, **kwargs):
-        """Plotting is outside the accelerated path."""
-        try:
-            import matplotlib  # noqa: F401
-        except Exception:
-            print("heatmap2d: matplotlib is not installed; plot skipped")
-            return None
-        from . import heatmap_generator
-        return heatmap_generator.render(*args, dimension=g.get("dimension"), **kwargs)
+        """Plotting is outside the accelerated path: signature kept,
+        nothing is drawn."""
+        return None
 
     def _heatmap(time_array, beta_array, schedule=None, topology=None, dimension=None):
         prob = _problem(g, flavor, schedule, topology, dimension)
@@ -351,19 +347,36 @@ def install(g, flavor):
         return 0
 
     def _sharded(time_array, beta):
+        """This rank's block of beta rows on its GPU (CUDA tensors all the way into the
+        collective: NCCL moves device memory only), same integrator selection as grid_eval."""
+        import torch
         kind = g.get("type_of_qw", "dependent")
         if kind == "dependent":
             prob = _problem(g, flavor)
+            if _rk45():
+                def fn(problem, t, b, rows, dev):
+                    return engine.rk45_heatmap(problem, t, b, rtol=g.get("rtolerance", 1e-6),
+                                               atol=g.get("atolerance", 1e-6), rows=rows,
+                                               device=dev)
+            else:
+                def fn(problem, t, b, rows, dev):
+                    return engine.rk4_heatmap(problem, t, b, rows=rows, device=dev)
         elif kind == "independent":
             prob = _problem(g, flavor, schedule="static", topology="circular")
+            if g.get("ti_method", "exact") == "exact":
+                def fn(problem, t, b, rows, dev):
+                    return engine.ti_exact_heatmap(problem, t, b, rows=rows, device=dev)
+            else:
+                def fn(problem, t, b, rows, dev):
+                    return engine.rk4_heatmap(problem, t, b, rows=rows, device=dev)
         else:
             raise ValueError("undefined type_of_qw: %r" % (kind,))
-        compute = None
-        if _rk45() and kind == "dependent":
-            def compute(problem, t, b, rows):
-                return engine.rk45_heatmap(problem, t, b, rtol=g.get("rtolerance", 1e-6),
-                                           atol=g.get("atolerance", 1e-6), rows=rows,
-                                           device=g.get("device"))
+
+        def compute(problem, t, b, rows):
+            dev = engine._device(g.get("device"))
+            return fn(problem, torch.from_numpy(np.ascontiguousarray(t)).to(dev),
+                      torch.from_numpy(np.ascontiguousarray(b)).to(dev), rows, dev)
+
         p, _ = engine.heatmap_sharded(prob, time_array, beta, compute=compute)
         return p
 

@@ -531,44 +531,62 @@ def shard_rows(n_rows, world_size, rank):
 
 
 def heatmap_sharded(problem, time_array, beta_array, group=None, compute=None,
-                    gather=True):
-    """Every rank integrates its block of beta rows; one all_gather assembles
-    probability[beta][T] on all ranks (``np.concatenate`` of BCB.py:288-292).
+                    gather=True, dst=None):
+    """Every rank integrates its block of beta rows; ONE collective assembles
+    probability[beta][T] (``ray.get`` + ``np.concatenate`` of BCB.py:284-292).
 
     ``compute(problem, time_array, beta_array, rows) -> (p, norm)`` defaults to the CUDA
-    path; CPU tests of the sharding logic inject their own.  Returns numpy arrays
-    (p, norm) of the full heatmap, or this rank's block when ``gather`` is False.
+    path; it may return CUDA tensors (they stay on the device through the collective),
+    CPU tensors or numpy arrays (CPU tests of the sharding logic inject the oracle here).
+    ``dst=None``: every rank gets the full heatmap (all_gather_into_tensor + one D2H per
+    rank); ``dst=r``: only rank r copies it to the host, the others return ``(None, None)``
+    (the reference's driver process is the only reader).  ``gather=False``: this rank's
+    block.  Returns numpy arrays (p, norm).
     """
     import torch.distributed as dist
     time_array = np.asarray(time_array, dtype=np.float64)
     beta_array = np.asarray(beta_array, dtype=np.float64)
     if dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+        backend = dist.get_backend(group)
     else:
-        world, rank = 1, 0
+        world, rank, backend = 1, 0, None
     b0, b1 = shard_rows(beta_array.size, world, rank)
-    on_gpu = compute is None
-    if on_gpu:
+    if compute is None:
         dev = _device()
         p, norm = rk4_heatmap(problem, torch.from_numpy(time_array).to(dev),
                               torch.from_numpy(beta_array).to(dev), rows=(b0, b1))
     else:
         p, norm = compute(problem, time_array, beta_array, (b0, b1))
-        p, norm = torch.from_numpy(np.ascontiguousarray(p)), torch.from_numpy(
-            np.ascontiguousarray(norm))
+        if not isinstance(p, torch.Tensor):
+            p = torch.from_numpy(np.ascontiguousarray(p))
+            norm = torch.from_numpy(np.ascontiguousarray(norm))
     if world == 1 or not gather:
         return p.cpu().numpy(), norm.cpu().numpy()
-    # pad to the largest block so a single all_gather_into_tensor-style call suffices
+    if backend == "nccl" and not p.is_cuda:          # NCCL moves device memory only
+        dev = _device()
+        p, norm = p.to(dev), norm.to(dev)
+    # equal blocks (padded to the largest): one all_gather_into_tensor, one D2H
     nT = time_array.size
     rows_max = -(-beta_array.size // world)
     send = torch.zeros((2, rows_max, nT), dtype=torch.float64, device=p.device)
     send[0, :b1 - b0] = p
     send[1, :b1 - b0] = norm
-    recv = [torch.empty_like(send) for _ in range(world)]
-    dist.all_gather(recv, send, group=group)
-    ps, ns = [], []
-    for r in range(world):
-        r0, r1 = shard_rows(beta_array.size, world, r)
-        ps.append(recv[r][0, :r1 - r0])
-        ns.append(recv[r][1, :r1 - r0])
-    return torch.cat(ps).cpu().numpy(), torch.cat(ns).cpu().numpy()
+    recv = torch.empty((world * 2, rows_max, nT), dtype=torch.float64, device=p.device)
+    dist.all_gather_into_tensor(recv, send, group=group)     # rank blocks along dim 0
+    if dst is not None and rank != dst:
+        return None, None
+    host = recv.cpu().numpy().reshape(world, 2, rows_max, nT)    # the single D2H copy
+    counts = [shard_rows(beta_array.size, world, r) for r in range(world)]
+    ps = np.concatenate([host[r, 0, :r1 - r0] for r, (r0, r1) in enumerate(counts)])
+    ns = np.concatenate([host[r, 1, :r1 - r0] for r, (r0, r1) in enumerate(counts)])
+    return ps, ns
+
+
+def sharded_d2h_bytes(n_beta, n_time, world, rank, dst=None):
+    """Bytes ``heatmap_sharded`` copies device -> host on ``rank`` (bench.py's e2e account)."""
+    if world == 1:
+        return 2 * n_beta * n_time * 8
+    if dst is not None and rank != dst:
+        return 0
+    return world * 2 * (-(-n_beta // world)) * n_time * 8
