@@ -422,6 +422,286 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
     cp_async_wait_pending<0>();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Blackwell data movement for the same pass: 1-D bulk copies (cp.async.bulk, the TMA engine;
+// SASS UBLKCP) with mbarrier transaction counts instead of per-lane cp.async / LDS / STG.
+//
+// The TMA engine is request-rate bound (a first version with one 128 / 256 byte copy per thread
+// segment ran at 4.0 TB/s where the cp.async kernel reaches 5.7), so a window moves in CHUNKS of
+// eight thread segments (2 KB with 16 sites per thread, 1 KB with 8): NCH = NT / 8 copies per
+// window and direction, issued by the first NCH lanes of warp 0, one chunk each.
+//   layout  chunk c lies at c * (8 SR + 1) sites of the slot: one pad element between chunks.
+//           Thread t works on segment seg = (t % NCH) * 8 + t / NCH, so the eight lanes of a
+//           quarter warp read from eight different chunks and their 16-byte loads fall into
+//           eight different bank groups ((chunk + r) mod 8): conflict-free without a pad per
+//           segment, which a bulk copy could not skip.  The halo mailbox is indexed by segment
+//           (padded the same way).
+//   load    lane c arrives on the slot's mbarrier with expect_tx(chunk bytes) and issues the
+//           copy HBM -> slot (two copies if the chunk straddles the end of the ring); the
+//           barrier completes when all NCH lanes have armed it and all bytes have landed.
+//   store   after the KB steps every thread writes its sites back into its place of the same
+//           slot (generic proxy) and fences to the async proxy; one block barrier; lane c
+//           issues the copy slot -> HBM of the central part of its chunk.
+//   reuse   at the start of the next window, once the block holds that window in registers,
+//           lane c waits until its store has been READ out of shared memory
+//           (cp.async.bulk.wait_group.read) and re-arms the slot with its chunk of the window
+//           DEPTH - 1 ahead.
+// Per window and thread this leaves SR shared loads, SR shared stores and one barrier outside
+// the arithmetic; the copies of the neighbouring windows run on the TMA engine underneath it.
+// The point's pass entry travels the same way (lane 0, one more bulk copy) into a ring one
+// deeper than the window ring, because the slowest thread may still read the entry of the
+// previous window when lane 0 re-arms a slot.
+// Nested form, aligned layout, full ring, n >= one window (the other cases keep cp.async).
+template <int SR>
+struct TmaGeo {
+    static constexpr int DEPTH = SR == 16 ? 2 : 3;
+    static constexpr int NT = Geo<SR>::NT;
+    static constexpr int NCH = NT / 8;                 // chunks per window
+    static constexpr int CHS = 8 * SR;                 // sites per chunk
+    static constexpr int SLOT = NCH * (CHS + 1);       // double2 per slot
+    static constexpr int MB = NT + NT / 8;             // mailbox entries per array
+    static __device__ __forceinline__ int seg(int t) { return (t % NCH) * 8 + t / NCH; }
+    static __device__ __forceinline__ int place(int sg) { return (sg / 8) * (CHS + 1) + (sg % 8) * SR; }
+    static __device__ __forceinline__ int mb(int sg) { return sg + sg / 8; }
+};
+
+template <int SR>
+struct TmaShared {
+    double2 xbuf[TmaGeo<SR>::DEPTH][TmaGeo<SR>::SLOT];
+    HPassEntry tab[TmaGeo<SR>::DEPTH + 1];
+    double2 mbox[4 * TmaGeo<SR>::MB];      // [parity][first/last][segment, padded]
+    unsigned long long full[TmaGeo<SR>::DEPTH];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QW_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra QW_MBAR_DONE;\n"
+        "bra QW_MBAR_WAIT;\n"
+        "QW_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                          unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+                 "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// lane c (< NCH) of warp 0: arm the slot of local iteration kk with chunk c of window w
+template <int KB, int SR>
+__device__ __forceinline__ void tma_issue_chunk(TmaShared<SR> &sh, const uint32_t kk,
+                                                const double2 *in, const HPassEntry *tab,
+                                                const int64_t n, const uint32_t w,
+                                                const uint32_t tiles, const int c)
+{
+    using G = TmaGeo<SR>;
+    constexpr int HALO = Win<KB, SR, true>::HALO, TILE = Win<KB, SR, true>::TILE;
+    constexpr uint32_t CHB = G::CHS * sizeof(double2);
+    const uint32_t local = w / tiles, tile = w - local * tiles;
+    int64_t j = (int64_t)tile * TILE - HALO + (int64_t)c * G::CHS;   // first site of the chunk
+    if (j < 0) j += n;                                               // n >= W: one wrap at most
+    if (j >= n) j -= n;
+    const uint32_t xs = kk % G::DEPTH, ts = kk % (G::DEPTH + 1);
+    unsigned long long *bar = &sh.full[xs];
+    double2 *dst = &sh.xbuf[xs][c * (G::CHS + 1)];
+    const double2 *src = in + (int64_t)local * n;
+    mbar_arrive_expect_tx(bar, c == 0 ? CHB + (uint32_t)sizeof(HPassEntry) : CHB);
+    const int64_t head = n - j;                                      // sites before the ring ends
+    if (head >= G::CHS) {
+        bulk_load(dst, src + j, CHB, bar);
+    } else {                                                         // multiples of SR sites
+        bulk_load(dst, src + j, (uint32_t)head * (uint32_t)sizeof(double2), bar);
+        bulk_load(dst + head, src, CHB - (uint32_t)head * (uint32_t)sizeof(double2), bar);
+    }
+    if (c == 0) bulk_load(&sh.tab[ts], tab + local, (uint32_t)sizeof(HPassEntry), bar);
+}
+
+// kb steps of the nested form on a thread's segment with open ends.  OWN: this WARP holds the
+// marked vertex of the window (one warp in about 2 x 69 at N = 65536); only its code contains the
+// oracle corrections (thread-level, `own` selects the thread), so the common path is free of
+// divergence handling -- with the branches in every level (first version) the step loop spent
+// 7 % of its samples on VOTEU / BSSY / BSYNC and could not be scheduled across them.
+template <int SR, bool OWN>
+__device__ __forceinline__ void tma_steps(HState<SR> &s, const HPassEntry &pe, const int kb,
+                                          double2 *fst, double2 *lst, const int MB, const int mt,
+                                          const int ml, const int mr, const bool own)
+{
+    const double2 zero2 = make_double2(0.0, 0.0);
+    double2 b0 = zero2, b1 = zero2, b2 = zero2, b3 = zero2;
+    for (int sidx = 0; sidx < kb; ++sidx) {
+#define QW_TMA_LEVEL(LEVEL, CBASE, NTERMS)                                              \
+        {                                                                               \
+            constexpr int par = (4 - LEVEL) & 1;                                        \
+            if (LEVEL < 4 || sidx > 0) __syncthreads();                                 \
+            const double2 hl = lst[par * MB + ml];                                      \
+            const double2 hr = fst[par * MB + mr];                                      \
+            const double rho = pe.rho[4 * sidx + LEVEL - 1];                            \
+            double2 o0, oL;                                                             \
+            if (OWN && LEVEL == 4 && own) {                                             \
+                b0 = make_double2(s.yr[HW0], s.yi[HW0]);                                \
+                b1 = make_double2(s.yr[HW0 - 1] + s.yr[HW0 + 1], s.yi[HW0 - 1] + s.yi[HW0 + 1]); \
+                b2 = make_double2(s.yr[HW0 - 2] + s.yr[HW0 + 2], s.yi[HW0 - 2] + s.yi[HW0 + 2]); \
+                b3 = make_double2(s.yr[HW0 - 3] + s.yr[HW0 + 3], s.yi[HW0 - 3] + s.yi[HW0 + 3]); \
+            }                                                                           \
+            hedges<SR, LEVEL>(s, rho, hl, hr, o0, oL);                                  \
+            hinterior<SR, LEVEL>(s, rho, o0, oL);                                       \
+            if (OWN && own) {                  /* oracle correction sigma_LEVEL */      \
+                const double2 *c = pe.c + 10 * sidx + CBASE;                            \
+                double2 sgm = cmul2(c[0], b0);                                          \
+                if (NTERMS > 1) sgm = cmul2_acc(c[1], b1, sgm);                         \
+                if (NTERMS > 2) sgm = cmul2_acc(c[2], b2, sgm);                         \
+                if (NTERMS > 3) sgm = cmul2_acc(c[3], b3, sgm);                         \
+                if (LEVEL > 1) { s.zr[HW0] += sgm.x; s.zi[HW0] += sgm.y; }              \
+                else { s.yr[HW0] += sgm.x; s.yi[HW0] += sgm.y; }                        \
+            }                                                                           \
+            if (LEVEL > 1) {                                                            \
+                fst[(par ^ 1) * MB + mt] = make_double2(s.zr[0], s.zi[0]);              \
+                lst[(par ^ 1) * MB + mt] = make_double2(s.zr[SR - 1], s.zi[SR - 1]);    \
+            } else {                                                                    \
+                fst[(par ^ 1) * MB + mt] = make_double2(s.yr[0], s.yi[0]);              \
+                lst[(par ^ 1) * MB + mt] = make_double2(s.yr[SR - 1], s.yi[SR - 1]);    \
+            }                                                                           \
+        }
+        QW_TMA_LEVEL(4, 0, 1)
+        QW_TMA_LEVEL(3, 1, 2)
+        QW_TMA_LEVEL(2, 3, 3)
+        QW_TMA_LEVEL(1, 6, 4)
+#undef QW_TMA_LEVEL
+    }
+}
+
+template <int KB, int SR>
+__global__ void __launch_bounds__(Geo<SR>::NT, Geo<SR>::BLOCKS_PER_SM)
+rk4_cycle_stream_tma(const QwParams prm, const double2 *__restrict__ in, double2 *__restrict__ out,
+                     const HPassEntry *__restrict__ tab, uint32_t tiles, uint32_t total)
+{
+    using G = TmaGeo<SR>;
+    static_assert(SR >= 2 * HW0 + 1 && sizeof(HPassEntry) % 16 == 0 && KB <= MAXKB, "layout");
+    constexpr int HALO = Win<KB, SR, true>::HALO;
+    constexpr int TILE = Win<KB, SR, true>::TILE;
+    constexpr int SNT = Geo<SR>::NT;
+    constexpr int DEPTH = G::DEPTH;
+    constexpr int MB = G::MB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TmaShared<SR> &sh = *reinterpret_cast<TmaShared<SR> *>(smem_raw);
+
+    const int t = threadIdx.x;
+    const int sg = G::seg(t);                          // the thread's segment of every window
+    const int64_t n = prm.n;
+    const int ml = G::mb(sg == 0 ? 0 : sg - 1), mr = G::mb(sg == SNT - 1 ? SNT - 1 : sg + 1);
+    const int mt = G::mb(sg);                          // open ends: the edge segments see themselves
+    double2 *fst = sh.mbox, *lst = sh.mbox + 2 * MB;
+    const uint32_t stride = gridDim.x;
+    const bool issuer = t < G::NCH;                    // lane c moves chunk c
+    // window idx = local * tiles + tile, advanced without divisions
+    const uint32_t dl = stride / tiles, dt = stride - dl * tiles;
+    uint32_t local = blockIdx.x / tiles, tile = blockIdx.x - local * tiles;
+
+    if (t == 0) {
+#pragma unroll
+        for (int k = 0; k < DEPTH; ++k) mbar_init(&sh.full[k], G::NCH);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (issuer) {
+#pragma unroll
+        for (int k = 0; k < DEPTH - 1; ++k) {
+            const uint64_t w = (uint64_t)blockIdx.x + (uint64_t)k * stride;
+            if (w < total) tma_issue_chunk<KB, SR>(sh, (uint32_t)k, in, tab, n, (uint32_t)w, tiles, t);
+        }
+    }
+
+    uint32_t kk = 0;
+    for (uint32_t idx = blockIdx.x; idx < total; idx += stride, ++kk) {
+        const int64_t first = (int64_t)tile * TILE - HALO;     // window start (may be < 0)
+        const uint32_t xs = kk % DEPTH, ts = kk % (DEPTH + 1);
+        double2 *seg = &sh.xbuf[xs][G::place(sg)];
+
+        mbar_wait(&sh.full[xs], (kk / DEPTH) & 1u);            // window idx and its entry landed
+        HState<SR> s;
+#pragma unroll
+        for (int r = 0; r < SR; ++r) {
+            const double2 v = seg[r];
+            s.yr[r] = v.x; s.yi[r] = v.y;
+            s.zr[r] = 0.0; s.zi[r] = 0.0;
+        }
+        const HPassEntry &pe = sh.tab[ts];
+        const int kb = pe.kb;
+        fst[mt] = make_double2(s.yr[0], s.yi[0]);
+        lst[mt] = make_double2(s.yr[SR - 1], s.yi[SR - 1]);
+        // the slot of the previous window: its stores have left shared memory -> re-arm it
+        if (issuer) {
+            const uint64_t w = (uint64_t)idx + (uint64_t)(DEPTH - 1) * stride;
+            if (kk > 0) bulk_wait_read0();
+            if (w < total)
+                tma_issue_chunk<KB, SR>(sh, kk + DEPTH - 1, in, tab, n, (uint32_t)w, tiles, t);
+        }
+        __syncthreads();                       // edge values published
+
+        if (kb > 0) {
+            // the marked vertex is logical site HW0 of the rotated ring: slot HW0 of the thread
+            // whose segment starts at a multiple of n
+            int64_t wrel = HW0 - first - (int64_t)sg * SR;
+            if (wrel < 0) wrel += n;
+            if (wrel >= n) wrel -= n;
+            const bool own = wrel == HW0;
+            if (__ballot_sync(0xffffffffu, own) != 0u)
+                tma_steps<SR, true>(s, pe, kb, fst, lst, MB, mt, ml, mr, own);
+            else
+                tma_steps<SR, false>(s, pe, kb, fst, lst, MB, mt, ml, mr, false);
+        }
+
+        // registers -> the thread's place in the slot; then lane c: central part of chunk c -> HBM
+#pragma unroll
+        for (int r = 0; r < SR; ++r) seg[r] = make_double2(s.yr[r], s.yi[r]);
+        fence_proxy_async();
+        __syncthreads();
+        if (issuer) {
+            int e0 = t * G::CHS, e1 = e0 + G::CHS;                 // window positions of the chunk
+            if (e0 < HALO) e0 = HALO;
+            if (e1 > HALO + TILE) e1 = HALO + TILE;
+            if (first + e1 > n) e1 = (int)(n - first);             // last tile: the ring ends
+            if (e1 > e0)
+                bulk_store(out + (int64_t)local * n + first + e0,
+                           &sh.xbuf[xs][t * (G::CHS + 1) + (e0 - t * G::CHS)],
+                           (uint32_t)(e1 - e0) * (uint32_t)sizeof(double2));
+            bulk_commit();
+        }
+        local += dl;
+        tile += dt;
+        if (tile >= tiles) { tile -= tiles; ++local; }
+    }
+    if (issuer) bulk_wait0();
+}
+
 __global__ void stream_init(double2 *buf, int64_t total, double amp)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -537,6 +817,45 @@ cudaError_t configure()
     return e;
 }
 
+template <int KB, int SR>
+cudaError_t configure_tma()
+{
+    static QwOncePerDevice configured;
+    if (!configured.needed()) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(rk4_cycle_stream_tma<KB, SR>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(TmaShared<SR>));
+    if (e == cudaSuccess) configured.mark();
+    return e;
+}
+
+// bulk-copy (TMA) data movement: nested form on the aligned full ring; QW_FLAG_CYCLE_LEGACY
+// keeps the cp.async kernel for A/B runs
+bool stream_tma(const QwParams &prm, int sr)
+{
+    return !(prm.flags & (QW_FLAG_NO_HORNER | QW_FLAG_CYCLE_LEGACY)) && !prm.mirror_m &&
+           prm.n % sr == 0 && prm.n >= 1024 && !((prm.flags & QW_FLAG_MIRROR) && prm.n >= 8192);
+}
+
+template <int KB, int SR>
+cudaError_t launch_pass_tma(const QwParams &prm, const double2 *in, double2 *out, void *tab,
+                            int64_t step0, int64_t points, cudaStream_t st)
+{
+    constexpr int TILE = Win<KB, SR, true>::TILE;
+    HPassEntry *etab = static_cast<HPassEntry *>(tab);
+    stream_pass_tables_horner<<<(unsigned)((points + 127) / 128), 128, 0, st>>>(prm, points, step0,
+                                                                               KB, etab);
+    const uint32_t tiles = (uint32_t)((prm.n + TILE - 1) / TILE);
+    const uint64_t total = (uint64_t)points * tiles;
+    uint32_t grid = (uint32_t)(sm_count() * Geo<SR>::BLOCKS_PER_SM);      // persistent
+    if (total < grid) grid = (uint32_t)total;
+    cudaError_t e = configure_tma<KB, SR>();
+    if (e != cudaSuccess) return e;
+    rk4_cycle_stream_tma<KB, SR><<<grid, Geo<SR>::NT, sizeof(TmaShared<SR>), st>>>(
+        prm, in, out, etab, tiles, (uint32_t)total);
+    return cudaGetLastError();
+}
+
 template <int KB, int SR, bool ALIGNED, bool HORNER>
 cudaError_t launch_pass_a(const QwParams &prm, const double2 *in, double2 *out, void *tab,
                           int64_t step0, int64_t points, cudaStream_t st)
@@ -580,6 +899,7 @@ template <int KB, int SR>
 cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, void *tab,
                         int64_t step0, int64_t points, cudaStream_t st)
 {
+    if (stream_tma(prm, SR)) return launch_pass_tma<KB, SR>(prm, in, out, tab, step0, points, st);
     if (stream_horner(prm, SR))
         return launch_pass_a<KB, SR, true, true>(prm, in, out, tab, step0, points, st);
     return prm.n % SR == 0
@@ -588,13 +908,20 @@ cudaError_t launch_pass(const QwParams &prm, const double2 *in, double2 *out, vo
 }
 
 template <int KB, int SR>
-cudaError_t plan_of(qw_plan *plan, bool horner)
+cudaError_t plan_of(qw_plan *plan, bool horner, int tma)
 {
     cudaFuncAttributes fa;
     int occ = 0;
     cudaError_t e;
     size_t smem;
-    if (horner) {
+    if (tma == 1) {
+        smem = sizeof(TmaShared<SR>);
+        e = configure_tma<KB, SR>();
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rk4_cycle_stream_tma<KB, SR>);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &occ, rk4_cycle_stream_tma<KB, SR>, Geo<SR>::NT, smem);
+    } else if (horner) {
         smem = sizeof(StreamShared<SR, true>);
         e = configure<KB, SR, true, true>();
         if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, rk4_cycle_stream<KB, SR, true, true>);
@@ -636,7 +963,8 @@ cudaError_t qw_stream_plan(const QwParams &prm, qw_plan *plan)
 {
     plan->path = 3;
     const int kb = stream_kb(prm), sr = stream_sr(prm);
-    return QW_STREAM_DISPATCH(plan_of, plan, stream_horner(prm, sr));
+    return QW_STREAM_DISPATCH(plan_of, plan, stream_horner(prm, sr),
+                              stream_tma(prm, sr) ? 1 : 0);
 }
 
 cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *launches)

@@ -285,7 +285,7 @@ def test_plan_reports_native_kernels(qw):
     assert qw.launch_count() == before + 1
 
 
-@pytest.mark.parametrize("n", [8, 64, 1000, 1016, 1024, 2050, 4100, 9001])
+@pytest.mark.parametrize("n", [8, 64, 1000, 1016, 1024, 1040, 2050, 2064, 4100, 8208, 9001])
 @pytest.mark.parametrize("kb_flag", [8, 16, 24, 0, 256, 256 | 8, 2048, 2048 | 8, 2048 | 16,
                                      2048 | 24])
 def test_streaming_kernel_vs_oracle(qw, n, kb_flag):
