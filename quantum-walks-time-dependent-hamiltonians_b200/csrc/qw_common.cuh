@@ -70,6 +70,8 @@ struct QwParams {
     int64_t stream_rot;           // streaming: psi is stored rotated, logical l = (j - rot) mod n
     int64_t mirror_m;             // streaming, QW_FLAG_MIRROR: sites of the half ring (n/2 + 1),
                                   // stored behind 3 mirrored ghost sites; 0 = full ring
+    int32_t stream_pad;           // streaming, bulk-copy kernel: psi is stored with one pad element
+                                  // after every stream_pad sites (0: dense)
 };
 
 struct QwPoint {

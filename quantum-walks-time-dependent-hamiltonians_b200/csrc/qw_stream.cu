@@ -68,10 +68,11 @@ struct PassEntry {
 // correction coefficients over (y_w, s1, s2, s3) per step.
 struct HPassEntry {
     double rho[4 * MAXKB];
-    double2 c[10 * MAXKB];
     int32_t kb;
     int32_t pad[3];
+    double2 c[10 * MAXKB];             // read by the one thread that holds the marked vertex
 };
+constexpr uint32_t HPASS_HEAD = 4 * MAXKB * sizeof(double) + 16;   // rho and kb
 
 template <int SR, bool HORNER>
 struct StreamShared {
@@ -82,9 +83,11 @@ struct StreamShared {
 };
 
 __global__ void stream_pass_tables_horner(const QwParams prm, int64_t count, int64_t step0,
-                                          int kbmax, HPassEntry *__restrict__ tab)
+                                          int kbmax, HPassEntry *__restrict__ tab,
+                                          unsigned int *__restrict__ counter = nullptr)
 {
     const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (local == 0 && counter) *counter = 0u;          // window counter of the bulk-copy kernel
     if (local >= count) return;
     const QwPoint pt = qw_point(prm, prm.point_offset + local);
     const int64_t todo = pt.steps - step0;
@@ -426,51 +429,69 @@ rk4_cycle_stream(const QwParams prm, const double2 *__restrict__ in, double2 *__
 // Blackwell data movement for the same pass: 1-D bulk copies (cp.async.bulk, the TMA engine;
 // SASS UBLKCP) with mbarrier transaction counts instead of per-lane cp.async / LDS / STG.
 //
-// The TMA engine is request-rate bound (a first version with one 128 / 256 byte copy per thread
-// segment ran at 4.0 TB/s where the cp.async kernel reaches 5.7), so a window moves in CHUNKS of
-// eight thread segments (2 KB with 16 sites per thread, 1 KB with 8): NCH = NT / 8 copies per
-// window and direction, issued by the first NCH lanes of warp 0, one chunk each.
-//   layout  chunk c lies at c * (8 SR + 1) sites of the slot: one pad element between chunks.
-//           Thread t works on segment seg = (t % NCH) * 8 + t / NCH, so the eight lanes of a
-//           quarter warp read from eight different chunks and their 16-byte loads fall into
-//           eight different bank groups ((chunk + r) mod 8): conflict-free without a pad per
-//           segment, which a bulk copy could not skip.  The halo mailbox is indexed by segment
-//           (padded the same way).
-//   load    lane c arrives on the slot's mbarrier with expect_tx(chunk bytes) and issues the
-//           copy HBM -> slot (two copies if the chunk straddles the end of the ring); the
-//           barrier completes when all NCH lanes have armed it and all bytes have landed.
+// What shaped it (measured on the N = 65536 grid, tools/ab_stream.py, tools/probe_stream.py):
+//  * one copy per thread segment (128 / 256 B) is request-rate bound in the TMA engine: 4.0 TB/s
+//    where the cp.async kernel reaches 5.7;
+//  * a bulk copy costs its issuing warp about 60 cycles, so with eight 2 KB chunks per window and
+//    direction (a pad element between chunks for the shared-memory banks) the issue work alone
+//    was 1100 cycles per window, all of it in front of the next window's arithmetic;
+//  * hence the pad lives in HBM too: psi is stored with ONE PAD ELEMENT AFTER EVERY 128 SITES
+//    (+0.8 % traffic).  A window -- 1024 sites plus its 8 pads -- is then contiguous in HBM and
+//    in shared memory, and moves with ONE bulk load and ONE bulk store (two where it wraps
+//    around the ring).
+// Bank conflicts: thread t works on segment seg = (t % 8) * (NT / 8) + t / 8, so the eight lanes
+// of a quarter warp read segments that lie 128 sites apart, i.e. behind 0, 1, ... 7 more pads:
+// their 16-byte loads fall into eight different bank groups whatever the window's offset within
+// a 128-site block.  The halo mailbox is indexed by segment and padded the same way.
+//   load    one thread arrives on the slot's mbarrier with expect_tx(window + entry bytes) and
+//           issues the copies; the barrier completes when all bytes have landed;
 //   store   after the KB steps every thread writes its sites back into its place of the same
-//           slot (generic proxy) and fences to the async proxy; one block barrier; lane c
-//           issues the copy slot -> HBM of the central part of its chunk.
-//   reuse   at the start of the next window, once the block holds that window in registers,
-//           lane c waits until its store has been READ out of shared memory
-//           (cp.async.bulk.wait_group.read) and re-arms the slot with its chunk of the window
-//           DEPTH - 1 ahead.
-// Per window and thread this leaves SR shared loads, SR shared stores and one barrier outside
-// the arithmetic; the copies of the neighbouring windows run on the TMA engine underneath it.
-// The point's pass entry travels the same way (lane 0, one more bulk copy) into a ring one
-// deeper than the window ring, because the slowest thread may still read the entry of the
-// previous window when lane 0 re-arms a slot.
-// Nested form, aligned layout, full ring, n >= one window (the other cases keep cp.async).
+//           slot (generic proxy) and fences to the async proxy; one block barrier; one thread
+//           issues the copy of the central part of the window to HBM;
+//   ring    three slots, window kk in slot kk % 3; window kk + 2 goes into the slot window
+//           kk - 1 has left, once the store of window kk - 1 has been READ out of shared memory
+//           (cp.async.bulk.wait_group.read).
+//           KB >= 4 (FP64-bound): thread 0 stores window kk at its end and thread 32 -- the other
+//           warp, side by side -- requests window kk + 2; the store it depends on is a whole
+//           window old.  KB <= 2 (HBM-bound): thread 0 requests window kk + 2 at the START of
+//           window kk, as soon as the block holds window kk in registers (two windows of lead).
+// Per window and thread this leaves SR shared loads, SR shared stores and two barriers outside
+// the arithmetic.  The head of the point's pass entry (rho, kb: 272 B) travels with the window
+// into a ring one deeper than the window ring; the correction coefficients are fetched by the
+// one warp per ring that holds the marked vertex.
+// Nested form, full ring, n a multiple of 128 and >= one window (other cases: cp.async kernel).
+constexpr int TMA_PADQ = 128;                          // sites between two pad elements
+
+__host__ __device__ __forceinline__ int64_t tma_padded(int64_t x)      // index of site x, x >= 0
+{
+    return x + x / TMA_PADQ;
+}
+
 template <int SR>
 struct TmaGeo {
-    static constexpr int DEPTH = SR == 16 ? 2 : 3;
+    static constexpr int DEPTH = 3;                    // window kk lives in slot kk % 3
     static constexpr int NT = Geo<SR>::NT;
-    static constexpr int NCH = NT / 8;                 // chunks per window
-    static constexpr int CHS = 8 * SR;                 // sites per chunk
-    static constexpr int SLOT = NCH * (CHS + 1);       // double2 per slot
-    static constexpr int MB = NT + NT / 8;             // mailbox entries per array
-    static __device__ __forceinline__ int seg(int t) { return (t % NCH) * 8 + t / NCH; }
-    static __device__ __forceinline__ int place(int sg) { return (sg / 8) * (CHS + 1) + (sg % 8) * SR; }
-    static __device__ __forceinline__ int mb(int sg) { return sg + sg / 8; }
+    static constexpr int W = Geo<SR>::W;
+    static constexpr int SLOT = W + W / TMA_PADQ;      // double2 per slot
+    static constexpr int MB = NT + 8;                  // mailbox entries per array
+    static __device__ __forceinline__ int seg(int t) { return (t % 8) * (NT / 8) + t / 8; }
+    static __device__ __forceinline__ int mb(int sg) { return sg + sg / (NT / 8); }
+};
+
+struct TmaHead {                           // the first HPASS_HEAD bytes of an HPassEntry
+    double rho[4 * MAXKB];
+    int32_t kb;
+    int32_t pad[3];
 };
 
 template <int SR>
 struct TmaShared {
     double2 xbuf[TmaGeo<SR>::DEPTH][TmaGeo<SR>::SLOT];
-    HPassEntry tab[TmaGeo<SR>::DEPTH + 1];
+    TmaHead tab[TmaGeo<SR>::DEPTH + 1];      // window kk's entry in tab[kk % (DEPTH + 1)]
+    double2 cown[10 * MAXKB];              // correction coefficients of the window with the marked vertex
     double2 mbox[4 * TmaGeo<SR>::MB];      // [parity][first/last][segment, padded]
     unsigned long long full[TmaGeo<SR>::DEPTH];
+    uint32_t widx[TmaGeo<SR>::DEPTH + 1];  // window index of iteration kk (0xffffffff: none left)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -514,33 +535,47 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// lane c (< NCH) of warp 0: arm the slot of local iteration kk with chunk c of window w
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ONE thread: arm the slot of local iteration kk with window w of the padded ring and the head of
+// its point's pass entry; w >= total: nothing left -- complete the barrier empty-handed so that
+// the block sees the end marker
 template <int KB, int SR>
-__device__ __forceinline__ void tma_issue_chunk(TmaShared<SR> &sh, const uint32_t kk,
-                                                const double2 *in, const HPassEntry *tab,
-                                                const int64_t n, const uint32_t w,
-                                                const uint32_t tiles, const int c)
+__device__ __forceinline__ void tma_issue_window(TmaShared<SR> &sh, const uint32_t kk,
+                                                 const double2 *in, const HPassEntry *tab,
+                                                 const int64_t n, const int64_t np,
+                                                 const uint32_t w, const uint32_t tiles,
+                                                 const uint32_t total)
 {
     using G = TmaGeo<SR>;
     constexpr int HALO = Win<KB, SR, true>::HALO, TILE = Win<KB, SR, true>::TILE;
-    constexpr uint32_t CHB = G::CHS * sizeof(double2);
-    const uint32_t local = w / tiles, tile = w - local * tiles;
-    int64_t j = (int64_t)tile * TILE - HALO + (int64_t)c * G::CHS;   // first site of the chunk
-    if (j < 0) j += n;                                               // n >= W: one wrap at most
-    if (j >= n) j -= n;
-    const uint32_t xs = kk % G::DEPTH, ts = kk % (G::DEPTH + 1);
+    constexpr uint32_t WB = G::SLOT * sizeof(double2);
+    const uint32_t xs = kk % G::DEPTH;
     unsigned long long *bar = &sh.full[xs];
-    double2 *dst = &sh.xbuf[xs][c * (G::CHS + 1)];
-    const double2 *src = in + (int64_t)local * n;
-    mbar_arrive_expect_tx(bar, c == 0 ? CHB + (uint32_t)sizeof(HPassEntry) : CHB);
-    const int64_t head = n - j;                                      // sites before the ring ends
-    if (head >= G::CHS) {
-        bulk_load(dst, src + j, CHB, bar);
-    } else {                                                         // multiples of SR sites
-        bulk_load(dst, src + j, (uint32_t)head * (uint32_t)sizeof(double2), bar);
-        bulk_load(dst + head, src, CHB - (uint32_t)head * (uint32_t)sizeof(double2), bar);
+    if (w >= total) {
+        sh.widx[kk % (G::DEPTH + 1)] = 0xffffffffu;
+        mbar_arrive(bar);
+        return;
     }
-    if (c == 0) bulk_load(&sh.tab[ts], tab + local, (uint32_t)sizeof(HPassEntry), bar);
+    sh.widx[kk % (G::DEPTH + 1)] = w;
+    const uint32_t local = w / tiles, tile = w - local * tiles;
+    double2 *dst = sh.xbuf[xs];
+    const double2 *src = in + (int64_t)local * np;
+    int64_t j = (int64_t)tile * TILE - HALO;                         // first site of the window
+    if (j < 0) j += n;                                               // n >= W: one wrap at most
+    const int64_t pj = tma_padded(j);
+    mbar_arrive_expect_tx(bar, WB + HPASS_HEAD);
+    bulk_load(&sh.tab[kk % (G::DEPTH + 1)], tab + local, HPASS_HEAD, bar);
+    const int64_t head = np - pj;                                    // elements before the ring ends
+    if (head >= G::SLOT) {
+        bulk_load(dst, src + pj, WB, bar);
+    } else {
+        bulk_load(dst, src + pj, (uint32_t)head * (uint32_t)sizeof(double2), bar);
+        bulk_load(dst + head, src, WB - (uint32_t)head * (uint32_t)sizeof(double2), bar);
+    }
 }
 
 // kb steps of the nested form on a thread's segment with open ends.  OWN: this WARP holds the
@@ -549,9 +584,9 @@ __device__ __forceinline__ void tma_issue_chunk(TmaShared<SR> &sh, const uint32_
 // divergence handling -- with the branches in every level (first version) the step loop spent
 // 7 % of its samples on VOTEU / BSSY / BSYNC and could not be scheduled across them.
 template <int SR, bool OWN>
-__device__ __forceinline__ void tma_steps(HState<SR> &s, const HPassEntry &pe, const int kb,
-                                          double2 *fst, double2 *lst, const int MB, const int mt,
-                                          const int ml, const int mr, const bool own)
+__device__ __forceinline__ void tma_steps(HState<SR> &s, const TmaHead &pe, const double2 *coef,
+                                          const int kb, double2 *fst, double2 *lst, const int MB,
+                                          const int mt, const int ml, const int mr, const bool own)
 {
     const double2 zero2 = make_double2(0.0, 0.0);
     double2 b0 = zero2, b1 = zero2, b2 = zero2, b3 = zero2;
@@ -573,7 +608,7 @@ __device__ __forceinline__ void tma_steps(HState<SR> &s, const HPassEntry &pe, c
             hedges<SR, LEVEL>(s, rho, hl, hr, o0, oL);                                  \
             hinterior<SR, LEVEL>(s, rho, o0, oL);                                       \
             if (OWN && own) {                  /* oracle correction sigma_LEVEL */      \
-                const double2 *c = pe.c + 10 * sidx + CBASE;                            \
+                const double2 *c = coef + 10 * sidx + CBASE;                            \
                 double2 sgm = cmul2(c[0], b0);                                          \
                 if (NTERMS > 1) sgm = cmul2_acc(c[1], b1, sgm);                         \
                 if (NTERMS > 2) sgm = cmul2_acc(c[2], b2, sgm);                         \
@@ -597,13 +632,27 @@ __device__ __forceinline__ void tma_steps(HState<SR> &s, const HPassEntry &pe, c
     }
 }
 
+// Development probe (-DQW_PROBE): cycles thread 0 of every block spends in the phases of a window,
+// summed over the launch; read with qw_debug_probe().
+#ifdef QW_PROBE
+__device__ unsigned long long qw_probe[8];
+__device__ unsigned long long qw_probe_blocks[3 * 1024];      // smid, start ns, end ns per block
+#define QW_PROBE_T(var) const long long var = clock64()
+#define QW_PROBE_ADD(i, a, b) if (t == 0) atomicAdd(&qw_probe[i], (unsigned long long)((b) - (a)))
+#else
+#define QW_PROBE_T(var)
+#define QW_PROBE_ADD(i, a, b)
+#endif
+
 template <int KB, int SR>
 __global__ void __launch_bounds__(Geo<SR>::NT, Geo<SR>::BLOCKS_PER_SM)
 rk4_cycle_stream_tma(const QwParams prm, const double2 *__restrict__ in, double2 *__restrict__ out,
-                     const HPassEntry *__restrict__ tab, uint32_t tiles, uint32_t total)
+                     const HPassEntry *__restrict__ tab, uint32_t tiles, uint32_t total,
+                     unsigned int *__restrict__ next_window)
 {
     using G = TmaGeo<SR>;
     static_assert(SR >= 2 * HW0 + 1 && sizeof(HPassEntry) % 16 == 0 && KB <= MAXKB, "layout");
+    static_assert(TMA_PADQ % SR == 0 && Geo<SR>::W % TMA_PADQ == 0, "segments must not straddle a pad");
     constexpr int HALO = Win<KB, SR, true>::HALO;
     constexpr int TILE = Win<KB, SR, true>::TILE;
     constexpr int SNT = Geo<SR>::NT;
@@ -614,38 +663,55 @@ rk4_cycle_stream_tma(const QwParams prm, const double2 *__restrict__ in, double2
 
     const int t = threadIdx.x;
     const int sg = G::seg(t);                          // the thread's segment of every window
-    const int64_t n = prm.n;
+    const int64_t n = prm.n, np = tma_padded(prm.n);   // sites / stored elements per point
     const int ml = G::mb(sg == 0 ? 0 : sg - 1), mr = G::mb(sg == SNT - 1 ? SNT - 1 : sg + 1);
     const int mt = G::mb(sg);                          // open ends: the edge segments see themselves
     double2 *fst = sh.mbox, *lst = sh.mbox + 2 * MB;
-    const uint32_t stride = gridDim.x;
-    const bool issuer = t < G::NCH;                    // lane c moves chunk c
-    // window idx = local * tiles + tile, advanced without divisions
-    const uint32_t dl = stride / tiles, dt = stride - dl * tiles;
-    uint32_t local = blockIdx.x / tiles, tile = blockIdx.x - local * tiles;
 
+    // Windows are handed out by an atomic counter, not by a fixed stride: co-resident blocks do
+    // not get equal shares of the FP64 pipe (measured: with equal window counts the blocks of one
+    // launch finished between 567 and 949 us), so a static split ends with a good part of the
+    // machine idle.  The loader thread draws an index one window ahead of its use, so the
+    // atomic's round trip is never waited for.
+    constexpr bool LATE = KB >= 4;
+    const bool storer = t == 0;
+    const bool loader = LATE ? t == 32 : t == 0;
+#ifdef QW_PROBE
+    if (t == 0 && blockIdx.x < 1024) {
+        unsigned sm; unsigned long long ns;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        qw_probe_blocks[3 * blockIdx.x] = sm;
+        qw_probe_blocks[3 * blockIdx.x + 1] = ns;
+    }
+#endif
     if (t == 0) {
 #pragma unroll
-        for (int k = 0; k < DEPTH; ++k) mbar_init(&sh.full[k], G::NCH);
+        for (int k = 0; k < DEPTH; ++k) mbar_init(&sh.full[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-
-    if (issuer) {
+    uint32_t wnext = 0xffffffffu;              // loader: the window it will request next
+    if (loader) {                              // windows 0 and 1 of this block
 #pragma unroll
-        for (int k = 0; k < DEPTH - 1; ++k) {
-            const uint64_t w = (uint64_t)blockIdx.x + (uint64_t)k * stride;
-            if (w < total) tma_issue_chunk<KB, SR>(sh, (uint32_t)k, in, tab, n, (uint32_t)w, tiles, t);
-        }
+        for (int k = 0; k < DEPTH - 1; ++k)
+            tma_issue_window<KB, SR>(sh, (uint32_t)k, in, tab, n, np, atomicAdd(next_window, 1u),
+                                     tiles, total);
+        wnext = atomicAdd(next_window, 1u);
     }
 
-    uint32_t kk = 0;
-    for (uint32_t idx = blockIdx.x; idx < total; idx += stride, ++kk) {
+    for (uint32_t kk = 0;; ++kk) {
+        const uint32_t xs = kk % DEPTH;
+        QW_PROBE_T(c0);
+        mbar_wait(&sh.full[xs], (kk / DEPTH) & 1u);            // window kk and its entry landed
+        QW_PROBE_T(c1);
+        const uint32_t idx = sh.widx[kk % (DEPTH + 1)];
+        if (idx == 0xffffffffu) break;                         // no window left (block-uniform)
+        const uint32_t local = idx / tiles, tile = idx - local * tiles;
         const int64_t first = (int64_t)tile * TILE - HALO;     // window start (may be < 0)
-        const uint32_t xs = kk % DEPTH, ts = kk % (DEPTH + 1);
-        double2 *seg = &sh.xbuf[xs][G::place(sg)];
-
-        mbar_wait(&sh.full[xs], (kk / DEPTH) & 1u);            // window idx and its entry landed
+        // position of the window within its 128-site block -> where the pads sit in the slot
+        const int fm = (int)((first + TMA_PADQ) % TMA_PADQ);   // first >= -HALO > -128
+        double2 *seg = &sh.xbuf[xs][sg * SR + (fm + sg * SR) / TMA_PADQ];
         HState<SR> s;
 #pragma unroll
         for (int r = 0; r < SR; ++r) {
@@ -653,53 +719,79 @@ rk4_cycle_stream_tma(const QwParams prm, const double2 *__restrict__ in, double2
             s.yr[r] = v.x; s.yi[r] = v.y;
             s.zr[r] = 0.0; s.zi[r] = 0.0;
         }
-        const HPassEntry &pe = sh.tab[ts];
+        const TmaHead &pe = sh.tab[kk % (DEPTH + 1)];
         const int kb = pe.kb;
         fst[mt] = make_double2(s.yr[0], s.yi[0]);
         lst[mt] = make_double2(s.yr[SR - 1], s.yi[SR - 1]);
-        // the slot of the previous window: its stores have left shared memory -> re-arm it
-        if (issuer) {
-            const uint64_t w = (uint64_t)idx + (uint64_t)(DEPTH - 1) * stride;
-            if (kk > 0) bulk_wait_read0();
-            if (w < total)
-                tma_issue_chunk<KB, SR>(sh, kk + DEPTH - 1, in, tab, n, (uint32_t)w, tiles, t);
+        if (!LATE && loader) {
+            if (kk > 0) bulk_wait_read0();     // my store of window kk - 1 has left its slot
+            tma_issue_window<KB, SR>(sh, kk + DEPTH - 1, in, tab, n, np, wnext, tiles, total);
+            if (wnext < total) wnext = atomicAdd(next_window, 1u);
         }
-        __syncthreads();                       // edge values published
+        // the marked vertex is logical site HW0 of the rotated ring: slot HW0 of the thread whose
+        // segment starts at a multiple of n
+        int64_t wrel = HW0 - first - (int64_t)sg * SR;
+        if (wrel < 0) wrel += n;
+        if (wrel >= n) wrel -= n;
+        const bool own = wrel == HW0;
+        const bool warp_owns = __ballot_sync(0xffffffffu, own) != 0u;
+        if (warp_owns && kb > 0) {             // its correction coefficients: HBM -> shared memory
+            const double2 *cg = tab[local].c;
+            for (int i = t & 31; i < 10 * kb; i += 32) sh.cown[i] = cg[i];
+        }
+        __syncthreads();                       // edge values (and coefficients) published
+        QW_PROBE_T(c2);
 
         if (kb > 0) {
-            // the marked vertex is logical site HW0 of the rotated ring: slot HW0 of the thread
-            // whose segment starts at a multiple of n
-            int64_t wrel = HW0 - first - (int64_t)sg * SR;
-            if (wrel < 0) wrel += n;
-            if (wrel >= n) wrel -= n;
-            const bool own = wrel == HW0;
-            if (__ballot_sync(0xffffffffu, own) != 0u)
-                tma_steps<SR, true>(s, pe, kb, fst, lst, MB, mt, ml, mr, own);
+            if (warp_owns)
+                tma_steps<SR, true>(s, pe, sh.cown, kb, fst, lst, MB, mt, ml, mr, own);
             else
-                tma_steps<SR, false>(s, pe, kb, fst, lst, MB, mt, ml, mr, false);
+                tma_steps<SR, false>(s, pe, sh.cown, kb, fst, lst, MB, mt, ml, mr, false);
         }
 
-        // registers -> the thread's place in the slot; then lane c: central part of chunk c -> HBM
+        // registers -> the thread's place in the slot; then thread 0: central part -> HBM, and
+        // (LATE) thread 32: the request for window kk + 2 into the slot window kk - 1 has left
+        // (thread 0 makes sure of that before the barrier: its store of window kk - 1 is a
+        // window old)
+        QW_PROBE_T(c3);
 #pragma unroll
         for (int r = 0; r < SR; ++r) seg[r] = make_double2(s.yr[r], s.yi[r]);
         fence_proxy_async();
+        if (LATE && storer) bulk_wait_read0();
         __syncthreads();
-        if (issuer) {
-            int e0 = t * G::CHS, e1 = e0 + G::CHS;                 // window positions of the chunk
-            if (e0 < HALO) e0 = HALO;
-            if (e1 > HALO + TILE) e1 = HALO + TILE;
-            if (first + e1 > n) e1 = (int)(n - first);             // last tile: the ring ends
-            if (e1 > e0)
-                bulk_store(out + (int64_t)local * n + first + e0,
-                           &sh.xbuf[xs][t * (G::CHS + 1) + (e0 - t * G::CHS)],
-                           (uint32_t)(e1 - e0) * (uint32_t)sizeof(double2));
+        QW_PROBE_T(c4);
+        if (storer) {
+            int64_t a = first + HALO, b = first + HALO + TILE;     // sites [a, b) of the ring
+            if (b > n) b = n;                                      // last tile: the ring ends
+            if (b > a) {
+                // padded positions relative to the window start; floor division for first < 0
+                const int64_t base = first + (first >= 0 ? first / TMA_PADQ : -1);
+                const int64_t pa = tma_padded(a), pb = tma_padded(b);
+                bulk_store(out + (int64_t)local * np + pa, sh.xbuf[xs] + (pa - base),
+                           (uint32_t)(pb - pa) * (uint32_t)sizeof(double2));
+            }
             bulk_commit();
         }
-        local += dl;
-        tile += dt;
-        if (tile >= tiles) { tile -= tiles; ++local; }
+        if (LATE && loader) {
+            tma_issue_window<KB, SR>(sh, kk + DEPTH - 1, in, tab, n, np, wnext, tiles, total);
+            if (wnext < total) wnext = atomicAdd(next_window, 1u);
+        }
+        QW_PROBE_T(c5);
+        QW_PROBE_ADD(0, c0, c1);
+        QW_PROBE_ADD(1, c1, c2);
+        QW_PROBE_ADD(2, c2, c3);
+        QW_PROBE_ADD(3, c3, c4);
+        QW_PROBE_ADD(4, c4, c5);
+        QW_PROBE_ADD(5, 0, 1);
     }
-    if (issuer) bulk_wait0();
+    if (storer) bulk_wait0();
+#ifdef QW_PROBE
+    if (t == 0 && blockIdx.x < 1024) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        qw_probe_blocks[3 * blockIdx.x + 2] = ns;
+    }
+#endif
 }
 
 __global__ void stream_init(double2 *buf, int64_t total, double amp)
@@ -751,10 +843,11 @@ __global__ void __launch_bounds__(512) stream_finish(const QwParams prm, const d
         }
         return;
     }
-    const double2 *src = buf + local * n;
+    const int64_t pq = prm.stream_pad;                     // one pad element after every pq sites
+    const double2 *src = buf + local * (pq ? n + n / pq : n);
     double nrm = 0.0;
     for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-        const double2 v = src[j];
+        const double2 v = src[pq ? j + j / pq : j];
         nrm = fma(v.x, v.x, fma(v.y, v.y, nrm));
         if (prm.psi) {                          // undo the rotation: physical (l + rot) mod n
             int64_t jp = j + prm.stream_rot;
@@ -766,7 +859,7 @@ __global__ void __launch_bounds__(512) stream_finish(const QwParams prm, const d
     if (threadIdx.x == 0) {
         int64_t lw = prm.target - prm.stream_rot;          // logical site of the marked vertex
         if (lw < 0) lw += n;
-        const double2 v = src[lw];
+        const double2 v = src[pq ? lw + lw / pq : lw];
         prm.p[pt.q] = fma(v.x, v.x, v.y * v.y) / tot.x;
         if (prm.norm) prm.norm[pt.q] = tot.x;
     }
@@ -834,17 +927,21 @@ cudaError_t configure_tma()
 bool stream_tma(const QwParams &prm, int sr)
 {
     return !(prm.flags & (QW_FLAG_NO_HORNER | QW_FLAG_CYCLE_LEGACY)) && !prm.mirror_m &&
-           prm.n % sr == 0 && prm.n >= 1024 && !((prm.flags & QW_FLAG_MIRROR) && prm.n >= 8192);
+           prm.n % TMA_PADQ == 0 && prm.n >= 1024 && sr > 0 &&
+           !((prm.flags & QW_FLAG_MIRROR) && prm.n >= 8192);
 }
 
 template <int KB, int SR>
 cudaError_t launch_pass_tma(const QwParams &prm, const double2 *in, double2 *out, void *tab,
                             int64_t step0, int64_t points, cudaStream_t st)
 {
+    // the window counter of this pass sits behind the pass entries (zeroed by the table kernel)
+    unsigned int *counter = reinterpret_cast<unsigned int *>(
+        static_cast<char *>(tab) + (size_t)points * sizeof(HPassEntry));
     constexpr int TILE = Win<KB, SR, true>::TILE;
     HPassEntry *etab = static_cast<HPassEntry *>(tab);
     stream_pass_tables_horner<<<(unsigned)((points + 127) / 128), 128, 0, st>>>(prm, points, step0,
-                                                                               KB, etab);
+                                                                               KB, etab, counter);
     const uint32_t tiles = (uint32_t)((prm.n + TILE - 1) / TILE);
     const uint64_t total = (uint64_t)points * tiles;
     uint32_t grid = (uint32_t)(sm_count() * Geo<SR>::BLOCKS_PER_SM);      // persistent
@@ -852,7 +949,7 @@ cudaError_t launch_pass_tma(const QwParams &prm, const double2 *in, double2 *out
     cudaError_t e = configure_tma<KB, SR>();
     if (e != cudaSuccess) return e;
     rk4_cycle_stream_tma<KB, SR><<<grid, Geo<SR>::NT, sizeof(TmaShared<SR>), st>>>(
-        prm, in, out, etab, tiles, (uint32_t)total);
+        prm, in, out, etab, tiles, (uint32_t)total, counter);
     return cudaGetLastError();
 }
 
@@ -954,6 +1051,23 @@ cudaError_t plan_of(qw_plan *plan, bool horner, int tma)
 
 }  // namespace
 
+#ifdef QW_PROBE
+extern "C" int qw_debug_probe_blocks(unsigned long long *out)
+{
+    return (int)cudaMemcpyFromSymbol(out, qw_probe_blocks, sizeof(unsigned long long) * 3 * 1024);
+}
+
+extern "C" int qw_debug_probe(unsigned long long *out, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, qw_probe, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(qw_probe, z, sizeof(z));
+    }
+    return (int)e;
+}
+#endif
+
 bool qw_stream_supported(const QwParams &prm)
 {
     return prm.topology == QW_TOPO_CYCLE && prm.n >= 8;
@@ -974,12 +1088,15 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     // QW_FLAG_MIRROR: the half ring w .. w + n/2 behind 3 mirrored ghost sites (the marked
     // vertex is stored index 3 = slot 3 of the first thread segment), reflecting window halos
     prm.mirror_m = stream_mirror(prm) ? prm.n / 2 + 1 : 0;
-    const int64_t n = prm.mirror_m ? prm.mirror_m + 3 : prm.n;        // stored sites per point
+    prm.stream_pad = stream_tma(prm, sr) ? TMA_PADQ : 0;
+    // stored elements per point
+    const int64_t n = prm.mirror_m ? prm.mirror_m + 3
+                                   : (prm.stream_pad ? tma_padded(prm.n) : prm.n);
     // aligned layout: the marked vertex is logical site 0 (stage form) or HW0 (nested form)
     prm.stream_rot = 0;
-    if (!prm.mirror_m && n % sr == 0) {
+    if (!prm.mirror_m && prm.n % sr == 0) {
         prm.stream_rot = prm.target - (stream_horner(prm, sr) ? HW0 : 0);
-        if (prm.stream_rot < 0) prm.stream_rot += n;
+        if (prm.stream_rot < 0) prm.stream_rot += prm.n;
     }
     // points in flight: bounded by ~8 GiB of ping-pong scratch and by 32-bit window indices
     int64_t chunk = (int64_t)(8ull << 30) / (2 * n * (int64_t)sizeof(double2));
@@ -994,7 +1111,7 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     double2 *bufB = bufA + chunk * n;
     void *tab = nullptr;
     const size_t entry = sizeof(HPassEntry) > sizeof(PassEntry) ? sizeof(HPassEntry) : sizeof(PassEntry);
-    e = cudaMallocAsync(&tab, (size_t)chunk * entry, st);
+    e = cudaMallocAsync(&tab, (size_t)chunk * entry + 64, st);    // + the window counter
     if (e != cudaSuccess) { cudaFreeAsync(bufA, st); return e; }
     const bool varying = prm.step_size > 0.0 || prm.n_steps != nullptr;
     if (varying) {
