@@ -196,13 +196,19 @@ def stream_measure(qw, torch, dev, reps=3):
             "actual_gbs_incl_halo_rereads": 32.0 / kb * halo * rate / 1e9,
             "frac_of_hbm_peak_actual": 32.0 / kb * halo * rate / 1e9 / peak})
     kb1 = out["variants"][0]
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_counters.json")) as fh:
+            ctr = json.load(fh).get("stream/KB1", {})
+    except Exception:
+        ctr = {}
     out["roofline"] = {            # the plain read-psi_n / write-psi_n+1 stream (KB = 1)
         "bound": "hbm", "achieved": kb1["algorithmic_gbs_at_32B_per_site_update"],
         "peak": peak, "unit": "GB/s", "frac": kb1["frac_of_hbm_peak_algorithmic"],
-        "traffic": 2100816000,
-        "traffic_note": "dram__bytes_read+write of one pass over 1024 points (ncu --set full, "
-                        "profiles/r1_stream_kb1_ncu_full.md); algorithmic bytes per pass = "
-                        "1024 x 65536 x 32 = 2147483648"}
+        "traffic": ctr.get("dram_bytes_per_pass"),
+        "algorithmic_bytes_per_launch": nT * nB * n * 32,
+        "traffic_note": ctr.get("dram_source", "no ncu capture committed for this kernel"),
+        "kernel": qw.plan(qw.Problem(n=n, topology="circular", schedule="lin", n_steps=S,
+                                     flags=8))}
     return out
 
 

@@ -29,6 +29,7 @@ cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan
 bool qw_rk45_supported(const QwParams &prm);
 cudaError_t qw_launch_rk45(QwParams prm, double rtol, double atol, int64_t *nfev, cudaStream_t st);
 int qw_horner_sites_per_thread(const QwParams &prm);
+int qw_horner_split(const QwParams &prm);
 cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan);
 cudaError_t qw_launch_adiabatic(int64_t n, int topology, int schedule, int gamma_on, int ref,
                                 const double *s, const double *gamma, int64_t n_points,
@@ -154,11 +155,25 @@ int run(QwParams &prm, cudaStream_t st)
         if (e != cudaSuccess) return cuda_fail(e, "symmetric complete-graph kernel launch");
         g_launches += 1;
         return 0;
-    case PATH_HORNER:
+    case PATH_HORNER: {
+        void *scratch = nullptr;
+        if (const int split = qw_horner_split(prm)) {
+            // partial norms of the blocks of a split point + one arrival counter per point
+            const size_t part = (size_t)prm.n_points * (size_t)split * 2 * sizeof(double);
+            const size_t done = (size_t)prm.n_points * sizeof(unsigned int);
+            e = cudaMallocAsync(&scratch, part + done, st);
+            if (e != cudaSuccess) return cuda_fail(e, "scratch allocation");
+            prm.split_part = (double *)scratch;
+            prm.split_done = (unsigned int *)((char *)scratch + part);
+            e = cudaMemsetAsync(prm.split_done, 0, done, st);
+            if (e != cudaSuccess) { cudaFreeAsync(scratch, st); return cuda_fail(e, "scratch reset"); }
+        }
         e = qw_launch_horner(prm, st, nullptr);
+        if (scratch) cudaFreeAsync(scratch, st);
         if (e != cudaSuccess) return cuda_fail(e, "nested-form kernel launch");
         g_launches += 1;
         return 0;
+    }
     case PATH_PACKED:
         e = qw_launch_packed(prm, st, nullptr);
         if (e != cudaSuccess) return cuda_fail(e, "packed kernel launch");

@@ -72,6 +72,12 @@ struct QwParams {
                                   // stored behind 3 mirrored ghost sites; 0 = full ring
     int32_t stream_pad;           // streaming, bulk-copy kernel: psi is stored with one pad element
                                   // after every stream_pad sites (0: dense)
+    // complete graph above 4096 vertices: a point is split over `split` thread blocks that share
+    // nothing but the tabulated (y_w, S) subsystem; partial norms meet in split_part, the last
+    // block of a point to arrive (split_done) writes p and norm
+    int32_t split;
+    double *split_part;           // [n_points][split][2]
+    unsigned int *split_done;     // [n_points], zero before the launch
 };
 
 struct QwPoint {

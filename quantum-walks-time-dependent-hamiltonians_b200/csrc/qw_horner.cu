@@ -485,25 +485,73 @@ __device__ __forceinline__ void complete_chunk(HState<R> &s, SH &sh, const int64
     }
 }
 
+// Which part of a point a block integrates.  Unsplit: everything.  Split (complete graph above
+// 4096 vertices): block b of `split` holds sites [off, off + nb) of the relabelled graph (site 0 =
+// the marked vertex), nb = n / split rounded up for the first n % split blocks, dealt out to its
+// threads as R sites to the first nfull and R - 1 to the others.
+struct CPart {
+    int64_t point;               // launch-order index of the point
+    int64_t off;                 // first site of the block
+    int32_t b, nact, nfull;
+};
+
+template <int R, bool SPLIT>
+__device__ __forceinline__ CPart complete_part(const QwParams &prm)
+{
+    CPart c;
+    if (!SPLIT) {
+        c.point = blockIdx.x; c.off = 0; c.b = 0; c.nact = prm.nact; c.nfull = prm.nfull;
+        return c;
+    }
+    const int64_t split = prm.split;
+    c.point = blockIdx.x / split;
+    c.b = (int)(blockIdx.x - c.point * split);
+    const int64_t base = prm.n / split, extra = prm.n - base * split;
+    const int64_t nb = base + (c.b < extra ? 1 : 0);
+    c.off = c.b * base + (c.b < extra ? c.b : extra);
+    c.nact = (int)((nb + R - 1) / R);
+    c.nfull = (int)(nb - (int64_t)c.nact * (R - 1));
+    return c;
+}
+
 // p, norm and psi(T) of a point from the workers' registers
-template <int R, typename SH>
+template <int R, bool SPLIT, typename SH>
 __device__ __forceinline__ void complete_epilogue(const HState<R> &s, SH &sh,
                                                   const QwParams &prm, const QwPoint &pt,
-                                                  const int t, const bool active, const bool full)
+                                                  const CPart &cp, const int t, const bool active,
+                                                  const bool full)
 {
     double nrm = 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
-    const double pw = (t == 0) ? fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]) : 0.0;
+    const double pw = (t == 0 && cp.b == 0) ? fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]) : 0.0;
     __syncthreads();
     const double2 tot = hblock_sum(make_double2(nrm, pw), sh.red);
     if (t == 0) {
-        prm.p[pt.q] = tot.y / tot.x;
-        if (prm.norm) prm.norm[pt.q] = tot.x;
+        if (!SPLIT) {
+            prm.p[pt.q] = tot.y / tot.x;
+            if (prm.norm) prm.norm[pt.q] = tot.x;
+        } else {
+            // partial sums meet in global memory; the last block of the point to arrive adds them
+            // in block order (deterministic) and writes the results
+            double *part = prm.split_part + (size_t)cp.point * (size_t)prm.split * 2;
+            part[2 * cp.b] = tot.x;
+            part[2 * cp.b + 1] = tot.y;
+            __threadfence();
+            const unsigned prev = atomicAdd(&prm.split_done[cp.point], 1u);
+            if (prev == (unsigned)prm.split - 1u) {
+                __threadfence();
+                const volatile double *vp = part;
+                double nsum = 0.0, psum = 0.0;
+                for (int b = 0; b < prm.split; ++b) { nsum += vp[2 * b]; psum += vp[2 * b + 1]; }
+                prm.p[pt.q] = psum / nsum;
+                if (prm.norm) prm.norm[pt.q] = nsum;
+            }
+        }
     }
-    if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + off(t) + r
+    if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + off + off(t) + r
         double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
-        const int64_t off_t = (int64_t)t * (R - 1) + (t < prm.nfull ? t : prm.nfull);
+        const int64_t off_t = cp.off + (int64_t)t * (R - 1) + (t < cp.nfull ? t : cp.nfull);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (r == R - 1 && !full) continue;                    // ghost
@@ -521,16 +569,18 @@ __device__ __forceinline__ void complete_epilogue(const HState<R> &s, SH &sh,
 // with eight worker warps and both duties in warp 8 (level-by-level scalar step), sub-partition
 // 0 issued 587 FP64 instructions per step against 520 on the others and everybody waited for
 // it at the chunk barrier (18 % of the warp samples).
-template <int R, int MAXNT, int MINB, int AUX, bool RAGGED>
+template <int R, int MAXNT, int MINB, int AUX, bool RAGGED, bool SPLIT = false>
 __global__ void __launch_bounds__(MAXNT + 32 * AUX, MINB) rk4_complete_horner(const QwParams prm)
 {
+    static_assert(!SPLIT || RAGGED, "a block of a split point holds an arbitrary number of sites");
     __shared__ CFShared sh;
-    const int t = threadIdx.x, nact = prm.nact;
+    const CPart cp = complete_part<R, SPLIT>(prm);
+    const int t = threadIdx.x, nact = cp.nact;
     const int lane = t & 31, warp = t >> 5, fwarp = (blockDim.x >> 5) - 1;
     const int swarp = fwarp - (AUX - 1);
-    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const QwPoint pt = qw_point(prm, cp.point);
     const bool active = t < nact;
-    const bool full = !RAGGED || t < prm.nfull;        // R sites; else R-1 and a ghost slot
+    const bool full = !RAGGED || t < cp.nfull;         // R sites; else R-1 and a ghost slot
     const double nfull = (double)prm.n;
     const double nd = active ? nfull : 0.0;
 
@@ -541,17 +591,19 @@ __global__ void __launch_bounds__(MAXNT + 32 * AUX, MINB) rk4_complete_horner(co
         s.yr[r] = (r == R - 1 && !full) ? 0.0 : amp; s.yi[r] = 0.0;
         s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
-    const double msk = (t == 0) ? 1.0 : 0.0;
+    const double msk = (t == 0 && cp.b == 0) ? 1.0 : 0.0;
     const int64_t nchunks = (pt.steps + QW_CHUNK - 1) / QW_CHUNK;
 #define QW_CNT(C) ((int)((pt.steps - (C) * QW_CHUNK) < QW_CHUNK ? (pt.steps - (C) * QW_CHUNK) : QW_CHUNK))
 
     double x0 = 1.0 / sqrt(nfull), x1 = 0.0, x2 = 0.0, x3 = 0.0;    // y_w, S(y) (scalar warp)
     if (nchunks > 0) {
-        // prologue: S(y) by direct summation; tables of chunks 0 and 1, scalars of chunk 0
+        // prologue: S(y) by direct summation (a split point: n times the uniform amplitude, the
+        // same in every block); tables of chunks 0 and 1, scalars of chunk 0
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) { a += s.yr[r]; b += s.yi[r]; }
-        const double2 Sy = hblock_sum(make_double2(a, b), sh.red);
+        double2 Sy = hblock_sum(make_double2(a, b), sh.red);
+        if (SPLIT) Sy = make_double2(nfull * (1.0 / sqrt(nfull)), 0.0);
         x2 = Sy.x; x3 = Sy.y;
         if (AUX == 2 && warp == fwarp && nchunks > 1)
             horner_fill_complete(sh.tab[1], sh.map[1], pt, QW_CHUNK, QW_CNT(1), prm.schedule,
@@ -586,7 +638,7 @@ __global__ void __launch_bounds__(MAXNT + 32 * AUX, MINB) rk4_complete_horner(co
     }
 #undef QW_CNT
 
-    complete_epilogue<R>(s, sh, prm, pt, t, active, full);
+    complete_epilogue<R, SPLIT>(s, sh, prm, pt, cp, t, active, full);
 }
 
 // Blocks of at most four worker warps: no auxiliary warp.  168 registers allow three warps per
@@ -610,16 +662,18 @@ __device__ __noinline__ void scalar_steps_call(const CSMap *map, const int cnt, 
     x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3;
 }
 
-template <int R, int MAXNT, int MINB, int MB, bool RAGGED>
+template <int R, int MAXNT, int MINB, int MB, bool RAGGED, bool SPLIT = false>
 __global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_folded(const QwParams prm)
 {
+    static_assert(!SPLIT || RAGGED, "a block of a split point holds an arbitrary number of sites");
     __shared__ CFSharedT<MB> sh;
-    const int t = threadIdx.x, nact = prm.nact;
+    const CPart cp = complete_part<R, SPLIT>(prm);
+    const int t = threadIdx.x, nact = cp.nact;
     const int lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
     const int swarp = nw - 1, fwarp = nw >= 4 ? 1 : 0;      // warp 0 carries the marked vertex
-    const QwPoint pt = qw_point(prm, blockIdx.x);
+    const QwPoint pt = qw_point(prm, cp.point);
     const bool active = t < nact;
-    const bool full = !RAGGED || t < prm.nfull;        // R sites; else R-1 and a ghost slot
+    const bool full = !RAGGED || t < cp.nfull;         // R sites; else R-1 and a ghost slot
     const double nfull = (double)prm.n;
     const double nd = active ? nfull : 0.0;
 
@@ -630,7 +684,7 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_folded(const QwParam
         s.yr[r] = (r == R - 1 && !full) ? 0.0 : amp; s.yi[r] = 0.0;
         s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
-    const double msk = (t == 0) ? 1.0 : 0.0;
+    const double msk = (t == 0 && cp.b == 0) ? 1.0 : 0.0;
     const int64_t nchunks = (pt.steps + QW_CHUNK - 1) / QW_CHUNK;
 #define QW_CNT(C) ((int)((pt.steps - (C) * QW_CHUNK) < QW_CHUNK ? (pt.steps - (C) * QW_CHUNK) : QW_CHUNK))
 
@@ -639,7 +693,8 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_folded(const QwParam
         double a = 0.0, b = 0.0;
 #pragma unroll
         for (int r = 0; r < R; ++r) { a += s.yr[r]; b += s.yi[r]; }
-        const double2 Sy = hblock_sum(make_double2(a, b), sh.red);
+        double2 Sy = hblock_sum(make_double2(a, b), sh.red);
+        if (SPLIT) Sy = make_double2(nfull * (1.0 / sqrt(nfull)), 0.0);
         x[2] = Sy.x; x[3] = Sy.y;
         if (warp == fwarp && fwarp != swarp && nchunks > 1)
             fill_complete_call(sh.tab[1], sh.map[MB - 1], &pt, QW_CHUNK, QW_CNT(1), prm.schedule,
@@ -675,7 +730,7 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_complete_folded(const QwParam
         }
     }
 #undef QW_CNT
-    complete_epilogue<R>(s, sh, prm, pt, t, active, full);
+    complete_epilogue<R, SPLIT>(s, sh, prm, pt, cp, t, active, full);
 }
 
 template <typename K>
@@ -700,7 +755,8 @@ cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cud
         plan->smem_bytes = (int)(fa.sharedSizeBytes + smem);
         return cudaSuccess;
     }
-    kernel<<<(unsigned)prm.n_points, threads, smem, st>>>(prm);
+    const int64_t blocks = prm.n_points * (prm.split > 1 ? prm.split : 1);
+    kernel<<<(unsigned)blocks, threads, smem, st>>>(prm);
     return cudaGetLastError();
 }
 
@@ -715,8 +771,24 @@ static bool horner_mirror(const QwParams &prm)
     return (prm.flags & QW_FLAG_MIRROR) && prm.topology == QW_TOPO_CYCLE && prm.n > 1086;
 }
 
+// Complete graph above 4096 vertices: blocks per point (0: not split).  The nested form needs
+// nothing from the other sites but the tabulated (y_w, S) subsystem, which every block advances
+// for itself, so a point splits over any number of blocks without communication; the partial
+// norms meet at the end (complete_epilogue).  Blocks hold 2049 .. 4096 sites.
+int qw_horner_split(const QwParams &prm)
+{
+    if (prm.topology != QW_TOPO_COMPLETE || prm.n <= 4096) return 0;
+    if (prm.flags & (QW_FLAG_EXACT_SUM | QW_FLAG_NO_HORNER | QW_FLAG_CYCLE_LEGACY |
+                     QW_FLAG_COMPLETE_FREE | QW_FLAG_FORCE_GENERIC))
+        return 0;
+    const int64_t split = (prm.n + 4095) / 4096;
+    if (split > 65536 || prm.n_points * split > 0x7fffffffLL) return 0;
+    return (int)split;
+}
+
 int qw_horner_sites_per_thread(const QwParams &prm)
 {
+    if (qw_horner_split(prm) > 1) return 16;
     if (horner_mirror(prm)) {
         // the half ring has n/2 + 1 sites: 17 sites per thread keep the "+ 1" from costing a
         // whole extra warp (n = 2048: 1025 = 61 threads x 17 instead of 65 x 16)
@@ -745,6 +817,21 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
     if (plan) {
         plan->path = cyc ? 5 : 6;
         plan->sites_per_thread = R;
+    }
+    if (const int split = qw_horner_split(prm)) {
+        // blocks of a split point: geometry per block inside the kernel (complete_part)
+        prm.split = split;
+        const int64_t nb = (prm.n + split - 1) / split;            // the largest block
+        const int bnact = (int)((nb + R - 1) / R);
+        const int bthreads = ((bnact + 31) / 32) * 32;
+        if (plan) {
+            plan->path = 6;
+            plan->sites_per_thread = R;
+            plan->steps_per_pass = split;                          // blocks per point
+        }
+        if (bthreads <= 192)       // up to 3072 sites per block: duties folded, two blocks per SM
+            return hlaunch(rk4_complete_folded<16, 192, 2, 2, true, true>, prm, bthreads, 0, st, plan);
+        return hlaunch(rk4_complete_horner<16, 256, 1, 2, true, true>, prm, bthreads + 64, 0, st, plan);
     }
     const bool ragged = prm.nfull != prm.nact;
 #define QW_HL(KERNEL, ...)                                                                  \

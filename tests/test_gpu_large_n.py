@@ -1,0 +1,53 @@
+"""Dimensions above one thread block's registers (4096 < N <= 32768 and beyond) against the C
+oracle: the complete graph split over blocks that share only the tabulated (y_w, S) subsystem,
+and the cycle graph resident across a thread-block cluster with DSMEM halos (north star:
+"resident ... for N up to about 8K")."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+P_TOL, PSI_TOL = 1e-10, 1e-11
+
+
+@pytest.mark.parametrize("n", [4097, 5000, 6144, 8192, 12289, 16384, 40000])
+def test_complete_graph_split_over_blocks(qw, n):
+    rng = np.random.default_rng(n)
+    for sched, go, S in (("cerf_3", "laplacian", 70), ("lin", "oracle", 33), ("sqrt", "oracle", 64)):
+        T = np.concatenate([[0.0], rng.uniform(10.0, 60.0, 3)]) if go == "laplacian" else \
+            np.concatenate([[0.0], rng.uniform(0.5, 3.0, 3) / n * 8])
+        g = rng.uniform(0.5, 2.0, 4) / n if go == "laplacian" else rng.uniform(0.3, 1.5, 4) * n
+        prob = qw.Problem(n=n, topology="complete", schedule=sched, gamma_on=go, n_steps=S)
+        pl = qw.plan(prob)
+        assert pl["path"] == "horner-complete" and pl["steps_per_pass"] == -(-n // 4096)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "complete", sched, T, g, n_steps=S, gamma_on=go,
+                                             return_psi=True)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+        assert np.abs(psi - psio).max() <= PSI_TOL
+
+
+def test_complete_graph_split_step_size_rule_target_and_grid(qw):
+    n = 9000
+    T = np.array([0.0, 0.0031, 0.00117, 0.0025])
+    g = np.array([1.0, 0.5, 2.0, 0.1]) * n
+    for target in (None, 0, 4500, 8999):
+        prob = qw.Problem(n=n, topology="complete", schedule="sqrt", step_size=1e-4, target=target)
+        p, norm = qw.rk4_batch(prob, T, g)
+        po, no, _ = c_oracle.rk4_batch(n, "complete", "sqrt", T, g, step_size=1e-4, target=target)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+    t, b = np.linspace(0.1, 80, 7), np.linspace(0.5 / n, 2.5 / n, 5)
+    prob = qw.Problem(n=n, topology="complete", schedule="cerf_3", gamma_on="laplacian", n_steps=96)
+    p, norm = qw.rk4_heatmap(prob, t, b)
+    po, no = c_oracle.heatmap(n, "complete", "cerf_3", t, b, n_steps=96, gamma_on="laplacian")
+    assert np.abs(p - po).max() <= P_TOL and np.argmax(p) == np.argmax(po)
+    lo, _ = qw.rk4_heatmap(prob, t, b, rows=(1, 4))
+    assert np.array_equal(lo, p[1:4])
+    # the two-variable reduction (QW_FLAG_MIRROR) and the catch-all kernel agree with the split one
+    ps, _ = qw.rk4_heatmap(qw.Problem(n=n, topology="complete", schedule="cerf_3",
+                                      gamma_on="laplacian", n_steps=96, flags=8192), t, b)
+    pg, _ = qw.rk4_heatmap(qw.Problem(n=n, topology="complete", schedule="cerf_3",
+                                      gamma_on="laplacian", n_steps=96, flags=1), t, b)
+    assert np.abs(ps - p).max() <= P_TOL and np.abs(pg - p).max() <= P_TOL
