@@ -248,7 +248,8 @@ typedef struct qw_plan {
                                 7 warp-packed cycle in nested form, 8 warp-packed cycle of any
                                 small dimension, 9 mirror-reduced cycle, 10 symmetry-reduced
                                 complete graph (both QW_FLAG_MIRROR), 11 warp-packed complete
-                                graph of any small dimension */
+                                graph of any small dimension, 12 cycle graph resident across a
+                                thread-block cluster (4097 .. 32768 sites) */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */
@@ -256,7 +257,8 @@ typedef struct qw_plan {
     int32_t smem_bytes;
     int32_t sm_count;
     int32_t steps_per_pass;  /* streaming path: RK4 steps fused per pass over HBM; packed
-                                path: points per warp; else 0 */
+                                path: points per warp; cluster path: CTAs per cluster; complete
+                                graph above 4096 vertices: blocks per point; else 0 */
 } qw_plan;
 
 /* Which kernel a large heatmap call (qw_rk4_grid_*) of this problem would run on the current

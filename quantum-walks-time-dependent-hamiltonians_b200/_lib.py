@@ -18,7 +18,7 @@ FLAG_NO_HORNER, FLAG_MIRROR = 2048, 8192
 PATH_NAMES = {0: "resident-cycle", 1: "resident-complete", 2: "generic", 3: "stream",
               4: "packed-cycle", 5: "horner-cycle", 6: "horner-complete",
               7: "packed-horner-cycle", 8: "packed-any-cycle", 9: "mirror-cycle",
-              10: "symmetric-complete", 11: "packed-complete"}
+              10: "symmetric-complete", 11: "packed-complete", 12: "cluster-cycle"}
 
 
 class QwProblem(ctypes.Structure):

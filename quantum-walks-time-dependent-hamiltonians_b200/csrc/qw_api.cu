@@ -30,6 +30,8 @@ bool qw_rk45_supported(const QwParams &prm);
 cudaError_t qw_launch_rk45(QwParams prm, double rtol, double atol, int64_t *nfev, cudaStream_t st);
 int qw_horner_sites_per_thread(const QwParams &prm);
 int qw_horner_split(const QwParams &prm);
+int qw_cluster_size(const QwParams &prm);
+cudaError_t qw_launch_cluster(QwParams prm, cudaStream_t st, qw_plan *plan);
 cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan);
 cudaError_t qw_launch_adiabatic(int64_t n, int topology, int schedule, int gamma_on, int ref,
                                 const double *s, const double *gamma, int64_t n_points,
@@ -94,7 +96,7 @@ int validate(const qw_problem *prob, QwParams *prm)
 }
 
 enum { PATH_RESIDENT = 0, PATH_GENERIC = 2, PATH_STREAM = 3, PATH_PACKED = 4, PATH_HORNER = 5,
-       PATH_MIRROR = 9, PATH_SYMMETRIC = 10 };
+       PATH_MIRROR = 9, PATH_SYMMETRIC = 10, PATH_CLUSTER = 12 };
 
 int choose_path(const QwParams &prm)
 {
@@ -112,6 +114,7 @@ int choose_path(const QwParams &prm)
     if (packed) return PATH_PACKED;
     if (horner) return PATH_HORNER;
     if (qw_resident_sites_per_thread(prm.n) > 0) return PATH_RESIDENT;
+    if (qw_cluster_size(prm) > 0) return PATH_CLUSTER;     // rings of 4097 .. 32768 sites
     if (qw_stream_supported(prm)) return PATH_STREAM;
     return PATH_GENERIC;
 }
@@ -174,6 +177,11 @@ int run(QwParams &prm, cudaStream_t st)
         g_launches += 1;
         return 0;
     }
+    case PATH_CLUSTER:
+        e = qw_launch_cluster(prm, st, nullptr);
+        if (e != cudaSuccess) return cuda_fail(e, "cluster kernel launch");
+        g_launches += 1;
+        return 0;
     case PATH_PACKED:
         e = qw_launch_packed(prm, st, nullptr);
         if (e != cudaSuccess) return cuda_fail(e, "packed kernel launch");
@@ -554,6 +562,7 @@ int qw_plan_query(const qw_problem *prob, qw_plan *plan)
     case PATH_HORNER: e = qw_launch_horner(prm, nullptr, plan); break;
     case PATH_MIRROR: e = qw_launch_mirror(prm, nullptr, plan); break;
     case PATH_SYMMETRIC: e = qw_launch_symmetric(prm, nullptr, plan); break;
+    case PATH_CLUSTER: e = qw_launch_cluster(prm, nullptr, plan); break;
     case PATH_STREAM: e = qw_stream_plan(prm, plan); break;
     default: {
         int blocks; size_t bytes;

@@ -51,3 +51,53 @@ def test_complete_graph_split_step_size_rule_target_and_grid(qw):
     pg, _ = qw.rk4_heatmap(qw.Problem(n=n, topology="complete", schedule="cerf_3",
                                       gamma_on="laplacian", n_steps=96, flags=1), t, b)
     assert np.abs(ps - p).max() <= P_TOL and np.abs(pg - p).max() <= P_TOL
+
+
+@pytest.mark.parametrize("n", [4097, 5000, 8192, 12289, 16384, 20000, 32768])
+def test_cycle_graph_resident_across_a_cluster(qw, n):
+    rng = np.random.default_rng(n)
+    T = np.concatenate([[0.0], rng.uniform(1.0, 9.0, 4)])
+    g = rng.uniform(0.1, 2.4, 5)
+    for sched, S in (("lin", 37), ("cbrt", 70)):
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S)
+        pl = qw.plan(prob)
+        assert pl["path"] == "cluster-cycle" and pl["steps_per_pass"] == -(-n // 4096)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, n_steps=S,
+                                             return_psi=True)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+        assert np.abs(psi - psio).max() <= PSI_TOL
+
+
+def test_cluster_step_size_rule_targets_and_grid(qw):
+    n = 9000
+    T = np.array([0.0, 0.31, 0.117, 0.25, 0.004])
+    g = np.array([1.0, 0.5, 2.0, 0.1, 0.7])
+    for target in (None, 0, 1, 2, 3, 4, 4499, 4500, 8997, 8999):
+        prob = qw.Problem(n=n, topology="circular", schedule="sqrt", step_size=1e-2, target=target)
+        assert qw.plan(prob)["path"] == "cluster-cycle"
+        p, norm = qw.rk4_batch(prob, T, g)
+        po, no, _ = c_oracle.rk4_batch(n, "circular", "sqrt", T, g, step_size=1e-2, target=target)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+    t, b = np.linspace(0.1, 12, 9), np.linspace(0, 2.5, 7)
+    prob = qw.Problem(n=8192, topology="circular", schedule="cerf_3", n_steps=96)
+    p, norm = qw.rk4_heatmap(prob, t, b)
+    po, no = c_oracle.heatmap(8192, "circular", "cerf_3", t, b, n_steps=96)
+    assert np.abs(p - po).max() <= P_TOL and np.argmax(p) == np.argmax(po)
+    lo, _ = qw.rk4_heatmap(prob, t, b, rows=(2, 5))
+    assert np.array_equal(lo, p[2:5])
+    # the streaming kernel and the half-ring reduction on the same grid
+    for flags in (2, 8192):
+        q, _ = qw.rk4_heatmap(qw.Problem(n=8192, topology="circular", schedule="cerf_3",
+                                         n_steps=96, flags=flags), t, b)
+        assert np.abs(q - p).max() <= P_TOL
+
+
+def test_cluster_long_run_keeps_the_halo_protocol_in_step(qw):
+    """Thousands of levels: the two-parity mailbox across CTAs must never slip a phase."""
+    n, S = 8192, 3000
+    T, g = np.array([700.0, 350.0]), np.array([1.2, 0.4])
+    prob = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=S)
+    p, norm = qw.rk4_batch(prob, T, g)
+    po, no, _ = c_oracle.rk4_batch(n, "circular", "lin", T, g, n_steps=S)
+    assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
