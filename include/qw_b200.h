@@ -103,7 +103,7 @@ enum {
     QW_FLAG_NO_ROTATE = 4096,    /* nested-form kernels: keep the marked vertex in warp 0 of
                                     every block instead of alternating the owner warp with the
                                     physical warp slot (A/B) */
-    QW_FLAG_MIRROR = 8192        /* cycle graph: integrate only the half ring w .. w + n/2 with
+    QW_FLAG_MIRROR = 8192,       /* cycle graph: integrate only the half ring w .. w + n/2 with
                                     reflecting ends (psi is mirror symmetric about the marked
                                     vertex for the uniform initial state every caller of the
                                     reference uses): same p, norm and psi with half the
@@ -114,6 +114,9 @@ enum {
                                     amplitude, one thread integrates the pair (psi_w, psi_other)
                                     of a point, any n, O(n_steps) work.
                                     Opt-in; ignored where it does not apply. */
+    QW_FLAG_FORCE_CLUSTER = 16384 /* cycle graph, 4097 .. 32768 sites: the thread-block-cluster
+                                    kernel also where the bulk-copy streaming kernel is preferred
+                                    (above 8192 sites when n is a multiple of 128); tests, A/B */
 };
 
 /* ---- the hot path -------------------------------------------------------------------- */

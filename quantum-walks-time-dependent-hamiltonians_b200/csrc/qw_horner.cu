@@ -301,29 +301,36 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 
 // ---------------------------------------------------------------------------------------------
 // Rings of 4097 .. 32768 sites: resident across a THREAD-BLOCK CLUSTER.  CTA r of a cluster of C
-// holds sites [off_r, off_r + n_r) of the relabelled ring (site 3 of CTA 0 = the marked vertex) in
-// the registers of up to 256 threads, exactly like the one-block kernel above; only the two halo
-// values that cross a CTA boundary travel through distributed shared memory:
-//   * every CTA has, per direction and mailbox parity, one 16-byte slot and one mbarrier;
-//   * after the edge sites of a level are updated, thread 0 stores its first value into the
-//     LEFT neighbour's slot (st.shared::cluster) and arrives on that CTA's mbarrier
-//     (mbarrier.arrive.release.cluster); the last active thread does the same to the right;
-//   * at the next level thread 0 / the last thread wait on their own mbarrier
-//     (try_wait.acquire.cluster) before reading the slot.  The interior sites of the level
-//     (14 of 16 per thread) sit between the remote store and that wait, which hides the ~215
-//     cycles of DSMEM latency.  No cluster-wide barrier in the time loop (it costs ~380 cycles,
-//     as much as a whole level).
-// Two parities suffice: the neighbour can refill a slot only after it has received the value this
-// CTA publishes AFTER reading the slot.  The k-th read of parity-0 slots happens at level 4 / 2 of
-// a step, of parity-1 slots at level 3 / 1, so the mbarrier phase a level waits for is a
-// compile-time constant: 0, 0, 1, 1 for levels 4, 3, 2, 1.
-// Every CTA builds the step tables for itself; the partial norms meet in CTA 0 at the end.
+// holds sites [off_r, off_r + n_r) of the relabelled ring in registers, like the one-block kernel
+// above; the two halo values that cross a CTA boundary travel through distributed shared memory.
+//   * Layout of a CTA: [left edge site][compute threads: R or R - 1 sites each][right edge site].
+//     The compute warps run the code of the one-block kernel unchanged (horner_steps); the two
+//     EDGE SITES belong to lanes 0 and 1 of an extra COMM WARP and appear to compute thread 0 /
+//     the last compute thread as ordinary mailbox neighbours.  (Two earlier versions kept the edge
+//     sites in the compute threads: the cross-CTA wait and the divergent edge code then sat at the
+//     end of every level of two of the eight warps, and with them of the whole block: 720 instead
+//     of ~485 cycles per level, 3.9e11 site-updates/s at N = 8192.)
+//   * Every CTA has, per side and mailbox parity, one 16-byte slot and one mbarrier.  Right after
+//     the block barrier of a level the comm lane reads its inner neighbour from the mailbox, waits
+//     for the neighbour CTA's value of the previous level (mbarrier.try_wait; it has had a whole
+//     level to arrive: DSMEM latency ~215 cycles), updates its site and sends the new value on with
+//     st.async: data + 16 bytes of the remote barrier's transaction count in one operation, no
+//     fence (st.shared::cluster + mbarrier.arrive.release.cluster compiles to ST + MEMBAR.ALL.GPU
+//     + SYNCS.ARRIVE; measured 2.5e11).  No cluster-wide barrier in the time loop.
+//   * Two parities suffice: the neighbour can refill a slot only after it has received the value
+//     this CTA publishes AFTER reading the slot.  The k-th read of the parity-0 slots happens at
+//     level 4 / 2 of a step, of the parity-1 slots at level 3 / 1, so the mbarrier phase a level
+//     waits for is a compile-time constant: 0, 0, 1, 1 for levels 4, 3, 2, 1.
+// The marked vertex is slot 3 of compute thread 0 of CTA 0 (the left edge site of CTA 0 is site
+// w - 4).  Every CTA builds the step tables for itself; the partial norms meet in CTA 0.
 struct ClusterShared {
     HornerStep st[QW_CHUNK];
     double red[2 * 32];
     double2 halo[2][2];                  // [left / right][parity]: written by the neighbour CTA
     unsigned long long bar[2][2];        // [left / right][parity]
     double2 csum[16];                    // CTA 0: (norm, |psi_w|^2) of every CTA
+    double2 edge_out[2];                 // the comm lanes' sites at the end (norm, psi)
+    int owner;
 };
 
 __device__ __forceinline__ uint32_t cl_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -350,17 +357,14 @@ __device__ __forceinline__ uint32_t cl_map(uint32_t addr, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-// Value into the neighbour CTA's slot, signalled on ITS mbarrier: st.async carries the data and
-// completes 16 bytes of the barrier's transaction count in one operation, without a fence (a
-// generic st.shared::cluster + mbarrier.arrive.release.cluster compiles to ST + MEMBAR.ALL.GPU +
-// SYNCS.ARRIVE: measured 2.5e11 site-updates/s at N = 8192, the fence dominated every level).
+// value into the neighbour CTA's slot, signalled on ITS mbarrier
 __device__ __forceinline__ void cl_send(uint32_t slot, uint32_t bar, double x, double y)
 {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
                  ::"r"(slot), "d"(x), "d"(y), "r"(bar) : "memory");
 }
-// The receiving thread arms its barrier for the 16 bytes (the only arrival of the phase; the
-// bytes may already be there) and waits for the phase.
+// The receiving lane arms its barrier for the 16 bytes (the only arrival of the phase; the bytes
+// may already be there) and waits for the phase.
 __device__ __forceinline__ void cl_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 16;" ::"r"(bar) : "memory");
@@ -375,149 +379,74 @@ __device__ __forceinline__ void cl_wait(uint32_t bar, uint32_t parity)
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 
-struct ClusterLinks {                     // addresses in the shared::cluster window
-    uint32_t to_left_slot[2], to_left_bar[2];      // the LEFT neighbour's right-hand slot / barrier
-    uint32_t to_right_slot[2], to_right_bar[2];    // the RIGHT neighbour's left-hand slot / barrier
-    uint32_t my_bar[2][2];                         // this CTA's barriers [left / right][parity]
-};
-
-// `cnt` steps.  edge_l / edge_r: this thread is thread 0 / the last active thread of its CTA; wel /
-// wer: its warp contains that thread.
-// The two sites of a CTA that need a value from another CTA are finished LAST: the level runs
-// with a zero in place of the missing neighbour, and once the interior is done the edge thread
-// waits for the neighbour CTA's value and adds its contribution (out = y - i rho (2c - l - r) is
-// linear in l: two FMAs), then sends its own new edge value on.  The DSMEM round trip is thus
-// hidden behind the interior of the same level instead of standing in front of it (first
-// version, edges first: 2.5e11 site-updates/s at N = 8192, slower than streaming).
-template <int R, bool OWN, bool RAGGED>
-__device__ __forceinline__ void cluster_steps(HState<R> &s, ClusterShared &sh, const ClusterLinks &lk,
-                                              double2 *first, double2 *last, const int nt,
-                                              const int t, const int tl, const int tr,
-                                              const int cnt, const double msk, const bool full_in,
-                                              const bool edge_l, const bool edge_r,
-                                              const bool wel, const bool wer)
+// The comm warp's side of `cnt` steps: lane 0 owns the CTA's left edge site, lane 1 the right one
+// (the other lanes only keep the block barriers company).  side = lane; me = mailbox index of the
+// lane's site; inner = mailbox index of the compute thread next to it.
+__device__ __forceinline__ void cluster_comm_steps(double &yr, double &yi, ClusterShared &sh,
+                                                   double2 *first, double2 *last, const int nt,
+                                                   const int side, const int me, const int inner,
+                                                   const uint32_t my_bar0, const uint32_t my_bar1,
+                                                   const uint32_t to_slot0, const uint32_t to_slot1,
+                                                   const uint32_t to_bar0, const uint32_t to_bar1,
+                                                   const int cnt, const bool lane_on)
 {
-    const bool full = RAGGED ? full_in : true;
+    double zr = 0.0, zi = 0.0;
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const HornerStep &hs = sh.st[sidx];
-        double sgl = 0.0;
-#define QW_CLUSTER_LEVEL(LEVEL)                                                             \
+#define QW_COMM_LEVEL(LEVEL)                                                                \
         {                                                                                   \
             constexpr int par = (4 - LEVEL) & 1;                                            \
             constexpr uint32_t phase = (LEVEL <= 2) ? 1u : 0u;                              \
             __syncthreads();                                                                \
-            double2 hl = last[par * nt + tl];                                               \
-            double2 hr = first[par * nt + tr];                                              \
-            if (edge_l) hl = make_double2(0.0, 0.0);                                        \
-            if (edge_r) hr = make_double2(0.0, 0.0);                                        \
-            const double rho = hs.rho[LEVEL - 1];                                           \
-            double2 o0, oL;                                                                 \
-            if (RAGGED && !full) {            /* ghost slot := the right neighbour's value */ \
-                if (LEVEL == 4) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }                 \
-                else { s.zr[R - 1] = hr.x; s.zi[R - 1] = hr.y; }                            \
-            }                                                                               \
-            if (OWN && LEVEL == 4) {                                                        \
-                double b[8];                                                                \
-                b[0] = s.yr[HW0];                     b[1] = s.yi[HW0];                     \
-                b[2] = s.yr[HW0 - 1] + s.yr[HW0 + 1]; b[3] = s.yi[HW0 - 1] + s.yi[HW0 + 1]; \
-                b[4] = s.yr[HW0 - 2] + s.yr[HW0 + 2]; b[5] = s.yi[HW0 - 2] + s.yi[HW0 + 2]; \
-                b[6] = s.yr[HW0 - 3] + s.yr[HW0 + 3]; b[7] = s.yi[HW0 - 3] + s.yi[HW0 + 3]; \
-                sgl = hs.coef[0][t & 7] * __shfl_sync(0xffffffffu, b[0], 0);                \
-                _Pragma("unroll")                                                           \
-                for (int k = 1; k < 8; ++k)                                                 \
-                    sgl = fma(hs.coef[k][t & 7], __shfl_sync(0xffffffffu, b[k], 0), sgl);   \
-            }                                                                               \
-            hedges<R, LEVEL>(s, rho, hl, hr, o0, oL);                                       \
-            hinterior<R, LEVEL>(s, rho, o0, oL);                                            \
-            {   /* publish inside the CTA: the last REAL site is slot R-1, or R-2 in a short thread */ \
-                const double lr = (LEVEL > 1) ? (full ? s.zr[R - 1] : s.zr[R - 2])          \
-                                              : (full ? s.yr[R - 1] : s.yr[R - 2]);         \
-                const double li = (LEVEL > 1) ? (full ? s.zi[R - 1] : s.zi[R - 2])          \
-                                              : (full ? s.yi[R - 1] : s.yi[R - 2]);         \
-                first[(par ^ 1) * nt + t] = (LEVEL > 1) ? make_double2(s.zr[0], s.zi[0])    \
-                                                        : make_double2(s.yr[0], s.yi[0]);   \
-                last[(par ^ 1) * nt + t] = make_double2(lr, li);                            \
-            }                                                                               \
-            if (wel) {                         /* warp-uniform */                           \
-                if (edge_l) {                                                               \
-                    cl_wait(lk.my_bar[0][par], phase);                                      \
-                    const double2 v = sh.halo[0][par];                                      \
-                    if (LEVEL > 1) { s.zr[0] = fma(-rho, v.y, s.zr[0]); s.zi[0] = fma(rho, v.x, s.zi[0]); } \
-                    else { s.yr[0] = fma(-rho, v.y, s.yr[0]); s.yi[0] = fma(rho, v.x, s.yi[0]); } \
-                    cl_send(lk.to_left_slot[par ^ 1], lk.to_left_bar[par ^ 1],              \
-                            (LEVEL > 1) ? s.zr[0] : s.yr[0], (LEVEL > 1) ? s.zi[0] : s.yi[0]); \
-                }                                                                           \
-            }                                                                               \
-            if (wer) {                         /* the last active thread holds R sites */   \
-                if (edge_r) {                                                               \
-                    cl_wait(lk.my_bar[1][par], phase);                                      \
-                    const double2 v = sh.halo[1][par];                                      \
-                    if (LEVEL > 1) { s.zr[R - 1] = fma(-rho, v.y, s.zr[R - 1]); s.zi[R - 1] = fma(rho, v.x, s.zi[R - 1]); } \
-                    else { s.yr[R - 1] = fma(-rho, v.y, s.yr[R - 1]); s.yi[R - 1] = fma(rho, v.x, s.yi[R - 1]); } \
-                    cl_send(lk.to_right_slot[par ^ 1], lk.to_right_bar[par ^ 1],            \
-                            (LEVEL > 1) ? s.zr[R - 1] : s.yr[R - 1],                        \
-                            (LEVEL > 1) ? s.zi[R - 1] : s.yi[R - 1]);                       \
-                }                                                                           \
-            }                                                                               \
-            if (OWN) {                                  /* oracle correction sigma_LEVEL */ \
-                const double sgr = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));          \
-                const double sgi = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);      \
-                if (LEVEL > 1) {                                                            \
-                    s.zr[HW0] = fma(msk, sgr, s.zr[HW0]);                                   \
-                    s.zi[HW0] = fma(msk, sgi, s.zi[HW0]);                                   \
-                } else {                                                                    \
-                    s.yr[HW0] = fma(msk, sgr, s.yr[HW0]);                                   \
-                    s.yi[HW0] = fma(msk, sgi, s.yi[HW0]);                                   \
-                }                                                                           \
+            if (lane_on) {                                                                  \
+                /* inner neighbour: the compute thread's edge value of the level's input */ \
+                const double2 in = side == 0 ? first[par * nt + inner] : last[par * nt + inner]; \
+                cl_wait(par ? my_bar1 : my_bar0, phase);                                    \
+                const double2 out = sh.halo[side][par];        /* the neighbour CTA's site */ \
+                const double rho = hs.rho[LEVEL - 1];                                       \
+                const double cr = (LEVEL == 4) ? yr : zr, ci = (LEVEL == 4) ? yi : zi;      \
+                double o_r, o_i;                                                            \
+                hsite(side == 0 ? out.x : in.x, side == 0 ? out.y : in.y, cr, ci,           \
+                      side == 0 ? in.x : out.x, side == 0 ? in.y : out.y, rho, yr, yi, o_r, o_i); \
+                if (LEVEL > 1) { zr = o_r; zi = o_i; } else { yr = o_r; yi = o_i; }         \
+                cl_send(par ? to_slot0 : to_slot1, par ? to_bar0 : to_bar1, o_r, o_i);      \
+                first[(par ^ 1) * nt + me] = make_double2(o_r, o_i);                        \
+                last[(par ^ 1) * nt + me] = make_double2(o_r, o_i);                         \
             }                                                                               \
         }
-        QW_CLUSTER_LEVEL(4)
-        QW_CLUSTER_LEVEL(3)
-        QW_CLUSTER_LEVEL(2)
-        QW_CLUSTER_LEVEL(1)
-#undef QW_CLUSTER_LEVEL
+        QW_COMM_LEVEL(4)
+        QW_COMM_LEVEL(3)
+        QW_COMM_LEVEL(2)
+        QW_COMM_LEVEL(1)
+#undef QW_COMM_LEVEL
     }
 }
 
+// blockDim = compute threads (rounded up to warps) + 32 (the comm warp)
 template <int R, bool RAGGED>
-__global__ void __launch_bounds__(256, 1) rk4_cycle_cluster(const QwParams prm)
+__global__ void __launch_bounds__(288, 1) rk4_cycle_cluster(const QwParams prm)
 {
     static_assert(R >= 2 * HW0 + 1, "the window w-3..w+3 must sit in one thread");
     extern __shared__ double2 mbox[];         // [2][2][blockDim.x]: parity, first/last
     __shared__ ClusterShared sh;
-    const int t = threadIdx.x, nt = blockDim.x;
+    const int t = threadIdx.x, nt = blockDim.x, ntc = nt - 32;       // ntc: compute threads
     const uint32_t rank = cl_rank(), csz = cl_size();
     const QwPoint pt = qw_point(prm, blockIdx.x / csz);
-    // this CTA's part of the ring
+    // this CTA's part of the ring: nb sites, two of them edge sites
     const int64_t base = prm.n / csz, extra = prm.n - base * csz;
     const int64_t nb = base + (rank < extra ? 1 : 0);
     const int64_t off = rank * base + (rank < extra ? rank : extra);
-    const int nact = (int)((nb + R - 1) / R);
-    const int nfull = (int)(nb - (int64_t)nact * (R - 1));
+    const int nact = (int)((nb - 2 + R - 1) / R);
+    const int nfull = (int)(nb - 2 - (int64_t)nact * (R - 1));
+    const bool comm = t >= ntc;
+    const int lane = t & 31;
     const bool active = t < nact;
-    // the SHORT threads (R - 1 sites and a ghost slot) come first here, so that the last active
-    // thread, whose slot R - 1 talks to the next CTA, always holds R sites
-    const int nshort = nact - nfull;
-    const bool full = !RAGGED || t >= nshort || !active;
-    const bool edge_l = t == 0, edge_r = t == nact - 1;
-    const bool wel = (t >> 5) == 0, wer = (t >> 5) == ((nact - 1) >> 5);
-    // neighbours inside the CTA; the edge threads' outer neighbours live in other CTAs
-    const int tl = active ? (t == 0 ? 0 : t - 1) : t;
-    const int tr = active ? (t == nact - 1 ? t : t + 1) : t;
+    const bool full = !RAGGED || t < nfull || !active;
+    const int me_l = ntc, me_r = ntc + 1;              // mailbox indices of the two edge sites
+    // neighbours: compute thread 0 / nact - 1 talk to the edge sites
+    const int tl = active ? (t == 0 ? me_l : t - 1) : t;
+    const int tr = active ? (t == nact - 1 ? me_r : t + 1) : t;
 
-    ClusterLinks lk;
-    {
-        const uint32_t left = rank == 0 ? csz - 1 : rank - 1, right = rank + 1 == csz ? 0 : rank + 1;
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            lk.to_left_slot[p] = cl_map(cl_smem(&sh.halo[1][p]), left);
-            lk.to_left_bar[p] = cl_map(cl_smem(&sh.bar[1][p]), left);
-            lk.to_right_slot[p] = cl_map(cl_smem(&sh.halo[0][p]), right);
-            lk.to_right_bar[p] = cl_map(cl_smem(&sh.bar[0][p]), right);
-            lk.my_bar[0][p] = cl_smem(&sh.bar[0][p]);
-            lk.my_bar[1][p] = cl_smem(&sh.bar[1][p]);
-        }
-    }
     if (t == 0) {
 #pragma unroll
         for (int d = 0; d < 2; ++d)
@@ -528,19 +457,34 @@ __global__ void __launch_bounds__(256, 1) rk4_cycle_cluster(const QwParams prm)
     }
 
     HState<R> s;
-    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+    const double amp0 = 1.0 / sqrt((double)prm.n);
+    const double amp = active ? amp0 : 0.0;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         s.yr[r] = amp; s.yi[r] = 0.0;
         s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
     double2 *first = mbox, *last = mbox + 2 * nt;      // [parity][thread]; a step starts at 0
-    first[t] = make_double2(s.yr[0], s.yi[0]);
-    last[t] = make_double2(s.yr[R - 1], s.yi[R - 1]);  // uniform start: any slot will do
+    first[t] = make_double2(comm ? amp0 : s.yr[0], 0.0);
+    last[t] = make_double2(comm ? amp0 : s.yr[R - 1], 0.0);   // uniform start: any slot will do
     cl_sync();                                         // every CTA's barriers exist
-    if (pt.steps > 0) {                                // fill #0 of the parity-0 slots
-        if (edge_l) cl_send(lk.to_left_slot[0], lk.to_left_bar[0], s.yr[0], s.yi[0]);
-        if (edge_r) cl_send(lk.to_right_slot[0], lk.to_right_bar[0], amp, 0.0);
+
+    // comm lane 0 / 1: the left / right edge site and its links
+    const bool lane_on = comm && lane < 2;
+    const int side = lane & 1;
+    uint32_t my_bar0 = 0, my_bar1 = 0, to_slot0 = 0, to_slot1 = 0, to_bar0 = 0, to_bar1 = 0;
+    double er = amp0, ei = 0.0;                        // the edge site (psi_n)
+    if (lane_on) {
+        const uint32_t nbr = side == 0 ? (rank == 0 ? csz - 1 : rank - 1)
+                                       : (rank + 1 == csz ? 0 : rank + 1);
+        my_bar0 = cl_smem(&sh.bar[side][0]);
+        my_bar1 = cl_smem(&sh.bar[side][1]);
+        // my left site is the RIGHT-hand halo of the CTA to the left, and vice versa
+        to_slot0 = cl_map(cl_smem(&sh.halo[side ^ 1][0]), nbr);
+        to_slot1 = cl_map(cl_smem(&sh.halo[side ^ 1][1]), nbr);
+        to_bar0 = cl_map(cl_smem(&sh.bar[side ^ 1][0]), nbr);
+        to_bar1 = cl_map(cl_smem(&sh.bar[side ^ 1][1]), nbr);
+        if (pt.steps > 0) cl_send(to_slot0, to_bar0, er, ei);        // fill #0 of the parity-0 slots
     }
 
     const int warp = t >> 5;
@@ -551,19 +495,28 @@ __global__ void __launch_bounds__(256, 1) rk4_cycle_cluster(const QwParams prm)
         __syncthreads();                               // the last chunk's table is no longer read
         horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on);
         __syncthreads();
-        if (owner_cta && warp == 0)
-            cluster_steps<R, true, RAGGED>(s, sh, lk, first, last, nt, t, tl, tr, cnt, msk, full,
-                                           edge_l, edge_r, wel, wer);
+        if (comm)
+            cluster_comm_steps(er, ei, sh, first, last, nt, side, side == 0 ? me_l : me_r,
+                               side == 0 ? 0 : nact - 1, my_bar0, my_bar1, to_slot0, to_slot1,
+                               to_bar0, to_bar1, cnt, lane_on);
+        else if (owner_cta && warp == 0)
+            horner_steps<R, true, RAGGED, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk,
+                                                 full, 0);
         else
-            cluster_steps<R, false, RAGGED>(s, sh, lk, first, last, nt, t, tl, tr, cnt, msk, full,
-                                            edge_l, edge_r, wel, wer);
+            horner_steps<R, false, RAGGED, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk,
+                                                  full, 0);
     }
 
     // p = |psi_w|^2 / ||psi||^2, ||psi||^2: partial sums to CTA 0
     double nrm = 0.0;
+    if (!comm) {
 #pragma unroll
-    for (int r = 0; r < R - 1; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
-    if (full) nrm = fma(s.yr[R - 1], s.yr[R - 1], fma(s.yi[R - 1], s.yi[R - 1], nrm));
+        for (int r = 0; r < R - 1; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+        if (full) nrm = fma(s.yr[R - 1], s.yr[R - 1], fma(s.yi[R - 1], s.yi[R - 1], nrm));
+    } else if (lane_on) {
+        nrm = fma(er, er, ei * ei);
+        sh.edge_out[side] = make_double2(er, ei);
+    }
     const double pw = (owner_cta && t == 0) ? fma(s.yr[HW0], s.yr[HW0], s.yi[HW0] * s.yi[HW0]) : 0.0;
     __syncthreads();
     const double2 tot = hblock_sum(make_double2(nrm, pw), sh.red);
@@ -578,16 +531,25 @@ __global__ void __launch_bounds__(256, 1) rk4_cycle_cluster(const QwParams prm)
         prm.p[pt.q] = psum / nsum;
         if (prm.norm) prm.norm[pt.q] = nsum;
     }
-    if (prm.psi && active) {      // undo the relabelling: slot r of thread t -> site w + off + off(t) + r - 3
+    if (prm.psi) {
+        // undo the relabelling: logical site l of the ring (CTA 0: l = 0 is its left edge site,
+        // l = 1 + HW0 the marked vertex) -> physical site w + l - 1 - HW0
         double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
-        const int64_t off_t = off + (int64_t)t * (R - 1) + (t > nshort ? t - nshort : 0);
+        const int64_t shift = (int64_t)prm.target - 1 - HW0;
+        if (active) {
+            const int64_t off_t = off + 1 + (int64_t)t * (R - 1) + (t < nfull ? t : nfull);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            if (r == R - 1 && !full) continue;                    // ghost
-            int64_t j = off_t + r - HW0 + prm.target;
+            for (int r = 0; r < R; ++r) {
+                if (r == R - 1 && !full) continue;                // ghost
+                int64_t j = (off_t + r + shift) % prm.n;
+                if (j < 0) j += prm.n;
+                out[j] = make_double2(s.yr[r], s.yi[r]);
+            }
+        }
+        if (lane_on) {
+            int64_t j = (off + (side == 0 ? 0 : nb - 1) + shift) % prm.n;
             if (j < 0) j += prm.n;
-            if (j >= prm.n) j -= prm.n;
-            out[j] = make_double2(s.yr[r], s.yi[r]);
+            out[j] = make_double2(er, ei);
         }
     }
 }
@@ -1087,6 +1049,12 @@ int qw_cluster_size(const QwParams &prm)
     if (prm.flags & (QW_FLAG_NO_HORNER | QW_FLAG_CYCLE_LEGACY | QW_FLAG_CYCLE_SPLIT |
                      QW_FLAG_FORCE_GENERIC | QW_FLAG_FORCE_STREAM | QW_FLAG_MIRROR))
         return 0;
+    // Measured (tools/ab_large_n.py): two CTAs (up to 8192 sites) tie with the bulk-copy streaming
+    // kernel at N = 8192 (4.8e11 site-updates/s) and win below (N = 5000: 4.3e11 against 2.6e11);
+    // larger clusters leave SMs idle (3: 148 = 49 x 3 + 1; 8: at most two per GPC) and lose to
+    // streaming with 8 steps per pass (N = 16384: 4.3e11 against 5.3e11) -- unless the ring is not
+    // a multiple of 128 sites, where streaming falls back to its cp.async kernel.
+    if (prm.n > 8192 && prm.n % 128 == 0 && !(prm.flags & QW_FLAG_FORCE_CLUSTER)) return 0;
     const int64_t c = (prm.n + 4095) / 4096;
     if (prm.n_points * c > 0x7fffffffLL) return 0;
     return (int)c;
@@ -1098,11 +1066,10 @@ cudaError_t qw_launch_cluster(QwParams prm, cudaStream_t st, qw_plan *plan)
     if (c == 0) return cudaErrorInvalidConfiguration;
     constexpr int R = 16;
     const int64_t nb = (prm.n + c - 1) / c;                        // the largest CTA
-    const int nact = (int)((nb + R - 1) / R);
-    const int threads = ((nact + 31) / 32) * 32;
+    const int nact = (int)((nb - 2 + R - 1) / R);                  // two sites live in the comm warp
+    const int threads = ((nact + 31) / 32) * 32 + 32;              // + the comm warp
     const size_t smem = (size_t)threads * 4 * sizeof(double2);
-    const bool ragged = prm.n % ((int64_t)c * R) != 0;             // some thread holds R - 1 sites
-    auto kernel = ragged ? rk4_cycle_cluster<R, true> : rk4_cycle_cluster<R, false>;
+    auto kernel = rk4_cycle_cluster<R, true>;      // n_r - 2 compute sites: some threads hold R - 1
     if (plan) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, kernel);

@@ -59,9 +59,13 @@ def test_cycle_graph_resident_across_a_cluster(qw, n):
     T = np.concatenate([[0.0], rng.uniform(1.0, 9.0, 4)])
     g = rng.uniform(0.1, 2.4, 5)
     for sched, S in (("lin", 37), ("cbrt", 70)):
-        prob = qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S)
+        # 16384 = QW_FLAG_FORCE_CLUSTER: above 8192 sites rings of a multiple of 128 sites go to
+        # the bulk-copy streaming kernel by default
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S, flags=16384)
         pl = qw.plan(prob)
         assert pl["path"] == "cluster-cycle" and pl["steps_per_pass"] == -(-n // 4096)
+        default = qw.plan(qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S))
+        assert default["path"] == ("stream" if n > 8192 and n % 128 == 0 else "cluster-cycle")
         p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
         po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, n_steps=S,
                                              return_psi=True)

@@ -428,8 +428,9 @@ def test_rk45_vs_scipy_on_the_stencil(qw, n, topo):
 
 
 def test_odd_shapes_and_catch_all_paths(qw):
-    """Degenerate grids, negative gamma, complete graphs beyond the resident limit (generic
-    kernel), a ring beyond it with the fixed-step-size rule (streaming kernel, ragged steps)."""
+    """Degenerate grids, negative gamma, a complete graph beyond one block (split over blocks;
+    the catch-all kernel only when forced), a ring beyond one block with the fixed-step-size rule
+    (cluster kernel by default, streaming kernel with ragged steps when forced)."""
     t, b = np.array([3.0]), np.array([-0.7])                    # 1 x 1 heatmap, gamma < 0
     prob = qw.Problem(n=33, topology="circular", schedule="cerf_5", n_steps=50)
     p, nrm = qw.rk4_heatmap(prob, t, b)
@@ -439,21 +440,24 @@ def test_odd_shapes_and_catch_all_paths(qw):
     po, no = c_oracle.heatmap(33, "circular", "cerf_5", np.linspace(0, 4, 7), b, n_steps=50)
     assert p.shape == (1, 7) and np.abs(p - po).max() <= P_TOL
 
-    n = 5000                                                    # complete, generic kernel
-    prob = qw.Problem(n=n, topology="complete", schedule="lin", gamma_on="laplacian", n_steps=40)
-    assert qw.plan(prob)["path"] == "generic"
+    n = 5000                                                    # complete: split / generic kernel
     T, g = np.array([5.0, 30.0]), np.array([1.0, 1.4]) / n
-    p, nrm = qw.rk4_batch(prob, T, g)
     po, no, _ = c_oracle.rk4_batch(n, "complete", "lin", T, g, n_steps=40, gamma_on="laplacian")
-    assert np.abs(p - po).max() <= P_TOL and np.abs(nrm - no).max() <= P_TOL
+    for flags, path in ((0, "horner-complete"), (1, "generic")):
+        prob = qw.Problem(n=n, topology="complete", schedule="lin", gamma_on="laplacian",
+                          n_steps=40, flags=flags)
+        assert qw.plan(prob)["path"] == path
+        p, nrm = qw.rk4_batch(prob, T, g)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(nrm - no).max() <= P_TOL
 
-    n = 6000                                                    # ring, streaming, step_size
-    prob = qw.Problem(n=n, topology="circular", schedule="sqrt", step_size=0.02)
-    assert qw.plan(prob)["path"] == "stream"
+    n = 6000                                                    # ring, step_size: cluster / streaming
     t, b = np.array([0.0, 0.11, 0.5, 0.33]), np.array([0.4, 1.9])
-    p, nrm = qw.rk4_heatmap(prob, t, b)
     po, no = c_oracle.heatmap(n, "circular", "sqrt", t, b, step_size=0.02)
-    assert np.abs(p - po).max() <= P_TOL and np.abs(nrm - no).max() <= P_TOL
+    for flags, path in ((0, "cluster-cycle"), (2, "stream")):
+        prob = qw.Problem(n=n, topology="circular", schedule="sqrt", step_size=0.02, flags=flags)
+        assert qw.plan(prob)["path"] == path
+        p, nrm = qw.rk4_heatmap(prob, t, b)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(nrm - no).max() <= P_TOL
 
 
 @pytest.mark.parametrize("n", [17, 33, 51, 71, 100, 200])
