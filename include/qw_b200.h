@@ -107,7 +107,8 @@ enum {
                                     reflecting ends (psi is mirror symmetric about the marked
                                     vertex for the uniform initial state every caller of the
                                     reference uses): same p, norm and psi with half the
-                                    arithmetic.  160 <= n <= 1087: one warp per point; up to
+                                    arithmetic.  6 <= n < 160: warp-packed half rings;
+                                    160 <= n <= 1087: one warp per point; up to
                                     8702: block-per-point kernel on the half ring; above:
                                     streaming kernel with half the HBM traffic.
                                     Complete graph: all unmarked vertices carry one common
@@ -146,6 +147,26 @@ int qw_rk4_batch_dev(const qw_problem *prob, const double *T, const double *gamm
 int qw_rk4_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_time,
                     const double *beta_array, int64_t n_beta, int64_t beta_begin,
                     int64_t beta_end, double *p, double *norm, void *stream);
+
+/* Several heatmaps in as few launches as possible: the reference's production sweep
+ * (BCB_latest.py:309-320: 4 schedules x 35 dimensions, 300 points each) and the three schedules
+ * of BASELINE config 2 are many SMALL problems, each far too small to fill the GPU.  Jobs whose
+ * warp-packed kernel coincides (same sites-per-lane geometry and step rule; dimension, schedule,
+ * target, gamma placement and axes may differ) go out as ONE grid in which every warp looks its
+ * problem up in a job table; the others are launched one after the other on the same stream.
+ * Results are bitwise those of separate qw_rk4_grid_dev calls.  All pointers are device
+ * pointers; jobs itself is a host array. */
+typedef struct qw_grid_job {
+    qw_problem prob;
+    const double *time_array;
+    int64_t n_time;
+    const double *beta_array;
+    int64_t n_beta, beta_begin, beta_end;
+    double *p;             /* [(beta_end-beta_begin)][n_time] */
+    double *norm;          /* same shape, nullable */
+} qw_grid_job;
+
+int qw_rk4_multi_grid_dev(const qw_grid_job *jobs, int64_t n_jobs, void *stream);
 
 /* Host-buffer forms of the two calls above (copies inside; device = CUDA ordinal). */
 int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gamma,
@@ -252,7 +273,8 @@ typedef struct qw_plan {
                                 small dimension, 9 mirror-reduced cycle, 10 symmetry-reduced
                                 complete graph (both QW_FLAG_MIRROR), 11 warp-packed complete
                                 graph of any small dimension, 12 cycle graph resident across a
-                                thread-block cluster (4097 .. 32768 sites) */
+                                thread-block cluster (4097 .. 32768 sites), 13 warp-packed half
+                                ring of a small cycle graph (QW_FLAG_MIRROR, 6 .. 159 sites) */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */

@@ -29,15 +29,18 @@ _dropin.install(globals(), "BCBL")
 
 
 def production_sweep(step_functions=("lin", "sqrt", "cbrt", "cerf_3"),
-                     dims=tuple(np.arange(3, 71 + 1, 2)), streams=16):
+                     dims=tuple(np.arange(3, 71 + 1, 2)), streams=16, fused=True):
     """The __main__ loop of BCB_latest.py:309-320.
 
     A production heatmap is 300 points on a ring of at most 71 sites: one launch occupies a few
-    per cent of the GPU and runs for as long as its longest point (latency bound).  With
-    ``streams`` > 1 (one process, fixed-step RK4, time-dependent walk) the heatmaps are
-    therefore issued round-robin on that many CUDA streams and collected once at the end; the
-    files written are the same.  ``streams`` = 1, a process group, 'rk45' or the
-    time-independent comparator take the reference's sequential loop."""
+    per cent of the GPU and runs for as long as its longest point.  ``fused`` (default; one
+    process, fixed-step RK4, time-dependent walk): all heatmaps of the sweep go to the library in
+    ONE call (``engine.rk4_heatmaps`` -> ``qw_rk4_multi_grid_dev``), which lays the problems that
+    share a warp-packed kernel end to end in one grid -- a handful of launches instead of 140;
+    the files written are bitwise those of the sequential loop.  ``fused=False`` and
+    ``streams`` > 1 issue one launch per heatmap round-robin on that many CUDA streams (round 1).
+    ``streams`` = 1 with ``fused=False``, a process group, 'rk45' or the time-independent
+    comparator take the reference's sequential loop."""
     global step_function, dimension
     import time as _time
 
@@ -46,8 +49,9 @@ def production_sweep(step_functions=("lin", "sqrt", "cbrt", "cerf_3"),
 
     from . import engine
 
-    sequential = (streams <= 1 or integrator != "rk4" or type_of_qw != "dependent"
-                  or (dist.is_available() and dist.is_initialized()))
+    sequential = (integrator != "rk4" or type_of_qw != "dependent"
+                  or (dist.is_available() and dist.is_initialized())
+                  or (not fused and streams <= 1))
     if sequential:
         for step in step_functions:
             step_function = step
@@ -56,18 +60,30 @@ def production_sweep(step_functions=("lin", "sqrt", "cbrt", "cerf_3"),
                 parallel_routine()                         # noqa: F821 (installed above)
         return
     dev = engine._device(device)
-    pool = [torch.cuda.Stream(device=dev) for _ in range(int(streams))]
     beta = np.asarray(PRODUCTION_BETA, dtype=np.float64)
     d_beta = torch.from_numpy(beta).to(dev)
-    pending, tic = [], _time.perf_counter()
+    tic = _time.perf_counter()
+    work = []
     for step in step_functions:
-        for k, dim in enumerate(dims):
+        for dim in dims:
             n = int(dim)
             time_array = [(np.pi / 4) * np.sqrt(n), np.sqrt(n), (np.pi / 2) * np.sqrt(n),
                           2 * np.sqrt(n)]
             prob = engine.Problem(n=n, topology=topology, schedule=step, gamma_on=gamma_on,
-                                  n_steps=n_steps, step_size=None if n_steps else step_size)
-            d_time = torch.tensor(time_array, dtype=torch.float64, device=dev)
+                                  n_steps=n_steps, step_size=None if n_steps else step_size,
+                                  flags=8192 if mirror else 0)
+            work.append((n, step, time_array, prob,
+                         torch.tensor(time_array, dtype=torch.float64, device=dev)))
+    if fused:
+        with torch.cuda.device(dev):
+            outs = engine.rk4_heatmaps([w[3] for w in work], [w[4] for w in work],
+                                       [d_beta] * len(work), device=dev)
+        pending = [(n, step, time_array, p) for (n, step, time_array, _, _), (p, _) in
+                   zip(work, outs)]
+    else:
+        pool = [torch.cuda.Stream(device=dev) for _ in range(int(streams))]
+        pending = []
+        for n, step, time_array, prob, d_time in work:
             st = pool[len(pending) % len(pool)]
             st.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(st):

@@ -11,7 +11,7 @@ as ``qwtdh_b200`` (alias module at the repository root) or through ``importlib``
 """
 
 from . import _lib, engine                                     # noqa: F401
-from .engine import (Problem, rk4_batch, rk4_heatmap, rk4_batch_host,    # noqa: F401
+from .engine import (Problem, rk4_batch, rk4_heatmap, rk4_heatmaps, rk4_batch_host,    # noqa: F401
                      rk4_heatmap_host, rhs, rk45_batch, rk45_heatmap, ti_exact_batch, ti_exact_heatmap, ensemble_stats, robustness_map, heatmap_summary, maximize_probability, plan,
                      adiabatic_batch, adiabatic_check, spectrum_batch,
                      fp64_peak_tflops, launch_count, shard_rows, heatmap_sharded, sharded_d2h_bytes,

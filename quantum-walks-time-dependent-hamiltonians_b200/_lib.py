@@ -18,7 +18,8 @@ FLAG_NO_HORNER, FLAG_MIRROR = 2048, 8192
 PATH_NAMES = {0: "resident-cycle", 1: "resident-complete", 2: "generic", 3: "stream",
               4: "packed-cycle", 5: "horner-cycle", 6: "horner-complete",
               7: "packed-horner-cycle", 8: "packed-any-cycle", 9: "mirror-cycle",
-              10: "symmetric-complete", 11: "packed-complete", 12: "cluster-cycle"}
+              10: "symmetric-complete", 11: "packed-complete", 12: "cluster-cycle",
+              13: "packed-mirror-cycle"}
 
 
 class QwProblem(ctypes.Structure):
@@ -26,6 +27,13 @@ class QwProblem(ctypes.Structure):
                 ("schedule", ctypes.c_int32), ("gamma_on", ctypes.c_int32),
                 ("flags", ctypes.c_int32), ("target", ctypes.c_int64),
                 ("step_size", ctypes.c_double), ("n_steps", ctypes.c_int64)]
+
+
+class QwGridJob(ctypes.Structure):
+    _fields_ = [("prob", QwProblem), ("time_array", ctypes.c_void_p), ("n_time", ctypes.c_int64),
+                ("beta_array", ctypes.c_void_p), ("n_beta", ctypes.c_int64),
+                ("beta_begin", ctypes.c_int64), ("beta_end", ctypes.c_int64),
+                ("p", ctypes.c_void_p), ("norm", ctypes.c_void_p)]
 
 
 class QwPlan(ctypes.Structure):
@@ -42,6 +50,7 @@ _pp = ctypes.POINTER(QwProblem)
 SIGNATURES = {
     "qw_rk4_batch_dev": (ctypes.c_int, [_pp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "qw_rk4_grid_dev": (ctypes.c_int, [_pp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "qw_rk4_multi_grid_dev": (ctypes.c_int, [ctypes.POINTER(QwGridJob), _i64, _vp]),
     "qw_rk4_batch_host": (ctypes.c_int, [_pp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, ctypes.c_int]),
     "qw_rk4_grid_host": (ctypes.c_int, [_pp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp,
                                         ctypes.c_int]),

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "qw_common.cuh"
 
@@ -25,6 +26,8 @@ cudaError_t qw_run_fp64_probe(double millis, double *tflops, cudaStream_t st, in
 cudaError_t qw_launch_summary(const double *p, const double *tarr, int64_t nb, int64_t nt,
                               double t_min, double *out, cudaStream_t st);
 bool qw_packed_supported(const QwParams &prm);
+cudaError_t qw_launch_packed_multi(const QwParams *prms, int n, unsigned char *taken,
+                                   cudaStream_t st, int64_t *launches);
 cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan);
 bool qw_rk45_supported(const QwParams &prm);
 cudaError_t qw_launch_rk45(QwParams prm, double rtol, double atol, int64_t *nfev, cudaStream_t st);
@@ -254,6 +257,56 @@ int qw_rk4_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_
     prm.n_time = n_time; prm.beta_begin = beta_begin;
     prm.p = p; prm.norm = norm;
     return run(prm, (cudaStream_t)stream);
+}
+
+int qw_rk4_multi_grid_dev(const qw_grid_job *jobs, int64_t n_jobs, void *stream)
+{
+    if (n_jobs < 0 || n_jobs > (1 << 20)) return fail(QW_E_SIZE, "bad number of jobs");
+    if (n_jobs == 0) return 0;
+    if (!jobs) return fail(QW_E_NULL, "jobs is NULL");
+    std::vector<QwParams> prms((size_t)n_jobs);
+    for (int64_t k = 0; k < n_jobs; ++k) {
+        const qw_grid_job &j = jobs[k];
+        QwParams &prm = prms[(size_t)k];
+        int rc = validate(&j.prob, &prm);
+        if (rc) return rc;
+        if (j.n_time < 0 || j.n_beta < 0 || j.beta_begin < 0 || j.beta_end < j.beta_begin ||
+            j.beta_end > j.n_beta)
+            return fail(QW_E_SIZE, "bad grid extents in job %lld", (long long)k);
+        prm.n_points = (j.beta_end - j.beta_begin) * j.n_time;
+        if (prm.n_points > 0 && (!j.time_array || !j.beta_array || !j.p))
+            return fail(QW_E_NULL, "time_array, beta_array and p are required (job %lld)",
+                        (long long)k);
+        prm.time_array = j.time_array; prm.beta_array = j.beta_array;
+        prm.n_time = j.n_time; prm.beta_begin = j.beta_begin;
+        prm.p = j.p; prm.norm = j.norm;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // problems that share a warp-packed kernel: one grid per kernel
+    std::vector<unsigned char> taken((size_t)n_jobs, 0);
+    std::vector<unsigned char> eligible((size_t)n_jobs, 0);
+    std::vector<QwParams> packed;
+    std::vector<int64_t> where;
+    for (int64_t k = 0; k < n_jobs; ++k)
+        if (prms[(size_t)k].n_points > 0 && choose_path(prms[(size_t)k]) == PATH_PACKED) {
+            packed.push_back(prms[(size_t)k]);
+            where.push_back(k);
+        }
+    if (packed.size() >= 2) {
+        std::vector<unsigned char> got(packed.size(), 0);
+        int64_t nl = 0;
+        keep_pool_cached();
+        cudaError_t e = qw_launch_packed_multi(packed.data(), (int)packed.size(), got.data(), st, &nl);
+        g_launches += nl;
+        if (e != cudaSuccess) return cuda_fail(e, "multi-problem packed launch");
+        for (size_t i = 0; i < packed.size(); ++i) taken[(size_t)where[i]] = got[i];
+    }
+    for (int64_t k = 0; k < n_jobs; ++k) {
+        if (taken[(size_t)k]) continue;
+        int rc = run(prms[(size_t)k], st);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 static int run_ti_exact(QwParams &prm, cudaStream_t st)

@@ -10,6 +10,10 @@
 // one small shared table per warp and each lane only scales them by its own h and gamma.
 // Same arithmetic as qw_resident.cu (reference path BCB.py:163-203, step rule
 // QW_Search.py:149-164).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "qw_stage.cuh"
 #include "qw_horner_level.cuh"
 
@@ -118,8 +122,13 @@ __device__ __forceinline__ double2 packed_factor(const QwParams &prm, const QwPo
 // COLUMN: fixed step size on a heatmap (packed_point).  A template switch, because the step
 // count then comes from memory and lives in a vector register; with the n_steps rule it is a
 // kernel parameter and the loop control stays in the uniform datapath (C1: 5 % latency).
-template <int R, int MINB, bool COLUMN>
-__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm, const int tpp_log2)
+// The kernels below are bodies (`prm` by reference, the warp's index within its problem as an
+// argument) with two entry points each: the single-problem kernel, whose parameters sit in the
+// constant bank, and a multi-problem kernel, whose warps look their problem up in a job table
+// (qw_rk4_multi_grid_dev: many small heatmaps in one grid).
+template <int R, bool COLUMN>
+__device__ __forceinline__ void packed_body(const QwParams &prm, const int64_t warp_id,
+                                            const int tpp_log2)
 {
     __shared__ PackedShared sh;
     const unsigned full = 0xffffffffu;
@@ -127,9 +136,9 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
     const int tpp = 1 << tpp_log2, groups = 32 >> tpp_log2;
     const int li = lane & (tpp - 1), grp = lane >> tpp_log2;
     bool valid;
-    const QwPoint pt = packed_point(prm, blockIdx.x, grp, groups, valid);
+    const QwPoint pt = packed_point(prm, warp_id, grp, groups, valid);
     __shared__ int64_t steps_slot;
-    const int64_t S = COLUMN ? packed_steps(prm, blockIdx.x, groups, &steps_slot)
+    const int64_t S = COLUMN ? packed_steps(prm, warp_id, groups, &steps_slot)
                              : prm.n_steps_uniform;
     const bool own = (li == 0);
     const int left = (li == 0) ? lane + tpp - 1 : lane - 1;
@@ -203,6 +212,47 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
     }
 }
 
+template <int R, int MINB, bool COLUMN>
+__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm, const int tpp_log2)
+{
+    packed_body<R, COLUMN>(prm, blockIdx.x, tpp_log2);
+}
+
+// One entry per problem of a multi-problem launch: warps [warp_begin, warp_end) of the grid.
+struct PackedJob {
+    QwParams prm;
+    int64_t warp_begin, warp_end;
+    int32_t a, b;                    // tpp_log2, - / lanes per point, lanes with R sites
+    int32_t pad[2];
+};
+
+// the calling warp's job -> shared memory; returns the warp's index within the job
+__device__ __forceinline__ int64_t packed_job_fetch(const PackedJob *jobs, const int n_jobs,
+                                                    PackedJob *mine)
+{
+    const int64_t w = blockIdx.x;
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (w >= jobs[mid].warp_end) lo = mid + 1; else hi = mid;
+    }
+    static_assert(sizeof(PackedJob) % 8 == 0, "copied in 8-byte words");
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(jobs + lo);
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(mine);
+    for (int i = threadIdx.x; i < (int)(sizeof(PackedJob) / 8); i += 32) dst[i] = src[i];
+    __syncwarp();
+    return w - mine->warp_begin;
+}
+
+template <int R, int MINB, bool COLUMN>
+__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_multi(const PackedJob *jobs,
+                                                                   const int n_jobs)
+{
+    __shared__ PackedJob job;
+    const int64_t w = packed_job_fetch(jobs, n_jobs, &job);
+    packed_body<R, COLUMN>(job.prm, w, job.a);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Packed layout for ANY small ring (the reference's own runs use odd dimensions 3 .. 71):
 // n = L (R - 1) + nfull sites of a point are dealt out over L lanes, R sites to the first
@@ -210,9 +260,14 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed(const QwParams prm,
 // G = 32 / L points, lanes beyond G L idle.  The last slot of a short lane is a ghost that is
 // loaded with the right neighbour's first value before every stage, and a short lane hands
 // slot R-2 to its left neighbour: two selects per stage, no FP64 work.  Stage form.
-template <int R, int MINB>
-__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams prm, const int L,
-                                                                 const int nfull)
+// MIRROR (QW_FLAG_MIRROR, rings below 160 sites; larger ones: rk4_cycle_mirror): the lanes hold
+// the half ring w .. w + n/2 (n/2 + 1 sites) with reflecting ends -- left of the marked vertex
+// its own right neighbour, right of the antipode the site before it (even n) or the last site
+// itself (odd n).  psi is mirror symmetric about the marked vertex for the uniform start, so p,
+// norm and psi are those of the full ring with half the arithmetic.
+template <int R, bool MIRROR>
+__device__ __forceinline__ void packed_any_body(const QwParams &prm, const int64_t warp_id,
+                                                const int L, const int nfull)
 {
     static_assert(R >= 2, "a short lane needs at least one real site");
     __shared__ PackedShared sh;
@@ -222,14 +277,16 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
     const int grp = lane / L, li = lane - grp * L;
     const bool lane_used = grp < groups;
     bool valid;
-    const QwPoint pt = packed_point(prm, blockIdx.x, lane_used ? grp : groups - 1, groups, valid);
+    const QwPoint pt = packed_point(prm, warp_id, lane_used ? grp : groups - 1, groups, valid);
     valid = valid && lane_used;
     __shared__ int64_t steps_slot;
-    const int64_t S = packed_steps(prm, blockIdx.x, groups, &steps_slot);
+    const int64_t S = packed_steps(prm, warp_id, groups, &steps_slot);
     const bool own = lane_used && li == 0;
     const bool full = !lane_used || li < nfull;        // R sites (idle lanes: R zeros)
     const int left = !lane_used ? lane : (li == 0 ? lane + L - 1 : lane - 1);
     const int right = !lane_used ? lane : (li == L - 1 ? lane - L + 1 : lane + 1);
+    const bool m_first = MIRROR && lane_used && li == 0, m_last = MIRROR && lane_used && li == L - 1;
+    const bool even = (prm.n & 1) == 0;
 
     const double h = pt.h;                       // 0 when T == 0: the state never moves
     const double gl = prm.gamma_on == QW_GAMMA_ON_LAPLACIAN ? pt.gamma : 1.0;
@@ -265,10 +322,25 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
                                             : (full ? s.ur[R - 1] : s.ur[R > 1 ? R - 2 : 0]); \
                 const double xli = (K == 0) ? (full ? s.yi[R - 1] : s.yi[R > 1 ? R - 2 : 0]) \
                                             : (full ? s.ui[R - 1] : s.ui[R > 1 ? R - 2 : 0]); \
-                const double2 hl = make_double2(__shfl_sync(full_mask, xlr, left),      \
-                                                __shfl_sync(full_mask, xli, left));     \
-                const double2 hr = make_double2(__shfl_sync(full_mask, xfr, right),     \
-                                                __shfl_sync(full_mask, xfi, right));    \
+                double2 hl = make_double2(__shfl_sync(full_mask, xlr, left),            \
+                                          __shfl_sync(full_mask, xli, left));           \
+                double2 hr = make_double2(__shfl_sync(full_mask, xfr, right),           \
+                                          __shfl_sync(full_mask, xfi, right));          \
+                if (MIRROR) {                 /* reflecting ends of the half ring: selects only */ \
+                    /* left of w: slot 1 (lane 0 holds >= 2 real sites).  Right of the      */ \
+                    /* antipode: odd n the last real site itself, even n the site before it */ \
+                    /* (a short lane of R = 2 holds one site: then the left neighbour's)    */ \
+                    constexpr int A = R - 1, B = R > 1 ? R - 2 : 0, C = R > 2 ? R - 3 : 0;  \
+                    const double f1r = (K == 0) ? s.yr[1] : s.ur[1], f1i = (K == 0) ? s.yi[1] : s.ui[1]; \
+                    const double ar = (K == 0) ? s.yr[A] : s.ur[A], ai = (K == 0) ? s.yi[A] : s.ui[A]; \
+                    const double br = (K == 0) ? s.yr[B] : s.ur[B], bi = (K == 0) ? s.yi[B] : s.ui[B]; \
+                    const double cr = (R > 2) ? ((K == 0) ? s.yr[C] : s.ur[C]) : hl.x;      \
+                    const double ci = (R > 2) ? ((K == 0) ? s.yi[C] : s.ui[C]) : hl.y;      \
+                    const double er = even ? (full ? br : cr) : (full ? ar : br);           \
+                    const double ei = even ? (full ? bi : ci) : (full ? ai : bi);           \
+                    hr = make_double2(m_last ? er : hr.x, m_last ? ei : hr.y);              \
+                    hl = make_double2(m_first ? f1r : hl.x, m_first ? f1i : hl.y);          \
+                }                                                                       \
                 if (!full) {                  /* ghost := the right neighbour's value */ \
                     if (K == 0) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }             \
                     else { s.ur[R - 1] = hr.x; s.ui[R - 1] = hr.y; }                    \
@@ -289,6 +361,15 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
 #pragma unroll
     for (int r = 0; r < R - 1; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
     if (full) nrm = fma(s.yr[R - 1], s.yr[R - 1], fma(s.yi[R - 1], s.yi[R - 1], nrm));
+    if (MIRROR) {          // every site of the half ring counts twice, except w and (even n) the antipode
+        nrm *= 2.0;
+        if (m_first) nrm -= fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]);
+        if (m_last && even) {
+            const double ar = full ? s.yr[R - 1] : s.yr[R > 1 ? R - 2 : 0];
+            const double ai = full ? s.yi[R - 1] : s.yi[R > 1 ? R - 2 : 0];
+            nrm -= fma(ar, ar, ai * ai);
+        }
+    }
     double tot = nrm;
     const int gbase = lane - li;
     for (int k = 1; k < L; ++k) {
@@ -309,8 +390,29 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
             int64_t j = off + r + prm.target;
             if (j >= prm.n) j -= prm.n;
             out[j] = make_double2(s.yr[r], s.yi[r]);
+            if (MIRROR) {                                         // the mirror image w - l
+                int64_t jm = prm.target - (off + r);
+                if (jm < 0) jm += prm.n;
+                out[jm] = make_double2(s.yr[r], s.yi[r]);
+            }
         }
     }
+}
+
+template <int R, int MINB, bool MIRROR = false>
+__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams prm, const int L,
+                                                                 const int nfull)
+{
+    packed_any_body<R, MIRROR>(prm, blockIdx.x, L, nfull);
+}
+
+template <int R, int MINB, bool MIRROR>
+__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any_multi(const PackedJob *jobs,
+                                                                       const int n_jobs)
+{
+    __shared__ PackedJob job;
+    const int64_t w = packed_job_fetch(jobs, n_jobs, &job);
+    packed_any_body<R, MIRROR>(job.prm, w, job.a, job.b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -450,20 +552,29 @@ cudaError_t launch_packed_complete(const QwParams &prm, cudaStream_t st, qw_plan
     return cudaGetLastError();
 }
 
-template <int R, int MINB>
+// sites of a point that the any-dimension kernel integrates: the ring, or the half ring
+// w .. w + n/2 under QW_FLAG_MIRROR
+static int64_t packed_any_sites(const QwParams &prm, bool mirror)
+{
+    return mirror ? prm.n / 2 + 1 : prm.n;
+}
+
+template <int R, int MINB, bool MIRROR>
 cudaError_t launch_packed_any(const QwParams &prm, cudaStream_t st, qw_plan *plan)
 {
-    const int L = (int)((prm.n + R - 1) / R);
-    const int nfull = (int)(prm.n - (int64_t)L * (R - 1));
+    const int64_t m = packed_any_sites(prm, MIRROR);
+    const int L = (int)((m + R - 1) / R);
+    const int nfull = (int)(m - (int64_t)L * (R - 1));
     const int groups = 32 / L;
     if (plan) {
         cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_packed_any<R, MINB>);
+        cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_packed_any<R, MINB, MIRROR>);
         if (e != cudaSuccess) return e;
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk4_cycle_packed_any<R, MINB>, 32, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk4_cycle_packed_any<R, MINB, MIRROR>,
+                                                          32, 0);
         if (e != cudaSuccess) return e;
-        plan->path = 8;
+        plan->path = MIRROR ? 13 : 8;
         plan->sites_per_thread = R;
         plan->threads_per_block = 32;
         plan->blocks_per_sm = nb;
@@ -473,7 +584,7 @@ cudaError_t launch_packed_any(const QwParams &prm, cudaStream_t st, qw_plan *pla
         return cudaSuccess;
     }
     const int64_t blocks = packed_warps(prm, groups);
-    rk4_cycle_packed_any<R, MINB><<<(unsigned)blocks, 32, 0, st>>>(prm, L, nfull);
+    rk4_cycle_packed_any<R, MINB, MIRROR><<<(unsigned)blocks, 32, 0, st>>>(prm, L, nfull);
     return cudaGetLastError();
 }
 
@@ -969,28 +1080,99 @@ static bool packed_horner(const QwParams &prm, int *tpp_log2)
     return (prm.n_points + per_warp - 1) / per_warp >= 2 * (int64_t)sms;
 }
 
-cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan)
+// half ring under QW_FLAG_MIRROR in the packed layout: rings of 6 .. 159 sites (from 160 on the
+// one-warp-per-point kernel rk4_cycle_mirror applies and is selected before this path)
+static bool packed_mirror(const QwParams &prm)
 {
+    return (prm.flags & QW_FLAG_MIRROR) && prm.topology == QW_TOPO_CYCLE && prm.n >= 6 &&
+           prm.n < 160 && packed_any_r(prm.n / 2 + 1) > 0;
+}
+
+// Which packed kernel a problem runs, as a small descriptor: also the key by which
+// qw_launch_packed_multi groups problems into one grid.
+struct PackedClass {
+    int kind;        // 0 none, 1 R 2^k ring, 2 any ring, 3 any ring / half ring (mirror),
+                     // 4 small complete graph, 5 nested form
+    int R;
+    int a, b;        // kind 1, 5: log2(lanes per point), - ; kind 2, 3, 4: lanes per point, lanes with R sites
+    int groups;      // points per warp
+    bool column;     // fixed step size on a heatmap (a warp takes rows of one T column)
+};
+
+static PackedClass packed_class(const QwParams &prm)
+{
+    PackedClass c = {0, 0, 0, 0, 0, prm.step_size > 0.0};
     int l = 0;
     if (prm.topology == QW_TOPO_COMPLETE) {
-        switch (packed_any_r(prm.n)) {
+        c.R = packed_any_r(prm.n);
+        if (c.R == 0) return c;
+        c.kind = 4;
+        c.a = (int)((prm.n + c.R - 1) / c.R);
+        c.b = (int)(prm.n - (int64_t)c.a * (c.R - 1));
+        c.groups = 32 / c.a;
+        return c;
+    }
+    if (packed_mirror(prm)) {
+        const int64_t m = prm.n / 2 + 1;
+        // (8 sites per lane wherever the deal works out, e.g. 36 sites on five lanes, was tried:
+        // more points per warp, but 423 instead of 299 ns per step and the sweep of
+        // BCB_latest.py:309-320 ends with its longest columns: 44.2 ms instead of 40.6)
+        c.kind = 3;
+        c.R = packed_any_r(m);
+        c.a = (int)((m + c.R - 1) / c.R);
+        c.b = (int)(m - (int64_t)c.a * (c.R - 1));
+        c.groups = 32 / c.a;
+        return c;
+    }
+    if (packed_horner(prm, &l)) {
+        c.kind = 5; c.R = 16; c.a = l; c.groups = 32 >> l;
+        return c;
+    }
+    const int R = qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l);
+    if (R > 0) {
+        c.kind = 1; c.R = R; c.a = l; c.groups = 32 >> l;
+        return c;
+    }
+    c.R = packed_any_r(prm.n);
+    if (c.R == 0) return c;
+    c.kind = 2;
+    c.a = (int)((prm.n + c.R - 1) / c.R);
+    c.b = (int)(prm.n - (int64_t)c.a * (c.R - 1));
+    c.groups = 32 / c.a;
+    return c;
+}
+
+cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan)
+{
+    const PackedClass c = packed_class(prm);
+    const int l = c.a;
+    switch (c.kind) {
+    case 4:
+        switch (c.R) {
         case 8: return launch_packed_complete<8, 12>(prm, st, plan);
         case 4: return launch_packed_complete<4, 16>(prm, st, plan);
         case 2: return launch_packed_complete<2, 16>(prm, st, plan);
         default: return cudaErrorInvalidConfiguration;
         }
-    }
-    if (packed_horner(prm, &l)) return launch_packed_horner(prm, l, st, plan);
-    const int R = qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l);
-    if (R == 0) {                    // not R * 2^k: R or R-1 sites per lane
-        switch (packed_any_r(prm.n)) {
-        case 8: return launch_packed_any<8, 12>(prm, st, plan);
-        case 4: return launch_packed_any<4, 16>(prm, st, plan);
-        case 2: return launch_packed_any<2, 16>(prm, st, plan);
+    case 3:
+        switch (c.R) {
+        case 8: return launch_packed_any<8, 12, true>(prm, st, plan);
+        case 4: return launch_packed_any<4, 16, true>(prm, st, plan);
+        case 2: return launch_packed_any<2, 16, true>(prm, st, plan);
         default: return cudaErrorInvalidConfiguration;
         }
+    case 5: return launch_packed_horner(prm, l, st, plan);
+    case 2:                          // not R * 2^k: R or R-1 sites per lane
+        switch (c.R) {
+        case 8: return launch_packed_any<8, 12, false>(prm, st, plan);
+        case 4: return launch_packed_any<4, 16, false>(prm, st, plan);
+        case 2: return launch_packed_any<2, 16, false>(prm, st, plan);
+        default: return cudaErrorInvalidConfiguration;
+        }
+    case 1: break;
+    default: return cudaErrorInvalidConfiguration;
     }
-    switch (R) {
+    switch (c.R) {
     case 16: return launch_packed<16, 8>(prm, l, st, plan);
     case 8:
         if (prm.flags & QW_FLAG_OCC4) return launch_packed<8, 16>(prm, l, st, plan);   // A/B
@@ -1004,4 +1186,105 @@ cudaError_t qw_launch_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan
     case 1: return launch_packed<1, 16>(prm, l, st, plan);
     default: return cudaErrorInvalidConfiguration;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Many problems, one grid.  Problems whose packed kernel coincides (same kind, sites per lane
+// and step rule) share a launch: their warps are laid end to end, longest problems first, and
+// every warp finds its problem in a job table (PackedJob).  Each problem keeps the geometry its
+// own launch would use, so the results are bitwise those of separate launches.  Returns, per
+// problem, whether it was taken (false: the caller launches it on its own).
+// Multi-capable: kind 1 with 8 sites per lane, kinds 2 and 3 (the classes of BASELINE config 2
+// and of the reference's production sweep, BCB_latest.py:309-320).
+static bool packed_multi_capable(const PackedClass &c)
+{
+    return c.kind == 1 || c.kind == 2 || c.kind == 3;
+}
+
+static long long packed_multi_key(const PackedClass &c)
+{
+    return (long long)c.kind * 1000 + c.R * 10 + (c.column ? 1 : 0);
+}
+
+cudaError_t qw_launch_packed_multi(const QwParams *prms, int n, unsigned char *taken,
+                                   cudaStream_t st, int64_t *launches)
+{
+    struct Item { int idx; PackedClass c; long long key; double work; };
+    std::vector<Item> items;
+    for (int i = 0; i < n; ++i) {
+        taken[i] = 0;
+        if (prms[i].n_points <= 0 || !qw_packed_supported(prms[i])) continue;
+        if (prms[i].flags & QW_FLAG_OCC4) continue;
+        const PackedClass c = packed_class(prms[i]);
+        if (!packed_multi_capable(c)) continue;
+        // a warp's work ~ sites per lane x its step count; a rough figure for the ordering only
+        double steps = (double)prms[i].n_steps_uniform;
+        if (c.column) steps = 1.0;            // refined per job below is not worth a device read
+        items.push_back({i, c, packed_multi_key(c), (double)prms[i].n * steps});
+    }
+    std::stable_sort(items.begin(), items.end(),
+                     [](const Item &x, const Item &y) { return x.key < y.key; });
+    cudaError_t err = cudaSuccess;
+    for (size_t b = 0; b < items.size() && err == cudaSuccess;) {
+        size_t e = b;
+        while (e < items.size() && items[e].key == items[b].key) ++e;
+        if (e - b >= 2) {
+            std::vector<Item> grp(items.begin() + b, items.begin() + e);
+            std::stable_sort(grp.begin(), grp.end(),
+                             [](const Item &x, const Item &y) { return x.work > y.work; });
+            std::vector<PackedJob> jobs(grp.size());
+            int64_t w = 0;
+            for (size_t k = 0; k < grp.size(); ++k) {
+                PackedJob &j = jobs[k];
+                memset(&j, 0, sizeof(j));
+                j.prm = prms[grp[k].idx];
+                j.a = grp[k].c.a;
+                j.b = grp[k].c.b;
+                j.warp_begin = w;
+                w += packed_warps(j.prm, grp[k].c.groups);
+                j.warp_end = w;
+            }
+            if (w > 0x7fffffffLL) { b = e; continue; }        // leave them to single launches
+            PackedJob *dj = nullptr;
+            err = cudaMallocAsync((void **)&dj, jobs.size() * sizeof(PackedJob), st);
+            if (err != cudaSuccess) break;
+            err = cudaMemcpyAsync(dj, jobs.data(), jobs.size() * sizeof(PackedJob),
+                                  cudaMemcpyHostToDevice, st);
+            const PackedClass &c = grp[0].c;
+            const int nj = (int)jobs.size();
+            const unsigned grid = (unsigned)w;
+            if (err == cudaSuccess) {
+#define QW_PM(KERNEL) KERNEL<<<grid, 32, 0, st>>>(dj, nj)
+                if (c.kind == 1) {
+#define QW_PM1(RR, MB)                                                                      \
+                    case RR:                                                                \
+                        if (c.column) QW_PM((rk4_cycle_packed_multi<RR, MB, true>));        \
+                        else QW_PM((rk4_cycle_packed_multi<RR, MB, false>));                \
+                        break;
+                    switch (c.R) {
+                        QW_PM1(16, 8) QW_PM1(8, 12) QW_PM1(7, 12) QW_PM1(6, 12) QW_PM1(5, 16)
+                        QW_PM1(4, 16) QW_PM1(3, 16) QW_PM1(2, 16) QW_PM1(1, 16)
+                    default: break;
+                    }
+#undef QW_PM1
+                } else if (c.kind == 2) {
+                    if (c.R == 8) QW_PM((rk4_cycle_packed_any_multi<8, 12, false>));
+                    else if (c.R == 4) QW_PM((rk4_cycle_packed_any_multi<4, 16, false>));
+                    else QW_PM((rk4_cycle_packed_any_multi<2, 16, false>));
+                } else {
+                    if (c.R == 8) QW_PM((rk4_cycle_packed_any_multi<8, 12, true>));
+                    else if (c.R == 4) QW_PM((rk4_cycle_packed_any_multi<4, 16, true>));
+                    else QW_PM((rk4_cycle_packed_any_multi<2, 16, true>));
+                }
+#undef QW_PM
+                err = cudaGetLastError();
+                ++*launches;
+            }
+            cudaFreeAsync(dj, st);
+            if (err == cudaSuccess)
+                for (size_t k = 0; k < grp.size(); ++k) taken[grp[k].idx] = 1;
+        }
+        b = e;
+    }
+    return err;
 }

@@ -160,6 +160,42 @@ def rk4_heatmap(problem, time_array, beta_array, rows=None, device=None):
         return p, norm
 
 
+def rk4_heatmaps(problems, time_arrays, beta_arrays, device=None):
+    """Several heatmaps in as few launches as possible (``qw_rk4_multi_grid_dev``): problems
+    whose warp-packed kernel coincides share ONE grid, the rest are launched one by one on the
+    same stream.  The reference's production sweep (BCB_latest.py:309-320) and the three
+    schedules of BASELINE config 2 are such collections of small problems.  Returns a list of
+    (p, norm) pairs, bitwise those of separate ``rk4_heatmap`` calls; host arrays in -> numpy
+    out (one synchronisation for all of them), CUDA tensors in -> CUDA tensors out."""
+    dev = _device(device)
+    lib = _lib.load()
+    n = len(problems)
+    if not (len(time_arrays) == n and len(beta_arrays) == n):
+        raise ValueError("one time axis and one beta axis per problem")
+    with torch.cuda.device(dev):
+        jobs = (_lib.QwGridJob * n)()
+        keep, outs, host = [], [], False
+        for k in range(n):
+            dT, h1 = _as_dev(time_arrays[k], dev)
+            dB, _ = _as_dev(beta_arrays[k], dev)
+            host = host or h1
+            nT, nB = dT.numel(), dB.numel()
+            p = torch.empty((nB, nT), dtype=torch.float64, device=dev)
+            norm = torch.empty((nB, nT), dtype=torch.float64, device=dev)
+            keep += [dT, dB]
+            outs.append((p, norm))
+            j = jobs[k]
+            j.prob = problems[k].c_struct()
+            j.time_array, j.n_time = dT.data_ptr(), nT
+            j.beta_array, j.n_beta, j.beta_begin, j.beta_end = dB.data_ptr(), nB, 0, nB
+            j.p, j.norm = p.data_ptr(), norm.data_ptr()
+        _lib.check(lib.qw_rk4_multi_grid_dev(jobs, n, _stream()))
+        if host:
+            torch.cuda.current_stream().synchronize()
+            return [(p.cpu().numpy(), nrm.cpu().numpy()) for p, nrm in outs]
+        return outs
+
+
 def rk4_heatmap_host(problem, time_array, beta_array, rows=None, device=0):
     """Same through the host-pointer C entry point (copies inside the library)."""
     lib = _lib.load()

@@ -263,23 +263,28 @@ def test_runge_kutta_error_main_block():
 
 
 def test_production_sweep_on_streams_writes_the_same_files(tmp_path, monkeypatch):
-    """BCB_latest.production_sweep: the multi-stream issue order must give the files of the
-    reference's sequential loop (names of BCB_latest.py:287-293), bit for bit."""
+    """BCB_latest.production_sweep: the fused multi-problem launch and the multi-stream issue
+    order must give the files of the reference's sequential loop (names of
+    BCB_latest.py:287-293), bit for bit -- with the half-ring reduction (default) and without."""
     bl = _mod("BCB_latest")
-    out = {}
-    for streams in (1, 8):
-        d = tmp_path / ("s%d" % streams)
-        d.mkdir()
-        monkeypatch.chdir(d)
-        bl.integrator, bl.n_steps, bl.step_size, bl.type_of_qw = "rk4", None, 1e-2, "dependent"
-        bl.topology = "circular"
-        bl.production_sweep(step_functions=("lin", "cerf_3"), dims=(5, 21, 51, 64), streams=streams)
-        out[streams] = {f.name: np.load(f) for f in sorted(d.glob("*.npy"))}
-    bl.step_size = 1e-3
-    assert sorted(out[1]) == sorted(out[8]) and len(out[1]) == 2 * 4 + 2 * 4
-    for name in out[1]:
-        assert np.array_equal(out[1][name], out[8][name]), name
-    assert out[8]["51_probability_lin.npy"].shape == (75, 4)
+    for mirror in (True, False):
+        out = {}
+        for mode, kw in (("seq", dict(streams=1, fused=False)), ("streams", dict(streams=8, fused=False)),
+                         ("fused", dict())):
+            d = tmp_path / ("%s_%d" % (mode, mirror))
+            d.mkdir()
+            monkeypatch.chdir(d)
+            bl.integrator, bl.n_steps, bl.step_size, bl.type_of_qw = "rk4", None, 1e-2, "dependent"
+            bl.topology, bl.mirror = "circular", mirror
+            bl.production_sweep(step_functions=("lin", "cerf_3"), dims=(5, 21, 23, 51, 64), **kw)
+            out[mode] = {f.name: np.load(f) for f in sorted(d.glob("*.npy"))}
+        assert sorted(out["seq"]) == sorted(out["fused"]) == sorted(out["streams"])
+        assert len(out["seq"]) == 2 * 5 + 2 * 5
+        for name in out["seq"]:
+            assert np.array_equal(out["seq"][name], out["fused"][name]), (mirror, name)
+            assert np.array_equal(out["seq"][name], out["streams"][name]), (mirror, name)
+        assert out["fused"]["51_probability_lin.npy"].shape == (75, 4)
+    bl.step_size, bl.mirror = 1e-3, True
 
 
 def test_mirror_knob_of_the_drop_in_modules():
@@ -300,6 +305,6 @@ def test_mirror_knob_of_the_drop_in_modules():
     full = bcb.grid_eval(t, b)
     bcb.mirror = True
     pair = bcb.grid_eval(t, b)
-    bcb.mirror, bcb.n_steps, bcb.step_size, bcb.topology = False, None, 1e-3, "circular"
+    bcb.mirror, bcb.n_steps, bcb.step_size, bcb.topology = True, None, 1e-3, "circular"
     assert np.isfinite(full).all() and full.max() > 0.1
     assert np.abs(full - pair).max() <= 1e-12 and np.argmax(full) == np.argmax(pair)

@@ -40,7 +40,30 @@ def sweep(streams):
     return t1 - t0, time.perf_counter() - t0
 
 
-for streams in (1, 8, 16, 35):
+def fused():
+    probs, ts = [], []
+    for step in ("lin", "sqrt", "cbrt", "cerf_3"):
+        for n in range(3, 72, 2):
+            probs.append(qw.Problem(n=n, topology="circular", schedule=step, step_size=1e-3,
+                                    flags=flags))
+            ts.append(tarr(n))
+    torch.cuda.synchronize()
+    l0 = qw.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    qw.rk4_heatmaps(probs, ts, [beta] * len(probs))
+    e1.record()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    return t1 - t0, time.perf_counter() - t0, e0.elapsed_time(e1), qw.launch_count() - l0
+
+
+fused()
+issue, total, gpu_ms, launches = fused()
+print("fused (qw_rk4_multi_grid_dev): issue %.1f ms  total %.1f ms  GPU %.1f ms  %d launches for 140 "
+      "heatmaps" % (issue * 1e3, total * 1e3, gpu_ms, launches))
+for streams in (1, 16):
     sweep(streams)
     issue, total = sweep(streams)
     print("streams=%2d  issue %.1f ms  total %.1f ms" % (streams, issue * 1e3, total * 1e3))
