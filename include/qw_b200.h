@@ -168,7 +168,11 @@ typedef struct qw_grid_job {
 
 int qw_rk4_multi_grid_dev(const qw_grid_job *jobs, int64_t n_jobs, void *stream);
 
-/* Host-buffer forms of the two calls above (copies inside; device = CUDA ordinal). */
+/* Host-buffer forms of the two calls above (copies inside; device = CUDA ordinal).  Staging
+ * (one pinned host buffer, one device buffer, one stream) is kept per host thread and reused, so
+ * a call allocates nothing; small calls are zero-copy (the kernels read and write the pinned
+ * buffer).  Up to 16 points on a graph of at most 32 vertices take the parallel-in-time kernels
+ * (qw_pit.cu): the single-point calls of the reference are latency bound. */
 int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gamma,
                       const int64_t *n_steps, int64_t n_points, double *p, double *norm,
                       void *psi, int device);
@@ -274,7 +278,8 @@ typedef struct qw_plan {
                                 complete graph (both QW_FLAG_MIRROR), 11 warp-packed complete
                                 graph of any small dimension, 12 cycle graph resident across a
                                 thread-block cluster (4097 .. 32768 sites), 13 warp-packed half
-                                ring of a small cycle graph (QW_FLAG_MIRROR, 6 .. 159 sites) */
+                                ring of a small cycle graph (QW_FLAG_MIRROR, 6 .. 159 sites),
+                                14 parallel-in-time (a handful of points, at most 32 vertices) */
     int32_t sites_per_thread;
     int32_t threads_per_block;
     int32_t blocks_per_sm;   /* occupancy from cudaOccupancyMaxActiveBlocksPerMultiprocessor */

@@ -19,7 +19,7 @@ PATH_NAMES = {0: "resident-cycle", 1: "resident-complete", 2: "generic", 3: "str
               4: "packed-cycle", 5: "horner-cycle", 6: "horner-complete",
               7: "packed-horner-cycle", 8: "packed-any-cycle", 9: "mirror-cycle",
               10: "symmetric-complete", 11: "packed-complete", 12: "cluster-cycle",
-              13: "packed-mirror-cycle"}
+              13: "packed-mirror-cycle", 14: "parallel-in-time"}
 
 
 class QwProblem(ctypes.Structure):

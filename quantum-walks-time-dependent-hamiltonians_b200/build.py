@@ -9,7 +9,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["qw_api.cu", "qw_resident.cu", "qw_generic.cu", "qw_stream.cu", "qw_packed.cu",
            "qw_cheb.cu", "qw_rk45.cu", "qw_aux.cu", "qw_horner.cu", "qw_adiabatic.cu",
-           "qw_symmetric.cu"]
+           "qw_symmetric.cu", "qw_pit.cu"]
 OUT = os.path.join(_HERE, "libqw_b200.so")
 OBJ_DIR = os.path.join(_HERE, "build")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

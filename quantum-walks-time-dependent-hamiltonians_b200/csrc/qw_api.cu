@@ -1,5 +1,6 @@
 // C ABI of the library (include/qw_b200.h): validation, kernel selection, host-buffer
 // forms.  No torch types; the Python shim passes raw device pointers and a stream handle.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -46,6 +47,10 @@ int qw_mirror_sites_per_lane(const QwParams &prm);
 cudaError_t qw_launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan);
 bool qw_symmetric_supported(const QwParams &prm);
 cudaError_t qw_launch_symmetric(const QwParams &prm, cudaStream_t st, qw_plan *plan);
+bool qw_pit_supported(const QwParams &prm, int64_t steps_bound);
+size_t qw_pit_scratch_bytes(const QwParams &prm, int64_t steps_bound);
+cudaError_t qw_launch_pit(const QwParams &prm, int64_t steps_bound, double2 *scratch,
+                          cudaStream_t st);
 bool qw_cheb_supported(const QwParams &prm);
 cudaError_t qw_launch_cheb(QwParams prm, cudaStream_t st);
 
@@ -99,12 +104,14 @@ int validate(const qw_problem *prob, QwParams *prm)
 }
 
 enum { PATH_RESIDENT = 0, PATH_GENERIC = 2, PATH_STREAM = 3, PATH_PACKED = 4, PATH_HORNER = 5,
-       PATH_MIRROR = 9, PATH_SYMMETRIC = 10, PATH_CLUSTER = 12 };
+       PATH_MIRROR = 9, PATH_SYMMETRIC = 10, PATH_CLUSTER = 12, PATH_PIT = 14 };
 
 int choose_path(const QwParams &prm)
 {
     if (prm.flags & QW_FLAG_FORCE_GENERIC) return PATH_GENERIC;
     if ((prm.flags & QW_FLAG_FORCE_STREAM) && qw_stream_supported(prm)) return PATH_STREAM;
+    // a handful of points on a tiny graph: cut the time axis (latency regime)
+    if (qw_pit_supported(prm, prm.steps_bound)) return PATH_PIT;
     if (qw_mirror_sites_per_lane(prm) > 0) return PATH_MIRROR;
     if (qw_symmetric_supported(prm)) return PATH_SYMMETRIC;
     const bool horner = !(prm.flags & (QW_FLAG_CYCLE_LEGACY | QW_FLAG_CYCLE_SPLIT |
@@ -180,6 +187,17 @@ int run(QwParams &prm, cudaStream_t st)
         g_launches += 1;
         return 0;
     }
+    case PATH_PIT: {
+        const int64_t bound = prm.steps_bound > 0 ? prm.steps_bound : prm.n_steps_uniform;
+        void *scratch = nullptr;
+        e = cudaMallocAsync(&scratch, qw_pit_scratch_bytes(prm, bound), st);
+        if (e != cudaSuccess) return cuda_fail(e, "scratch allocation");
+        e = qw_launch_pit(prm, bound, (double2 *)scratch, st);
+        cudaFreeAsync(scratch, st);
+        if (e != cudaSuccess) return cuda_fail(e, "parallel-in-time kernel launch");
+        g_launches += 2;
+        return 0;
+    }
     case PATH_CLUSTER:
         e = qw_launch_cluster(prm, st, nullptr);
         if (e != cudaSuccess) return cuda_fail(e, "cluster kernel launch");
@@ -226,9 +244,9 @@ struct DevBuf {
 
 extern "C" {
 
-int qw_rk4_batch_dev(const qw_problem *prob, const double *T, const double *gamma,
-                     const int64_t *n_steps, const int64_t *order, int64_t n_points,
-                     double *p, double *norm, void *psi, void *stream)
+static int batch_dev_impl(const qw_problem *prob, const double *T, const double *gamma,
+                          const int64_t *n_steps, const int64_t *order, int64_t n_points,
+                          double *p, double *norm, void *psi, void *stream, int64_t steps_bound)
 {
     QwParams prm;
     int rc = validate(prob, &prm);
@@ -238,7 +256,15 @@ int qw_rk4_batch_dev(const qw_problem *prob, const double *T, const double *gamm
     prm.T = T; prm.gamma = gamma; prm.n_steps = n_steps; prm.order = order;
     prm.n_points = n_points;
     prm.p = p; prm.norm = norm; prm.psi = (double2 *)psi;
+    prm.steps_bound = steps_bound;
     return run(prm, (cudaStream_t)stream);
+}
+
+int qw_rk4_batch_dev(const qw_problem *prob, const double *T, const double *gamma,
+                     const int64_t *n_steps, const int64_t *order, int64_t n_points,
+                     double *p, double *norm, void *psi, void *stream)
+{
+    return batch_dev_impl(prob, T, gamma, n_steps, order, n_points, p, norm, psi, stream, 0);
 }
 
 int qw_rk4_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_time,
@@ -417,6 +443,57 @@ int qw_rk45_grid_dev(const qw_problem *prob, const double *time_array, int64_t n
     return run_rk45(prm, rtol, atol, nullptr, (cudaStream_t)stream);
 }
 
+// Staging of the host-buffer entry points, kept per host thread: one pinned host buffer, one
+// device buffer and one stream, grown on demand and reused -- a call makes no allocation
+// (cudaMalloc + cudaFree cost more than a small kernel: the round-1 path spent 224 of its 432 us
+// on them and on the framework's tensors for BASELINE config 1).
+namespace {
+struct HostStage {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    void *pinned = nullptr, *dev = nullptr;
+    size_t pinned_bytes = 0, dev_bytes = 0;
+    cudaError_t prepare(int d, size_t host_need, size_t dev_need)
+    {
+        cudaError_t e = cudaSetDevice(d);
+        if (e != cudaSuccess) return e;
+        if (d != device) {
+            release();
+            device = d;
+            if ((e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return e;
+        }
+        if (host_need > pinned_bytes) {
+            if (pinned) cudaFreeHost(pinned);
+            pinned = nullptr; pinned_bytes = 0;
+            const size_t want = host_need < 65536 ? 65536 : host_need;
+            if ((e = cudaHostAlloc(&pinned, want, cudaHostAllocDefault))) return e;
+            pinned_bytes = want;
+        }
+        if (dev_need > dev_bytes) {
+            if (dev) cudaFree(dev);
+            dev = nullptr; dev_bytes = 0;
+            if ((e = cudaMalloc(&dev, dev_need))) return e;
+            dev_bytes = dev_need;
+        }
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (device >= 0 && cudaSetDevice(device) == cudaSuccess) {
+            if (stream) cudaStreamDestroy(stream);
+            if (pinned) cudaFreeHost(pinned);
+            if (dev) cudaFree(dev);
+        }
+        stream = nullptr; pinned = nullptr; dev = nullptr;
+        pinned_bytes = dev_bytes = 0; device = -1;
+    }
+    // no destructor work: at thread exit the CUDA context may already be gone
+};
+thread_local HostStage g_stage;
+
+int64_t steps_of(double T, double h) { const double r = T / h; return r > 0.0 ? (int64_t)r : 0; }
+}  // namespace
+
 int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gamma,
                       const int64_t *n_steps, int64_t n_points, double *p, double *norm,
                       void *psi, int device)
@@ -424,31 +501,48 @@ int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gam
     if (n_points < 0) return fail(QW_E_SIZE, "n_points < 0");
     if (n_points > 0 && (!T || !gamma || !p)) return fail(QW_E_NULL, "T, gamma and p are required");
     if (!prob) return fail(QW_E_NULL, "qw_problem is NULL");
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    const size_t nb = (size_t)n_points * sizeof(double);
-    DevBuf dT, dG, dS, dP, dN, dPsi;
-    if ((e = dT.alloc(nb)) || (e = dG.alloc(nb)) || (e = dP.alloc(nb)) || (e = dN.alloc(nb)))
-        return cuda_fail(e, "cudaMalloc");
-    if (n_steps && (e = dS.alloc((size_t)n_points * sizeof(int64_t)))) return cuda_fail(e, "cudaMalloc");
-    const size_t psib = psi ? (size_t)n_points * (size_t)prob->n * sizeof(double2) : 0;
-    if (psi && (e = dPsi.alloc(psib))) return cuda_fail(e, "cudaMalloc");
-    cudaStream_t st = nullptr;
-    if ((e = cudaMemcpyAsync(dT.p, T, nb, cudaMemcpyHostToDevice, st)) ||
-        (e = cudaMemcpyAsync(dG.p, gamma, nb, cudaMemcpyHostToDevice, st)))
+    if (n_points == 0) return 0;
+    // the largest step count of the call (the host has T): lets a handful of points on a tiny
+    // graph take the parallel-in-time path under every step rule
+    int64_t bound = 0;
+    if (prob->step_size > 0.0) {
+        for (int64_t q = 0; q < n_points; ++q) bound = std::max(bound, steps_of(T[q], prob->step_size));
+    } else if (n_steps) {
+        for (int64_t q = 0; q < n_points; ++q) bound = std::max(bound, n_steps[q]);
+    } else {
+        bound = prob->n_steps;
+    }
+    // layout of the staging buffers: T | gamma | n_steps | p | norm | psi
+    const size_t np = (size_t)n_points;
+    const size_t in_bytes = np * 8 * (n_steps ? 3 : 2);
+    const size_t psib = psi ? np * (size_t)prob->n * sizeof(double2) : 0;
+    const size_t out_bytes = np * 16 + psib;
+    // small calls: the kernels read and write the pinned buffer directly (unified addressing) --
+    // no copy commands at all, one launch and one synchronisation
+    const bool zero_copy = in_bytes + out_bytes <= 65536;
+    cudaError_t e = g_stage.prepare(device, in_bytes + out_bytes, zero_copy ? 0 : in_bytes + out_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "staging buffers");
+    char *h = (char *)g_stage.pinned;
+    memcpy(h, T, np * 8);
+    memcpy(h + np * 8, gamma, np * 8);
+    if (n_steps) memcpy(h + np * 16, n_steps, np * 8);
+    cudaStream_t st = g_stage.stream;
+    char *d = zero_copy ? h : (char *)g_stage.dev;
+    if (!zero_copy && (e = cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st)))
         return cuda_fail(e, "H2D copy");
-    if (n_steps && (e = cudaMemcpyAsync(dS.p, n_steps, (size_t)n_points * sizeof(int64_t),
-                                        cudaMemcpyHostToDevice, st)))
-        return cuda_fail(e, "H2D copy");
-    int rc = qw_rk4_batch_dev(prob, (double *)dT.p, (double *)dG.p, (int64_t *)dS.p, nullptr,
-                              n_points, (double *)dP.p, (double *)dN.p, dPsi.p, st);
+    double *dp = (double *)(d + in_bytes), *dn = dp + np;
+    void *dpsi = psi ? (void *)(dn + np) : nullptr;
+    int rc = batch_dev_impl(prob, (double *)d, (double *)(d + np * 8),
+                            n_steps ? (int64_t *)(d + np * 16) : nullptr, nullptr, n_points, dp, dn,
+                            dpsi, st, bound > 0 ? bound : 0);
     if (rc) return rc;
-    if ((e = cudaMemcpyAsync(p, dP.p, nb, cudaMemcpyDeviceToHost, st))) return cuda_fail(e, "D2H copy");
-    if (norm && (e = cudaMemcpyAsync(norm, dN.p, nb, cudaMemcpyDeviceToHost, st)))
-        return cuda_fail(e, "D2H copy");
-    if (psi && (e = cudaMemcpyAsync(psi, dPsi.p, psib, cudaMemcpyDeviceToHost, st)))
+    if (!zero_copy && (e = cudaMemcpyAsync(h + in_bytes, d + in_bytes, out_bytes,
+                                           cudaMemcpyDeviceToHost, st)))
         return cuda_fail(e, "D2H copy");
     if ((e = cudaStreamSynchronize(st))) return cuda_fail(e, "kernel execution");
+    memcpy(p, h + in_bytes, np * 8);
+    if (norm) memcpy(norm, h + in_bytes + np * 8, np * 8);
+    if (psi) memcpy(psi, h + in_bytes + np * 16, psib);
     return 0;
 }
 
@@ -616,6 +710,7 @@ int qw_plan_query(const qw_problem *prob, qw_plan *plan)
     case PATH_MIRROR: e = qw_launch_mirror(prm, nullptr, plan); break;
     case PATH_SYMMETRIC: e = qw_launch_symmetric(prm, nullptr, plan); break;
     case PATH_CLUSTER: e = qw_launch_cluster(prm, nullptr, plan); break;
+    case PATH_PIT: plan->path = 14; plan->sites_per_thread = 1; plan->threads_per_block = 32 * (int)prm.n; break;
     case PATH_STREAM: e = qw_stream_plan(prm, plan); break;
     default: {
         int blocks; size_t bytes;

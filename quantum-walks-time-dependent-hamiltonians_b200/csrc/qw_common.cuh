@@ -75,6 +75,8 @@ struct QwParams {
     // complete graph above 4096 vertices: a point is split over `split` thread blocks that share
     // nothing but the tabulated (y_w, S) subsystem; partial norms meet in split_part, the last
     // block of a point to arrive (split_done) writes p and norm
+    int64_t steps_bound;          // largest step count of the call if the HOST knows it (host-buffer
+                                  // entry points; the uniform n_steps rule needs no bound), else 0
     int32_t split;
     double *split_part;           // [n_points][split][2]
     unsigned int *split_done;     // [n_points], zero before the launch

@@ -111,9 +111,26 @@ def longest_first_order(n_steps):
 
 
 def rk4_batch(problem, T, gamma, n_steps=None, order=None, return_psi=False, device=None):
-    """Integrate independent (T_q, gamma_q) points.  Returns (p, norm[, psi])."""
+    """Integrate independent (T_q, gamma_q) points.  Returns (p, norm[, psi]).
+
+    Host inputs (lists, numpy arrays) go straight to the host-buffer entry point of the library
+    (``qw_rk4_batch_host``: persistent pinned staging, no framework tensors, and for a handful of
+    points on a tiny graph the parallel-in-time kernels): the single-point calls of the reference
+    (evaluate_probability, the SciPy optimisers) are latency bound."""
     dev = _device(device)
     lib = _lib.load()
+    host_in = not any(isinstance(x, torch.Tensor) for x in (T, gamma, n_steps, order))
+    if host_in and order is None:
+        Th = np.ascontiguousarray(np.atleast_1d(np.asarray(T, dtype=np.float64)))
+        gh = np.atleast_1d(np.asarray(gamma, dtype=np.float64))
+        if gh.size == 1 and Th.size > 1:
+            gh = np.full(Th.shape, gh[0])
+        if Th.shape != gh.shape or Th.ndim != 1:
+            raise ValueError("T and gamma must have the same length")
+        if n_steps is not None and np.size(n_steps) != Th.size:
+            raise ValueError("n_steps must have one entry per point")
+        return rk4_batch_host(problem, Th, gh, n_steps=n_steps, return_psi=return_psi,
+                              device=dev.index if dev.index is not None else 0)
     with torch.cuda.device(dev):
         dT, host = _as_dev(T, dev)
         dG, _ = _as_dev(gamma, dev)

@@ -78,3 +78,42 @@ def test_multi_problem_launch_n_steps_rule_and_device_tensors(qw):
         p, norm = qw.rk4_heatmap(prob, t, b)
         assert torch.equal(p, pm) and torch.equal(norm, nm)
     assert qw.rk4_heatmaps([], [], []) == []
+
+
+@pytest.mark.parametrize("topo,n", [("circular", 3), ("circular", 5), ("circular", 16),
+                                    ("circular", 31), ("circular", 32), ("complete", 1),
+                                    ("complete", 2), ("complete", 15), ("complete", 32)])
+def test_parallel_in_time_vs_oracle(qw, topo, n):
+    """A handful of points on a tiny graph: the time axis is cut into chunk propagators
+    (qw_pit.cu).  Every schedule, both step rules, custom target, psi, T = 0."""
+    rng = np.random.default_rng(n)
+    scale = 1.0 if topo == "circular" else 1.0 / max(n, 1)
+    T = np.array([0.0, 3.0, 16.0, 7.7, 0.4]) * scale
+    g = np.array([1.0, 0.3, 1.0, 2.2, 1.7]) * (1.0 if topo == "circular" else n)
+    for sched in ("lin", "sqrt", "cbrt", "cerf_3", "cerf_5", "cerf_7", "static"):
+        for kw in (dict(n_steps=1024), dict(n_steps=130), dict(step_size=2e-3 * scale)):
+            target = None if sched != "cbrt" else min(1, n - 1)
+            prob = qw.Problem(n=n, topology=topo, schedule=sched, target=target, **kw)
+            p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)       # host entry: any rule
+            po, no, psio, _ = c_oracle.rk4_batch(n, topo, sched, T, g, target=target,
+                                                 return_psi=True, **kw)
+            assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL, (sched, kw)
+            assert np.abs(psi - psio).max() <= PSI_TOL, (sched, kw)
+    prob = qw.Problem(n=n, topology=topo, schedule="lin", n_steps=1024)
+    assert qw.plan(prob)["path"] in ("parallel-in-time", "packed-cycle", "packed-any-cycle",
+                                     "packed-complete", "generic", "resident-complete")
+    # the warp-packed / resident kernels on the same points (QW_FLAG_NO_PACK keeps PIT off)
+    pk, nk = qw.rk4_batch(qw.Problem(n=n, topology=topo, schedule="lin", n_steps=1024, flags=512),
+                          T, g)
+    pp, np_ = qw.rk4_batch(prob, T, g)
+    assert np.abs(pk - pp).max() <= 1e-12 and np.abs(nk - np_).max() <= 1e-12
+
+
+def test_config1_value_and_host_entry(qw):
+    prob = qw.Problem(n=16, topology="circular", schedule="lin", n_steps=1024)
+    p, norm = qw.rk4_batch(prob, [16.0], [1.0])
+    assert abs(p[0] - 0.42038739054526) < 1e-10          # SURVEY.md Appendix A, row 0
+    big_T = np.linspace(0.1, 16, 5000)
+    pb, nb = qw.rk4_batch(prob, big_T, np.full(5000, 1.0))   # staged copies, throughput kernel
+    po, no, _ = c_oracle.rk4_batch(16, "circular", "lin", big_T, np.full(5000, 1.0), n_steps=1024)
+    assert np.abs(pb - po).max() <= P_TOL and np.abs(nb - no).max() <= P_TOL
