@@ -115,9 +115,15 @@ enum {
                                     amplitude, one thread integrates the pair (psi_w, psi_other)
                                     of a point, any n, O(n_steps) work.
                                     Opt-in; ignored where it does not apply. */
-    QW_FLAG_FORCE_CLUSTER = 16384 /* cycle graph, 4097 .. 32768 sites: the thread-block-cluster
+    QW_FLAG_FORCE_CLUSTER = 16384, /* cycle graph, 4097 .. 32768 sites: the thread-block-cluster
                                     kernel also where the bulk-copy streaming kernel is preferred
                                     (above 8192 sites when n is a multiple of 128); tests, A/B */
+    QW_FLAG_FIXED_GEOMETRY = 32768 /* kernel and lane geometry as for a call that fills the
+                                    machine, whatever its size (no latency geometries, no
+                                    parallel-in-time path): a point's result then depends on the
+                                    problem only, not on how a sweep is cut into calls -- the
+                                    shards of a multi-GPU heatmap are bitwise the rows of the
+                                    one-GPU heatmap (parallel_routine sets it) */
 };
 
 /* ---- the hot path -------------------------------------------------------------------- */
@@ -300,6 +306,11 @@ int qw_plan_query(const qw_problem *prob, qw_plan *plan);
  * with a dependent-free register-only kernel running for about `millis` ms: the FP64
  * roofline denominator (MEASURED_PEAKS.json carries no FP64 figure). */
 int qw_fp64_peak_probe(double millis, double *tflops, void *stream);
+
+/* Scratch of the large-N paths (streaming, catch-all, split, parallel-in-time, job tables) comes
+ * from a memory pool owned by the library (one per device; up to 1 GiB stays cached between
+ * calls).  This synchronises the current device and returns the pool's memory to the driver. */
+int qw_scratch_trim(void);
 
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 int64_t qw_launch_count(void);

@@ -71,7 +71,8 @@ def production_sweep(step_functions=("lin", "sqrt", "cbrt", "cerf_3"),
                           2 * np.sqrt(n)]
             prob = engine.Problem(n=n, topology=topology, schedule=step, gamma_on=gamma_on,
                                   n_steps=n_steps, step_size=None if n_steps else step_size,
-                                  flags=8192 if mirror else 0)
+                                  flags=(8192 if mirror else 0) | _dropin.FIXED_GEOMETRY)
+            # (fixed geometry, as parallel_routine: the files do not depend on how the sweep is issued)
             work.append((n, step, time_array, prob,
                          torch.tensor(time_array, dtype=torch.float64, device=dev)))
     if fused:

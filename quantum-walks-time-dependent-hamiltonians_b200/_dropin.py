@@ -39,7 +39,10 @@ def _topology(g, flavor):
     return "circular" if flavor in ("SS", "RKE") else g.get("topology", "circular")
 
 
-def _problem(g, flavor, schedule=None, topology=None, dimension=None):
+FIXED_GEOMETRY = 32768        # QW_FLAG_FIXED_GEOMETRY
+
+
+def _problem(g, flavor, schedule=None, topology=None, dimension=None, extra_flags=0):
     n_steps, step_size = g.get("n_steps"), g.get("step_size")
     if n_steps is not None:
         step_size = None
@@ -50,8 +53,8 @@ def _problem(g, flavor, schedule=None, topology=None, dimension=None):
         n=int(dim), topology=_topology(g, flavor) if topology is None else topology,
         schedule=_schedule_name(g, flavor) if schedule is None else schedule,
         gamma_on=g.get("gamma_on", "oracle"), n_steps=n_steps, step_size=step_size,
-        flags=8192 if g.get("mirror", True) else 0)        # QW_FLAG_MIRROR: exact symmetry
-                                                           # reduction for the uniform start
+        flags=(8192 if g.get("mirror", True) else 0) | extra_flags)   # QW_FLAG_MIRROR: exact
+                                                           # symmetry reduction for the uniform start
 
 
 def _marked_vertex(n):
@@ -352,7 +355,8 @@ def install(g, flavor):
         import torch
         kind = g.get("type_of_qw", "dependent")
         if kind == "dependent":
-            prob = _problem(g, flavor)
+            # fixed geometry: the files do not depend on the number of GPUs the rows are cut over
+            prob = _problem(g, flavor, extra_flags=FIXED_GEOMETRY)
             if _rk45():
                 def fn(problem, t, b, rows, dev):
                     return engine.rk45_heatmap(problem, t, b, rtol=g.get("rtolerance", 1e-6),
@@ -362,7 +366,8 @@ def install(g, flavor):
                 def fn(problem, t, b, rows, dev):
                     return engine.rk4_heatmap(problem, t, b, rows=rows, device=dev)
         elif kind == "independent":
-            prob = _problem(g, flavor, schedule="static", topology="circular")
+            prob = _problem(g, flavor, schedule="static", topology="circular",
+                            extra_flags=FIXED_GEOMETRY)
             if g.get("ti_method", "exact") == "exact":
                 def fn(problem, t, b, rows, dev):
                     return engine.ti_exact_heatmap(problem, t, b, rows=rows, device=dev)

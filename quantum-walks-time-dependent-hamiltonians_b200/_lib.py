@@ -66,6 +66,7 @@ SIGNATURES = {
     "qw_heatmap_summary_dev": (ctypes.c_int, [_vp, _vp, _i64, _i64, _dbl, _vp, _vp]),
     "qw_adiabatic_batch_dev": (ctypes.c_int, [_pp, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "qw_spectrum_batch_dev": (ctypes.c_int, [_pp, _vp, _vp, _i64, _vp, _vp]),
+    "qw_scratch_trim": (ctypes.c_int, []),
     "qw_plan_query": (ctypes.c_int, [_pp, ctypes.POINTER(QwPlan)]),
     "qw_fp64_peak_probe": (ctypes.c_int, [_dbl, ctypes.POINTER(ctypes.c_double), _vp]),
     "qw_launch_count": (ctypes.c_int64, []),

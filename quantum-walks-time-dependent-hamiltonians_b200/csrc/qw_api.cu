@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "qw_common.cuh"
@@ -129,21 +130,40 @@ int choose_path(const QwParams &prm)
     return PATH_GENERIC;
 }
 
-// The large-N paths take their scratch from the device's stream-ordered pool.  Keep freed
-// scratch cached in the pool (default: released to the OS at the next synchronisation, which
-// costs milliseconds per GiB on every call).
-void keep_pool_cached()
+// per-device state of the library: its scratch pool and the SM count
+struct DeviceState {
+    std::atomic<int> ready{0};
+    cudaMemPool_t pool = nullptr;
+    int sms = 0;
+};
+DeviceState g_dev[64];
+std::mutex g_dev_mutex;
+
+DeviceState *device_state()
 {
-    static std::atomic<uint32_t> done_mask{0};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return;
-    if (done_mask.load() & (1u << dev)) return;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    DeviceState &d = g_dev[dev];
+    if (d.ready.load(std::memory_order_acquire)) return &d;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    if (d.ready.load(std::memory_order_relaxed)) return &d;
+    if (cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        d.sms <= 0)
+        d.sms = 148;
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    if (cudaMemPoolCreate(&d.pool, &props) == cudaSuccess) {
+        uint64_t keep = 1ull << 30;        // cached between calls; more goes back to the driver
+        cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+        d.pool = nullptr;                  // fall back to the default pool, attributes untouched
+        cudaGetLastError();
     }
-    done_mask.fetch_or(1u << dev);
+    d.ready.store(1, std::memory_order_release);
+    return &d;
 }
 
 int run(QwParams &prm, cudaStream_t st)
@@ -151,7 +171,6 @@ int run(QwParams &prm, cudaStream_t st)
     if (prm.n_points == 0) return 0;
     cudaError_t e;
     const int path = choose_path(prm);
-    if (path != PATH_RESIDENT) keep_pool_cached();
     switch (path) {
     case PATH_RESIDENT:
         e = qw_launch_resident(prm, st, nullptr);
@@ -174,15 +193,15 @@ int run(QwParams &prm, cudaStream_t st)
             // partial norms of the blocks of a split point + one arrival counter per point
             const size_t part = (size_t)prm.n_points * (size_t)split * 2 * sizeof(double);
             const size_t done = (size_t)prm.n_points * sizeof(unsigned int);
-            e = cudaMallocAsync(&scratch, part + done, st);
+            e = qw_scratch_alloc(&scratch, part + done, st);
             if (e != cudaSuccess) return cuda_fail(e, "scratch allocation");
             prm.split_part = (double *)scratch;
             prm.split_done = (unsigned int *)((char *)scratch + part);
             e = cudaMemsetAsync(prm.split_done, 0, done, st);
-            if (e != cudaSuccess) { cudaFreeAsync(scratch, st); return cuda_fail(e, "scratch reset"); }
+            if (e != cudaSuccess) { qw_scratch_free(scratch, st); return cuda_fail(e, "scratch reset"); }
         }
         e = qw_launch_horner(prm, st, nullptr);
-        if (scratch) cudaFreeAsync(scratch, st);
+        if (scratch) qw_scratch_free(scratch, st);
         if (e != cudaSuccess) return cuda_fail(e, "nested-form kernel launch");
         g_launches += 1;
         return 0;
@@ -190,10 +209,10 @@ int run(QwParams &prm, cudaStream_t st)
     case PATH_PIT: {
         const int64_t bound = prm.steps_bound > 0 ? prm.steps_bound : prm.n_steps_uniform;
         void *scratch = nullptr;
-        e = cudaMallocAsync(&scratch, qw_pit_scratch_bytes(prm, bound), st);
+        e = qw_scratch_alloc(&scratch, qw_pit_scratch_bytes(prm, bound), st);
         if (e != cudaSuccess) return cuda_fail(e, "scratch allocation");
         e = qw_launch_pit(prm, bound, (double2 *)scratch, st);
-        cudaFreeAsync(scratch, st);
+        qw_scratch_free(scratch, st);
         if (e != cudaSuccess) return cuda_fail(e, "parallel-in-time kernel launch");
         g_launches += 2;
         return 0;
@@ -212,6 +231,11 @@ int run(QwParams &prm, cudaStream_t st)
         int64_t nl = 0;
         e = qw_launch_stream(prm, st, &nl);
         g_launches += nl;
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            return fail(QW_E_UNSUPPORTED, "dimension %lld: the two state buffers of one point do "
+                        "not fit the free device memory", (long long)prm.n);
+        }
         if (e != cudaSuccess) return cuda_fail(e, "streaming kernel launch");
         return 0;
     }
@@ -219,14 +243,19 @@ int run(QwParams &prm, cudaStream_t st)
         int blocks = 0;
         size_t bytes = 0;
         e = qw_generic_geometry(prm, &blocks, &bytes, nullptr);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            return fail(QW_E_UNSUPPORTED, "dimension %lld: five state vectors of one point do not "
+                        "fit the free device memory", (long long)prm.n);
+        }
         if (e != cudaSuccess) return cuda_fail(e, "generic kernel geometry");
         void *scratch = nullptr;
-        e = cudaMallocAsync(&scratch, bytes, st);
+        e = qw_scratch_alloc(&scratch, bytes, st);
         if (e != cudaSuccess) return cuda_fail(e, "scratch allocation");
         prm.scratch = (double2 *)scratch;
         e = qw_launch_generic(prm, blocks, st);
         g_launches += 1;
-        cudaError_t e2 = cudaFreeAsync(scratch, st);
+        cudaError_t e2 = qw_scratch_free(scratch, st);
         if (e != cudaSuccess) return cuda_fail(e, "generic kernel launch");
         if (e2 != cudaSuccess) return cuda_fail(e2, "scratch free");
         return 0;
@@ -242,7 +271,31 @@ struct DevBuf {
 
 }  // namespace
 
+cudaError_t qw_scratch_alloc(void **ptr, size_t bytes, cudaStream_t st)
+{
+    DeviceState *d = device_state();
+    if (d && d->pool) return cudaMallocFromPoolAsync(ptr, bytes ? bytes : 16, d->pool, st);
+    return cudaMallocAsync(ptr, bytes ? bytes : 16, st);
+}
+
+cudaError_t qw_scratch_free(void *ptr, cudaStream_t st) { return cudaFreeAsync(ptr, st); }
+
+int qw_sm_count()
+{
+    DeviceState *d = device_state();
+    return d ? d->sms : 148;
+}
+
 extern "C" {
+
+int qw_scratch_trim(void)
+{
+    DeviceState *d = device_state();
+    if (!d || !d->pool) return 0;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemPoolTrimTo(d->pool, 0);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "scratch pool trim");
+}
 
 static int batch_dev_impl(const qw_problem *prob, const double *T, const double *gamma,
                           const int64_t *n_steps, const int64_t *order, int64_t n_points,
@@ -321,7 +374,6 @@ int qw_rk4_multi_grid_dev(const qw_grid_job *jobs, int64_t n_jobs, void *stream)
     if (packed.size() >= 2) {
         std::vector<unsigned char> got(packed.size(), 0);
         int64_t nl = 0;
-        keep_pool_cached();
         cudaError_t e = qw_launch_packed_multi(packed.data(), (int)packed.size(), got.data(), st, &nl);
         g_launches += nl;
         if (e != cudaSuccess) return cuda_fail(e, "multi-problem packed launch");
@@ -512,11 +564,12 @@ int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gam
     } else {
         bound = prob->n_steps;
     }
-    // layout of the staging buffers: T | gamma | n_steps | p | norm | psi
+    // layout of the staging buffers: T | gamma | n_steps | (pad) | psi | p | norm -- psi is
+    // written with 16-byte stores, so the output section starts on a 16-byte boundary
     const size_t np = (size_t)n_points;
-    const size_t in_bytes = np * 8 * (n_steps ? 3 : 2);
+    const size_t in_bytes = (np * 8 * (n_steps ? 3 : 2) + 15) / 16 * 16;
     const size_t psib = psi ? np * (size_t)prob->n * sizeof(double2) : 0;
-    const size_t out_bytes = np * 16 + psib;
+    const size_t out_bytes = psib + np * 16;
     // small calls: the kernels read and write the pinned buffer directly (unified addressing) --
     // no copy commands at all, one launch and one synchronisation
     const bool zero_copy = in_bytes + out_bytes <= 65536;
@@ -530,8 +583,8 @@ int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gam
     char *d = zero_copy ? h : (char *)g_stage.dev;
     if (!zero_copy && (e = cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st)))
         return cuda_fail(e, "H2D copy");
-    double *dp = (double *)(d + in_bytes), *dn = dp + np;
-    void *dpsi = psi ? (void *)(dn + np) : nullptr;
+    void *dpsi = psi ? (void *)(d + in_bytes) : nullptr;
+    double *dp = (double *)(d + in_bytes + psib), *dn = dp + np;
     int rc = batch_dev_impl(prob, (double *)d, (double *)(d + np * 8),
                             n_steps ? (int64_t *)(d + np * 16) : nullptr, nullptr, n_points, dp, dn,
                             dpsi, st, bound > 0 ? bound : 0);
@@ -540,9 +593,9 @@ int qw_rk4_batch_host(const qw_problem *prob, const double *T, const double *gam
                                            cudaMemcpyDeviceToHost, st)))
         return cuda_fail(e, "D2H copy");
     if ((e = cudaStreamSynchronize(st))) return cuda_fail(e, "kernel execution");
-    memcpy(p, h + in_bytes, np * 8);
-    if (norm) memcpy(norm, h + in_bytes + np * 8, np * 8);
-    if (psi) memcpy(psi, h + in_bytes + np * 16, psib);
+    memcpy(p, h + in_bytes + psib, np * 8);
+    if (norm) memcpy(norm, h + in_bytes + psib + np * 8, np * 8);
+    if (psi) memcpy(psi, h + in_bytes, psib);
     return 0;
 }
 

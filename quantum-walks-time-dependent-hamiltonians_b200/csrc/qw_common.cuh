@@ -38,6 +38,15 @@ struct QwOncePerDevice {
     }
 };
 
+// Scratch of the large-N paths comes from a memory pool OWNED BY THE LIBRARY (one per device,
+// release threshold 1 GiB: freed scratch above that goes back to the driver at the next
+// synchronisation), not from the device's default pool, whose attributes belong to the
+// application.  qw_scratch_trim() (C ABI) returns everything.
+cudaError_t qw_scratch_alloc(void **ptr, size_t bytes, cudaStream_t st);
+cudaError_t qw_scratch_free(void *ptr, cudaStream_t st);
+// multiprocessors of the current device (cached per device)
+int qw_sm_count();
+
 struct QwParams {
     int64_t n;
     int32_t topology, schedule, gamma_on, flags;

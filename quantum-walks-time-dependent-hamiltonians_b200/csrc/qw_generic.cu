@@ -134,8 +134,17 @@ cudaError_t qw_generic_geometry(const QwParams &prm, int *blocks, size_t *scratc
     int64_t nb = (int64_t)sms * occ;
     if (nb > prm.n_points) nb = prm.n_points;
     if (nb < 1) nb = 1;
+    // five complex vectors per running block: no more blocks than three quarters of the free
+    // memory hold (at least one; if even one does not fit, the caller reports it as unsupported)
+    const size_t per_block = 5 * (size_t)prm.n * sizeof(double2);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+        const int64_t fit = (int64_t)((free_b / 4 * 3) / per_block);
+        if (fit < 1) return cudaErrorMemoryAllocation;
+        if (nb > fit) nb = fit;
+    }
     *blocks = (int)nb;
-    *scratch_bytes = (size_t)nb * 5 * (size_t)prm.n * sizeof(double2);
+    *scratch_bytes = (size_t)nb * per_block;
     if (plan) {
         cudaFuncAttributes fa;
         e = cudaFuncGetAttributes(&fa, rk4_generic);

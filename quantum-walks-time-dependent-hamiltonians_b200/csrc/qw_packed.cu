@@ -997,16 +997,15 @@ static bool packed_fits(int64_t n, int R, int max_tpp, int *tpp_log2)
 //    N = 256, R = 16 packed vs R = 8 block-per-point: 5.03e11 vs 4.71e11 site-updates/s (C4).
 //  * a handful of points (C1: one): the smallest R, i.e. as many lanes per point as possible,
 //    which minimises the latency of a stage.
+// the batch size the geometry is chosen for
+static int64_t packed_batch(const QwParams &prm)
+{
+    return (prm.flags & QW_FLAG_FIXED_GEOMETRY) ? (int64_t)1 << 40 : prm.n_points;
+}
+
 int qw_packed_geometry(int64_t n, int64_t n_points, int max_r, int *tpp_log2)
 {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            sms <= 0)
-            sms = 148;
-    }
+    const int sms = qw_sm_count();
     const int cand[9] = {8, 16, 7, 6, 5, 4, 3, 2, 1};
     for (int i = 0; i < 9; ++i) {
         const int R = cand[i];
@@ -1055,7 +1054,7 @@ bool qw_packed_supported(const QwParams &prm)
     if (prm.topology == QW_TOPO_COMPLETE)      // small complete graphs: any-dimension layout only
         return prm.n < 256 && packed_any_r(prm.n) > 0 && !(prm.flags & QW_FLAG_EXACT_SUM);
     if (!(prm.topology == QW_TOPO_CYCLE && prm.n >= 3)) return false;
-    return qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l) > 0 ||
+    return qw_packed_geometry(prm.n, packed_batch(prm), (prm.flags & QW_FLAG_R8) ? 8 : 16, &l) > 0 ||
            packed_any_r(prm.n) > 0;
 }
 
@@ -1069,15 +1068,8 @@ static bool packed_horner(const QwParams &prm, int *tpp_log2)
     // enough warps to fill the machine twice, as for the throughput geometries above;
     // smaller batches keep the latency-oriented stage-form geometries
     const int64_t per_warp = 32 >> *tpp_log2;
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-            sms <= 0)
-            sms = 148;
-    }
-    return (prm.n_points + per_warp - 1) / per_warp >= 2 * (int64_t)sms;
+    const int sms = qw_sm_count();
+    return (packed_batch(prm) + per_warp - 1) / per_warp >= 2 * (int64_t)sms;
 }
 
 // half ring under QW_FLAG_MIRROR in the packed layout: rings of 6 .. 159 sites (from 160 on the
@@ -1128,7 +1120,7 @@ static PackedClass packed_class(const QwParams &prm)
         c.kind = 5; c.R = 16; c.a = l; c.groups = 32 >> l;
         return c;
     }
-    const int R = qw_packed_geometry(prm.n, prm.n_points, (prm.flags & QW_FLAG_R8) ? 8 : 16, &l);
+    const int R = qw_packed_geometry(prm.n, packed_batch(prm), (prm.flags & QW_FLAG_R8) ? 8 : 16, &l);
     if (R > 0) {
         c.kind = 1; c.R = R; c.a = l; c.groups = 32 >> l;
         return c;
@@ -1246,7 +1238,7 @@ cudaError_t qw_launch_packed_multi(const QwParams *prms, int n, unsigned char *t
             }
             if (w > 0x7fffffffLL) { b = e; continue; }        // leave them to single launches
             PackedJob *dj = nullptr;
-            err = cudaMallocAsync((void **)&dj, jobs.size() * sizeof(PackedJob), st);
+            err = qw_scratch_alloc((void **)&dj, jobs.size() * sizeof(PackedJob), st);
             if (err != cudaSuccess) break;
             err = cudaMemcpyAsync(dj, jobs.data(), jobs.size() * sizeof(PackedJob),
                                   cudaMemcpyHostToDevice, st);
@@ -1280,7 +1272,7 @@ cudaError_t qw_launch_packed_multi(const QwParams *prms, int n, unsigned char *t
                 err = cudaGetLastError();
                 ++*launches;
             }
-            cudaFreeAsync(dj, st);
+            qw_scratch_free(dj, st);
             if (err == cudaSuccess)
                 for (size_t k = 0; k < grp.size(); ++k) taken[grp[k].idx] = 1;
         }

@@ -185,7 +185,8 @@ int qw_pit_chunk(int64_t steps)
 bool qw_pit_supported(const QwParams &prm, int64_t steps_bound)
 {
     if (prm.flags & (QW_FLAG_FORCE_GENERIC | QW_FLAG_FORCE_STREAM | QW_FLAG_NO_PACK |
-                     QW_FLAG_NO_HORNER | QW_FLAG_CYCLE_LEGACY | QW_FLAG_EXACT_SUM))
+                     QW_FLAG_NO_HORNER | QW_FLAG_CYCLE_LEGACY | QW_FLAG_EXACT_SUM |
+                     QW_FLAG_FIXED_GEOMETRY))
         return false;
     if (prm.n > 32 || (prm.topology == QW_TOPO_CYCLE && prm.n < 3)) return false;
     if (prm.n_points < 1 || prm.n_points > 16 || prm.order) return false;

@@ -885,18 +885,7 @@ int stream_kb(const QwParams &prm)
     return stream_sr(prm) == 16 ? 8 : 4;
 }
 
-int g_sm_count = 0;
-
-int sm_count()
-{
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
-    }
-    return g_sm_count;
-}
+int sm_count() { return qw_sm_count(); }
 
 template <int KB, int SR, bool ALIGNED, bool HORNER>
 cudaError_t configure()
@@ -1102,21 +1091,27 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
     int64_t chunk = (int64_t)(8ull << 30) / (2 * n * (int64_t)sizeof(double2));
     const int64_t tiles_max = n / (1024 - 64) + 2;
     if (chunk > (int64_t)0x7fffffff / tiles_max) chunk = (int64_t)0x7fffffff / tiles_max;
-    if (chunk < 1) chunk = 1;
+    if (chunk < 1) chunk = 1;                  // one point above the 8 GiB budget: try anyway
     if (chunk > prm.n_points) chunk = prm.n_points;
+    {
+        size_t free_b = 0, total_b = 0;        // ... unless not even one point fits the device
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+            (size_t)2 * (size_t)n * sizeof(double2) > free_b / 8 * 7)
+            return cudaErrorMemoryAllocation;
+    }
     double2 *bufA = nullptr;
     unsigned long long *dmax = nullptr;
-    cudaError_t e = cudaMallocAsync((void **)&bufA, (size_t)chunk * 2 * n * sizeof(double2), st);
+    cudaError_t e = qw_scratch_alloc((void **)&bufA, (size_t)chunk * 2 * n * sizeof(double2), st);
     if (e != cudaSuccess) return e;
     double2 *bufB = bufA + chunk * n;
     void *tab = nullptr;
     const size_t entry = sizeof(HPassEntry) > sizeof(PassEntry) ? sizeof(HPassEntry) : sizeof(PassEntry);
-    e = cudaMallocAsync(&tab, (size_t)chunk * entry + 64, st);    // + the window counter
-    if (e != cudaSuccess) { cudaFreeAsync(bufA, st); return e; }
+    e = qw_scratch_alloc(&tab, (size_t)chunk * entry + 64, st);    // + the window counter
+    if (e != cudaSuccess) { qw_scratch_free(bufA, st); return e; }
     const bool varying = prm.step_size > 0.0 || prm.n_steps != nullptr;
     if (varying) {
-        e = cudaMallocAsync((void **)&dmax, sizeof(unsigned long long), st);
-        if (e != cudaSuccess) { cudaFreeAsync(bufA, st); cudaFreeAsync(tab, st); return e; }
+        e = qw_scratch_alloc((void **)&dmax, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) { qw_scratch_free(bufA, st); qw_scratch_free(tab, st); return e; }
     }
     const double amp = 1.0 / sqrt((double)prm.n);
 
@@ -1147,8 +1142,8 @@ cudaError_t qw_launch_stream(const QwParams &prm_in, cudaStream_t st, int64_t *l
         ++*launches;
         e = cudaGetLastError();
     }
-    cudaFreeAsync(bufA, st);
-    cudaFreeAsync(tab, st);
-    if (dmax) cudaFreeAsync(dmax, st);
+    qw_scratch_free(bufA, st);
+    qw_scratch_free(tab, st);
+    if (dmax) qw_scratch_free(dmax, st);
     return e;
 }

@@ -117,3 +117,23 @@ def test_config1_value_and_host_entry(qw):
     pb, nb = qw.rk4_batch(prob, big_T, np.full(5000, 1.0))   # staged copies, throughput kernel
     po, no, _ = c_oracle.rk4_batch(16, "circular", "lin", big_T, np.full(5000, 1.0), n_steps=1024)
     assert np.abs(pb - po).max() <= P_TOL and np.abs(nb - no).max() <= P_TOL
+
+
+def test_fixed_geometry_makes_results_independent_of_the_cut(qw):
+    """QW_FLAG_FIXED_GEOMETRY (32768): a point's result depends on the problem only -- a row
+    block, a single row and a three-point call are bitwise the rows of the whole heatmap."""
+    t, b = np.linspace(0.1, 40, 9), np.linspace(0, 2.5, 14)
+    for n, topo in ((16, "circular"), (64, "circular"), (71, "circular"), (256, "circular"),
+                    (30, "complete")):
+        for flags in (32768, 32768 | MIRROR):
+            bb = b if topo == "circular" else b * n
+            tt = t if topo == "circular" else t / n
+            prob = qw.Problem(n=n, topology=topo, schedule="cerf_3", n_steps=200, flags=flags)
+            p, norm = qw.rk4_heatmap(prob, tt, bb)
+            for rows in ((0, 14), (3, 9), (13, 14)):
+                ps, ns = qw.rk4_heatmap(prob, tt, bb, rows=rows)
+                assert np.array_equal(ps, p[rows[0]:rows[1]]) and np.array_equal(ns, norm[rows[0]:rows[1]])
+            pb, nb = qw.rk4_batch(prob, tt[[1, 4, 8]], bb[[2, 2, 11]])
+            assert np.array_equal(pb, p[[2, 2, 11], [1, 4, 8]])
+    lib = qw._lib.load()
+    assert lib.qw_scratch_trim() == 0
