@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Run every BASELINE.json config at full size on one GPU and print a markdown table
 (SURVEY.md section 8d): wall time (CUDA events), site-updates/s, grid-points/s, the physics
-read-outs (best cell, tau, I, robustness) and a parity spot-check against the C oracle.
+read-outs (best cell, tau, I, robustness) and a spot check against the C oracle (the parity
+tests proper -- every cell of C2, all 1e5 realisations of C4, strided sub-grids of C3 / C5 -- are
+tests/test_gpu_fullsize.py, part of pytest -m gpu).
 
     python tests/run_configs.py [--skip-long] > profiles/rNN_configs.md
 
@@ -72,11 +74,14 @@ def main():
     a = ap.parse_args()
     print("# BASELINE configs at full size, one B200 (%s)" % torch.cuda.get_device_name(0))
     print()
-    print("Device-resident inputs, CUDA events, one warm-up run; parity = max |dp| against the C "
-          "oracle on 6 random cells of the same grid. FP64 peak measured: %.2f TFLOP/s."
+    print("Device-resident inputs, CUDA events, one warm-up run; spot check = max |dp| against the C "
+          "oracle on 6 random cells of the same grid (full-size parity: tests/test_gpu_fullsize.py). "
+          "Rows marked 'half ring' / 'pair' use the exact symmetry reductions the drop-in modules "
+          "default to (QW_FLAG_MIRROR); their site-updates/s count FULL-ring site-updates. "
+          "FP64 peak measured: %.2f TFLOP/s."
           % qw.fp64_peak_tflops(300.0))
     print()
-    print("| config | kernel | points | ms | site-updates/s | grid-points/s | read-out | parity |")
+    print("| config | kernel | points | ms | site-updates/s | grid-points/s | read-out | spot check |")
     print("|---|---|---|---|---|---|---|---|")
 
     # C1: cycle N=16, single point, n_steps 1024
@@ -84,13 +89,16 @@ def main():
     T1, g1 = torch.tensor([16.0], dtype=torch.float64, device=DEV), torch.tensor(
         [1.0], dtype=torch.float64, device=DEV)
     ms, (p, nrm) = timed(lambda: qw.rk4_batch(prob, T1, g1), reps=5)
-    t0 = time.perf_counter()
-    ph, _ = qw.rk4_batch(prob, [16.0], [1.0])
-    host_us = (time.perf_counter() - t0) * 1e6
-    print("| C1 cycle N=16 (T,gamma)=(16,1) lin S=1024 | packed-cycle, small batch: R=1 x 16 "
-          "lanes | 1 | %.3f | "
+    host = []
+    for _ in range(101):                           # the first call creates the staging buffers
+        t0 = time.perf_counter()
+        ph, _ = qw.rk4_batch(prob, [16.0], [1.0])
+        host.append((time.perf_counter() - t0) * 1e6)
+    host_us = float(np.median(host[1:]))
+    print("| C1 cycle N=16 (T,gamma)=(16,1) lin S=1024 | parallel-in-time: 23 chunk propagators "
+          "+ combine | 1 | %.3f | "
           "%.3e | %.3e | p=%.14f (reference RK4 n=1024: 0.42038739054526); %.0f us per point "
-          "device, %.0f us through the host API | %.1e |"
+          "device, %.0f us through the host API (median of 100 calls) | %.1e |"
           % (ms, 16 * 1024 / (ms * 1e-3), 1 / (ms * 1e-3), ph[0], ms * 1e3, host_us,
              abs(ph[0] - 0.4203873905452587)), flush=True)
 
@@ -153,6 +161,10 @@ def main():
         heatmap_row("C3 complete N=4096 256x256 %s S=2048 gamma-on-L" % sched,
                     dict(n=n, topology="complete", schedule=sched, gamma_on="laplacian",
                          n_steps=2048), t, b)
+    heatmap_row("C3 complete N=4096 256x256 cerf_3 S=2048 gamma-on-L, (psi_w, psi_other) pair "
+                "(drop-in default)",
+                dict(n=n, topology="complete", schedule="cerf_3", gamma_on="laplacian",
+                     n_steps=2048, flags=8192), t, b)
 
     # C4: robustness ensemble, cycle N=256, 1e5 noisy realisations
     n = 256
@@ -196,12 +208,25 @@ def main():
     t, b = np.linspace(0.1, 1024, 1024), np.linspace(0, 2.5, rows)
     heatmap_row("C5 cycle N=1024 %dx1024 lin S=4096" % rows,
                 dict(n=1024, topology="circular", schedule="lin", n_steps=4096), t, b)
+    heatmap_row("C5 cycle N=1024 %dx1024 lin S=4096, half ring (drop-in default)" % rows,
+                dict(n=1024, topology="circular", schedule="lin", n_steps=4096, flags=8192), t, b)
     # C5 streaming variant
     t, b = np.linspace(0.1, 64, 32), np.linspace(0, 2.5, 32)
-    for flag, kb in ((8, 1), (24, 4), (0, 8)):
-        heatmap_row("C5-stream cycle N=65536 32x32 lin S=256, %d step(s)/pass" % kb,
+    for flag, kb in ((8, 1), (24, 4), (0, 8), (8192, 8)):
+        heatmap_row("C5-stream cycle N=65536 32x32 lin S=256, %d step(s)/pass%s"
+                    % (kb, ", half ring" if flag == 8192 else ""),
                     dict(n=65536, topology="circular", schedule="lin", n_steps=256, flags=flag),
                     t, b, reps=2, check=True)
+    # above one thread block: rings across a cluster / split complete graphs
+    t, b = np.linspace(0.1, 50, 64), np.linspace(0.2, 2.5, 37)
+    for n in (5000, 8192):
+        heatmap_row("cycle N=%d 37x64 cerf_3 S=512 (thread-block cluster)" % n,
+                    dict(n=n, topology="circular", schedule="cerf_3", n_steps=512), t, b, reps=2)
+    for n in (8192, 16384):
+        heatmap_row("complete N=%d 37x64 cerf_3 S=512 gamma-on-L (split over blocks)" % n,
+                    dict(n=n, topology="complete", schedule="cerf_3", gamma_on="laplacian",
+                         n_steps=512), np.linspace(0.1, 100, 64), np.linspace(0.5 / n, 2.5 / n, 37),
+                    reps=2)
 
 
 if __name__ == "__main__":

@@ -197,6 +197,46 @@ __global__ void __launch_bounds__(64, MINB) kD(int steps, double seed, double *s
     if (s == 123.456) sink[0] = s;
 }
 
+// G: the nested level in DIFFERENCE form: d_r = x_r - x_{r-1} (DADD), v_r = d_r - d_{r+1} (DADD),
+// out = fma(rho, v, y) -- the same three instructions per component, but two two-operand DADDs
+// instead of DADD + DFMA-with-immediate (round 2: does the cheaper operand pattern pay?)
+template <bool SYNC, int MINB>
+__global__ void __launch_bounds__(64, MINB) kG(int steps, double seed, double *sink)
+{
+    constexpr int R = 16;
+    __shared__ double tab[64];
+    if (threadIdx.x < 64) tab[threadIdx.x] = 1e-3 * seed * (1.0 + 1e-3 * threadIdx.x);
+    __syncthreads();
+    double yr[R], yi[R], zr[R], zi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { yr[r] = seed + r + threadIdx.x; yi[r] = 0.5 * r; zr[r] = 0; zi[r] = 0; }
+    double rho = 1e-3 * seed;
+    for (int st = 0; st < steps; ++st) {
+#pragma unroll
+        for (int lev = 0; lev < 4; ++lev) {
+            if (SYNC) __syncthreads();
+            rho = ((volatile double *)tab)[(4 * st + lev) & 63];
+            double dr[R + 1], di[R + 1];
+#pragma unroll
+            for (int r = 0; r <= R; ++r) {
+                const int a = r % R, b = (r + R - 1) % R;
+                dr[r] = (lev == 0 ? yr[a] : zr[a]) - (lev == 0 ? yr[b] : zr[b]);
+                di[r] = (lev == 0 ? yi[a] : zi[a]) - (lev == 0 ? yi[b] : zi[b]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double vr = dr[r] - dr[r + 1], vi = di[r] - di[r + 1];
+                if (lev == 3) { yr[r] = fma(rho, vi, yr[r]); yi[r] = fma(-rho, vr, yi[r]); }
+                else { zr[r] = fma(rho, vi, yr[r]); zi[r] = fma(-rho, vr, yi[r]); }
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) s += yr[r] + yi[r];
+    if (s == 123.456) sink[0] = s;
+}
+
 template <typename K>
 void run(const char *name, K k, int blocks_per_sm, int threads, int iters, double inst_per_thread_iter)
 {
@@ -224,8 +264,16 @@ void run(const char *name, K k, int blocks_per_sm, int threads, int iters, doubl
     cudaFree(sink);
 }
 
-int main()
+int main(int argc, char **argv)
 {
+    if (argc > 1) {          // round 2: only the level forms
+        run("E nested level, barrier/level", kD<true, 4, 1>, 4, 64, 20000, 16 * 24.0);
+        run("E nested level, barrier/level", kD<true, 6, 1>, 6, 64, 20000, 16 * 24.0);
+        run("G difference form, barrier/level", kG<true, 4>, 4, 64, 20000, 16 * 24.0 + 4 * 2.0);
+        run("G difference form, barrier/level", kG<true, 6>, 6, 64, 20000, 16 * 24.0 + 4 * 2.0);
+        run("G difference form, no barrier", kG<false, 6>, 6, 64, 20000, 16 * 24.0 + 4 * 2.0);
+        return 0;
+    }
     run("A dfma 1 varying operand", kA, 2, 256, 4000, 256.0);
     run("A dfma 1 varying operand", kA, 1, 256, 4000, 256.0);
     run("B dfma 3 varying operands", kB, 2, 256, 4000, 256.0);
