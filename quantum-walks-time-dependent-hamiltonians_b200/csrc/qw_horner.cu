@@ -33,19 +33,30 @@
 
 namespace {
 
-// Shared-memory form for the cycle kernel.  The four corrections are evaluated by eight lanes
-// of the owner warp at once: lane 2m + c holds component c (0 re, 1 im) of sigma_{4-m} as a
-// real dot product of length 8 with (re, im) of (y_w, s1, s2, s3), s_k = y_{w-k} + y_{w+k}.
-// coef[k][lane]: conflict-free for the lanes' loads; 69 doubles: conflict-free fill.
+// Shared-memory form for the cycle kernel.  The four corrections are evaluated by ALL 32 lanes of
+// the owner warp at once: lane 8q + l forms the two terms that s_q = y_{w-q} + y_{w+q} (s_0 = 2 y_w)
+// contributes to output l, and two butterfly additions over q finish the dot products; output
+// l = 2m + c is component c (0 re, 1 im) of  y_w + sigma_{4-m},  i.e. the identity is folded into
+// the coefficients of y_w, so that the owner simply uses the value as the ADDEND of the level's
+// axpy at the marked vertex: 6 FP64 warp-instructions per step (2 DADD, DMUL, DFMA, 2 DADD)
+// instead of the 22 of the first version (6 sums + a dot product of length 8 in eight lanes + 8
+// masked corrections), which cost the hot kernel 9 % (tools/hot_probe.cu: the owner warp was the
+// longer of the two warps of a block at every barrier).
+// coef2[lane] = the lane's two coefficients (of Re s_q, Im s_q): one conflict-free LDS.128.
 struct HornerStep {
     double rho[4];
-    double coef[8][8];
-    double pad;
+    double2 coef2[32];
+    double2 c4;                          // sigma_4 = c4 y_w (the owner forms it itself)
 };
 
 struct HornerShared {
     HornerStep st[QW_CHUNK];
     double red[2 * 32];
+    double2 win[8];                      // slots 0 .. 6 of the owner thread (y_{w-3} .. y_{w+3}; half
+                                         // ring: y_w .. y_{w+3}), published by the owner; not [W0]
+    double2 priv[64];                    // the owner WARP's y[W0], lane by lane (HR_UNION: + helper's)
+    double tq[8];                        // the helper warp's outputs (-, t_3, t_2, t_1)
+    double2 zero;
     int owner;
 };
 
@@ -53,7 +64,8 @@ struct HornerShared {
 // multiplication, tau = t / T by division).  Caller synchronises before and after.
 __device__ __forceinline__ void horner_fill_cycle(HornerStep *tab, const QwPoint &pt,
                                                   const int64_t n0, const int cnt,
-                                                  const int schedule, const int gamma_on)
+                                                  const int schedule, const int gamma_on,
+                                                  const bool fold4)
 {
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
         const double t0 = (double)(n0 + i) * pt.h;
@@ -68,14 +80,19 @@ __device__ __forceinline__ void horner_fill_cycle(HornerStep *tab, const QwPoint
         HornerStep &o = tab[i];
 #pragma unroll
         for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
+        o.c4 = c[0];
         const int base[4] = {0, 1, 3, 6};              // first coefficient of sigma_4 .. sigma_1
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {              // term k multiplies (b_k.re, b_k.im)
-                const double2 ck = (k <= m) ? c[base[m] + k] : make_double2(0.0, 0.0);
-                o.coef[2 * k][2 * m] = ck.x;      o.coef[2 * k + 1][2 * m] = -ck.y;      // re
-                o.coef[2 * k][2 * m + 1] = ck.y;  o.coef[2 * k + 1][2 * m + 1] = ck.x;   // im
+            for (int k = 0; k < 4; ++k) {              // term k multiplies (Re s_k, Im s_k)
+                double2 ck = (k <= m) ? c[base[m] + k] : make_double2(0.0, 0.0);
+                if (k == 0) {                          // y_w + sigma; the lanes form s_0 = 2 y_w
+                    ck.x = 0.5 * ((m > 0 || fold4) ? ck.x + 1.0 : ck.x);
+                    ck.y = 0.5 * ck.y;
+                }
+                o.coef2[8 * k + 2 * m] = make_double2(ck.x, -ck.y);        // re
+                o.coef2[8 * k + 2 * m + 1] = make_double2(ck.y, ck.x);     // im
             }
         }
     }
@@ -105,10 +122,17 @@ __device__ __forceinline__ unsigned warp_slot()
     return w;
 }
 
-// `cnt` RK4 steps with the table in shared memory.  OWN: this warp holds the marked vertex.
-// Its correction arithmetic is issued by all lanes of the warp (an FP64 instruction costs the
-// same pipe time whatever its mask) and masked by msk = 1 in the owner thread, 0 elsewhere,
-// so that it is straight-line code the compiler interleaves with the interior sites.
+// `cnt` RK4 steps with the table in shared memory.
+// ROLE of the calling warp in the oracle correction (see HornerStep).  The FP64 pipe of an SM
+// sub-partition is DISPATCH bound: an FP64 warp-instruction takes two issue cycles, every other
+// instruction one, and the warps of a block move in lockstep through the level barriers, so what
+// counts is the instruction total of the LONGEST warp (tools/hot_probe.cu: with all the
+// correction work in the owner warp the kernel lost 9 %, half of it to the imbalance).  Hence
+//   HR_OWNER  publishes y_{w-3..w+3} before the step's first barrier, picks up sigma_4, t_3, t_2,
+//             t_1 after the second and uses t_l = y_w + sigma_l as the addend of its marked slot;
+//   HR_HELPER (another warp of the block) forms the four dot products during level 4;
+//   HR_SELF   one-warp blocks: both duties, every t_l folded (level 4 included);
+//   HR_PLAIN  everybody else.
 // A step has four levels, so the mailbox parity of a level is a compile-time constant: level 4
 // and 2 read buffer 0 and write buffer 1, level 3 and 1 the other way round.
 // (A pairwise bar.arrive / bar.sync handshake between the two warps of a block instead of the
@@ -122,26 +146,100 @@ __device__ __forceinline__ unsigned warp_slot()
 // slot 0 of thread 0, whose left neighbour is its own slot 1; the last thread's right neighbour
 // is the mirror image about the antipode (mend = 1: even n, the site before the last; mend = 2:
 // odd n, the last site itself; 0: not the last thread).
-template <int R, bool OWN, bool RAGGED, bool MIRROR>
+// hooks for tools/hot_probe.cu (ablation timing); the library never defines them
+#ifndef QW_LEVEL_BAR
+#define QW_LEVEL_BAR() __syncthreads()
+#endif
+#ifndef QW_MBOX_LD
+#define QW_MBOX_LD(x) (x)
+#endif
+constexpr int HR_PLAIN = 0, HR_SELF = 1, HR_OWNER = 2, HR_HELPER = 3, HR_UNION = 4;
+
+// Before the first step: the owner warp's lanes store their y[W0], the owner its window.
+template <int R, bool MIRROR>
+__device__ __forceinline__ void horner_first_window(const HState<R> &s, double2 *win,
+                                                    double2 *priv, const int lane, const bool own)
+{
+    constexpr int W0 = MIRROR ? 0 : HW0;
+    priv[lane] = make_double2(s.yr[W0], s.yi[W0]);
+    if (own) {
+#pragma unroll
+        for (int r = 0; r < (MIRROR ? 4 : 7); ++r) win[r] = make_double2(s.yr[r], s.yi[r]);
+    }
+}
+
+// lane 8q + l: the terms of s_q = y_{w-q} + y_{w+q} in output l, then the sum over q; every lane
+// ends up with output l = lane & 7.  wa, wb: where the lane finds its two sites (horner_window_addr)
+__device__ __forceinline__ double horner_window_dot(const uint32_t wa, const uint32_t wb,
+                                                    const HornerStep &hs, const int lane)
+{
+    const double2 ya = lds2(wa), yb = lds2(wb);
+    const double2 cf = hs.coef2[lane];
+    double v = fma(cf.y, ya.y + yb.y, cf.x * (ya.x + yb.x));
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
+// slot of the owner thread -> its shared-memory copy: the marked slot lives in priv[owner lane]
+template <bool MIRROR>
+__device__ __forceinline__ uint32_t horner_window_addr(const int slot, const double2 *win,
+                                                       const double2 *priv)
+{
+    return slot == (MIRROR ? 0 : HW0) ? smem_u32(priv) : smem_u32(win + slot);
+}
+
+struct HornerOracle {                    // shared-memory pieces of the oracle correction
+    double2 *win, *priv;
+    double *tq;
+    const double2 *zero;
+    int owner_lane0;                     // thread index of the owner (lane 0 of its warp)
+};
+
+template <int R, int ROLE, bool RAGGED, bool MIRROR>
 __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab, double2 *first,
                                              double2 *last, const int nt, const int t,
                                              const int tl, const int tr, const int cnt,
-                                             const double msk, const bool full_in, const int mend)
+                                             const bool own, const bool full_in, const int mend,
+                                             const HornerOracle &oc)
 {
     constexpr int W0 = MIRROR ? 0 : HW0;
+    constexpr bool OWNS = ROLE == HR_SELF || ROLE == HR_OWNER || ROLE == HR_UNION;
+    constexpr bool OWNER = ROLE == HR_OWNER || ROLE == HR_UNION;
+    constexpr bool HELPS = ROLE == HR_HELPER || ROLE == HR_UNION;
+    constexpr int WS = OWNS ? W0 : -1;
+    constexpr int PUBW = OWNS ? (MIRROR ? 4 : 7) : 0;
     const bool full = RAGGED ? full_in : true;
+    const int lane = t & 31;
+    // owner warp: where a lane finds the addend of its marked slot at levels 3, 2, 1 -- the owner
+    // lane the helper's t_3, t_2, t_1, every other lane its own y[W0]
+    const uint32_t a_priv = smem_u32(oc.priv + (ROLE == HR_UNION ? (t - oc.owner_lane0) & 63 : lane));
+    const int helps = ROLE == HR_HELPER || (ROLE == HR_UNION && ((t ^ oc.owner_lane0) & 32));
+    const uint32_t a_t = (OWNS && own) ? smem_u32(oc.tq) : a_priv;
+    const uint32_t a_ts = (OWNS && own) ? 16u : 0u;
+    const uint32_t a_win = smem_u32(oc.win);
+    // helper (and HR_SELF): the two window sites of lane 8q + l
+    const int q = lane >> 3;
+    const uint32_t wa = horner_window_addr<MIRROR>(MIRROR ? q : HW0 - q, oc.win, oc.priv);
+    const uint32_t wb = horner_window_addr<MIRROR>(MIRROR ? q : HW0 + q, oc.win, oc.priv);
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const HornerStep &hs = tab[sidx];
-        double sgl = 0.0;                          // this lane's component of its sigma
 #define QW_LX_R(LV, r) ((LV == 4) ? s.yr[r] : s.zr[r])
 #define QW_LX_I(LV, r) ((LV == 4) ? s.yi[r] : s.zi[r])
 #define QW_HORNER_LEVEL(LEVEL)                                                              \
         {                                                                                   \
             constexpr int par = (4 - LEVEL) & 1;                                            \
-            __syncthreads();                                                                \
-            double2 hl = last[par * nt + tl];                                               \
-            double2 hr = first[par * nt + tr];                                              \
+            QW_LEVEL_BAR();                                                                 \
+            double2 hl = QW_MBOX_LD(last[par * nt + tl]);                                   \
+            double2 hr = QW_MBOX_LD(first[par * nt + tr]);                                  \
             const double rho = hs.rho[LEVEL - 1];                                           \
+            double2 tw = make_double2(0.0, 0.0);    /* owner warp: addend of the marked slot */ \
+            if (OWNER && LEVEL < 4) tw = lds2(a_t + (4 - LEVEL) * a_ts);                    \
+            if (OWNER && LEVEL == 4) {              /* y_w + c4 y_w; c4 = 0 in the other lanes */ \
+                const double2 c4 = *(own ? &hs.c4 : oc.zero);                               \
+                tw = cmul2_acc(c4, make_double2(s.yr[W0], s.yi[W0]),                        \
+                               make_double2(s.yr[W0], s.yi[W0]));                           \
+            }                                                                               \
             double2 o0, oL;                                                                 \
             if (MIRROR) {                     /* reflecting ends of the half ring */        \
                 if (t == 0) hl = make_double2(QW_LX_R(LEVEL, 1), QW_LX_I(LEVEL, 1));                            \
@@ -156,24 +254,22 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
                 if (LEVEL == 4) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }                 \
                 else { s.zr[R - 1] = hr.x; s.zi[R - 1] = hr.y; }                            \
             }                                                                               \
-            if (OWN && LEVEL == 4) {                                                        \
-                /* y_w and the neighbour sums at distance 1..3 (meaningful in the owner */  \
-                /* lane), broadcast; every lane then forms its own dot product          */  \
-                double b[8];                  /* MIRROR: y_{w-k} = y_{w+k} = slot k */       \
-                b[0] = s.yr[W0];                                  b[1] = s.yi[W0];          \
-                b[2] = s.yr[MIRROR ? 1 : W0 - 1] + s.yr[W0 + 1];                            \
-                b[3] = s.yi[MIRROR ? 1 : W0 - 1] + s.yi[W0 + 1];                            \
-                b[4] = s.yr[MIRROR ? 2 : W0 - 2] + s.yr[W0 + 2];                            \
-                b[5] = s.yi[MIRROR ? 2 : W0 - 2] + s.yi[W0 + 2];                            \
-                b[6] = s.yr[MIRROR ? 3 : W0 - 3] + s.yr[W0 + 3];                            \
-                b[7] = s.yi[MIRROR ? 3 : W0 - 3] + s.yi[W0 + 3];                            \
-                sgl = hs.coef[0][t & 7] * __shfl_sync(0xffffffffu, b[0], 0);                \
-                _Pragma("unroll")                                                           \
-                for (int k = 1; k < 8; ++k)                                                 \
-                    sgl = fma(hs.coef[k][t & 7], __shfl_sync(0xffffffffu, b[k], 0), sgl);   \
+            if (ROLE == HR_SELF) {            /* one-warp block: every level from the dot product */ \
+                if (LEVEL == 4) sgl = horner_window_dot(wa, wb, hs, lane);                  \
+                tw.x = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));                      \
+                tw.y = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);                  \
+                if (!own) tw = make_double2(s.yr[W0], s.yi[W0]);                            \
             }                                                                               \
-            hedges<R, LEVEL>(s, rho, hl, hr, o0, oL);                                       \
-            hinterior<R, LEVEL>(s, rho, o0, oL);                                            \
+            if (HELPS && LEVEL == 4) {                                                      \
+                const double v = horner_window_dot(wa, wb, hs, lane);                       \
+                if (helps && lane < 8) oc.tq[lane] = v;                                     \
+            }                                                                               \
+            hedges<R, LEVEL, WS, PUBW>(s, rho, hl, hr, o0, oL, tw.x, tw.y, a_win, (int)own); \
+            hinterior<R, LEVEL, WS, PUBW>(s, rho, o0, oL, tw.x, tw.y, a_win, (int)own);     \
+            if (OWNS && LEVEL == 1) {         /* the next step's y[W0], lane by lane */     \
+                sts2(a_priv, s.yr[W0], s.yi[W0]);                                           \
+                if (ROLE == HR_SELF) __syncwarp();                                          \
+            }                                                                               \
             {   /* publish: the last REAL site is slot R-1, or R-2 in a short thread */     \
                 const double lr = (LEVEL > 1) ? (full ? s.zr[R - 1] : s.zr[R - 2])          \
                                               : (full ? s.yr[R - 1] : s.yr[R - 2]);         \
@@ -183,18 +279,8 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
                                                         : make_double2(s.yr[0], s.yi[0]);   \
                 last[(par ^ 1) * nt + t] = make_double2(lr, li);                            \
             }                                                                               \
-            if (OWN) {                                  /* oracle correction sigma_LEVEL */ \
-                const double sgr = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));          \
-                const double sgi = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);      \
-                if (LEVEL > 1) {                                                            \
-                    s.zr[W0] = fma(msk, sgr, s.zr[W0]);                                     \
-                    s.zi[W0] = fma(msk, sgi, s.zi[W0]);                                     \
-                } else {                                                                    \
-                    s.yr[W0] = fma(msk, sgr, s.yr[W0]);                                     \
-                    s.yi[W0] = fma(msk, sgi, s.yi[W0]);                                     \
-                }                                                                           \
-            }                                                                               \
         }
+        double sgl = 0.0;                          // HR_SELF: this lane's output
         QW_HORNER_LEVEL(4)
         QW_HORNER_LEVEL(3)
         QW_HORNER_LEVEL(2)
@@ -211,8 +297,9 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
     static_assert(!MIRROR || RAGGED, "the half ring has an arbitrary number of sites");
     constexpr int W0 = MIRROR ? 0 : HW0;
     static_assert(R >= 2 * HW0 + 1, "the window w-3..w+3 must sit in one thread");
-    extern __shared__ double2 mbox[];         // [2][2][blockDim.x]: parity, first/last
+    extern __shared__ double2 mbox[];         // [2][2][MAXNT]: parity, first/last
     __shared__ HornerShared sh;
+    constexpr int NTS = MAXNT;                // mailbox stride: offsets become immediates
     const int t = threadIdx.x, nt = blockDim.x, nact = prm.nact, nfull = prm.nfull;
     const QwPoint pt = qw_point(prm, blockIdx.x);
     const bool active = t < nact;
@@ -240,23 +327,49 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
         s.yr[r] = amp; s.yi[r] = 0.0;
         s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
-    double2 *first = mbox, *last = mbox + 2 * nt;      // [parity][thread]; a step starts at 0
+    double2 *first = mbox, *last = mbox + 2 * NTS;     // [parity][thread]; a step starts at 0
     first[t] = make_double2(s.yr[0], s.yi[0]);
     last[t] = make_double2(s.yr[R - 1], s.yi[R - 1]);  // uniform start: any slot will do
 
     const int warp = t >> 5;
+    const int helper = ((ht >> 5) + 1) % (nt >> 5);    // the warp that forms the dot products
+    const HornerOracle oc = {sh.win, sh.priv, sh.tq, &sh.zero, ht};
+    if (t == 0) sh.zero = make_double2(0.0, 0.0);
+#ifdef QW_ABL_UNION
+    horner_first_window<R, MIRROR>(s, sh.win, sh.priv, (t - ht) & 63, own);
+#else
+    if (warp == (ht >> 5)) horner_first_window<R, MIRROR>(s, sh.win, sh.priv, t & 31, own);
+#endif
     for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
         const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
         __syncthreads();                               // the last chunk's table is no longer read
-        horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on);
+#ifdef QW_ABL_NOREFILL
+        if (n0 == 0)
+#endif
+        horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, nt == 32);
         __syncthreads();
-        const double msk = own ? 1.0 : 0.0;
-        if (warp == (ht >> 5))
-            horner_steps<R, true, RAGGED, MIRROR>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk,
-                                                  full, mend);
-        else
-            horner_steps<R, false, RAGGED, MIRROR>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk,
-                                                   full, mend);
+#define QW_HS(ROLE) horner_steps<R, ROLE, RAGGED, MIRROR>(s, sh.st, first, last, NTS, t, tl, tr, \
+                                                          cnt, own, full, mend, oc)
+#if defined(QW_ABL_NOOWN)
+        QW_HS(HR_PLAIN);
+#else
+        if (nt == 32) QW_HS(HR_SELF);
+#ifdef QW_ABL_UNION
+        else if (nt == 64) QW_HS(HR_UNION);
+#endif
+#ifdef QW_ABL_NOOWNER
+        else if (warp == (ht >> 5)) QW_HS(HR_PLAIN);
+#else
+        else if (warp == (ht >> 5)) QW_HS(HR_OWNER);
+#endif
+#ifdef QW_ABL_NOHELPER
+        else if (warp == helper) QW_HS(HR_PLAIN);
+#else
+        else if (warp == helper) QW_HS(HR_HELPER);
+#endif
+        else QW_HS(HR_PLAIN);
+#endif
+#undef QW_HS
     }
 
     // p = |psi_w|^2 / ||psi||^2, ||psi||^2 (BCB.py:189-199, Runge_Kutta_Error.py:103)
@@ -326,6 +439,10 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 struct ClusterShared {
     HornerStep st[QW_CHUNK];
     double red[2 * 32];
+    double2 win[8];                      // as in HornerShared
+    double2 priv[64];
+    double tq[8];
+    double2 zero;
     double2 halo[2][2];                  // [left / right][parity]: written by the neighbour CTA
     unsigned long long bar[2][2];        // [left / right][parity]
     double2 csum[16];                    // CTA 0: (norm, |psi_w|^2) of every CTA
@@ -489,22 +606,25 @@ __global__ void __launch_bounds__(288, 1) rk4_cycle_cluster(const QwParams prm)
 
     const int warp = t >> 5;
     const bool owner_cta = rank == 0;
-    const double msk = (owner_cta && t == 0) ? 1.0 : 0.0;
+    const bool own = owner_cta && t == 0;
+    const HornerOracle oc = {sh.win, sh.priv, sh.tq, &sh.zero, 0};
+    if (t == 0) sh.zero = make_double2(0.0, 0.0);
+    if (owner_cta && warp == 0) horner_first_window<R, false>(s, sh.win, sh.priv, t & 31, own);
     for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
         const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
         __syncthreads();                               // the last chunk's table is no longer read
-        horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on);
+        horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, false);
         __syncthreads();
+#define QW_HS(ROLE) horner_steps<R, ROLE, RAGGED, false>(s, sh.st, first, last, nt, t, tl, tr, \
+                                                         cnt, own, full, 0, oc)
         if (comm)
             cluster_comm_steps(er, ei, sh, first, last, nt, side, side == 0 ? me_l : me_r,
                                side == 0 ? 0 : nact - 1, my_bar0, my_bar1, to_slot0, to_slot1,
                                to_bar0, to_bar1, cnt, lane_on);
-        else if (owner_cta && warp == 0)
-            horner_steps<R, true, RAGGED, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk,
-                                                 full, 0);
-        else
-            horner_steps<R, false, RAGGED, false>(s, sh.st, first, last, nt, t, tl, tr, cnt, msk,
-                                                  full, 0);
+        else if (owner_cta && warp == 0) QW_HS(HR_OWNER);
+        else if (owner_cta && warp == 1) QW_HS(HR_HELPER);     // every CTA has >= 3 compute warps
+        else QW_HS(HR_PLAIN);
+#undef QW_HS
     }
 
     // p = |psi_w|^2 / ||psi||^2, ||psi||^2: partial sums to CTA 0
@@ -1125,7 +1245,9 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
     prm.nfull = (int)(sites - (int64_t)prm.nact * (R - 1));       // threads with R sites
     const int threads = ((prm.nact + 31) / 32) * 32;
     const bool cyc = prm.topology == QW_TOPO_CYCLE;
-    const size_t smem = cyc ? (size_t)threads * 4 * sizeof(double2) : 0;
+    // cycle kernels: mailbox [2][2][MAXNT] of the instantiation chosen below (set by QW_MB)
+    size_t smem = 0;
+#define QW_MB(MAXNT) smem = (size_t)(MAXNT) * 4 * sizeof(double2)
     if (plan) {
         plan->path = cyc ? 5 : 6;
         plan->sites_per_thread = R;
@@ -1179,25 +1301,30 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
     const int bthreads = threads;
     if (mirror) {                                  // R = 17, up to 255 registers
 #define QW_HM(...) return hlaunch(rk4_cycle_horner<__VA_ARGS__, true, true>, prm, bthreads, smem, st, plan)
-        if (threads <= 64) { QW_HM(17, 64, 4); }
-        if (threads <= 128) { QW_HM(17, 128, 2); }
+        if (threads <= 64) { QW_MB(64); QW_HM(17, 64, 4); }
+        if (threads <= 128) { QW_MB(128); QW_HM(17, 128, 2); }
+        QW_MB(256);
         QW_HM(17, 256, 1);
 #undef QW_HM
     }
     if (R == 16) {
         // register file = 16 K per SM sub-partition: 2 / 3 warps there allow 255 / 168 registers
-        if (threads <= 64 && (prm.flags & QW_FLAG_OCC4)) { QW_HL(rk4_cycle_horner, 16, 64, 4); }
-        if (threads <= 64) { QW_HL(rk4_cycle_horner, 16, 64, 6); }
+        if (threads <= 64 && (prm.flags & QW_FLAG_OCC4)) { QW_MB(64); QW_HL(rk4_cycle_horner, 16, 64, 4); }
+        if (threads <= 64) { QW_MB(64); QW_HL(rk4_cycle_horner, 16, 64, 6); }
         // 5 or 6 warps: two blocks per SM at 168 registers (one block at 200: QW_FLAG_OCC4, A/B)
         if (threads > 128 && threads <= 192 && !(prm.flags & QW_FLAG_OCC4)) {
+            QW_MB(192);
             QW_HL(rk4_cycle_horner, 16, 192, 2);
         }
-        if (threads <= 128) { QW_HL(rk4_cycle_horner, 16, 128, 3); }
+        if (threads <= 128) { QW_MB(128); QW_HL(rk4_cycle_horner, 16, 128, 3); }
+        QW_MB(256);
         QW_HL(rk4_cycle_horner, 16, 256, 1);
     }
-    if (threads <= 64) { QW_HL(rk4_cycle_horner, 8, 64, 8); }
-    if (threads <= 128) { QW_HL(rk4_cycle_horner, 8, 128, 4); }
-    if (threads <= 256) { QW_HL(rk4_cycle_horner, 8, 256, 2); }
+    if (threads <= 64) { QW_MB(64); QW_HL(rk4_cycle_horner, 8, 64, 8); }
+    if (threads <= 128) { QW_MB(128); QW_HL(rk4_cycle_horner, 8, 128, 4); }
+    if (threads <= 256) { QW_MB(256); QW_HL(rk4_cycle_horner, 8, 256, 2); }
+    QW_MB(512);
     QW_HL(rk4_cycle_horner, 8, 512, 1);
+#undef QW_MB
 #undef QW_HL
 }

@@ -135,20 +135,59 @@ struct HState {
 #define HO_R(r) ((LEVEL == 1) ? s.yr[r] : s.zr[r])
 #define HO_I(r) ((LEVEL == 1) ? s.yi[r] : s.zi[r])
 
-template <int R, int LEVEL>
+// 16-byte shared-memory accesses by 32-bit address (the owner / helper code of the resident kernels
+// selects its addresses per lane)
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ double2 lds2(const uint32_t a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+
+// predicated store: a branch around a handful of stores cost the owner warp 3 % of its time in
+// branch resolution (ncu source page)
+__device__ __forceinline__ void sts2_if(const uint32_t a, const double x, const double y,
+                                        const int on)
+{
+    asm volatile("{\n.reg .pred p;\nsetp.ne.s32 p, %3, 0;\n@p st.shared.v2.f64 [%0], {%1, %2};\n}"
+                 ::"r"(a), "d"(x), "d"(y), "r"(on) : "memory");
+}
+
+__device__ __forceinline__ void sts2(const uint32_t a, const double x, const double y)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x), "d"(y) : "memory");
+}
+
+// WS >= 0: the addend of slot WS is (wr, wi) instead of y[WS] -- the owner of the marked vertex
+// passes y_w + sigma_LEVEL there (the oracle correction folded into the level's axpy).
+// PUBW > 0 (level 1 only): the new values of slots 0 .. PUBW-1 except WS go to pub[slot] as soon
+// as they exist, stored by the lanes with `on` set (the owner publishes the window around the
+// marked vertex for the next step's corrections).
+template <int R, int LEVEL, int WS = -1, int PUBW = 0>
 __device__ __forceinline__ void hedges(HState<R> &s, const double rho, const double2 hl,
-                                       const double2 hr, double2 &o0, double2 &oL)
+                                       const double2 hr, double2 &o0, double2 &oL,
+                                       const double wr = 0.0, const double wi = 0.0,
+                                       const uint32_t pub = 0, const int on = 0)
 {
     o0 = make_double2(HX_R(0), HX_I(0));
     oL = make_double2(HX_R(R - 1), HX_I(R - 1));
-    hsite(hl.x, hl.y, o0.x, o0.y, HX_R(1), HX_I(1), rho, s.yr[0], s.yi[0], HO_R(0), HO_I(0));
+    hsite(hl.x, hl.y, o0.x, o0.y, HX_R(1), HX_I(1), rho, WS == 0 ? wr : s.yr[0],
+          WS == 0 ? wi : s.yi[0], HO_R(0), HO_I(0));
+    if (LEVEL == 1 && PUBW > 0 && WS != 0) sts2_if(pub, HO_R(0), HO_I(0), on);
     hsite(HX_R(R - 2), HX_I(R - 2), oL.x, oL.y, hr.x, hr.y, rho, s.yr[R - 1], s.yi[R - 1],
           HO_R(R - 1), HO_I(R - 1));
 }
 
-template <int R, int LEVEL>
+template <int R, int LEVEL, int WS = -1, int PUBW = 0>
 __device__ __forceinline__ void hinterior(HState<R> &s, const double rho, const double2 o0,
-                                          const double2 oL)
+                                          const double2 oL, const double wr = 0.0,
+                                          const double wi = 0.0, const uint32_t pub = 0,
+                                          const int on = 0)
 {
     double pr = o0.x, pi = o0.y;
 #pragma unroll
@@ -156,7 +195,9 @@ __device__ __forceinline__ void hinterior(HState<R> &s, const double rho, const 
         const double cr = HX_R(r), ci = HX_I(r);
         const double nr = (r + 1 < R - 1) ? HX_R(r + 1 < R ? r + 1 : r) : oL.x;
         const double ni = (r + 1 < R - 1) ? HX_I(r + 1 < R ? r + 1 : r) : oL.y;
-        hsite(pr, pi, cr, ci, nr, ni, rho, s.yr[r], s.yi[r], HO_R(r), HO_I(r));
+        hsite(pr, pi, cr, ci, nr, ni, rho, WS == r ? wr : s.yr[r], WS == r ? wi : s.yi[r],
+              HO_R(r), HO_I(r));
+        if (LEVEL == 1 && r < PUBW && r != WS) sts2_if(pub + 16 * r, HO_R(r), HO_I(r), on);
         pr = cr;
         pi = ci;
     }

@@ -494,10 +494,7 @@ struct TmaShared {
     uint32_t widx[TmaGeo<SR>::DEPTH + 1];  // window index of iteration kk (0xffffffff: none left)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
+// smem_u32: qw_horner_level.cuh
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
