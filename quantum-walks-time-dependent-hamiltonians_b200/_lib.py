@@ -5,7 +5,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqw_b200.so")
+# QW_B200_LIB: another build of the same library (A/B timing of two versions, tools/r2_ab_sizes.sh)
+LIB_PATH = os.environ.get("QW_B200_LIB") or os.path.join(_HERE, "libqw_b200.so")
 
 # enums of include/qw_b200.h
 TOPO_COMPLETE, TOPO_CYCLE = 0, 1

@@ -33,28 +33,15 @@
 
 namespace {
 
-// Shared-memory form for the cycle kernel.  The four corrections are evaluated by ALL 32 lanes of
-// the owner warp at once: lane 8q + l forms the two terms that s_q = y_{w-q} + y_{w+q} (s_0 = 2 y_w)
-// contributes to output l, and two butterfly additions over q finish the dot products; output
-// l = 2m + c is component c (0 re, 1 im) of  y_w + sigma_{4-m},  i.e. the identity is folded into
-// the coefficients of y_w, so that the owner simply uses the value as the ADDEND of the level's
-// axpy at the marked vertex: 6 FP64 warp-instructions per step (2 DADD, DMUL, DFMA, 2 DADD)
-// instead of the 22 of the first version (6 sums + a dot product of length 8 in eight lanes + 8
-// masked corrections), which cost the hot kernel 9 % (tools/hot_probe.cu: the owner warp was the
-// longer of the two warps of a block at every barrier).
-// coef2[lane] = the lane's two coefficients (of Re s_q, Im s_q): one conflict-free LDS.128.
-struct HornerStep {
-    double rho[4];
-    double2 coef2[32];
-    double2 c4;                          // sigma_4 = c4 y_w (the owner forms it itself)
-};
-
+// CH steps per table refill: one thread per step, so blocks of two warps and more refill 64 steps
+// at a time (a refill is ~800 instructions in the lanes that have a step, while the other warps wait)
+template <int CH>
 struct HornerShared {
-    HornerStep st[QW_CHUNK];
+    HornerStep st[CH];
     double red[2 * 32];
     double2 win[8];                      // slots 0 .. 6 of the owner thread (y_{w-3} .. y_{w+3}; half
                                          // ring: y_w .. y_{w+3}), published by the owner; not [W0]
-    double2 priv[64];                    // the owner WARP's y[W0], lane by lane (HR_UNION: + helper's)
+    double2 priv[32];                    // the owner WARP's y[W0], lane by lane
     double tq[8];                        // the helper warp's outputs (-, t_3, t_2, t_1)
     double2 zero;
     int owner;
@@ -76,25 +63,7 @@ __device__ __forceinline__ void horner_fill_cycle(HornerStep *tab, const QwPoint
         HornerCoef hc;
         horner_coefficients(hc, pt.h, ad1, ad2, ad4, 2.0, 6.0);     // L_ww = 2, (L^2)_ww = 6
         horner_cycle_sum_basis(hc.c);
-        const double2 *c = hc.c;
-        HornerStep &o = tab[i];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
-        o.c4 = c[0];
-        const int base[4] = {0, 1, 3, 6};              // first coefficient of sigma_4 .. sigma_1
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {              // term k multiplies (Re s_k, Im s_k)
-                double2 ck = (k <= m) ? c[base[m] + k] : make_double2(0.0, 0.0);
-                if (k == 0) {                          // y_w + sigma; the lanes form s_0 = 2 y_w
-                    ck.x = 0.5 * ((m > 0 || fold4) ? ck.x + 1.0 : ck.x);
-                    ck.y = 0.5 * ck.y;
-                }
-                o.coef2[8 * k + 2 * m] = make_double2(ck.x, -ck.y);        // re
-                o.coef2[8 * k + 2 * m + 1] = make_double2(ck.y, ck.x);     // im
-            }
-        }
+        horner_step_store(tab[i], hc, fold4);
     }
 }
 
@@ -150,10 +119,13 @@ __device__ __forceinline__ unsigned warp_slot()
 #ifndef QW_LEVEL_BAR
 #define QW_LEVEL_BAR() __syncthreads()
 #endif
-#ifndef QW_MBOX_LD
-#define QW_MBOX_LD(x) (x)
+#ifndef QW_OCC_R16_64
+#define QW_OCC_R16_64 6                  // blocks per SM of the 64-thread R = 16 cycle kernel
 #endif
-constexpr int HR_PLAIN = 0, HR_SELF = 1, HR_OWNER = 2, HR_HELPER = 3, HR_UNION = 4;
+#ifndef QW_HCHUNK
+#define QW_HCHUNK 32                     // steps per table refill in blocks of two warps and more
+#endif
+constexpr int HR_PLAIN = 0, HR_SELF = 1, HR_OWNER = 2, HR_HELPER = 3;
 
 // Before the first step: the owner warp's lanes store their y[W0], the owner its window.
 template <int R, bool MIRROR>
@@ -168,32 +140,11 @@ __device__ __forceinline__ void horner_first_window(const HState<R> &s, double2 
     }
 }
 
-// lane 8q + l: the terms of s_q = y_{w-q} + y_{w+q} in output l, then the sum over q; every lane
-// ends up with output l = lane & 7.  wa, wb: where the lane finds its two sites (horner_window_addr)
-__device__ __forceinline__ double horner_window_dot(const uint32_t wa, const uint32_t wb,
-                                                    const HornerStep &hs, const int lane)
-{
-    const double2 ya = lds2(wa), yb = lds2(wb);
-    const double2 cf = hs.coef2[lane];
-    double v = fma(cf.y, ya.y + yb.y, cf.x * (ya.x + yb.x));
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 16);
-    return v;
-}
-
-// slot of the owner thread -> its shared-memory copy: the marked slot lives in priv[owner lane]
-template <bool MIRROR>
-__device__ __forceinline__ uint32_t horner_window_addr(const int slot, const double2 *win,
-                                                       const double2 *priv)
-{
-    return slot == (MIRROR ? 0 : HW0) ? smem_u32(priv) : smem_u32(win + slot);
-}
-
 struct HornerOracle {                    // shared-memory pieces of the oracle correction
     double2 *win, *priv;
     double *tq;
     const double2 *zero;
-    int owner_lane0;                     // thread index of the owner (lane 0 of its warp)
+    bool helps;                          // HR_HELPER: this warp's dot products are the ones stored
 };
 
 template <int R, int ROLE, bool RAGGED, bool MIRROR>
@@ -204,17 +155,16 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
                                              const HornerOracle &oc)
 {
     constexpr int W0 = MIRROR ? 0 : HW0;
-    constexpr bool OWNS = ROLE == HR_SELF || ROLE == HR_OWNER || ROLE == HR_UNION;
-    constexpr bool OWNER = ROLE == HR_OWNER || ROLE == HR_UNION;
-    constexpr bool HELPS = ROLE == HR_HELPER || ROLE == HR_UNION;
+    constexpr bool OWNS = ROLE == HR_SELF || ROLE == HR_OWNER;
+    constexpr bool OWNER = ROLE == HR_OWNER;
+    constexpr bool HELPS = ROLE == HR_HELPER;
     constexpr int WS = OWNS ? W0 : -1;
     constexpr int PUBW = OWNS ? (MIRROR ? 4 : 7) : 0;
     const bool full = RAGGED ? full_in : true;
     const int lane = t & 31;
     // owner warp: where a lane finds the addend of its marked slot at levels 3, 2, 1 -- the owner
     // lane the helper's t_3, t_2, t_1, every other lane its own y[W0]
-    const uint32_t a_priv = smem_u32(oc.priv + (ROLE == HR_UNION ? (t - oc.owner_lane0) & 63 : lane));
-    const int helps = ROLE == HR_HELPER || (ROLE == HR_UNION && ((t ^ oc.owner_lane0) & 32));
+    const uint32_t a_priv = smem_u32(oc.priv + lane);
     const uint32_t a_t = (OWNS && own) ? smem_u32(oc.tq) : a_priv;
     const uint32_t a_ts = (OWNS && own) ? 16u : 0u;
     const uint32_t a_win = smem_u32(oc.win);
@@ -230,8 +180,8 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
         {                                                                                   \
             constexpr int par = (4 - LEVEL) & 1;                                            \
             QW_LEVEL_BAR();                                                                 \
-            double2 hl = QW_MBOX_LD(last[par * nt + tl]);                                   \
-            double2 hr = QW_MBOX_LD(first[par * nt + tr]);                                  \
+            double2 hl = last[par * nt + tl];                                               \
+            double2 hr = first[par * nt + tr];                                              \
             const double rho = hs.rho[LEVEL - 1];                                           \
             double2 tw = make_double2(0.0, 0.0);    /* owner warp: addend of the marked slot */ \
             if (OWNER && LEVEL < 4) tw = lds2(a_t + (4 - LEVEL) * a_ts);                    \
@@ -262,7 +212,7 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
             }                                                                               \
             if (HELPS && LEVEL == 4) {                                                      \
                 const double v = horner_window_dot(wa, wb, hs, lane);                       \
-                if (helps && lane < 8) oc.tq[lane] = v;                                     \
+                if (lane < 8 && oc.helps) oc.tq[lane] = v;                                  \
             }                                                                               \
             hedges<R, LEVEL, WS, PUBW>(s, rho, hl, hr, o0, oL, tw.x, tw.y, a_win, (int)own); \
             hinterior<R, LEVEL, WS, PUBW>(s, rho, o0, oL, tw.x, tw.y, a_win, (int)own);     \
@@ -298,7 +248,8 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
     constexpr int W0 = MIRROR ? 0 : HW0;
     static_assert(R >= 2 * HW0 + 1, "the window w-3..w+3 must sit in one thread");
     extern __shared__ double2 mbox[];         // [2][2][MAXNT]: parity, first/last
-    __shared__ HornerShared sh;
+    constexpr int CH = MAXNT >= 64 ? QW_HCHUNK : QW_CHUNK;
+    __shared__ HornerShared<CH> sh;
     constexpr int NTS = MAXNT;                // mailbox stride: offsets become immediates
     const int t = threadIdx.x, nt = blockDim.x, nact = prm.nact, nfull = prm.nfull;
     const QwPoint pt = qw_point(prm, blockIdx.x);
@@ -333,20 +284,20 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 
     const int warp = t >> 5;
     const int helper = ((ht >> 5) + 1) % (nt >> 5);    // the warp that forms the dot products
-    const HornerOracle oc = {sh.win, sh.priv, sh.tq, &sh.zero, ht};
+    // Blocks of five warps and more: the owner warp does all of it (HR_SELF), as a one-warp block
+    // does.  Measured (tools/r2_ab_sizes.sh): N = 3000 5.40e11 against 5.18e11 with the split,
+    // N = 4096 6.30e11 against 6.0-6.2e11; N = 2048 (four warps) 6.47e11 against 6.64e11.
+    const bool selfish = nt > 128;
+    const HornerOracle oc = {sh.win, sh.priv, sh.tq, &sh.zero, warp == helper};
     if (t == 0) sh.zero = make_double2(0.0, 0.0);
-#ifdef QW_ABL_UNION
-    horner_first_window<R, MIRROR>(s, sh.win, sh.priv, (t - ht) & 63, own);
-#else
     if (warp == (ht >> 5)) horner_first_window<R, MIRROR>(s, sh.win, sh.priv, t & 31, own);
-#endif
-    for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
-        const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
+    for (int64_t n0 = 0; n0 < pt.steps; n0 += CH) {
+        const int cnt = (int)((pt.steps - n0 < CH) ? (pt.steps - n0) : CH);
         __syncthreads();                               // the last chunk's table is no longer read
 #ifdef QW_ABL_NOREFILL
         if (n0 == 0)
 #endif
-        horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, nt == 32);
+        horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, nt == 32 || selfish);
         __syncthreads();
 #define QW_HS(ROLE) horner_steps<R, ROLE, RAGGED, MIRROR>(s, sh.st, first, last, NTS, t, tl, tr, \
                                                           cnt, own, full, mend, oc)
@@ -354,19 +305,9 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
         QW_HS(HR_PLAIN);
 #else
         if (nt == 32) QW_HS(HR_SELF);
-#ifdef QW_ABL_UNION
-        else if (nt == 64) QW_HS(HR_UNION);
-#endif
-#ifdef QW_ABL_NOOWNER
-        else if (warp == (ht >> 5)) QW_HS(HR_PLAIN);
-#else
+        else if (selfish) { if (warp == (ht >> 5)) QW_HS(HR_SELF); else QW_HS(HR_PLAIN); }
         else if (warp == (ht >> 5)) QW_HS(HR_OWNER);
-#endif
-#ifdef QW_ABL_NOHELPER
-        else if (warp == helper) QW_HS(HR_PLAIN);
-#else
         else if (warp == helper) QW_HS(HR_HELPER);
-#endif
         else QW_HS(HR_PLAIN);
 #endif
 #undef QW_HS
@@ -440,7 +381,7 @@ struct ClusterShared {
     HornerStep st[QW_CHUNK];
     double red[2 * 32];
     double2 win[8];                      // as in HornerShared
-    double2 priv[64];
+    double2 priv[32];
     double tq[8];
     double2 zero;
     double2 halo[2][2];                  // [left / right][parity]: written by the neighbour CTA
@@ -607,7 +548,7 @@ __global__ void __launch_bounds__(288, 1) rk4_cycle_cluster(const QwParams prm)
     const int warp = t >> 5;
     const bool owner_cta = rank == 0;
     const bool own = owner_cta && t == 0;
-    const HornerOracle oc = {sh.win, sh.priv, sh.tq, &sh.zero, 0};
+    const HornerOracle oc = {sh.win, sh.priv, sh.tq, &sh.zero, owner_cta && warp == 1};
     if (t == 0) sh.zero = make_double2(0.0, 0.0);
     if (owner_cta && warp == 0) horner_first_window<R, false>(s, sh.win, sh.priv, t & 31, own);
     for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
@@ -1112,7 +1053,7 @@ template <typename K>
 cudaError_t hlaunch(K kernel, const QwParams &prm, int threads, size_t smem, cudaStream_t st,
                     qw_plan *plan)
 {
-    if (smem + sizeof(HornerShared) > 48 * 1024) {     // static + dynamic above the default cap
+    if (smem + sizeof(HornerShared<QW_HCHUNK>) > 48 * 1024) {     // static + dynamic above the default cap
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
@@ -1310,7 +1251,7 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
     if (R == 16) {
         // register file = 16 K per SM sub-partition: 2 / 3 warps there allow 255 / 168 registers
         if (threads <= 64 && (prm.flags & QW_FLAG_OCC4)) { QW_MB(64); QW_HL(rk4_cycle_horner, 16, 64, 4); }
-        if (threads <= 64) { QW_MB(64); QW_HL(rk4_cycle_horner, 16, 64, 6); }
+        if (threads <= 64) { QW_MB(64); QW_HL(rk4_cycle_horner, 16, 64, QW_OCC_R16_64); }
         // 5 or 6 warps: two blocks per SM at 168 registers (one block at 200: QW_FLAG_OCC4, A/B)
         if (threads > 128 && threads <= 192 && !(prm.flags & QW_FLAG_OCC4)) {
             QW_MB(192);

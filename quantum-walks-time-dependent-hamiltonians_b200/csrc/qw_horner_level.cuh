@@ -101,6 +101,50 @@ __device__ __forceinline__ void horner_cycle_sum_basis(double2 *c)
     c[9] = make_double2(-c[9].x, -c[9].y);
 }
 
+// Shared-memory form for the cycle kernel.  The four corrections are evaluated by ALL 32 lanes of
+// the owner warp at once: lane 8q + l forms the two terms that s_q = y_{w-q} + y_{w+q} (s_0 = 2 y_w)
+// contributes to output l, and two butterfly additions over q finish the dot products; output
+// l = 2m + c is component c (0 re, 1 im) of  y_w + sigma_{4-m},  i.e. the identity is folded into
+// the coefficients of y_w, so that the owner simply uses the value as the ADDEND of the level's
+// axpy at the marked vertex: 6 FP64 warp-instructions per step (2 DADD, DMUL, DFMA, 2 DADD)
+// instead of the 22 of the first version (6 sums + a dot product of length 8 in eight lanes + 8
+// masked corrections), which cost the hot kernel 9 % (tools/hot_probe.cu: the owner warp was the
+// longer of the two warps of a block at every barrier).
+// coef2[lane] = the lane's two coefficients (of Re s_q, Im s_q): one conflict-free LDS.128.
+struct HornerStepBase {                  // the one-warp forms (every addend from the dot product)
+    double rho[4];
+    double2 coef2[32];
+};
+struct HornerStep : HornerStepBase {
+    double2 c4;                          // sigma_4 = c4 y_w (the owner forms it itself)
+};
+
+
+// One step's table entry from the coefficients in the sum basis (horner_cycle_sum_basis).
+// fold4: the identity is folded into sigma_4's coefficient as well (the one-warp forms take all
+// four addends from the dot product; the owner / helper form computes y_w + c4 y_w itself).
+__device__ __forceinline__ void horner_step_store(HornerStepBase &o, const HornerCoef &hc,
+                                                  const bool fold4)
+{
+    const double2 *c = hc.c;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
+    const int base[4] = {0, 1, 3, 6};              // first coefficient of sigma_4 .. sigma_1
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {              // term k multiplies (Re s_k, Im s_k)
+            double2 ck = (k <= m) ? c[base[m] + k] : make_double2(0.0, 0.0);
+            if (k == 0) {                          // y_w + sigma; the lanes form s_0 = 2 y_w
+                ck.x = 0.5 * ((m > 0 || fold4) ? ck.x + 1.0 : ck.x);
+                ck.y = 0.5 * ck.y;
+            }
+            o.coef2[8 * k + 2 * m] = make_double2(ck.x, -ck.y);        // re
+            o.coef2[8 * k + 2 * m + 1] = make_double2(ck.y, ck.x);     // im
+        }
+    }
+}
+
 __device__ __forceinline__ double2 cmul2(const double2 c, const double2 v)
 {
     return make_double2(fma(c.x, v.x, -c.y * v.y), fma(c.x, v.y, c.y * v.x));
@@ -201,6 +245,34 @@ __device__ __forceinline__ void hinterior(HState<R> &s, const double rho, const 
         pr = cr;
         pi = ci;
     }
+}
+
+// lane 8q + l: the terms of s_q = y_{w-q} + y_{w+q} in output l, then the sum over q; every lane
+// ends up with output l = lane & 7.  wa, wb: where the lane finds its two sites (horner_window_addr)
+__device__ __forceinline__ void horner_step_store(HornerStep &o, const HornerCoef &hc,
+                                                  const bool fold4)
+{
+    horner_step_store(static_cast<HornerStepBase &>(o), hc, fold4);
+    o.c4 = hc.c[0];
+}
+
+__device__ __forceinline__ double horner_window_dot(const uint32_t wa, const uint32_t wb,
+                                                    const HornerStepBase &hs, const int lane)
+{
+    const double2 ya = lds2(wa), yb = lds2(wb);
+    const double2 cf = hs.coef2[lane];
+    double v = fma(cf.y, ya.y + yb.y, cf.x * (ya.x + yb.x));
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
+// slot of the owner thread -> its shared-memory copy: the marked slot lives in priv[owner lane]
+template <bool MIRROR>
+__device__ __forceinline__ uint32_t horner_window_addr(const int slot, const double2 *win,
+                                                       const double2 *priv)
+{
+    return slot == (MIRROR ? 0 : HW0) ? smem_u32(priv) : smem_u32(win + slot);
 }
 
 }  // namespace

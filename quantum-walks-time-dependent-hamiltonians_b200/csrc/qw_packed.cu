@@ -609,21 +609,24 @@ static int packed_any_r(int64_t n)
 // has its own table: a refill computes 32 coefficient sets -- 32 / G steps for each of the
 // G = 32 / TPP points -- one per lane.  The marked vertex is slot 3 of the first lane of a
 // point's group; eight lanes of the group evaluate its four corrections at once.
-struct PackedStep {                  // as HornerStep in qw_horner.cu
-    double rho[4];
-    double coef[8][8];
-    double pad;
-};
-
-template <int MINB>
-__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwParams prm,
-                                                                    const int tpp_log2)
+// Oracle correction (round 2, as the one-warp form of qw_horner.cu): the first lane of a group
+// publishes its window y_{w-3} .. y_{w+3} in shared memory, the group's TPP lanes form the four dot
+// products y_w + sigma_l -- lane 8 qg + l the terms of 32 / TPP sums s_q in output l, then a
+// butterfly over qg -- and the owner takes them as the ADDEND of its marked slot: 6 / 9 / 16 FP64
+// warp-instructions per step for 32 / 16 / 8 lanes per point instead of 22, two shuffle stages
+// instead of 24 shuffles.
+template <int MINB, int TPP_LOG2>
+__global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwParams prm)
 {
     constexpr int R = 16;
-    __shared__ PackedStep tab[32];               // [group][step of the chunk]
+    constexpr int tpp_log2 = TPP_LOG2;
+    constexpr int QPL = 32 >> TPP_LOG2;          // sums s_q per lane: 1, 2, 4
+    __shared__ HornerStepBase tab[32];           // [group][step of the chunk]
+    __shared__ double2 win[4][8];                // [group]: slots 0 .. 6 of the group's first lane
+    __shared__ double2 tq2[4][4];                // [group]: y_w + sigma_4 .. y_w + sigma_1
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
-    const int tpp = 1 << tpp_log2, groups = 32 >> tpp_log2, ch = 32 / groups;   // ch = tpp
+    constexpr int tpp = 1 << tpp_log2, groups = 32 >> tpp_log2, ch = 32 / groups;   // ch = tpp
     const int li = lane & (tpp - 1), grp = lane >> tpp_log2, gbase = grp << tpp_log2;
     bool valid;
     const QwPoint pt = packed_point(prm, blockIdx.x, grp, groups, valid);
@@ -631,7 +634,8 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
     const int64_t S = packed_steps(prm, blockIdx.x, groups, &steps_slot);
     const int left = (li == 0) ? lane + tpp - 1 : lane - 1;
     const int right = (li == tpp - 1) ? lane - tpp + 1 : lane + 1;
-    const double msk = (li == 0) ? 1.0 : 0.0;
+    const bool own = li == 0;
+    const uint32_t a_win = smem_u32(&win[grp][0]), a_tq = smem_u32(&tq2[grp][0]);
     // the lane's refill duty: step (lane % ch) of point (lane / ch) of this warp
     const int fgrp = lane / ch, fstep = lane - fgrp * ch;
     bool fvalid;
@@ -645,16 +649,19 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
         s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
 
+    if (own) {
+#pragma unroll
+        for (int r = 0; r < 7; ++r) win[grp][r] = make_double2(s.yr[r], s.yi[r]);
+    }
     for (int64_t n0 = 0; n0 < S; n0 += ch) {
         __syncwarp();
         if (n0 + fstep < S && fpt.steps == 0) {        // T == 0: identity step (BCB.py:72-73)
-            PackedStep &o = tab[lane];
+            HornerStepBase &o = tab[lane];
 #pragma unroll
             for (int k = 0; k < 4; ++k) o.rho[k] = 0.0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-#pragma unroll
-                for (int m = 0; m < 8; ++m) o.coef[k][m] = 0.0;
+            for (int k = 0; k < 32; ++k)           // y_w + 0: the identity on s_0 = 2 y_w
+                o.coef2[k] = make_double2(k < 8 && !(k & 1) ? 0.5 : 0.0, k < 8 && (k & 1) ? 0.5 : 0.0);
         } else if (n0 + fstep < S) {
             const double t0 = (double)(n0 + fstep) * fpt.h;
             const double2 ad1 = qw_operator_scalars(t0 / fpt.T, fpt.gamma, prm.schedule, prm.gamma_on);
@@ -665,25 +672,12 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
             HornerCoef hc;
             horner_coefficients(hc, fpt.h, ad1, ad2, ad4, 2.0, 6.0);
             horner_cycle_sum_basis(hc.c);
-            PackedStep &o = tab[lane];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
-            const int base[4] = {0, 1, 3, 6};
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const double2 ck = (k <= m) ? hc.c[base[m] + k] : make_double2(0.0, 0.0);
-                    o.coef[2 * k][2 * m] = ck.x;      o.coef[2 * k + 1][2 * m] = -ck.y;
-                    o.coef[2 * k][2 * m + 1] = ck.y;  o.coef[2 * k + 1][2 * m + 1] = ck.x;
-                }
-            }
+            horner_step_store(tab[lane], hc, true);
         }
         __syncwarp();
         const int cnt = (int)((S - n0 < ch) ? (S - n0) : ch);
         for (int sidx = 0; sidx < cnt; ++sidx) {
-            const PackedStep &hs = tab[grp * ch + sidx];
-            double sgl = 0.0;
+            const HornerStepBase &hs = tab[grp * ch + sidx];
 #define QW_PH_LEVEL(LEVEL)                                                                  \
             {                                                                               \
                 const double xfr = (LEVEL == 4) ? s.yr[0] : s.zr[0];                        \
@@ -695,26 +689,30 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
                 const double2 hr = make_double2(__shfl_sync(full, xfr, right),              \
                                                 __shfl_sync(full, xfi, right));             \
                 const double rho = hs.rho[LEVEL - 1];                                       \
-                if (LEVEL == 4) {                                                           \
-                    double bb[8];                                                           \
-                    bb[0] = s.yr[HW0];                     bb[1] = s.yi[HW0];               \
-                    bb[2] = s.yr[HW0 - 1] + s.yr[HW0 + 1]; bb[3] = s.yi[HW0 - 1] + s.yi[HW0 + 1]; \
-                    bb[4] = s.yr[HW0 - 2] + s.yr[HW0 + 2]; bb[5] = s.yi[HW0 - 2] + s.yi[HW0 + 2]; \
-                    bb[6] = s.yr[HW0 - 3] + s.yr[HW0 + 3]; bb[7] = s.yi[HW0 - 3] + s.yi[HW0 + 3]; \
-                    sgl = hs.coef[0][li & 7] * __shfl_sync(full, bb[0], gbase);             \
+                if (LEVEL == 4) {                 /* the window was published at level 1 */ \
+                    const int qg = li >> 3, l = li & 7;                                     \
+                    double v = 0.0;                                                         \
                     _Pragma("unroll")                                                       \
-                    for (int k = 1; k < 8; ++k)                                             \
-                        sgl = fma(hs.coef[k][li & 7], __shfl_sync(full, bb[k], gbase), sgl); \
+                    for (int j = 0; j < QPL; ++j) {                                         \
+                        const int q = qg * QPL + j;                                         \
+                        const double2 ya = lds2(a_win + 16 * (HW0 - q));                    \
+                        const double2 yb = lds2(a_win + 16 * (HW0 + q));                    \
+                        const double2 cf = hs.coef2[8 * q + l];                             \
+                        v = fma(cf.y, ya.y + yb.y, fma(cf.x, ya.x + yb.x, v));              \
+                    }                                                                       \
+                    if (TPP_LOG2 >= 4) v += __shfl_xor_sync(full, v, 8);                    \
+                    if (TPP_LOG2 >= 5) v += __shfl_xor_sync(full, v, 16);                   \
+                    if (li < 8) reinterpret_cast<double *>(&tq2[grp][0])[li] = v;           \
+                    __syncwarp();                                                           \
                 }                                                                           \
+                const double2 tw = lds2(a_tq + 16 * (4 - LEVEL));                           \
+                const double wr = own ? tw.x : s.yr[HW0], wi = own ? tw.y : s.yi[HW0];      \
                 double2 o0, oL;                                                             \
-                hedges<R, LEVEL>(s, rho, hl, hr, o0, oL);                                   \
-                hinterior<R, LEVEL>(s, rho, o0, oL);                                        \
-                const double sgr = __shfl_sync(full, sgl, gbase + 2 * (4 - LEVEL));         \
-                const double sgi = __shfl_sync(full, sgl, gbase + 2 * (4 - LEVEL) + 1);     \
-                if (LEVEL > 1) {                                                            \
-                    s.zr[HW0] = fma(msk, sgr, s.zr[HW0]); s.zi[HW0] = fma(msk, sgi, s.zi[HW0]); \
-                } else {                                                                    \
-                    s.yr[HW0] = fma(msk, sgr, s.yr[HW0]); s.yi[HW0] = fma(msk, sgi, s.yi[HW0]); \
+                hedges<R, LEVEL, HW0, 7>(s, rho, hl, hr, o0, oL, wr, wi, a_win, (int)own);  \
+                hinterior<R, LEVEL, HW0, 7>(s, rho, o0, oL, wr, wi, a_win, (int)own);       \
+                if (LEVEL == 1) {                 /* y[HW0] completes the next step's window */ \
+                    sts2_if(a_win + 16 * HW0, s.yr[HW0], s.yi[HW0], (int)own);              \
+                    __syncwarp();                                                           \
                 }                                                                           \
             }
             QW_PH_LEVEL(4)
@@ -761,7 +759,9 @@ template <int R, int MINB>
 __global__ void __launch_bounds__(32, MINB) rk4_cycle_mirror(const QwParams prm, const int L,
                                                              const int nfull)
 {
-    __shared__ PackedStep tab[32];
+    __shared__ HornerStepBase tab[32];            // 12 blocks per SM: 18 KB of shared memory each
+    __shared__ double2 win[4], priv[32];          // lane 0's slots 1 .. 3; every lane's y[0]
+    __shared__ double tq[8];                      // y_w + sigma_4 .. y_w + sigma_1 (re, im)
     __shared__ int64_t steps_slot;
     const unsigned fm = 0xffffffffu;
     const int lane = threadIdx.x;
@@ -774,7 +774,15 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_mirror(const QwParams prm,
     const bool first = lane == 0, lastl = lane == L - 1;
     const bool even = (prm.n & 1) == 0;
     const int left = first ? lane : lane - 1, right = lane + 1 < 32 ? lane + 1 : lane;
-    const double msk = first ? 1.0 : 0.0;
+    // Oracle correction as in the one-warp form of qw_horner.cu (HR_SELF): the 32 lanes form the
+    // four dot products from lane 0's window in shared memory (6 FP64 warp-instructions), lane 0
+    // takes y_w + sigma_l as the addend of slot 0, every other lane its own y[0] -- from shared
+    // memory, so that no select is needed (round 1: 22 instructions and 36 shuffles per step).
+    const int q = lane >> 3;
+    const uint32_t wq = q == 0 ? smem_u32(priv) : smem_u32(win + q);   // y_{w-q} = y_{w+q} = slot q
+    const uint32_t a_priv = smem_u32(priv + lane);
+    const uint32_t a_t = first ? smem_u32(tq) : a_priv, a_ts = first ? 16u : 0u;
+    const uint32_t a_win = smem_u32(win);
 
     HState<R> s;
     const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
@@ -784,6 +792,11 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_mirror(const QwParams prm,
         s.zr[r] = 0.0; s.zi[r] = 0.0;
     }
 
+    priv[lane] = make_double2(s.yr[0], s.yi[0]);
+    if (first) {
+#pragma unroll
+        for (int r = 1; r < 4; ++r) win[r] = make_double2(s.yr[r], s.yi[r]);
+    }
     for (int64_t n0 = 0; n0 < S; n0 += 32) {
         __syncwarp();
         if (n0 + lane < S) {
@@ -796,25 +809,12 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_mirror(const QwParams prm,
             HornerCoef hc;
             horner_coefficients(hc, pt.h, ad1, ad2, ad4, 2.0, 6.0);
             horner_cycle_sum_basis(hc.c);
-            PackedStep &o = tab[lane];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o.rho[k] = hc.rho[k];
-            const int base[4] = {0, 1, 3, 6};
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const double2 ck = (k <= m) ? hc.c[base[m] + k] : make_double2(0.0, 0.0);
-                    o.coef[2 * k][2 * m] = ck.x;      o.coef[2 * k + 1][2 * m] = -ck.y;
-                    o.coef[2 * k][2 * m + 1] = ck.y;  o.coef[2 * k + 1][2 * m + 1] = ck.x;
-                }
-            }
+            horner_step_store(tab[lane], hc, true);
         }
         __syncwarp();
         const int cnt = (int)((S - n0 < 32) ? (S - n0) : 32);
         for (int sidx = 0; sidx < cnt; ++sidx) {
-            const PackedStep &hs = tab[sidx];
-            double sgl = 0.0;
+            const HornerStepBase &hs = tab[sidx];
 #define QW_MX_R(LV, r) ((LV == 4) ? s.yr[r] : s.zr[r])
 #define QW_MX_I(LV, r) ((LV == 4) ? s.yi[r] : s.zi[r])
 #define QW_MIRROR_LEVEL(LEVEL)                                                              \
@@ -835,25 +835,17 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_mirror(const QwParams prm,
                 }                                                                           \
                 const double rho = hs.rho[LEVEL - 1];                                       \
                 if (LEVEL == 4) {                                                           \
-                    double bb[8];                        /* y_w, s_k = 2 y_{w+k} */          \
-                    bb[0] = s.yr[0];           bb[1] = s.yi[0];                             \
-                    bb[2] = s.yr[1] + s.yr[1]; bb[3] = s.yi[1] + s.yi[1];                   \
-                    bb[4] = s.yr[2] + s.yr[2]; bb[5] = s.yi[2] + s.yi[2];                   \
-                    bb[6] = s.yr[3] + s.yr[3]; bb[7] = s.yi[3] + s.yi[3];                   \
-                    sgl = hs.coef[0][lane & 7] * __shfl_sync(fm, bb[0], 0);                 \
-                    _Pragma("unroll")                                                       \
-                    for (int k = 1; k < 8; ++k)                                             \
-                        sgl = fma(hs.coef[k][lane & 7], __shfl_sync(fm, bb[k], 0), sgl);    \
+                    const double v = horner_window_dot(wq, wq, hs, lane);                   \
+                    if (lane < 8) tq[lane] = v;                                             \
+                    __syncwarp();                                                           \
                 }                                                                           \
+                const double2 tw = lds2(a_t + (4 - LEVEL) * a_ts);                          \
                 double2 o0, oL;                                                             \
-                hedges<R, LEVEL>(s, rho, hl, hr, o0, oL);                                   \
-                hinterior<R, LEVEL>(s, rho, o0, oL);                                        \
-                const double sgr = __shfl_sync(fm, sgl, 2 * (4 - LEVEL));                   \
-                const double sgi = __shfl_sync(fm, sgl, 2 * (4 - LEVEL) + 1);               \
-                if (LEVEL > 1) {                                                            \
-                    s.zr[0] = fma(msk, sgr, s.zr[0]); s.zi[0] = fma(msk, sgi, s.zi[0]);     \
-                } else {                                                                    \
-                    s.yr[0] = fma(msk, sgr, s.yr[0]); s.yi[0] = fma(msk, sgi, s.yi[0]);     \
+                hedges<R, LEVEL, 0, 4>(s, rho, hl, hr, o0, oL, tw.x, tw.y, a_win, (int)first); \
+                hinterior<R, LEVEL, 0, 4>(s, rho, o0, oL, tw.x, tw.y, a_win, (int)first);   \
+                if (LEVEL == 1) {                 /* the next step's y[0]; window complete */ \
+                    sts2(a_priv, s.yr[0], s.yi[0]);                                         \
+                    __syncwarp();                                                           \
                 }                                                                           \
             }
             QW_MIRROR_LEVEL(4)
@@ -925,16 +917,18 @@ cudaError_t launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan)
     return cudaGetLastError();
 }
 
-cudaError_t launch_packed_horner(const QwParams &prm, int tpp_log2, cudaStream_t st, qw_plan *plan)
+template <int TPP_LOG2>
+cudaError_t launch_packed_horner_t(const QwParams &prm, cudaStream_t st, qw_plan *plan)
 {
     constexpr int MINB = 12;
-    const int groups = 32 >> tpp_log2;
+    constexpr int groups = 32 >> TPP_LOG2;
+    auto kernel = rk4_cycle_packed_horner<MINB, TPP_LOG2>;
     if (plan) {
         cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, rk4_cycle_packed_horner<MINB>);
+        cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
         if (e != cudaSuccess) return e;
         int nb = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk4_cycle_packed_horner<MINB>, 32, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32, 0);
         if (e != cudaSuccess) return e;
         plan->path = 7;
         plan->sites_per_thread = 16;
@@ -946,8 +940,15 @@ cudaError_t launch_packed_horner(const QwParams &prm, int tpp_log2, cudaStream_t
         return cudaSuccess;
     }
     const int64_t blocks = packed_warps(prm, groups);
-    rk4_cycle_packed_horner<MINB><<<(unsigned)blocks, 32, 0, st>>>(prm, tpp_log2);
+    kernel<<<(unsigned)blocks, 32, 0, st>>>(prm);
     return cudaGetLastError();
+}
+
+cudaError_t launch_packed_horner(const QwParams &prm, int tpp_log2, cudaStream_t st, qw_plan *plan)
+{
+    if (tpp_log2 == 3) return launch_packed_horner_t<3>(prm, st, plan);
+    if (tpp_log2 == 4) return launch_packed_horner_t<4>(prm, st, plan);
+    return launch_packed_horner_t<5>(prm, st, plan);
 }
 
 template <int R, int MINB>
