@@ -39,7 +39,7 @@ template <int CH>
 struct HornerShared {
     HornerStep st[CH];
     double red[2 * 32];
-    double2 win[8];                      // slots 0 .. 6 of the owner thread (y_{w-3} .. y_{w+3}; half
+    double2 win[4];                      // slots 0 .. 3 of the owner thread (y_{w-3} .. y_w; half
                                          // ring: y_w .. y_{w+3}), published by the owner; not [W0]
     double2 priv[32];                    // the owner WARP's y[W0], lane by lane
     double tq[8];                        // the helper warp's outputs (-, t_3, t_2, t_1)
@@ -136,7 +136,7 @@ __device__ __forceinline__ void horner_first_window(const HState<R> &s, double2 
     priv[lane] = make_double2(s.yr[W0], s.yi[W0]);
     if (own) {
 #pragma unroll
-        for (int r = 0; r < (MIRROR ? 4 : 7); ++r) win[r] = make_double2(s.yr[r], s.yi[r]);
+        for (int r = 0; r < 4; ++r) win[r] = make_double2(s.yr[r], s.yi[r]);
     }
 }
 
@@ -159,7 +159,7 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
     constexpr bool OWNER = ROLE == HR_OWNER;
     constexpr bool HELPS = ROLE == HR_HELPER;
     constexpr int WS = OWNS ? W0 : -1;
-    constexpr int PUBW = OWNS ? (MIRROR ? 4 : 7) : 0;
+    constexpr int PUBW = OWNS ? (MIRROR ? 4 : HW0) : 0;     // window: slots 0 .. 3 (W0 is in priv)
     const bool full = RAGGED ? full_in : true;
     const int lane = t & 31;
     // owner warp: where a lane finds the addend of its marked slot at levels 3, 2, 1 -- the owner
@@ -168,10 +168,9 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
     const uint32_t a_t = (OWNS && own) ? smem_u32(oc.tq) : a_priv;
     const uint32_t a_ts = (OWNS && own) ? 16u : 0u;
     const uint32_t a_win = smem_u32(oc.win);
-    // helper (and HR_SELF): the two window sites of lane 8q + l
+    // helper (and HR_SELF): the window site y_{w-q} of lane 8q + l
     const int q = lane >> 3;
     const uint32_t wa = horner_window_addr<MIRROR>(MIRROR ? q : HW0 - q, oc.win, oc.priv);
-    const uint32_t wb = horner_window_addr<MIRROR>(MIRROR ? q : HW0 + q, oc.win, oc.priv);
     for (int sidx = 0; sidx < cnt; ++sidx) {
         const HornerStep &hs = tab[sidx];
 #define QW_LX_R(LV, r) ((LV == 4) ? s.yr[r] : s.zr[r])
@@ -205,13 +204,13 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
                 else { s.zr[R - 1] = hr.x; s.zi[R - 1] = hr.y; }                            \
             }                                                                               \
             if (ROLE == HR_SELF) {            /* one-warp block: every level from the dot product */ \
-                if (LEVEL == 4) sgl = horner_window_dot(wa, wb, hs, lane);                  \
+                if (LEVEL == 4) sgl = horner_window_dot(wa, hs, lane);                  \
                 tw.x = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));                      \
                 tw.y = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);                  \
                 if (!own) tw = make_double2(s.yr[W0], s.yi[W0]);                            \
             }                                                                               \
             if (HELPS && LEVEL == 4) {                                                      \
-                const double v = horner_window_dot(wa, wb, hs, lane);                       \
+                const double v = horner_window_dot(wa, hs, lane);                       \
                 if (lane < 8 && oc.helps) oc.tq[lane] = v;                                  \
             }                                                                               \
             hedges<R, LEVEL, WS, PUBW>(s, rho, hl, hr, o0, oL, tw.x, tw.y, a_win, (int)own); \
@@ -287,7 +286,11 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
     // Blocks of five warps and more: the owner warp does all of it (HR_SELF), as a one-warp block
     // does.  Measured (tools/r2_ab_sizes.sh): N = 3000 5.40e11 against 5.18e11 with the split,
     // N = 4096 6.30e11 against 6.0-6.2e11; N = 2048 (four warps) 6.47e11 against 6.64e11.
+#ifdef QW_ABL_SELFISH
+    const bool selfish = true;
+#else
     const bool selfish = nt > 128;
+#endif
     const HornerOracle oc = {sh.win, sh.priv, sh.tq, &sh.zero, warp == helper};
     if (t == 0) sh.zero = make_double2(0.0, 0.0);
     if (warp == (ht >> 5)) horner_first_window<R, MIRROR>(s, sh.win, sh.priv, t & 31, own);
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_horner(const QwParams p
 struct ClusterShared {
     HornerStep st[QW_CHUNK];
     double red[2 * 32];
-    double2 win[8];                      // as in HornerShared
+    double2 win[4];                      // as in HornerShared
     double2 priv[32];
     double tq[8];
     double2 zero;

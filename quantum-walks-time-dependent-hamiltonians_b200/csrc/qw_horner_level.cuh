@@ -102,15 +102,21 @@ __device__ __forceinline__ void horner_cycle_sum_basis(double2 *c)
 }
 
 // Shared-memory form for the cycle kernel.  The four corrections are evaluated by ALL 32 lanes of
-// the owner warp at once: lane 8q + l forms the two terms that s_q = y_{w-q} + y_{w+q} (s_0 = 2 y_w)
+// the owner (or helper) warp at once: lane 8q + l forms the two terms that s_q = y_{w-q} + y_{w+q}
 // contributes to output l, and two butterfly additions over q finish the dot products; output
 // l = 2m + c is component c (0 re, 1 im) of  y_w + sigma_{4-m},  i.e. the identity is folded into
 // the coefficients of y_w, so that the owner simply uses the value as the ADDEND of the level's
-// axpy at the marked vertex: 6 FP64 warp-instructions per step (2 DADD, DMUL, DFMA, 2 DADD)
-// instead of the 22 of the first version (6 sums + a dot product of length 8 in eight lanes + 8
-// masked corrections), which cost the hot kernel 9 % (tools/hot_probe.cu: the owner warp was the
-// longer of the two warps of a block at every barrier).
-// coef2[lane] = the lane's two coefficients (of Re s_q, Im s_q): one conflict-free LDS.128.
+// axpy at the marked vertex.
+// MIRROR SYMMETRY: the state is symmetric about the marked vertex bit for bit -- every caller
+// starts from the uniform state (BCB.py:179-180; the C ABI has no other start), H(t) is invariant
+// under the reflection and the neighbour sums of the level are commutative -- so s_q = 2 y_{w-q}
+// exactly and only the sites w-3 .. w are needed: the factor 2 is folded into the coefficients
+// (exact), a lane multiplies ONE window site: 4 FP64 warp-instructions per step (DMUL, DFMA, 2
+// DADD) instead of the 22 of the first version (6 sums + a dot product of length 8 in eight lanes
+// + 8 masked corrections), which cost the hot kernel 9 % (tools/hot_probe.cu: the owner warp was
+// the longer of the two warps of a block at every barrier).  tests/test_gpu_horner.py checks the
+// symmetry of psi itself bitwise.
+// coef2[lane] = the lane's two coefficients (of Re y_{w-q}, Im y_{w-q}): one conflict-free LDS.128.
 struct HornerStepBase {                  // the one-warp forms (every addend from the dot product)
     double rho[4];
     double2 coef2[32];
@@ -135,9 +141,11 @@ __device__ __forceinline__ void horner_step_store(HornerStepBase &o, const Horne
 #pragma unroll
         for (int k = 0; k < 4; ++k) {              // term k multiplies (Re s_k, Im s_k)
             double2 ck = (k <= m) ? c[base[m] + k] : make_double2(0.0, 0.0);
-            if (k == 0) {                          // y_w + sigma; the lanes form s_0 = 2 y_w
-                ck.x = 0.5 * ((m > 0 || fold4) ? ck.x + 1.0 : ck.x);
-                ck.y = 0.5 * ck.y;
+            if (k == 0) {                          // y_w + sigma
+                if (m > 0 || fold4) ck.x += 1.0;
+            } else {                               // s_k = 2 y_{w-k}
+                ck.x *= 2.0;
+                ck.y *= 2.0;
             }
             o.coef2[8 * k + 2 * m] = make_double2(ck.x, -ck.y);        // re
             o.coef2[8 * k + 2 * m + 1] = make_double2(ck.y, ck.x);     // im
@@ -247,8 +255,6 @@ __device__ __forceinline__ void hinterior(HState<R> &s, const double rho, const 
     }
 }
 
-// lane 8q + l: the terms of s_q = y_{w-q} + y_{w+q} in output l, then the sum over q; every lane
-// ends up with output l = lane & 7.  wa, wb: where the lane finds its two sites (horner_window_addr)
 __device__ __forceinline__ void horner_step_store(HornerStep &o, const HornerCoef &hc,
                                                   const bool fold4)
 {
@@ -256,12 +262,14 @@ __device__ __forceinline__ void horner_step_store(HornerStep &o, const HornerCoe
     o.c4 = hc.c[0];
 }
 
-__device__ __forceinline__ double horner_window_dot(const uint32_t wa, const uint32_t wb,
-                                                    const HornerStepBase &hs, const int lane)
+// lane 8q + l: the term of y_{w-q} in output l, then the sum over q; every lane ends up with
+// output l = lane & 7.  wa: where the lane finds y_{w-q} (horner_window_addr)
+__device__ __forceinline__ double horner_window_dot(const uint32_t wa, const HornerStepBase &hs,
+                                                    const int lane)
 {
-    const double2 ya = lds2(wa), yb = lds2(wb);
+    const double2 ya = lds2(wa);
     const double2 cf = hs.coef2[lane];
-    double v = fma(cf.y, ya.y + yb.y, cf.x * (ya.x + yb.x));
+    double v = fma(cf.y, ya.y, cf.x * ya.x);
     v += __shfl_xor_sync(0xffffffffu, v, 8);
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     return v;

@@ -610,11 +610,11 @@ static int packed_any_r(int64_t n)
 // G = 32 / TPP points -- one per lane.  The marked vertex is slot 3 of the first lane of a
 // point's group; eight lanes of the group evaluate its four corrections at once.
 // Oracle correction (round 2, as the one-warp form of qw_horner.cu): the first lane of a group
-// publishes its window y_{w-3} .. y_{w+3} in shared memory, the group's TPP lanes form the four dot
-// products y_w + sigma_l -- lane 8 qg + l the terms of 32 / TPP sums s_q in output l, then a
-// butterfly over qg -- and the owner takes them as the ADDEND of its marked slot: 6 / 9 / 16 FP64
-// warp-instructions per step for 32 / 16 / 8 lanes per point instead of 22, two shuffle stages
-// instead of 24 shuffles.
+// publishes its window y_{w-3} .. y_w in shared memory (mirror symmetry: qw_horner_level.cuh), the
+// group's TPP lanes form the four dot products y_w + sigma_l -- lane 8 qg + l the terms of 32 / TPP
+// window sites in output l, then a butterfly over qg -- and the owner takes them as the ADDEND of
+// its marked slot: 4 / 5 / 8 FP64 warp-instructions per step for 32 / 16 / 8 lanes per point
+// instead of 22, two shuffle stages instead of 24 shuffles.
 template <int MINB, int TPP_LOG2>
 __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwParams prm)
 {
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
     constexpr int tpp_log2 = TPP_LOG2;
     constexpr int QPL = 32 >> TPP_LOG2;          // sums s_q per lane: 1, 2, 4
     __shared__ HornerStepBase tab[32];           // [group][step of the chunk]
-    __shared__ double2 win[4][8];                // [group]: slots 0 .. 6 of the group's first lane
+    __shared__ double2 win[4][4];                // [group]: slots 0 .. 3 of the group's first lane
     __shared__ double2 tq2[4][4];                // [group]: y_w + sigma_4 .. y_w + sigma_1
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
 
     if (own) {
 #pragma unroll
-        for (int r = 0; r < 7; ++r) win[grp][r] = make_double2(s.yr[r], s.yi[r]);
+        for (int r = 0; r <= HW0; ++r) win[grp][r] = make_double2(s.yr[r], s.yi[r]);
     }
     for (int64_t n0 = 0; n0 < S; n0 += ch) {
         __syncwarp();
@@ -660,8 +660,8 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
 #pragma unroll
             for (int k = 0; k < 4; ++k) o.rho[k] = 0.0;
 #pragma unroll
-            for (int k = 0; k < 32; ++k)           // y_w + 0: the identity on s_0 = 2 y_w
-                o.coef2[k] = make_double2(k < 8 && !(k & 1) ? 0.5 : 0.0, k < 8 && (k & 1) ? 0.5 : 0.0);
+            for (int k = 0; k < 32; ++k)           // y_w + 0: the identity on y_w
+                o.coef2[k] = make_double2(k < 8 && !(k & 1) ? 1.0 : 0.0, k < 8 && (k & 1) ? 1.0 : 0.0);
         } else if (n0 + fstep < S) {
             const double t0 = (double)(n0 + fstep) * fpt.h;
             const double2 ad1 = qw_operator_scalars(t0 / fpt.T, fpt.gamma, prm.schedule, prm.gamma_on);
@@ -696,9 +696,8 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
                     for (int j = 0; j < QPL; ++j) {                                         \
                         const int q = qg * QPL + j;                                         \
                         const double2 ya = lds2(a_win + 16 * (HW0 - q));                    \
-                        const double2 yb = lds2(a_win + 16 * (HW0 + q));                    \
                         const double2 cf = hs.coef2[8 * q + l];                             \
-                        v = fma(cf.y, ya.y + yb.y, fma(cf.x, ya.x + yb.x, v));              \
+                        v = fma(cf.y, ya.y, fma(cf.x, ya.x, v));                            \
                     }                                                                       \
                     if (TPP_LOG2 >= 4) v += __shfl_xor_sync(full, v, 8);                    \
                     if (TPP_LOG2 >= 5) v += __shfl_xor_sync(full, v, 16);                   \
@@ -708,8 +707,8 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
                 const double2 tw = lds2(a_tq + 16 * (4 - LEVEL));                           \
                 const double wr = own ? tw.x : s.yr[HW0], wi = own ? tw.y : s.yi[HW0];      \
                 double2 o0, oL;                                                             \
-                hedges<R, LEVEL, HW0, 7>(s, rho, hl, hr, o0, oL, wr, wi, a_win, (int)own);  \
-                hinterior<R, LEVEL, HW0, 7>(s, rho, o0, oL, wr, wi, a_win, (int)own);       \
+                hedges<R, LEVEL, HW0, HW0>(s, rho, hl, hr, o0, oL, wr, wi, a_win, (int)own); \
+                hinterior<R, LEVEL, HW0, HW0>(s, rho, o0, oL, wr, wi, a_win, (int)own);     \
                 if (LEVEL == 1) {                 /* y[HW0] completes the next step's window */ \
                     sts2_if(a_win + 16 * HW0, s.yr[HW0], s.yi[HW0], (int)own);              \
                     __syncwarp();                                                           \
@@ -835,7 +834,7 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_mirror(const QwParams prm,
                 }                                                                           \
                 const double rho = hs.rho[LEVEL - 1];                                       \
                 if (LEVEL == 4) {                                                           \
-                    const double v = horner_window_dot(wq, wq, hs, lane);                   \
+                    const double v = horner_window_dot(wq, hs, lane);                   \
                     if (lane < 8) tq[lane] = v;                                             \
                     __syncwarp();                                                           \
                 }                                                                           \

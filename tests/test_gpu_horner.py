@@ -527,3 +527,26 @@ def test_packed_complete_step_size_heatmap_and_long_run(qw):
                                          gamma_on="laplacian", return_psi=True)
     assert np.abs(pl - po).max() <= 1e-11 and np.abs(nl - no).max() <= 1e-11
     assert np.abs(psil - psio).max() <= 1e-11
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,target", [(128, None), (256, 7), (512, None), (520, 100), (1001, None),
+                                      (1024, None), (1024, 0), (2048, 2047), (3000, None),
+                                      (4096, 1234), (5000, None), (8192, 3)])
+def test_full_ring_state_is_mirror_symmetric_bit_for_bit(qw, n, target):
+    """The oracle correction of the nested kernels reads only the sites w-3 .. w (s_q = 2 y_{w-q},
+    qw_horner_level.cuh): the full-ring state must be symmetric about the marked vertex BITWISE --
+    uniform start (BCB.py:179-180), reflection-invariant H(t), commutative neighbour sums -- in the
+    warp-packed, block-per-point and cluster kernels, for ragged layouts and any target."""
+    kw = dict(n=n, topology="circular", schedule="cerf_3", n_steps=96)
+    if target is not None:
+        kw["target"] = target
+    prob = qw.Problem(**kw)
+    T, g = np.array([3.0, 11.0, 40.0]), np.array([0.4, 1.1, 2.3])
+    p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+    w = (n - 1) // 2 if target is None else target
+    k = np.arange(1, n // 2 + 1)
+    assert np.array_equal(psi[:, (w + k) % n], psi[:, (w - k) % n]), (n, target)
+    po, no, psio, _ = c_oracle.rk4_batch(n, "circular", "cerf_3", T, g, n_steps=96,
+                                         target=w, return_psi=True)
+    assert np.abs(p - po).max() <= P_TOL and np.abs(psi - psio).max() <= PSI_TOL
