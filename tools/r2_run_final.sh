@@ -5,7 +5,7 @@ python bench.py --scaling strong --steps 3 --warmup 3 --no-stream --no-cpu-basel
 for w in c2 c3 c4; do python bench.py --workload $w --no-stream --cpu-seconds 5 > gpurun_out/r2_bench_${w}_n1.json 2>> gpurun_out/r2_bench_c5_n1.err; done
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_ref_n1.json 2>> gpurun_out/r2_bench_c5_n1.err
 python tests/run_configs.py > gpurun_out/r2_configs.md 2> gpurun_out/r2_configs.err
-tail -3 gpurun_out/r2_bench_c5_n1.err gpurun_out/r2_configs.err
+tail -n 3 gpurun_out/r2_bench_c5_n1.err; tail -n 3 gpurun_out/r2_configs.err
 python - <<PY
 import json
 for f in ["r2_bench_c5_n1", "r2_bench_c5_strong_n1", "r2_bench_c2_n1", "r2_bench_c3_n1", "r2_bench_c4_n1", "r2_bench_ref_n1"]:
