@@ -15,6 +15,10 @@
 #include <vector>
 
 #include "qw_stage.cuh"
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
 #include "qw_horner_level.cuh"
 
 namespace {
@@ -223,7 +227,8 @@ struct PackedJob {
     QwParams prm;
     int64_t warp_begin, warp_end;
     int32_t a, b;                    // tpp_log2, - / lanes per point, lanes with R sites
-    int32_t pad[2];
+    int64_t warp_offset;             // index within the problem of the entry's first warp (a problem
+                                     // with a fixed step size has one entry per T column)
 };
 
 // the calling warp's job -> shared memory; returns the warp's index within the job
@@ -241,7 +246,7 @@ __device__ __forceinline__ int64_t packed_job_fetch(const PackedJob *jobs, const
     unsigned long long *dst = reinterpret_cast<unsigned long long *>(mine);
     for (int i = threadIdx.x; i < (int)(sizeof(PackedJob) / 8); i += 32) dst[i] = src[i];
     __syncwarp();
-    return w - mine->warp_begin;
+    return w - mine->warp_begin + mine->warp_offset;
 }
 
 template <int R, int MINB, bool COLUMN>
@@ -406,6 +411,12 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any(const QwParams 
     packed_any_body<R, MIRROR>(prm, blockIdx.x, L, nfull);
 }
 
+#ifndef QW_ANY4_MINB
+#define QW_ANY4_MINB 16
+#endif
+#ifndef QW_ANY2_MINB
+#define QW_ANY2_MINB 16
+#endif
 template <int R, int MINB, bool MIRROR>
 __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_any_multi(const PackedJob *jobs,
                                                                        const int n_jobs)
@@ -1198,6 +1209,34 @@ static long long packed_multi_key(const PackedClass &c)
     return (long long)c.kind * 1000 + c.R * 10 + (c.column ? 1 : 0);
 }
 
+// The library's own streams for concurrent class grids (per device, created on first use).
+struct MultiStreams {
+    static constexpr int N = 4;
+    std::mutex mutex;
+    cudaStream_t aux[N] = {};
+    cudaEvent_t fork = nullptr, join[N] = {};
+    bool ok = false;
+};
+
+static MultiStreams *multi_streams()
+{
+    static MultiStreams table[64];
+    static std::mutex create;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    MultiStreams &m = table[dev];
+    std::lock_guard<std::mutex> lock(create);
+    if (!m.ok) {
+        bool good = cudaEventCreateWithFlags(&m.fork, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < MultiStreams::N && good; ++i)
+            good = cudaStreamCreateWithFlags(&m.aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+                   cudaEventCreateWithFlags(&m.join[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!good) { cudaGetLastError(); return nullptr; }
+        m.ok = true;
+    }
+    return &m;
+}
+
 cudaError_t qw_launch_packed_multi(const QwParams *prms, int n, unsigned char *taken,
                                    cudaStream_t st, int64_t *launches)
 {
@@ -1216,27 +1255,82 @@ cudaError_t qw_launch_packed_multi(const QwParams *prms, int n, unsigned char *t
     }
     std::stable_sort(items.begin(), items.end(),
                      [](const Item &x, const Item &y) { return x.key < y.key; });
-    cudaError_t err = cudaSuccess;
-    for (size_t b = 0; b < items.size() && err == cudaSuccess;) {
+    // one grid per kernel class; the grids run CONCURRENTLY (fork / join on the library's own
+    // streams): a class of short problems is a single latency-bound wave (the production sweep
+    // of BCB_latest.py:309-320: rings of 7 .. 29 sites, 6.9 ms at 32 % of the FP64 pipe) that
+    // hides behind the big class instead of queueing in front of it.  Small classes are issued
+    // first, the largest one last and on the caller's stream.
+    struct Group { size_t b, e; double work; };
+    std::vector<Group> groups;
+    for (size_t b = 0; b < items.size();) {
         size_t e = b;
         while (e < items.size() && items[e].key == items[b].key) ++e;
         if (e - b >= 2) {
+            double work = 0.0;
+            for (size_t k = b; k < e; ++k)
+                work += (double)prms[items[k].idx].n * (double)prms[items[k].idx].n_points;
+            groups.push_back({b, e, work});
+        }
+        b = e;
+    }
+    std::stable_sort(groups.begin(), groups.end(),
+                     [](const Group &x, const Group &y) { return x.work < y.work; });
+    MultiStreams *ms = groups.size() > 1 ? multi_streams() : nullptr;
+    std::unique_lock<std::mutex> lock;
+    if (ms) {
+        lock = std::unique_lock<std::mutex>(ms->mutex);
+        if (cudaEventRecord(ms->fork, st) != cudaSuccess) { cudaGetLastError(); ms = nullptr; }
+    }
+    cudaError_t err = cudaSuccess;
+    std::vector<int> used;
+    for (size_t gi = 0; gi < groups.size() && err == cudaSuccess; ++gi) {
+        const size_t b = groups[gi].b, e = groups[gi].e;
+        cudaStream_t gst = st;
+        if (ms && gi + 1 < groups.size()) {            // not the largest: an auxiliary stream
+            const int a = (int)(gi % MultiStreams::N);
+            gst = ms->aux[a];
+            err = cudaStreamWaitEvent(gst, ms->fork, 0);
+            if (err != cudaSuccess) break;
+            if (std::find(used.begin(), used.end(), a) == used.end()) used.push_back(a);
+        }
+        {
+            cudaStream_t st = gst;                     // the group's stream from here on
             std::vector<Item> grp(items.begin() + b, items.begin() + e);
             std::stable_sort(grp.begin(), grp.end(),
                              [](const Item &x, const Item &y) { return x.work > y.work; });
-            std::vector<PackedJob> jobs(grp.size());
+            // Fixed step size on heatmaps: a warp's length is its column's T, so the grid walks
+            // the problems column rank by column rank -- every problem's longest column first,
+            // then every second-longest ... -- which is close to longest-first over the whole grid
+            // (the production sweep: makespan 27.3 k steps instead of 30.9 k, ideal 24.7 k).
+            std::vector<PackedJob> jobs;
             int64_t w = 0;
-            for (size_t k = 0; k < grp.size(); ++k) {
-                PackedJob &j = jobs[k];
-                memset(&j, 0, sizeof(j));
-                j.prm = prms[grp[k].idx];
-                j.a = grp[k].c.a;
-                j.b = grp[k].c.b;
-                j.warp_begin = w;
-                w += packed_warps(j.prm, grp[k].c.groups);
-                j.warp_end = w;
+            int64_t max_cols = 1;
+            if (grp[0].c.column)
+                for (size_t k = 0; k < grp.size(); ++k)
+                    max_cols = std::max<int64_t>(max_cols, prms[grp[k].idx].n_time);
+            for (int64_t rank = 0; rank < max_cols; ++rank) {
+                for (size_t k = 0; k < grp.size(); ++k) {
+                    const QwParams &pk = prms[grp[k].idx];
+                    const int64_t total = packed_warps(pk, grp[k].c.groups);
+                    int64_t first = 0, count = total;
+                    if (grp[k].c.column) {
+                        if (rank >= pk.n_time) continue;
+                        count = total / pk.n_time;         // warps per column
+                        first = rank * count;
+                    }
+                    PackedJob j;
+                    memset(&j, 0, sizeof(j));
+                    j.prm = pk;
+                    j.a = grp[k].c.a;
+                    j.b = grp[k].c.b;
+                    j.warp_begin = w;
+                    j.warp_offset = first;
+                    w += count;
+                    j.warp_end = w;
+                    jobs.push_back(j);
+                }
             }
-            if (w > 0x7fffffffLL) { b = e; continue; }        // leave them to single launches
+            if (w > 0x7fffffffLL) continue;                    // leave them to single launches
             PackedJob *dj = nullptr;
             err = qw_scratch_alloc((void **)&dj, jobs.size() * sizeof(PackedJob), st);
             if (err != cudaSuccess) break;
@@ -1265,8 +1359,8 @@ cudaError_t qw_launch_packed_multi(const QwParams *prms, int n, unsigned char *t
                     else QW_PM((rk4_cycle_packed_any_multi<2, 16, false>));
                 } else {
                     if (c.R == 8) QW_PM((rk4_cycle_packed_any_multi<8, 12, true>));
-                    else if (c.R == 4) QW_PM((rk4_cycle_packed_any_multi<4, 16, true>));
-                    else QW_PM((rk4_cycle_packed_any_multi<2, 16, true>));
+                    else if (c.R == 4) QW_PM((rk4_cycle_packed_any_multi<4, QW_ANY4_MINB, true>));
+                    else QW_PM((rk4_cycle_packed_any_multi<2, QW_ANY2_MINB, true>));
                 }
 #undef QW_PM
                 err = cudaGetLastError();
@@ -1276,7 +1370,11 @@ cudaError_t qw_launch_packed_multi(const QwParams *prms, int n, unsigned char *t
             if (err == cudaSuccess)
                 for (size_t k = 0; k < grp.size(); ++k) taken[grp[k].idx] = 1;
         }
-        b = e;
+    }
+    for (int a : used) {                               // join: the caller's stream waits for all
+        cudaError_t e2 = cudaEventRecord(ms->join[a], ms->aux[a]);
+        if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, ms->join[a], 0);
+        if (e2 != cudaSuccess && err == cudaSuccess) err = e2;
     }
     return err;
 }
