@@ -160,8 +160,12 @@ int qw_rk4_grid_dev(const qw_problem *prob, const double *time_array, int64_t n_
  * warp-packed kernel coincides (same sites-per-lane geometry and step rule; dimension, schedule,
  * target, gamma placement and axes may differ) go out as ONE grid in which every warp looks its
  * problem up in a job table; the others are launched one after the other on the same stream.
- * Results are bitwise those of separate qw_rk4_grid_dev calls.  All pointers are device
- * pointers; jobs itself is a host array. */
+ * Two or more such grids run CONCURRENTLY on streams owned by the library (forked from and
+ * joined back into `stream`: work queued on `stream` before the call is seen by all of them,
+ * work queued after it waits for all of them), and with a fixed step size a grid walks the
+ * problems T column by T column, longest first.  Output buffers of different jobs must not
+ * overlap.  Results are bitwise those of separate qw_rk4_grid_dev calls.  All pointers are
+ * device pointers; jobs itself is a host array. */
 typedef struct qw_grid_job {
     qw_problem prob;
     const double *time_array;
