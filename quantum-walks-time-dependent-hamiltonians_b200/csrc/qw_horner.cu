@@ -17,7 +17,11 @@
 // (y_w, (Ly)_w, (L^2 y)_w, (L^3 y)_w) with coefficients that depend on the step's operator
 // scalars only; they are tabulated per step next to r1..r4 by the block's own threads
 // (one thread per step of a 32-step chunk).  tests/horner_model.py is the numpy statement of
-// this algebra, checked against the oracle on the CPU.
+// this algebra, checked against the oracle on the CPU.  How the four scalars are evaluated and
+// applied at run time -- as the ADDEND y_w + sigma_l of the level's axpy at the marked vertex,
+// from dot products over the window y_{w-3} .. y_w that one warp forms with all 32 lanes, split
+// over an owner and a helper warp -- is described at HornerStep (qw_horner_level.cuh) and at
+// horner_steps below.
 //
 // Any dimension: n = nact (R - 1) + nfull sites are dealt out as R sites to the first nfull
 // threads and R - 1 to the others (possible whenever n >= R^2).  The last slot of a short
@@ -33,8 +37,8 @@
 
 namespace {
 
-// CH steps per table refill: one thread per step, so blocks of two warps and more refill 64 steps
-// at a time (a refill is ~800 instructions in the lanes that have a step, while the other warps wait)
+// CH steps per table refill, one thread per step (a refill is ~800 instructions in the lanes that
+// have a step, while the other warps wait; 64 instead of 32 steps per refill measured no gain)
 template <int CH>
 struct HornerShared {
     HornerStep st[CH];
