@@ -488,8 +488,11 @@ __device__ __forceinline__ void cluster_comm_steps(double &yr, double &yi, Clust
 }
 
 // blockDim = compute threads (rounded up to warps) + 32 (the comm warp)
-template <int R, bool RAGGED>
-__global__ void __launch_bounds__(288, 1) rk4_cycle_cluster(const QwParams prm)
+// MAXNT / MINB: 288 threads, one CTA per SM (up to 4096 sites per CTA), or 160 threads, two CTAs
+// per SM (up to 2050 sites per CTA, twice as many CTAs per cluster): two independent barrier
+// domains per SM instead of one.
+template <int R, bool RAGGED, int MAXNT, int MINB>
+__global__ void __launch_bounds__(MAXNT, MINB) rk4_cycle_cluster(const QwParams prm)
 {
     static_assert(R >= 2 * HW0 + 1, "the window w-3..w+3 must sit in one thread");
     extern __shared__ double2 mbox[];         // [2][2][blockDim.x]: parity, first/last
@@ -561,7 +564,7 @@ __global__ void __launch_bounds__(288, 1) rk4_cycle_cluster(const QwParams prm)
     for (int64_t n0 = 0; n0 < pt.steps; n0 += QW_CHUNK) {
         const int cnt = (int)((pt.steps - n0 < QW_CHUNK) ? (pt.steps - n0) : QW_CHUNK);
         __syncthreads();                               // the last chunk's table is no longer read
-        horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, false);
+        horner_fill_cycle(sh.st, pt, n0, cnt, prm.schedule, prm.gamma_on, ntc > 128);
         __syncthreads();
 #define QW_HS(ROLE) horner_steps<R, ROLE, RAGGED, false>(s, sh.st, first, last, nt, t, tl, tr, \
                                                          cnt, own, full, 0, oc)
@@ -569,8 +572,9 @@ __global__ void __launch_bounds__(288, 1) rk4_cycle_cluster(const QwParams prm)
             cluster_comm_steps(er, ei, sh, first, last, nt, side, side == 0 ? me_l : me_r,
                                side == 0 ? 0 : nact - 1, my_bar0, my_bar1, to_slot0, to_slot1,
                                to_bar0, to_bar1, cnt, lane_on);
+        else if (owner_cta && warp == 0 && ntc > 128) QW_HS(HR_SELF);   // as the one-block kernel
         else if (owner_cta && warp == 0) QW_HS(HR_OWNER);
-        else if (owner_cta && warp == 1) QW_HS(HR_HELPER);     // every CTA has >= 3 compute warps
+        else if (owner_cta && warp == 1 && ntc <= 128) QW_HS(HR_HELPER);   // >= 2 compute warps
         else QW_HS(HR_PLAIN);
 #undef QW_HS
     }
@@ -1123,7 +1127,13 @@ int qw_cluster_size(const QwParams &prm)
     // streaming with 8 steps per pass (N = 16384: 4.3e11 against 5.3e11) -- unless the ring is not
     // a multiple of 128 sites, where streaming falls back to its cp.async kernel.
     if (prm.n > 8192 && prm.n % 128 == 0 && !(prm.flags & QW_FLAG_FORCE_CLUSTER)) return 0;
-    const int64_t c = (prm.n + 4095) / 4096;
+    int64_t c = (prm.n + 4095) / 4096;
+    // Above 8192 sites: small CTAs (at most 2050 sites, 160 threads, two per SM) where the cluster
+    // stays portable -- N = 12289: 4.43e11 with six small CTAs against 3.65e11 with four big ones;
+    // up to 8192 sites the big CTAs win (N = 8192: 4.98e11 against 4.65e11, N = 5000: 4.48e11
+    // against 3.69e11).  QW_FLAG_OCC4: always one CTA of up to 4096 sites per SM (A/B).
+    const int64_t c_small = (prm.n + 2049) / 2050;
+    if (prm.n > 8192 && c_small <= 8 && !(prm.flags & QW_FLAG_OCC4)) c = c_small;
     if (prm.n_points * c > 0x7fffffffLL) return 0;
     return (int)c;
 }
@@ -1137,7 +1147,8 @@ cudaError_t qw_launch_cluster(QwParams prm, cudaStream_t st, qw_plan *plan)
     const int nact = (int)((nb - 2 + R - 1) / R);                  // two sites live in the comm warp
     const int threads = ((nact + 31) / 32) * 32 + 32;              // + the comm warp
     const size_t smem = (size_t)threads * 4 * sizeof(double2);
-    auto kernel = rk4_cycle_cluster<R, true>;      // n_r - 2 compute sites: some threads hold R - 1
+    // n_r - 2 compute sites: some threads hold R - 1
+    auto kernel = threads <= 160 ? rk4_cycle_cluster<R, true, 160, 2> : rk4_cycle_cluster<R, true, 288, 1>;
     if (plan) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
@@ -1145,7 +1156,7 @@ cudaError_t qw_launch_cluster(QwParams prm, cudaStream_t st, qw_plan *plan)
         plan->path = 12;
         plan->sites_per_thread = R;
         plan->threads_per_block = threads;
-        plan->blocks_per_sm = 1;
+        plan->blocks_per_sm = threads <= 160 ? 2 : 1;
         plan->regs_per_thread = fa.numRegs;
         plan->smem_bytes = (int)(fa.sharedSizeBytes + smem);
         plan->steps_per_pass = c;                                  // CTAs per cluster

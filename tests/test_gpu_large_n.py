@@ -58,19 +58,25 @@ def test_cycle_graph_resident_across_a_cluster(qw, n):
     rng = np.random.default_rng(n)
     T = np.concatenate([[0.0], rng.uniform(1.0, 9.0, 4)])
     g = rng.uniform(0.1, 2.4, 5)
+    # CTAs per cluster: up to 4096 sites each, or (above 8192 sites, while the cluster stays
+    # portable) up to 2050 sites each, two CTAs per SM; 128 = QW_FLAG_OCC4 keeps the big CTAs
+    small = -(-n // 2050)
+    ctas = {0: small if n > 8192 and small <= 8 else -(-n // 4096), 128: -(-n // 4096)}
     for sched, S in (("lin", 37), ("cbrt", 70)):
-        # 16384 = QW_FLAG_FORCE_CLUSTER: above 8192 sites rings of a multiple of 128 sites go to
-        # the bulk-copy streaming kernel by default
-        prob = qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S, flags=16384)
-        pl = qw.plan(prob)
-        assert pl["path"] == "cluster-cycle" and pl["steps_per_pass"] == -(-n // 4096)
         default = qw.plan(qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S))
         assert default["path"] == ("stream" if n > 8192 and n % 128 == 0 else "cluster-cycle")
-        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
         po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, n_steps=S,
                                              return_psi=True)
-        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
-        assert np.abs(psi - psio).max() <= PSI_TOL
+        for geometry in ((0, 128) if ctas[0] != ctas[128] else (0,)):
+            # 16384 = QW_FLAG_FORCE_CLUSTER: above 8192 sites rings of a multiple of 128 sites go
+            # to the bulk-copy streaming kernel by default
+            prob = qw.Problem(n=n, topology="circular", schedule=sched, n_steps=S,
+                              flags=16384 | geometry)
+            pl = qw.plan(prob)
+            assert pl["path"] == "cluster-cycle" and pl["steps_per_pass"] == ctas[geometry]
+            p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+            assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+            assert np.abs(psi - psio).max() <= PSI_TOL
 
 
 def test_cluster_step_size_rule_targets_and_grid(qw):

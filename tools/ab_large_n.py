@@ -18,7 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--topology", default="complete")
 ap.add_argument("--sizes", default="4096,5000,8192,12289,16384")
 ap.add_argument("--steps", type=int, default=512)
-ap.add_argument("--flags", default="0,1")
+ap.add_argument("--flags", default="0,1")  # 128: cluster kernel with one big CTA per SM
 ap.add_argument("--points", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda")
