@@ -207,11 +207,13 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
                 if (LEVEL == 4) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }                 \
                 else { s.zr[R - 1] = hr.x; s.zi[R - 1] = hr.y; }                            \
             }                                                                               \
-            if (ROLE == HR_SELF) {            /* one-warp block: every level from the dot product */ \
-                if (LEVEL == 4) sgl = horner_window_dot(wa, hs, lane);                  \
-                tw.x = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL));                      \
-                tw.y = __shfl_sync(0xffffffffu, sgl, 2 * (4 - LEVEL) + 1);                  \
-                if (!own) tw = make_double2(s.yr[W0], s.yi[W0]);                            \
+            if (ROLE == HR_SELF) {            /* the owner warp does it all: every addend from */ \
+                if (LEVEL == 4) {             /* the dot product, through shared memory         */ \
+                    const double v = horner_window_dot(wa, hs, lane);                       \
+                    if (lane < 8) oc.tq[lane] = v;                                          \
+                    __syncwarp();                                                           \
+                }                                                                           \
+                tw = lds2(a_t + (4 - LEVEL) * a_ts);                                        \
             }                                                                               \
             if (HELPS && LEVEL == 4) {                                                      \
                 const double v = horner_window_dot(wa, hs, lane);                       \
@@ -233,7 +235,6 @@ __device__ __forceinline__ void horner_steps(HState<R> &s, const HornerStep *tab
                 last[(par ^ 1) * nt + t] = make_double2(lr, li);                            \
             }                                                                               \
         }
-        double sgl = 0.0;                          // HR_SELF: this lane's output
         QW_HORNER_LEVEL(4)
         QW_HORNER_LEVEL(3)
         QW_HORNER_LEVEL(2)
