@@ -103,6 +103,56 @@ def rk4_horner(n, topology, schedule, T, gamma, n_steps, gamma_on, target=None):
     return float(np.abs(y[w]) ** 2) / norm, norm, y
 
 
+# ---- cycle graph: the run-time form of the correction (csrc/qw_horner_level.cuh, HornerStep) ----
+
+def cycle_window_table(C):
+    """Per level l the four complex coefficients of (y_w, y_{w-1}, y_{w-2}, y_{w-3}) in
+    t_l = y_w + sigma_l, as horner_step_store tabulates them: change of basis to the neighbour
+    sums s_q = y_{w-q} + y_{w+q} (Ly = 2y - s1, L^2y = 6y - 4s1 + s2, L^3y = 20y - 15s1 + 6s2 - s3),
+    the identity folded into the coefficient of y_w, and s_q = 2 y_{w-q} (the state is mirror
+    symmetric about the marked vertex) folded into the others."""
+    basis = np.array([[1, 0, 0, 0], [2, -1, 0, 0], [6, -4, 1, 0], [20, -15, 6, -1]], dtype=complex)
+    tab = {}
+    for level in (1, 2, 3, 4):
+        c = np.asarray(C[level], dtype=complex) @ basis
+        c[0] += 1.0
+        c[1:] *= 2.0
+        tab[level] = c
+    return tab
+
+
+def horner_step_addend(y, w, rho, tab):
+    """One step as the kernels run it: the level's axpy at the marked vertex takes t_l (a dot
+    product over the one-sided window y_w .. y_{w-3} of the step's start) as its addend."""
+    n = y.shape[0]
+    win = np.array([y[w], y[(w - 1) % n], y[(w - 2) % n], y[(w - 3) % n]])
+    z = y
+    for level in (4, 3, 2, 1):
+        mz = -1j * rho[level - 1] * lap(z, TOPOLOGY_CYCLE)
+        znew = y + mz
+        znew[w] = tab[level] @ win + mz[w]
+        z = znew
+    return z
+
+
+def rk4_horner_addend(n, schedule, T, gamma, n_steps, gamma_on, target=None):
+    w = (n - 1) // 2 if target is None else target
+    y = np.full(n, 1 / np.sqrt(n), dtype=complex)
+    h = T / n_steps
+    asym = 0.0
+    for s in range(n_steps):
+        t = s * h
+        a1, d1 = (float(x) for x in operator_scalars(t / T, gamma, schedule, gamma_on))
+        a2, d2 = (float(x) for x in operator_scalars((t + 0.5 * h) / T, gamma, schedule, gamma_on))
+        a4, d4 = (float(x) for x in operator_scalars((t + h) / T, gamma, schedule, gamma_on))
+        rho, C = step_coefficients(h, a1, a2, a4, d1, d2, d4, 2.0, 6.0)
+        y = horner_step_addend(y, w, rho, cycle_window_table(C))
+        k = np.arange(1, n // 2 + 1)
+        asym = max(asym, float(np.abs(y[(w + k) % n] - y[(w - k) % n]).max()))
+    norm = float(np.sum(np.abs(y) ** 2))
+    return float(np.abs(y[w]) ** 2) / norm, norm, y, asym
+
+
 # ---- complete graph: the marked-vertex subsystem as a linear map (csrc/qw_horner.cu, CSMap) ----
 
 def complete_subsystem_map(rho, C, n):

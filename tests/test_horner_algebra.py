@@ -29,6 +29,21 @@ def test_nested_form_equals_rk4(n, topo, sched, T, g, S, go):
     assert np.abs(psi - psio[0]).max() <= 1e-13
 
 
+@pytest.mark.parametrize("n,topo,sched,T,g,S,go", [c for c in CASES if c[1] == "circular"])
+def test_addend_form_on_the_one_sided_window_equals_rk4(n, topo, sched, T, g, S, go):
+    """What the kernels execute since round 2 (HornerStep in csrc/qw_horner_level.cuh): t_l =
+    y_w + sigma_l as the addend of the marked slot, from the window y_w .. y_{w-3} only."""
+    from horner_model import rk4_horner_addend
+
+    for target in (None, 0, n - 1):
+        p, norm, psi, asym = rk4_horner_addend(n, sched, T, g, S, go, target=target)
+        po, no, psio = rk4_L2(n, topo, sched, [T], [g], n_steps=S, gamma_on=go, return_psi=True,
+                              target=target)
+        assert abs(p - po[0]) <= 1e-13 and abs(norm - no[0]) <= 1e-13
+        assert np.abs(psi - psio[0]).max() <= 1e-13
+        assert asym <= 1e-15            # numpy's roll-based stencil is symmetric to rounding
+
+
 def test_static_schedule_gives_the_autonomous_ratios():
     """Equal operator scalars in all stages: r = h a (1, 1/2, 1/3, 1/4)."""
     rho, _ = step_coefficients(0.1, 0.7, 0.7, 0.7, -0.3, -0.3, -0.3, 2.0, 6.0)
