@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(32, MINB) rk4_cycle_packed_horner(const QwPara
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
     constexpr int tpp = 1 << tpp_log2, groups = 32 >> tpp_log2, ch = 32 / groups;   // ch = tpp
-    const int li = lane & (tpp - 1), grp = lane >> tpp_log2, gbase = grp << tpp_log2;
+    const int li = lane & (tpp - 1), grp = lane >> tpp_log2;
     bool valid;
     const QwPoint pt = packed_point(prm, blockIdx.x, grp, groups, valid);
     __shared__ int64_t steps_slot;
