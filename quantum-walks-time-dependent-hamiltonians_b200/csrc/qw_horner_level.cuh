@@ -197,7 +197,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
 __device__ __forceinline__ double2 lds2(const uint32_t a)
 {
     double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    // "memory": the compiler must not move ordinary shared-memory stores (e.g. the dot products
+    // written just before a __syncwarp) across this load
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
     return v;
 }
 
