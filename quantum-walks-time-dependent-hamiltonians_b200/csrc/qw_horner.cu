@@ -1102,14 +1102,33 @@ static bool horner_mirror(const QwParams &prm)
 // Complete graph above 4096 vertices: blocks per point (0: not split).  The nested form needs
 // nothing from the other sites but the tabulated (y_w, S) subsystem, which every block advances
 // for itself, so a point splits over any number of blocks without communication; the partial
-// norms meet at the end (complete_epilogue).  Blocks hold 2049 .. 4096 sites.
+// norms meet at the end (complete_epilogue).
+// Blocks of two to four warps (1024 .. 2048 sites; three to six of them per SM) hide one
+// another's barriers better than one block of up to 4096 sites per SM.  Among those block counts
+// the cheapest wins: cost = blocks x warps per block x the measured cost of a warp in a block of
+// that many warps (site-updates/s per filled lane, tools/ab_large_n.py with 2368 points: four
+// warps 9.2e11, two 8.7e11, three 7.8e11); ties: the fewest blocks.  Measured against blocks of
+// 2049 .. 4096 sites (QW_FLAG_OCC4 keeps that rule for A/B): N = 5000 6.1e11 -> 8.5e11 (5 x 1000
+// sites in two full warps instead of 2 x 2500 in five), 8192 8.7e11 -> 9.2e11, 12289 6.6e11 ->
+// 8.1e11, 16384 8.7e11 -> 9.2e11, 40000 8.5e11 -> 9.0e11 (profiles/r2_ab_complete_split_rule.txt).
 int qw_horner_split(const QwParams &prm)
 {
     if (prm.topology != QW_TOPO_COMPLETE || prm.n <= 4096) return 0;
     if (prm.flags & (QW_FLAG_EXACT_SUM | QW_FLAG_NO_HORNER | QW_FLAG_CYCLE_LEGACY |
                      QW_FLAG_COMPLETE_FREE | QW_FLAG_FORCE_GENERIC))
         return 0;
-    const int64_t split = (prm.n + 4095) / 4096;
+    int64_t split = (prm.n + 4095) / 4096;
+    if (!(prm.flags & QW_FLAG_OCC4)) {
+        static const int64_t warp_cost[5] = {0, 106, 106, 118, 100};
+        const int64_t lo = (prm.n + 2047) / 2048, hi = (prm.n + 1023) / 1024;
+        int64_t best = INT64_MAX;
+        for (int64_t s = lo; s <= hi; ++s) {
+            const int64_t nb = (prm.n + s - 1) / s;                // the largest block
+            const int64_t warps = ((nb + 15) / 16 + 31) / 32;      // 2 .. 4
+            const int64_t cost = s * warps * warp_cost[warps];
+            if (cost < best) { best = cost; split = s; }
+        }
+    }
     if (split > 65536 || prm.n_points * split > 0x7fffffffLL) return 0;
     return (int)split;
 }

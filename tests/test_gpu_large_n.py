@@ -12,6 +12,22 @@ pytestmark = pytest.mark.gpu
 P_TOL, PSI_TOL = 1e-10, 1e-11
 
 
+def _split_blocks(n):
+    """qw_horner_split: blocks of 1024 .. 2048 sites, cost = blocks x warps x cost of a warp."""
+    ceil = lambda a, b: -(-a // b)
+    warp_cost = {2: 106, 3: 118, 4: 100}
+    cost = {}
+    for s in range(ceil(n, 2048), ceil(n, 1024) + 1):
+        warps = ceil(ceil(ceil(n, s), 16), 32)
+        cost[s] = s * warps * warp_cost[warps]
+    return min(cost, key=lambda s: (cost[s], s))
+
+
+def test_split_rule_examples():
+    assert [_split_blocks(n) for n in (4097, 5000, 6144, 8192, 9000, 12289, 16384, 40000)] == \
+        [5, 5, 3, 4, 9, 13, 8, 20]
+
+
 @pytest.mark.parametrize("n", [4097, 5000, 6144, 8192, 12289, 16384, 40000])
 def test_complete_graph_split_over_blocks(qw, n):
     rng = np.random.default_rng(n)
@@ -19,14 +35,18 @@ def test_complete_graph_split_over_blocks(qw, n):
         T = np.concatenate([[0.0], rng.uniform(10.0, 60.0, 3)]) if go == "laplacian" else \
             np.concatenate([[0.0], rng.uniform(0.5, 3.0, 3) / n * 8])
         g = rng.uniform(0.5, 2.0, 4) / n if go == "laplacian" else rng.uniform(0.3, 1.5, 4) * n
-        prob = qw.Problem(n=n, topology="complete", schedule=sched, gamma_on=go, n_steps=S)
-        pl = qw.plan(prob)
-        assert pl["path"] == "horner-complete" and pl["steps_per_pass"] == -(-n // 4096)
-        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
         po, no, psio, _ = c_oracle.rk4_batch(n, "complete", sched, T, g, n_steps=S, gamma_on=go,
                                              return_psi=True)
-        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
-        assert np.abs(psi - psio).max() <= PSI_TOL
+        # default: the block count of 1024 .. 2048 sites each that idles the fewest lanes;
+        # QW_FLAG_OCC4 (128): blocks of 2049 .. 4096 sites (qw_horner_split)
+        for flags, blocks in ((0, _split_blocks(n)), (128, -(-n // 4096))):
+            prob = qw.Problem(n=n, topology="complete", schedule=sched, gamma_on=go, n_steps=S,
+                              flags=flags)
+            pl = qw.plan(prob)
+            assert pl["path"] == "horner-complete" and pl["steps_per_pass"] == blocks
+            p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+            assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL
+            assert np.abs(psi - psio).max() <= PSI_TOL
 
 
 def test_complete_graph_split_step_size_rule_target_and_grid(qw):
