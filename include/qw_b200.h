@@ -89,7 +89,11 @@ enum {
                                     registers instead of two at 168 (A/B);
                                     complete graph: one auxiliary warp with both duties
                                     instead of scalar warp + table warp (above 3072 sites) or
-                                    of duties folded into the worker warps (up to 3072) (A/B) */
+                                    of duties folded into the worker warps (up to 3072) (A/B);
+                                    complete graph above 4096 vertices: a point split into
+                                    blocks of 2049 .. 4096 sites instead of the measured-cost
+                                    rule over blocks of 1024 .. 2048 sites (A/B);
+                                    cluster kernel: CTAs of up to 4096 sites above 8192 (A/B) */
     QW_FLAG_R8 = 256,            /* resident kernels: at most 8 sites per thread (default: 16
                                     where n % 16 == 0 and n/16 >= 32; A/B only) */
     QW_FLAG_NO_PACK = 512,       /* do not use the warp-packed kernel for small rings (A/B) */
