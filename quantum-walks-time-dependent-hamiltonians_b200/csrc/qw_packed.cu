@@ -927,6 +927,205 @@ cudaError_t launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan)
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same half-ring kernel for half rings that fill at most half a warp: LP = 8 or 16 lanes per
+// point, G = 4 or 2 points per warp (BASELINE config 4, N = 256: 129 sites = 8 lanes of 17 / 16
+// sites; one point per warp left 17 of 32 lanes idle and lost to the FULL-ring nested kernel,
+// 29.9 against 22.5 ms for 1e5 points).  As in rk4_cycle_packed_horner every point of the warp
+// has its own coefficient table -- a refill computes 32 / G steps for each of the G points, one
+// set per lane -- its own window (slots 1 .. 3 of the group's first lane; slot 0 in priv) and its
+// own four corrections: lane 8 qg + l of a group sums the terms of QPL window sites in output l,
+// a butterfly over qg follows for 16 lanes per point.  All points of a warp share the step
+// count (qw_packed_supported: the n_steps rule, or a heatmap column under a fixed step size).
+template <int R, int MINB, int LLOG2>
+__global__ void __launch_bounds__(32, MINB) rk4_cycle_mirror_packed(const QwParams prm,
+                                                                    const int L, const int nfull)
+{
+    constexpr int LP = 1 << LLOG2, G = 32 >> LLOG2, CH = LP;     // CH steps per refill and point
+    constexpr int QPL = 32 >> LLOG2;                             // window terms per lane: 4, 2
+    __shared__ HornerStepBase tab[32];            // [group][step of the chunk]
+    __shared__ double2 win[G][4], priv[32];       // slots 1 .. 3 of a group's first lane; every lane's y[0]
+    __shared__ double tq[G][8];                   // y_w + sigma_4 .. y_w + sigma_1 (re, im)
+    const unsigned fm = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int li = lane & (LP - 1), grp = lane >> LLOG2;
+    bool valid;
+    const QwPoint pt = packed_point(prm, blockIdx.x, grp, G, valid);
+    // the step count passes through tq (written next inside the time loop, behind a __syncwarp):
+    // with four points per warp the block must not exceed 18432 bytes for 12 blocks per SM
+    const int64_t S = packed_steps(prm, blockIdx.x, G, reinterpret_cast<int64_t *>(&tq[0][0]));
+    const bool active = li < L;
+    const bool full = li < nfull || !active;
+    const bool first = li == 0, lastl = li == L - 1;
+    const bool even = (prm.n & 1) == 0;
+    const int left = first ? lane : lane - 1, right = lane + 1 < 32 ? lane + 1 : lane;
+    // the lane's terms of the four dot products: window site q = qg QPL + j in output l
+    const int qg = li >> 3, l = li & 7;
+    uint32_t wq[QPL];
+#pragma unroll
+    for (int j = 0; j < QPL; ++j) {
+        const int q = qg * QPL + j;
+        wq[j] = q == 0 ? smem_u32(priv + (lane - li)) : smem_u32(&win[grp][q]);
+    }
+    const uint32_t a_priv = smem_u32(priv + lane);
+    const uint32_t a_t = first ? smem_u32(&tq[grp][0]) : a_priv, a_ts = first ? 16u : 0u;
+    const uint32_t a_win = smem_u32(&win[grp][0]);
+    // the lane's refill duty: step (lane % CH) of point (lane / CH) of this warp
+    const int fgrp = lane / CH, fstep = lane - fgrp * CH;
+    bool fvalid;
+    const QwPoint fpt = packed_point(prm, blockIdx.x, fgrp, G, fvalid);
+
+    HState<R> s;
+    const double amp = active ? 1.0 / sqrt((double)prm.n) : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s.yr[r] = (r == R - 1 && !full) ? 0.0 : amp; s.yi[r] = 0.0;
+        s.zr[r] = 0.0; s.zi[r] = 0.0;
+    }
+
+    priv[lane] = make_double2(s.yr[0], s.yi[0]);
+    if (first) {
+#pragma unroll
+        for (int r = 1; r < 4; ++r) win[grp][r] = make_double2(s.yr[r], s.yi[r]);
+    }
+    for (int64_t n0 = 0; n0 < S; n0 += CH) {
+        __syncwarp();
+        if (n0 + fstep < S && fpt.steps == 0) {        // T == 0: identity step (BCB.py:72-73)
+            HornerStepBase &o = tab[lane];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o.rho[k] = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)           // y_w + 0: the identity on y_w
+                o.coef2[k] = make_double2(k < 8 && !(k & 1) ? 1.0 : 0.0, k < 8 && (k & 1) ? 1.0 : 0.0);
+        } else if (n0 + fstep < S) {
+            const double t0 = (double)(n0 + fstep) * fpt.h;
+            const double2 ad1 = qw_operator_scalars(t0 / fpt.T, fpt.gamma, prm.schedule, prm.gamma_on);
+            const double2 ad2 = qw_operator_scalars((t0 + 0.5 * fpt.h) / fpt.T, fpt.gamma,
+                                                    prm.schedule, prm.gamma_on);
+            const double2 ad4 = qw_operator_scalars((t0 + fpt.h) / fpt.T, fpt.gamma, prm.schedule,
+                                                    prm.gamma_on);
+            HornerCoef hc;
+            horner_coefficients(hc, fpt.h, ad1, ad2, ad4, 2.0, 6.0);
+            horner_cycle_sum_basis(hc.c);
+            horner_step_store(tab[lane], hc, true);
+        }
+        __syncwarp();
+        const int cnt = (int)((S - n0 < CH) ? (S - n0) : CH);
+        for (int sidx = 0; sidx < cnt; ++sidx) {
+            const HornerStepBase &hs = tab[grp * CH + sidx];
+#define QW_MX_R(LV, r) ((LV == 4) ? s.yr[r] : s.zr[r])
+#define QW_MX_I(LV, r) ((LV == 4) ? s.yi[r] : s.zi[r])
+#define QW_MIRROR_LEVEL(LEVEL)                                                              \
+            {                                                                               \
+                /* last real slot (a short lane's slot R-1 is a ghost) and the one before */ \
+                const double lr = full ? QW_MX_R(LEVEL, R - 1) : QW_MX_R(LEVEL, R - 2);     \
+                const double li_ = full ? QW_MX_I(LEVEL, R - 1) : QW_MX_I(LEVEL, R - 2);    \
+                const double br = full ? QW_MX_R(LEVEL, R - 2) : QW_MX_R(LEVEL, R - 3);     \
+                const double bi = full ? QW_MX_I(LEVEL, R - 2) : QW_MX_I(LEVEL, R - 3);     \
+                double2 hl = make_double2(__shfl_sync(fm, lr, left), __shfl_sync(fm, li_, left)); \
+                double2 hr = make_double2(__shfl_sync(fm, QW_MX_R(LEVEL, 0), right),        \
+                                          __shfl_sync(fm, QW_MX_I(LEVEL, 0), right));       \
+                if (first) hl = make_double2(QW_MX_R(LEVEL, 1), QW_MX_I(LEVEL, 1));     /* mirror about w */ \
+                if (lastl) hr = even ? make_double2(br, bi) : make_double2(lr, li_);        \
+                if (!full) {                                                                \
+                    if (LEVEL == 4) { s.yr[R - 1] = hr.x; s.yi[R - 1] = hr.y; }             \
+                    else { s.zr[R - 1] = hr.x; s.zi[R - 1] = hr.y; }                        \
+                }                                                                           \
+                const double rho = hs.rho[LEVEL - 1];                                       \
+                if (LEVEL == 4) {                                                           \
+                    double v = 0.0;                                                         \
+                    _Pragma("unroll")                                                       \
+                    for (int j = 0; j < QPL; ++j) {                                         \
+                        const double2 ya = lds2(wq[j]);                                     \
+                        const double2 cf = hs.coef2[8 * (qg * QPL + j) + l];                \
+                        v = fma(cf.y, ya.y, fma(cf.x, ya.x, v));                            \
+                    }                                                                       \
+                    if (LLOG2 >= 4) v += __shfl_xor_sync(fm, v, 8);                         \
+                    if (li < 8) tq[grp][li] = v;                                            \
+                    __syncwarp();                                                           \
+                }                                                                           \
+                const double2 tw = lds2(a_t + (4 - LEVEL) * a_ts);                          \
+                double2 o0, oL;                                                             \
+                hedges<R, LEVEL, 0, 4>(s, rho, hl, hr, o0, oL, tw.x, tw.y, a_win, (int)first); \
+                hinterior<R, LEVEL, 0, 4>(s, rho, o0, oL, tw.x, tw.y, a_win, (int)first);   \
+                if (LEVEL == 1) {                 /* the next step's y[0]; window complete */ \
+                    sts2(a_priv, s.yr[0], s.yi[0]);                                         \
+                    __syncwarp();                                                           \
+                }                                                                           \
+            }
+            QW_MIRROR_LEVEL(4)
+            QW_MIRROR_LEVEL(3)
+            QW_MIRROR_LEVEL(2)
+            QW_MIRROR_LEVEL(1)
+#undef QW_MIRROR_LEVEL
+#undef QW_MX_R
+#undef QW_MX_I
+        }
+    }
+
+    // ||psi||^2: every site of the half ring counts twice, except w and (even n) the antipode
+    double nrm = 0.0;
+#pragma unroll
+    for (int r = 0; r < R - 1; ++r) nrm = fma(s.yr[r], s.yr[r], fma(s.yi[r], s.yi[r], nrm));
+    if (full) nrm = fma(s.yr[R - 1], s.yr[R - 1], fma(s.yi[R - 1], s.yi[R - 1], nrm));
+    nrm *= 2.0;
+    const double pw = fma(s.yr[0], s.yr[0], s.yi[0] * s.yi[0]);
+    if (first) nrm -= pw;
+    if (lastl && even) {
+        const double ar = full ? s.yr[R - 1] : s.yr[R - 2], ai = full ? s.yi[R - 1] : s.yi[R - 2];
+        nrm -= fma(ar, ar, ai * ai);
+    }
+    if (!active) nrm = 0.0;
+#pragma unroll
+    for (int o = LP >> 1; o > 0; o >>= 1) nrm += __shfl_xor_sync(fm, nrm, o);
+    if (first && valid) {
+        prm.p[pt.q] = pw / nrm;
+        if (prm.norm) prm.norm[pt.q] = nrm;
+    }
+    if (prm.psi && active && valid) {     // both mirror images: w + l and w - l
+        double2 *out = prm.psi + (size_t)pt.q * (size_t)prm.n;
+        const int64_t off = (int64_t)li * (R - 1) + (li < nfull ? li : nfull);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r == R - 1 && !full) continue;
+            int64_t a = prm.target + off + r, b = prm.target - off - r;
+            if (a >= prm.n) a -= prm.n;
+            if (b < 0) b += prm.n;
+            out[a] = make_double2(s.yr[r], s.yi[r]);
+            out[b] = make_double2(s.yr[r], s.yi[r]);
+        }
+    }
+}
+
+template <int R, int MINB, int LLOG2>
+cudaError_t launch_mirror_packed(const QwParams &prm, cudaStream_t st, qw_plan *plan)
+{
+    const int64_t m = prm.n / 2 + 1;                 // sites of the half ring
+    const int L = (int)((m + R - 1) / R);
+    const int nfull = (int)(m - (int64_t)L * (R - 1));
+    constexpr int G = 32 >> LLOG2;
+    auto kernel = rk4_cycle_mirror_packed<R, MINB, LLOG2>;
+    if (plan) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+        if (e != cudaSuccess) return e;
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, 32, 0);
+        if (e != cudaSuccess) return e;
+        plan->path = 9;
+        plan->sites_per_thread = R;
+        plan->threads_per_block = 32;
+        plan->blocks_per_sm = nb;
+        plan->regs_per_thread = fa.numRegs;
+        plan->smem_bytes = (int)fa.sharedSizeBytes;
+        plan->steps_per_pass = G;               // points per warp
+        return cudaSuccess;
+    }
+    const int64_t blocks = packed_warps(prm, G);
+    kernel<<<(unsigned)blocks, 32, 0, st>>>(prm, L, nfull);
+    return cudaGetLastError();
+}
+
 template <int TPP_LOG2>
 cudaError_t launch_packed_horner_t(const QwParams &prm, cudaStream_t st, qw_plan *plan)
 {
@@ -1042,8 +1241,47 @@ int qw_mirror_sites_per_lane(const QwParams &prm)
     return 0;
 }
 
+// Half rings of at most 16 lanes: 2 or 4 points per warp (rk4_cycle_mirror_packed).  Returns the
+// sites per lane (17 or 9) and the lanes per point (8 or 16) of the geometry that fills the most
+// lanes, or 0: one point per warp fills nearly as many, the step rule gives the points of a warp
+// no common step count (qw_packed_supported), the batch does not fill the machine twice (a few
+// points: one warp each is the faster way; not under QW_FLAG_FIXED_GEOMETRY), QW_FLAG_NO_PACK.
+// A point of L lanes holds L (R - 1) + 1 .. L R sites.
+static int mirror_packed_geometry(const QwParams &prm, int *llog2)
+{
+    const int r1 = qw_mirror_sites_per_lane(prm);
+    if (r1 == 0 || (prm.flags & (QW_FLAG_NO_PACK | QW_FLAG_OCC4))) return 0;
+    const bool uniform = prm.step_size == 0.0 && prm.n_steps == nullptr;
+    const bool columns = prm.step_size > 0.0 && prm.time_array != nullptr &&
+                         prm.order == nullptr && prm.n_time > 0;
+    if (!(uniform || columns)) return 0;
+    const int64_t m = prm.n / 2 + 1;
+    // (17 sites on 16 lanes never beats 9 sites per lane, one or two points per warp, by 10 %)
+    const int cand[2][2] = {{17, 3}, {9, 4}};
+    int best = 0;
+    int64_t best_fill = m * 110 / r1;                // one point per warp: m / (32 r1), + 10 %
+    for (int i = 0; i < 2; ++i) {
+        const int R = cand[i][0], lp = 1 << cand[i][1], g = 32 / lp;
+        if (R == 17 && (prm.flags & QW_FLAG_R8)) continue;         // A/B
+        const int64_t L = (m + R - 1) / R;
+        if (L > lp || m < L * (R - 1) + 1) continue;
+        const int64_t fill = g * m * 100 / R;        // x 32: the lanes' slots that hold a site
+        if (fill > best_fill) { best_fill = fill; best = R; *llog2 = cand[i][1]; }
+    }
+    if (best == 0) return 0;
+    const int64_t g = 32 >> *llog2;
+    if ((packed_batch(prm) + g - 1) / g < 2 * (int64_t)qw_sm_count()) return 0;
+    return best;
+}
+
 cudaError_t qw_launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan)
 {
+    int llog2 = 0;
+    switch (mirror_packed_geometry(prm, &llog2)) {
+    case 17: return launch_mirror_packed<17, 12, 3>(prm, st, plan);
+    case 9: return launch_mirror_packed<9, 12, 4>(prm, st, plan);
+    default: break;
+    }
     switch (qw_mirror_sites_per_lane(prm)) {
     case 17:
         if (prm.flags & QW_FLAG_OCC4) return launch_mirror<17, 8>(prm, st, plan);   // A/B: 196 registers

@@ -349,6 +349,80 @@ def test_mirror_reduced_streaming_vs_oracle(qw, n, kb_flag):
         assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched)
 
 
+FIXED, NO_PACK, R8 = 32768, 512, 256
+
+
+def _mirror_packed_geometry(n, r8=False):
+    """(sites per lane, points per warp) as mirror_packed_geometry of qw_packed.cu picks them."""
+    m = n // 2 + 1
+    r1 = 9 if (m >= 81 and (m + 8) // 9 <= 32) else 17
+    best, best_fill = (r1, 1), m * 110 // r1
+    for R, lp in ((17, 8), (9, 16)):
+        L = -(-m // R)
+        if (R == 17 and r8) or L > lp or m < L * (R - 1) + 1:
+            continue
+        fill = (32 // lp) * m * 100 // R
+        if fill > best_fill:
+            best, best_fill = (R, 32 // lp), fill
+    return best
+
+
+def test_mirror_packed_geometry_examples():
+    assert [_mirror_packed_geometry(n) for n in (160, 200, 255, 256, 271, 272, 287, 288, 512)] == \
+        [(17, 4), (17, 4), (9, 2), (17, 4), (17, 4), (9, 2), (9, 2), (9, 1), (9, 1)]
+    assert _mirror_packed_geometry(256, r8=True) == (9, 2)
+
+
+@pytest.mark.parametrize("n,flags", [(160, 0), (161, 0), (170, 0), (200, 0), (200, R8), (255, 0),
+                                     (256, 0), (256, R8), (257, 0), (270, 0), (271, 0), (272, 0),
+                                     (286, 0), (287, 0), (288, 0), (512, 0)])
+def test_mirror_reduced_kernel_points_packed_per_warp(qw, n, flags):
+    """Half rings of at most 16 lanes: two or four points per warp (BASELINE config 4 with the
+    drop-in default).  QW_FLAG_FIXED_GEOMETRY gives small calls the geometry of large ones, so
+    the packed kernel is what runs here: against the full-ring oracle and against the
+    one-point-per-warp kernel (QW_FLAG_NO_PACK), with points of T = 0 inside a warp, batch sizes
+    that leave groups of the last warp idle, both step rules, targets, psi."""
+    r, per_warp = _mirror_packed_geometry(n, bool(flags & R8))
+    pl = qw.plan(qw.Problem(n=n, topology="circular", n_steps=1, flags=MIRROR | flags))
+    assert pl["path"] == "mirror-cycle" and pl["steps_per_pass"] == per_warp, pl
+    assert pl["sites_per_thread"] == r and pl["blocks_per_sm"] == 12, pl
+    pl1 = qw.plan(qw.Problem(n=n, topology="circular", n_steps=1, flags=MIRROR | NO_PACK))
+    assert pl1["path"] == "mirror-cycle" and pl1["steps_per_pass"] == 1, pl1
+    rng = np.random.default_rng(n)
+    for sched, gamma_on, target, S, npts in [("lin", "oracle", None, 100, 11),
+                                             ("cbrt", "laplacian", 0, 37, 5),
+                                             ("cerf_5", "oracle", n - 1, 64, 8),
+                                             ("static", "laplacian", 7, 3, 1)]:
+        T = rng.uniform(0.0, 9.0, npts)
+        g = rng.uniform(0.0, 2.5, npts)
+        T[npts // 2] = 0.0
+        g[0] = 0.0
+        prob = qw.Problem(n=n, topology="circular", schedule=sched, gamma_on=gamma_on,
+                          target=target, n_steps=S, flags=MIRROR | FIXED | flags)
+        p, norm, psi = qw.rk4_batch(prob, T, g, return_psi=True)
+        po, no, psio, _ = c_oracle.rk4_batch(n, "circular", sched, T, g, gamma_on=gamma_on,
+                                             target=target, return_psi=True, n_steps=S)
+        assert np.abs(p - po).max() <= P_TOL, (n, sched)
+        assert np.abs(norm - no).max() <= P_TOL, (n, sched)
+        assert np.abs(psi - psio).max() <= PSI_TOL, (n, sched)
+        prob1 = qw.Problem(n=n, topology="circular", schedule=sched, gamma_on=gamma_on,
+                           target=target, n_steps=S, flags=MIRROR | NO_PACK)
+        p1, norm1 = qw.rk4_batch(prob1, T, g)
+        assert np.abs(p - p1).max() <= 1e-13 and np.abs(norm - norm1).max() <= 1e-13
+    # heatmaps through the grid entry point: the n_steps rule and a fixed step size (a warp takes
+    # rows of one T column), identical argmax, row shards bitwise the rows of the whole
+    t, b = np.linspace(0.0, 12.0, 5), np.linspace(0.0, 2.5, 11)
+    for rule in (dict(n_steps=48), dict(step_size=0.08)):
+        prob = qw.Problem(n=n, topology="circular", schedule="cerf_3", flags=MIRROR | FIXED | flags,
+                          **rule)
+        p, norm = qw.rk4_heatmap(prob, t, b)
+        po, no = c_oracle.heatmap(n, "circular", "cerf_3", t, b, **rule)
+        assert np.abs(p - po).max() <= P_TOL and np.abs(norm - no).max() <= P_TOL, (n, rule)
+        assert np.argmax(p) == np.argmax(po)
+        lo, _ = qw.rk4_heatmap(prob, t, b, rows=(3, 8))
+        assert np.array_equal(lo, p[3:8])
+
+
 @pytest.mark.parametrize("n,flags", [(1087, 0), (1088, 0), (2048, 0), (3000, 0),
                                      (4096, 0), (4097, 0), (8190, 0), (8191, 0), (8702, 0)])
 def test_mirror_reduced_block_kernel_vs_oracle(qw, n, flags):
