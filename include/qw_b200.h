@@ -112,7 +112,9 @@ enum {
                                     vertex for the uniform initial state every caller of the
                                     reference uses): same p, norm and psi with half the
                                     arithmetic.  6 <= n < 160: warp-packed half rings;
-                                    160 <= n <= 1087: one warp per point; up to
+                                    160 <= n <= 1087: one warp per point, or -- half rings of
+                                    at most 16 lanes (n <= 287) in batches that fill the
+                                    machine -- two or four points per warp; up to
                                     8702: block-per-point kernel on the half ring; above:
                                     streaming kernel with half the HBM traffic.
                                     Complete graph: all unmarked vertices carry one common

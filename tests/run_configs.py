@@ -188,6 +188,18 @@ def main():
           % (ms, 1e5 * n * 512 / (ms * 1e-3), 1e5 / (ms * 1e-3), T0, g0, p0, st["mean"], st["std"],
              p0 - st["mean"], "/".join("%.4f" % v for v in st["fraction_ge"].values()),
              float(np.abs(p[:8].cpu().numpy() - po).max())), flush=True)
+    # the same ensemble with the drop-in default: half ring, four points per warp
+    probm = qw.Problem(n=n, topology="circular", schedule="lin", n_steps=512, flags=8192)
+    msm, (pm, _) = timed(lambda: qw.rk4_batch(probm, dT, dg), reps=3)
+    stm = qw.ensemble_stats(pm)
+    plm = qw.plan(probm)
+    print("| C4 cycle N=256 1e5 noisy (T,gamma), half ring (drop-in default) | %s R=%d x %d thr, "
+          "%d points per warp | 100000 | %.1f | %.3e | %.3e | mean %.6f std %.6f; max |dp| vs the "
+          "full-ring kernel %.1e | %.1e |"
+          % (plm["path"], plm["sites_per_thread"], plm["threads_per_block"], plm["steps_per_pass"],
+             msm, 1e5 * n * 512 / (msm * 1e-3), 1e5 / (msm * 1e-3), stm["mean"], stm["std"],
+             float((pm - p).abs().max()), float(np.abs(pm[:8].cpu().numpy() - po).max())),
+          flush=True)
     if not a.skip_long:
         # localization ensemble: T0 = N^2/2, S = 131072
         T0l = n * n / 2.0
