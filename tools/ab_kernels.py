@@ -23,7 +23,9 @@ VARIANTS = {
            ("v2 R=16", 2048), ("v2 R=8 occ3", 2048 | 256), ("v2 R=8 occ4", 2048 | 256 | 128),
            ("v2 R=8 mbarrier occ3", 256 | 64), ("v1 R=8 legacy occ3", 256 | 32),
            ("v1 R=8 legacy occ4", 256 | 32 | 128)],
-    "c4": [("packed nested (default)", 0), ("packed stage form", 2048), ("horner R=8 one warp per point", 512), ("v2 occ3", 512 | 2048), ("v2 occ4", 128), ("v1 legacy occ3", 32),
+    "c4": [("packed nested (default)", 0), ("mirror-reduced, four points per warp (drop-in default)", 8192),
+           ("mirror-reduced, two points per warp", 8192 | 256), ("mirror-reduced, one warp per point", 8192 | 512),
+           ("packed stage form", 2048), ("horner R=8 one warp per point", 512), ("v2 occ3", 512 | 2048), ("v2 occ4", 128), ("v1 legacy occ3", 32),
            ("v1 legacy occ4", 32 | 128)],
     "c2": [("packed (default)", 0), ("packed 16 warps/SM at 128 regs", 128), ("packed R<=8", 256), ("v2 R=2 CTA-per-point", 512)],
     "c3": [("complete horner R=16 (default)", 0), ("complete horner R=16, one aux warp", 128),
