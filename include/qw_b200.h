@@ -113,7 +113,7 @@ enum {
                                     reference uses): same p, norm and psi with half the
                                     arithmetic.  6 <= n < 160: warp-packed half rings;
                                     160 <= n <= 1087: one warp per point, or -- half rings of
-                                    at most 16 lanes (n <= 287) in batches that fill the
+                                    at most 16 lanes (n <= 543) in batches that fill the
                                     machine -- two or four points per warp; up to
                                     8702: block-per-point kernel on the half ring; above:
                                     streaming kernel with half the HBM traffic.

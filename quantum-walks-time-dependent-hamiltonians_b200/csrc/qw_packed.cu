@@ -1256,17 +1256,19 @@ static int mirror_packed_geometry(const QwParams &prm, int *llog2)
                          prm.order == nullptr && prm.n_time > 0;
     if (!(uniform || columns)) return 0;
     const int64_t m = prm.n / 2 + 1;
-    // (17 sites on 16 lanes never beats 9 sites per lane, one or two points per warp, by 10 %)
-    const int cand[2][2] = {{17, 3}, {9, 4}};
+    // score = the lanes' slots that hold a site (x 32), weighted: 17 sites per lane run about
+    // 10 % faster per filled slot than 9 (tools/ab_large_n.py, N = 160 .. 286), and one point per
+    // warp (32 steps per table refill, 9 sites per lane in this range) gets the same bonus
+    const int cand[3][2] = {{17, 3}, {17, 4}, {9, 4}};
     int best = 0;
-    int64_t best_fill = m * 110 / r1;                // one point per warp: m / (32 r1), + 10 %
-    for (int i = 0; i < 2; ++i) {
+    int64_t best_score = m * 110 / r1;
+    for (int i = 0; i < 3; ++i) {
         const int R = cand[i][0], lp = 1 << cand[i][1], g = 32 / lp;
         if (R == 17 && (prm.flags & QW_FLAG_R8)) continue;         // A/B
         const int64_t L = (m + R - 1) / R;
         if (L > lp || m < L * (R - 1) + 1) continue;
-        const int64_t fill = g * m * 100 / R;        // x 32: the lanes' slots that hold a site
-        if (fill > best_fill) { best_fill = fill; best = R; *llog2 = cand[i][1]; }
+        const int64_t score = g * m * (R == 17 ? 110 : 100) / R;
+        if (score > best_score) { best_score = score; best = R; *llog2 = cand[i][1]; }
     }
     if (best == 0) return 0;
     const int64_t g = 32 >> *llog2;
@@ -1278,7 +1280,9 @@ cudaError_t qw_launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan
 {
     int llog2 = 0;
     switch (mirror_packed_geometry(prm, &llog2)) {
-    case 17: return launch_mirror_packed<17, 12, 3>(prm, st, plan);
+    case 17:
+        if (llog2 == 3) return launch_mirror_packed<17, 12, 3>(prm, st, plan);
+        return launch_mirror_packed<17, 12, 4>(prm, st, plan);
     case 9: return launch_mirror_packed<9, 12, 4>(prm, st, plan);
     default: break;
     }
