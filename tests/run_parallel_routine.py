@@ -31,8 +31,10 @@ def main():
     dist.broadcast_object_list(box, src=0)
     os.chdir(box[0])
     ok = True
+    # 256: the half ring with four points per warp (rk4_cycle_mirror_packed, column mode)
     for dim, sched, topo in ((51, "lin", "circular"), (64, "cerf_3", "circular"),
-                             (1024, "sqrt", "circular"), (300, "lin", "complete")):
+                             (256, "cerf_3", "circular"), (1024, "sqrt", "circular"),
+                             (300, "lin", "complete")):
         bcb.dimension, bcb.step_function, bcb.topology = dim, sched, topo
         bcb.type_of_qw, bcb.n_steps, bcb.step_size = "dependent", None, 0.02
         ub_t, ub_b = (12.0, 2.0) if topo == "circular" else (12.0 / dim, 2.0 * dim)
