@@ -1257,17 +1257,19 @@ static int mirror_packed_geometry(const QwParams &prm, int *llog2)
     if (!(uniform || columns)) return 0;
     const int64_t m = prm.n / 2 + 1;
     // score = the lanes' slots that hold a site (x 32), weighted: 17 sites per lane run about
-    // 10 % faster per filled slot than 9 (tools/ab_large_n.py, N = 160 .. 286), and one point per
-    // warp (32 steps per table refill, 9 sites per lane in this range) gets the same bonus
-    const int cand[3][2] = {{17, 3}, {17, 4}, {9, 4}};
+    // 10 % faster per filled slot than 9 (tools/ab_large_n.py, N = 160 .. 286; 13 and 15 in
+    // between), and one point per warp (32 steps per table refill, 9 sites per lane in this
+    // range) gets the same bonus.  13 and 15 sites per lane fill the gaps between the half rings
+    // that fit 17-site lanes (16 L + 1 .. 17 L sites).
+    const int cand[7][2] = {{17, 3}, {15, 3}, {13, 3}, {17, 4}, {15, 4}, {13, 4}, {9, 4}};
     int best = 0;
     int64_t best_score = m * 110 / r1;
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 7; ++i) {
         const int R = cand[i][0], lp = 1 << cand[i][1], g = 32 / lp;
-        if (R == 17 && (prm.flags & QW_FLAG_R8)) continue;         // A/B
+        if (R != 9 && (prm.flags & QW_FLAG_R8)) continue;          // A/B
         const int64_t L = (m + R - 1) / R;
         if (L > lp || m < L * (R - 1) + 1) continue;
-        const int64_t score = g * m * (R == 17 ? 110 : 100) / R;
+        const int64_t score = g * m * (100 + (R - 9) * 10 / 8) / R;
         if (score > best_score) { best_score = score; best = R; *llog2 = cand[i][1]; }
     }
     if (best == 0) return 0;
@@ -1283,6 +1285,12 @@ cudaError_t qw_launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan
     case 17:
         if (llog2 == 3) return launch_mirror_packed<17, 12, 3>(prm, st, plan);
         return launch_mirror_packed<17, 12, 4>(prm, st, plan);
+    case 15:
+        if (llog2 == 3) return launch_mirror_packed<15, 12, 3>(prm, st, plan);
+        return launch_mirror_packed<15, 12, 4>(prm, st, plan);
+    case 13:
+        if (llog2 == 3) return launch_mirror_packed<13, 12, 3>(prm, st, plan);
+        return launch_mirror_packed<13, 12, 4>(prm, st, plan);
     case 9: return launch_mirror_packed<9, 12, 4>(prm, st, plan);
     default: break;
     }

@@ -357,20 +357,20 @@ def _mirror_packed_geometry(n, r8=False):
     m = n // 2 + 1
     r1 = 9 if (m >= 81 and (m + 8) // 9 <= 32) else 17
     best, best_score = (r1, 1), m * 110 // r1
-    for R, lp in ((17, 8), (17, 16), (9, 16)):
+    for R, lp in ((17, 8), (15, 8), (13, 8), (17, 16), (15, 16), (13, 16), (9, 16)):
         L = -(-m // R)
-        if (R == 17 and r8) or L > lp or m < L * (R - 1) + 1:
+        if (R != 9 and r8) or L > lp or m < L * (R - 1) + 1:
             continue
-        score = (32 // lp) * m * (110 if R == 17 else 100) // R
+        score = (32 // lp) * m * (100 + (R - 9) * 10 // 8) // R
         if score > best_score:
             best, best_score = (R, 32 // lp), score
     return best
 
 
 def test_mirror_packed_geometry_examples():
-    assert [_mirror_packed_geometry(n) for n in (160, 200, 255, 256, 271, 272, 287, 288, 300, 310,
+    assert [_mirror_packed_geometry(n) for n in (160, 178, 200, 256, 271, 286, 288, 310, 350,
                                                  512, 542, 544, 576)] == \
-        [(17, 4), (17, 4), (9, 2), (17, 4), (17, 4), (9, 2), (9, 2), (17, 2), (17, 2), (9, 1),
+        [(17, 4), (13, 4), (13, 4), (17, 4), (17, 4), (9, 2), (13, 2), (13, 2), (13, 2),
          (17, 2), (17, 2), (9, 1), (17, 1)]
     assert _mirror_packed_geometry(256, r8=True) == (9, 2)
 
@@ -378,6 +378,8 @@ def test_mirror_packed_geometry_examples():
 @pytest.mark.parametrize("n,flags", [(160, 0), (161, 0), (170, 0), (200, 0), (200, R8), (255, 0),
                                      (256, 0), (256, R8), (257, 0), (270, 0), (271, 0), (272, 0),
                                      (286, 0), (287, 0), (288, 0), (300, 0), (305, 0), (310, 0),
+                                     (178, 0), (179, 0), (172, 0), (188, 0), (220, 0), (238, 0),
+                                     (318, 0), (350, 0), (383, 0), (415, 0), (447, 0), (478, 0),
                                      (480, 0), (512, 0), (513, 0), (542, 0), (543, 0), (574, 0)])
 def test_mirror_reduced_kernel_points_packed_per_warp(qw, n, flags):
     """Half rings of at most 16 lanes: two or four points per warp (BASELINE config 4 with the
