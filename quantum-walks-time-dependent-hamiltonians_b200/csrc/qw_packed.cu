@@ -1231,13 +1231,20 @@ int qw_packed_geometry(int64_t n, int64_t n_points, int max_r, int *tpp_log2)
 }
 
 // sites per lane of the mirror-reduced kernel (one point per warp), or 0: the half ring
-// n/2 + 1 = L (R - 1) + nfull must fit 32 lanes with R in {17, 9} and n/2 + 1 >= R^2
+// n/2 + 1 = L (R - 1) + nfull must fit 32 lanes (and L >= R, so that 1 <= nfull <= L).  The
+// fewest sites per lane that fit fill the most lanes: N = 600 is 28 lanes of 11 sites (86 % of
+// the slots) instead of 18 lanes of 17 (55 %).  QW_FLAG_NO_PACK: 9 or 17 only (A/B).
 int qw_mirror_sites_per_lane(const QwParams &prm)
 {
     if (!(prm.flags & QW_FLAG_MIRROR) || prm.topology != QW_TOPO_CYCLE) return 0;
     const int64_t m = prm.n / 2 + 1;
-    if (m >= 81 && (m + 8) / 9 <= 32) return 9;
-    if (m >= 289 && (m + 16) / 17 <= 32) return 17;
+    if (m < 81) return 0;
+    const int cand[5] = {9, 11, 13, 15, 17};
+    for (int i = 0; i < 5; ++i) {
+        const int R = cand[i];
+        if ((prm.flags & QW_FLAG_NO_PACK) && R != 9 && R != 17) continue;
+        if ((m + R - 1) / R <= 32) return R;
+    }
     return 0;
 }
 
@@ -1298,6 +1305,9 @@ cudaError_t qw_launch_mirror(const QwParams &prm, cudaStream_t st, qw_plan *plan
     case 17:
         if (prm.flags & QW_FLAG_OCC4) return launch_mirror<17, 8>(prm, st, plan);   // A/B: 196 registers
         return launch_mirror<17, 12>(prm, st, plan);
+    case 15: return launch_mirror<15, 12>(prm, st, plan);
+    case 13: return launch_mirror<13, 12>(prm, st, plan);
+    case 11: return launch_mirror<11, 12>(prm, st, plan);
     case 9: return launch_mirror<9, 12>(prm, st, plan);
     default: return cudaErrorInvalidConfiguration;
     }

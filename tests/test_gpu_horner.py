@@ -272,14 +272,18 @@ def test_packed_kernels_fixed_step_size_on_heatmaps(qw, n):
 MIRROR = 8192
 
 
-@pytest.mark.parametrize("n", [160, 161, 255, 256, 511, 512, 574, 575, 777, 1000, 1023, 1024, 1085,
-                               1086])
+@pytest.mark.parametrize("n", [160, 161, 255, 256, 511, 512, 574, 575, 576, 600, 703, 704, 777, 831,
+                               832, 900, 959, 960, 1000, 1023, 1024, 1085, 1086])
 def test_mirror_reduced_kernel_vs_oracle(qw, n):
     """QW_FLAG_MIRROR: the half ring with reflecting ends, one warp per point, against the
-    full-ring oracle -- even and odd n, both register geometries (9 / 17 sites per lane), all
+    full-ring oracle -- even and odd n, every register geometry (9 .. 17 sites per lane), all
     schedules, both gamma placements, both step rules, custom targets, psi (both images)."""
     pl = qw.plan(qw.Problem(n=n, topology="circular", n_steps=1, flags=MIRROR))
     assert pl["path"] == "mirror-cycle", pl
+    if n >= 544:        # one point per warp: the fewest sites per lane that fit 32 lanes
+        m = n // 2 + 1
+        assert pl["steps_per_pass"] == 1, pl
+        assert pl["sites_per_thread"] == next(R for R in (9, 11, 13, 15, 17) if -(-m // R) <= 32)
     rng = np.random.default_rng(n)
     for sched, gamma_on, target, rule in [("lin", "oracle", None, dict(n_steps=100)),
                                           ("cbrt", "laplacian", 0, dict(n_steps=37)),
@@ -355,7 +359,7 @@ FIXED, NO_PACK, R8 = 32768, 512, 256
 def _mirror_packed_geometry(n, r8=False):
     """(sites per lane, points per warp) as mirror_packed_geometry of qw_packed.cu picks them."""
     m = n // 2 + 1
-    r1 = 9 if (m >= 81 and (m + 8) // 9 <= 32) else 17
+    r1 = next(R for R in (9, 11, 13, 15, 17) if -(-m // R) <= 32)     # one point per warp
     best, best_score = (r1, 1), m * 110 // r1
     for R, lp in ((17, 8), (15, 8), (13, 8), (17, 16), (15, 16), (13, 16), (9, 16)):
         L = -(-m // R)
@@ -371,7 +375,7 @@ def test_mirror_packed_geometry_examples():
     assert [_mirror_packed_geometry(n) for n in (160, 178, 200, 256, 271, 286, 288, 310, 350,
                                                  512, 542, 544, 576)] == \
         [(17, 4), (13, 4), (13, 4), (17, 4), (17, 4), (9, 2), (13, 2), (13, 2), (13, 2),
-         (17, 2), (17, 2), (9, 1), (17, 1)]
+         (17, 2), (17, 2), (9, 1), (11, 1)]
     assert _mirror_packed_geometry(256, r8=True) == (9, 2)
 
 
