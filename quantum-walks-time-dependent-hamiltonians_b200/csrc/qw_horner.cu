@@ -1202,9 +1202,34 @@ int qw_horner_sites_per_thread(const QwParams &prm)
     if (qw_horner_split(prm) > 1) return 16;
     if (horner_mirror(prm)) {
         // the half ring has n/2 + 1 sites: 17 sites per thread keep the "+ 1" from costing a
-        // whole extra warp (n = 2048: 1025 = 61 threads x 17 instead of 65 x 16)
+        // whole extra warp (n = 2048: 1025 = 61 threads x 17 instead of 65 x 16).  Where 17-site
+        // threads leave much of the last warp empty, or a block of five or six warps alone on its
+        // SM, 13 or 9 sites per thread do better (n = 1100: 551 sites = 62 threads of 9, six
+        // blocks per SM, instead of 33 of 17 in two warps: 5.5e11 -> 9.2e11 full-ring
+        // site-updates/s).  The choice maximises filled slots x a weight per R x a weight for the
+        // warps resident per SM, all three measured (tools/ab_large_n.py, profiles/
+        // r2_ab_mirror_block_r.txt: per filled slot 9 sites run at 0.95, 13 at 1.05, 17 at 1.06;
+        // five warps per SM at 0.6, six at 0.8, seven at 0.92 of eight and more; blocks of three
+        // warps at 0.9); ties to the larger R.  QW_FLAG_NO_PACK: 17 only (A/B).
         const int64_t m = prm.n / 2 + 1;
-        return (m + 16) / 17 <= 256 ? 17 : 0;
+        if ((m + 16) / 17 > 256) return 0;
+        if (prm.flags & QW_FLAG_NO_PACK) return 17;
+        const int cand[3][2] = {{17, 106}, {13, 105}, {9, 95}};
+        int best = 17;
+        int64_t best_score = -1;
+        for (int i = 0; i < 3; ++i) {
+            const int R = cand[i][0];
+            const int64_t nact = (m + R - 1) / R, warps = (nact + 31) / 32;
+            if (nact > 256) continue;
+            // blocks per SM of the instantiations in qw_launch_horner
+            const int64_t blocks = warps <= 2 ? (R == 17 ? 4 : 6) : warps <= 4 ? (R == 17 ? 2 : 3) : 1;
+            const int64_t resident = blocks * warps;
+            const int64_t occ = resident >= 8 ? 100 : resident == 7 ? 92 : resident == 6 ? 80 : 60;
+            const int64_t shape = warps == 3 ? 90 : 100;    // blocks of three warps run slower
+            const int64_t score = m * cand[i][1] * occ * shape / (R * warps * 32);
+            if (score > best_score) { best_score = score; best = R; }
+        }
+        return best;
     }
     const int64_t n = prm.n;
     if (prm.topology != QW_TOPO_CYCLE && (prm.flags & QW_FLAG_EXACT_SUM)) return 0;
@@ -1278,8 +1303,20 @@ cudaError_t qw_launch_horner(QwParams prm, cudaStream_t st, qw_plan *plan)
         QW_HL(rk4_complete_horner, 8, 512, 1, 1);
     }
     const int bthreads = threads;
-    if (mirror) {                                  // R = 17, up to 255 registers
+    if (mirror) {                                  // R = 17: up to 255 registers
 #define QW_HM(...) return hlaunch(rk4_cycle_horner<__VA_ARGS__, true, true>, prm, bthreads, smem, st, plan)
+        if (R == 9) {
+            if (threads <= 64) { QW_MB(64); QW_HM(9, 64, 6); }
+            if (threads <= 128) { QW_MB(128); QW_HM(9, 128, 3); }
+            QW_MB(256);
+            QW_HM(9, 256, 1);
+        }
+        if (R == 13) {
+            if (threads <= 64) { QW_MB(64); QW_HM(13, 64, 6); }
+            if (threads <= 128) { QW_MB(128); QW_HM(13, 128, 3); }
+            QW_MB(256);
+            QW_HM(13, 256, 1);
+        }
         if (threads <= 64) { QW_MB(64); QW_HM(17, 64, 4); }
         if (threads <= 128) { QW_MB(128); QW_HM(17, 128, 2); }
         QW_MB(256);

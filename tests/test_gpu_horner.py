@@ -432,14 +432,41 @@ def test_mirror_reduced_kernel_points_packed_per_warp(qw, n, flags):
         assert np.array_equal(lo, p[3:8])
 
 
-@pytest.mark.parametrize("n,flags", [(1087, 0), (1088, 0), (2048, 0), (3000, 0),
-                                     (4096, 0), (4097, 0), (8190, 0), (8191, 0), (8702, 0)])
+def _block_mirror_sites_per_thread(n):
+    """qw_horner_sites_per_thread under QW_FLAG_MIRROR: filled slots x weight of R x weight of
+    the warps resident per SM, ties to the larger R."""
+    m = n // 2 + 1
+    score = {}
+    for R, w in ((17, 106), (13, 105), (9, 95)):
+        nact = -(-m // R)
+        if nact > 256:
+            continue
+        warps = -(-nact // 32)
+        blocks = (4 if R == 17 else 6) if warps <= 2 else (2 if R == 17 else 3) if warps <= 4 else 1
+        resident = blocks * warps
+        occ = 100 if resident >= 8 else {7: 92, 6: 80}.get(resident, 60)
+        score[R] = m * w * occ * (90 if warps == 3 else 100) // (R * warps * 32)
+    return max(score, key=lambda R: (score[R], R))
+
+
+def test_block_mirror_geometry_examples():
+    assert [_block_mirror_sites_per_thread(n) for n in (1088, 1100, 1300, 2048, 2200, 2500, 3000,
+                                                        3300, 4096, 4606, 5000, 6656, 8192,
+                                                        8702)] == \
+        [9, 9, 13, 17, 9, 13, 13, 13, 17, 9, 13, 17, 17, 17]
+
+
+@pytest.mark.parametrize("n,flags", [(1087, 0), (1088, 0), (1100, 0), (1300, 0), (1664, 0),
+                                     (2048, 0), (2200, 0), (2500, 0), (3000, 0), (3300, 0),
+                                     (4096, 0), (4097, 0), (4606, 0), (4607, 0), (5000, 0), (6656, 0),
+                                     (8190, 0), (8191, 0), (8702, 0), (2200, 512)])
 def test_mirror_reduced_block_kernel_vs_oracle(qw, n, flags):
     """QW_FLAG_MIRROR between 1087 and 8191 sites: the half ring in the block-per-point nested
     kernel (reflecting ends in thread 0 and in the last thread)."""
     pl = qw.plan(qw.Problem(n=n, topology="circular", n_steps=1, flags=MIRROR | flags))
     assert pl["path"] == ("mirror-cycle" if n // 2 + 1 <= 544 else "horner-cycle"), pl
-    assert pl["sites_per_thread"] == 17
+    if n // 2 + 1 > 544:
+        assert pl["sites_per_thread"] == (17 if flags & 512 else _block_mirror_sites_per_thread(n))
     rng = np.random.default_rng(n)
     for sched, gamma_on, target, rule in [("lin", "oracle", None, dict(n_steps=70)),
                                           ("sqrt", "laplacian", 3, dict(n_steps=33)),
