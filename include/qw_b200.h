@@ -96,8 +96,10 @@ enum {
                                     cluster kernel: CTAs of up to 4096 sites above 8192 (A/B) */
     QW_FLAG_R8 = 256,            /* resident kernels: at most 8 sites per thread (default: 16
                                     where n % 16 == 0 and n/16 >= 32; A/B only) */
-    QW_FLAG_NO_PACK = 512,       /* do not use the warp-packed kernel for small rings, nor more
-                                    than one point per warp in the half-ring kernel (A/B) */
+    QW_FLAG_NO_PACK = 512,       /* do not use the warp-packed kernel for small rings; half-ring
+                                    kernels: one point per warp and 9 or 17 sites per lane only
+                                    (one warp per point), 17 sites per thread only (block per
+                                    point) instead of the geometry chosen for the fill (A/B) */
     QW_FLAG_COMPLETE_FREE = 1024,/* complete graph: barrier-free variant (stage sums through an
                                     acquire/release table) instead of one barrier per stage;
                                     measured equal, A/B only */
